@@ -1,0 +1,163 @@
+/*
+ * abm_b200.h -- C-ABI of libabm_b200.so: the B200 (sm_100a) implementation of the per-step
+ * cell-update hot path of Python-hiPSC-ABM.
+ *
+ * Every entry point replaces one of the reference's JIT functions or the numpy/igraph host work
+ * around it (file:line under /root/reference/ABM is cited per function).  The reference binds this
+ * path through Numba; the replacement binding is ctypes.
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers (e.g. torch tensor.data_ptr()) unless the name ends in _host.
+ *   - The caller owns every buffer, including workspaces; the library allocates nothing persistent.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises,
+ *     except the *_sync helpers that must hand a count back to the host.
+ *   - Return value: 0 ok; >0 capacity overflow (the wrapper grows the buffer and calls again, mirroring
+ *     the reference's grow-and-retry loops simulation.py:217-221, 277-281); <0 invalid argument (-1) or
+ *     -(1000+cudaError_t).  Nothing throws across the ABI; abm_last_error() describes the last failure.
+ *   - Cell ids, bin ids, row offsets are int32; positions/forces/fields are float64 exactly as the
+ *     reference holds them (simulation.py:136-149 dtypes).
+ *   - Positions are (N,3) row-major float64 ("AoS", the reference's `locations`), radii (N,) float64.
+ */
+#ifndef ABM_B200_H
+#define ABM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABM_B200_ABI_VERSION 1
+
+/* ---- library ----------------------------------------------------------------------------------- */
+int abm_abi_version(void);          /* == ABM_B200_ABI_VERSION */
+int abm_compiled_arch(void);        /* 100 : built for sm_100a only */
+const char *abm_last_error(void);   /* thread-local text of the last non-zero return */
+/* fills sm_count / cc_major / cc_minor of the current device; <0 if there is no CUDA device */
+int abm_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- spatial binning: counting sort ------------------------------------------------------------
+ * Replaces Simulation.assign_bins + assign_bins_jit (simulation.py:190-223, backend.py:31-50).
+ * dims[k] = ceil(size[k]/distance)+3 and bin = floor_divide(x,distance)+1 exactly as the reference;
+ * coordinates are clamped into [0,dims-1] (the reference wraps negative indices to an always-empty
+ * bin; the edge sets agree, DESIGN.md "bins").  Linear bin id = (bz*dims[1]+by)*dims[0]+bx.         */
+int abm_bin_dims_host(const double size_host[3], double distance, int32_t dims_host[3]);
+
+/* bytes of scratch abm_bin_sort needs for n cells and nbins bins */
+size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins);
+
+/* Outputs:
+ *   bin_start  (nbins+1) int32  exclusive prefix of per-bin counts, bin_start[nbins] = n
+ *   sorted_id  (n)       int32  sorted slot -> cell id; ascending id inside a bin (the reference's
+ *                               serial fill order, backend.py:36-48)
+ *   sorted_pos (n,4)     f64    {x,y,z,radius} of the cell in that slot (32-byte rows)
+ *   sorted_bin (n)       int32  linear bin of the slot
+ *   max_count  (1)       int32  largest bin population (what drives the reference's max_agents)   */
+int abm_bin_sort(const double *locations, const double *radii, int64_t n, const double size_host[3],
+                 double distance, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
+                 int32_t *sorted_bin, int32_t *max_count, void *workspace, size_t workspace_bytes,
+                 void *stream);
+
+/* Reference-shaped dense outputs of assign_bins (simulation.py:206-213) from a finished sort:
+ *   bins (dims0,dims1,dims2,max_agents) int64 [reference index order x,y,z], bins_help (dims0,dims1,dims2)
+ *   int64, bin_locations (n,3) int64.  bins/bins_help must be zero-filled by the caller.           */
+int abm_bins_dense(const double *locations, int64_t n, const double size_host[3], double distance,
+                   const int32_t *bin_start, const int32_t *sorted_id, int64_t max_agents, int64_t *bins,
+                   int64_t *bins_help, int64_t *bin_locations, void *stream);
+
+/* ---- fixed-radius neighbour search -> CSR -------------------------------------------------------
+ * Replaces get_neighbors_cpu/gpu + the edges[if_edge] compaction + graph.add_edges (+ simplify when
+ * clear=False) (backend.py:64-160, simulation.py:225-288).
+ * Graph format ("row CSR"): for cell i its neighbours are cols[row_start[i] .. row_start[i]+row_len[i]),
+ * both directions stored (j in row i <=> i in row j), ascending.  Rows are packed without gaps but in
+ * no particular order (warp-aggregated reservation), so row_start is explicit.  Wherever a graph is an
+ * INPUT, row_start may be NULL, meaning fixed-stride rows: row i starts at i*row_stride.
+ * An edge exists iff sqrt(dx*dx+dy*dy+dz*dz) <= distance evaluated in fp64 without FMA (bit-identical
+ * to the oracle).  If old_* is non-NULL the result is the union with that graph (clear=False).
+ *   cursor (1) int32 : zeroed by the call, ends as the number of column entries needed (= 2*edges).
+ * Returns 0; the caller reads *cursor (abm_read_i32_sync) and, if it exceeds cols_capacity, grows
+ * cols and calls again (rows are only valid when cursor <= cols_capacity).                         */
+int abm_neighbor_search(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,
+                        const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
+                        const double *locations, const int32_t *old_row_start, int64_t old_row_stride,
+                        const int32_t *old_row_len, const int32_t *old_cols, int32_t *row_start,
+                        int32_t *row_len, int32_t *cols, int64_t cols_capacity, int32_t *cursor, void *stream);
+
+/* synchronises `stream` and returns *device_value through value_host */
+int abm_read_i32_sync(const int32_t *device_value, int32_t *value_host, void *stream);
+
+/* (i<j) edge list of a row-CSR graph in canonical order (sorted by i, then j), as the reference's
+ * get_edgelist() after simplify() (cell_methods.py:352).  scan_ws: abm_graph_edge_list_workspace_bytes(n).
+ * edges (E,2) int64.  n_edges (1) int32 receives E.  Two launches, no host sync.                  */
+size_t abm_graph_edge_list_workspace_bytes(int64_t n);
+int abm_graph_edge_list(const int32_t *row_start, int64_t row_stride, const int32_t *row_len,
+                        const int32_t *cols, int64_t n, int32_t *scan_ws, size_t scan_ws_bytes, int64_t *edges,
+                        int64_t edges_capacity, int32_t *n_edges, void *stream);
+
+/* ---- JKR forces over graph rows ------------------------------------------------------------------
+ * Replaces jkr_forces_cpu/gpu + jkr_graph.delete_edges (cell_backend.py:6-115, cell_methods.py:342-384).
+ * Row-owner accumulation (each cell sums its own bonds in ascending partner id = the serial
+ * reference's += order), so no atomics and run-to-run identical.  Broken bonds (d <= -0.360562) are
+ * removed from both rows in place (row_len shrinks).  jkr_forces (N,3) is ACCUMULATED into.       */
+int abm_jkr_forces(const int32_t *row_start, int64_t row_stride, int32_t *row_len, int32_t *cols,
+                   const double *locations, const double *radii, double *jkr_forces, int64_t n, double poisson,
+                   double youngs, double adhesion_const, void *stream);
+
+/* Replaces apply_forces_cpu/gpu (cell_backend.py:118-172): Stokes velocity, Euler step, clamp to
+ * [0,size] per axis, same operation order as the reference (bit-identical for identical inputs).
+ * If jkr_forces_to_zero is non-NULL that (N,3) array is zeroed afterwards (cell_methods.py:436).   */
+int abm_apply_forces(const double *jkr_forces, const double *motility_forces, double *locations,
+                     const double *radii, int64_t n, double stokes, const double size_host[3], double move_dt,
+                     double *jkr_forces_to_zero, void *stream);
+
+/* ---- fused mechanics substep ---------------------------------------------------------------------
+ * One launch = get_neighbors("jkr_graph", distance, clear=False) + calculate_jkr() + apply_forces
+ * integration for one of the 11 substeps of CellMethods.apply_forces (cell_methods.py:399-436).
+ * Input: a sort of the CURRENT locations made with bin edge >= abm_jkr_reach() (so every bond that
+ * can survive lies inside the 27-bin stencil), the bond graph from the previous substep (old_*; rows
+ * may be unsorted) and the motility forces.  Output: the new bond graph in fixed-stride rows
+ * (row i at new_cols[i*row_stride], length new_row_len[i], ascending if sort_rows) and the moved
+ * locations (written in place; the kernel only reads positions from sorted_pos).
+ * A bond (i,j) exists afterwards iff (dist <= distance or it existed before) and d > -0.360562.
+ *   reach            : bin edge of the sort, >= abm_jkr_reach(distance, max(radii), ...).
+ *   max_len (1) int32: raised (atomicMax) by rows that needed more than row_stride entries; a value
+ *   > row_stride afterwards means those rows were truncated: grow row_stride and redo the substep
+ *   from the saved locations.  The caller zeroes it.                                                */
+double abm_jkr_reach(double distance, double max_radius, double poisson, double youngs, double adhesion_const);
+
+int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,
+                    const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
+                    double reach, const int32_t *old_row_start, int64_t old_row_stride,
+                    const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len, int32_t *new_cols,
+                    int64_t row_stride, int32_t *max_len, int sort_rows, const double *motility_forces,
+                    double *locations, double poisson, double youngs, double adhesion_const, double stokes,
+                    const double size_host[3], double move_dt, void *stream);
+
+/* ---- morphogen diffusion ---------------------------------------------------------------------------
+ * Replaces CellMethods.update_diffusion + update_diffusion_jit (cell_methods.py:441-468,
+ * cell_backend.py:175-204) for one (gx,gy) float64 plane, row-major (the reference's field[:,:,0]).
+ * clamp to [0,max_concentration] -> `steps` FTCS Jacobi substeps with reflecting walls, the last one
+ * with last_dt -> multiply by (1-degradation).  Same operation order as the reference, no FMA:
+ * bit-identical.  scratch: gx*gy doubles.  use_tma: 1 = TMA-staged tiles (needs gy even and
+ * 16-byte aligned pointers, returns -1 otherwise), 0 = plain staged loads.  Substeps ping-pong between
+ * field and scratch: if result_in_scratch_host is NULL the result is copied back into `field` when
+ * `steps` is odd; otherwise no copy is made and *result_in_scratch_host says where the result is.   */
+int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t gy, int64_t steps, double diffuse_dt,
+                  double last_dt, double diffuse_const, double spat_res2, double max_concentration,
+                  double degradation, int use_tma, int *result_in_scratch_host, void *stream);
+
+/* Replaces per-cell get_concentration (cell_methods.py:470-483) for all cells: nearest grid point
+ * idx = ceil(floor(2x/h)/2); field is (gx,gy,gz) row-major.  sampled (N,) f64.                    */
+int abm_sample_concentrations(const double *locations, int64_t n, const double *field,
+                              const int64_t gsize_host[3], double spat_res, double *sampled, void *stream);
+
+/* Replaces per-cell adjust_morphogens (cell_methods.py:485-521) for all cells: amounts[i] is shared
+ * equally by the in-bounds corner points closer than spat_res (fp64 atomic adds).                 */
+int abm_deposit_morphogens(const double *locations, const double *amounts, int64_t n, double *field,
+                           const int64_t gsize_host[3], double spat_res, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABM_B200_H */

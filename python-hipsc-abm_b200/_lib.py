@@ -1,0 +1,91 @@
+"""ctypes binding of libabm_b200.so (the C-ABI declared in include/abm_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libabm_b200.so")
+
+P = C.c_void_p          # device pointer / stream
+I64 = C.c_int64
+I32 = C.c_int
+F64 = C.c_double
+SZ = C.c_size_t
+D3 = C.POINTER(C.c_double)    # host double[3]
+I3 = C.POINTER(C.c_int32)     # host int32[3]
+L3 = C.POINTER(C.c_int64)     # host int64[3]
+
+# name -> (restype, argtypes); must list every symbol of include/abm_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "abm_abi_version": (I32, []),
+    "abm_compiled_arch": (I32, []),
+    "abm_last_error": (C.c_char_p, []),
+    "abm_device_info": (I32, [C.POINTER(I32), C.POINTER(I32), C.POINTER(I32)]),
+    "abm_bin_dims_host": (I32, [D3, F64, I3]),
+    "abm_bin_sort_workspace_bytes": (SZ, [I64, I64]),
+    "abm_bin_sort": (I32, [P, P, I64, D3, F64, P, P, P, P, P, P, SZ, P]),
+    "abm_bins_dense": (I32, [P, I64, D3, F64, P, P, I64, P, P, P, P]),
+    "abm_neighbor_search": (I32, [P, P, P, P, I64, I3, F64, P, P, I64, P, P, P, P, P, I64, P, P]),
+    "abm_read_i32_sync": (I32, [P, C.POINTER(C.c_int32), P]),
+    "abm_graph_edge_list_workspace_bytes": (SZ, [I64]),
+    "abm_graph_edge_list": (I32, [P, I64, P, P, I64, P, SZ, P, I64, P, P]),
+    "abm_jkr_forces": (I32, [P, I64, P, P, P, P, P, I64, F64, F64, F64, P]),
+    "abm_apply_forces": (I32, [P, P, P, P, I64, F64, D3, F64, P, P]),
+    "abm_jkr_reach": (F64, [F64, F64, F64, F64, F64]),
+    "abm_jkr_substep": (I32, [P, P, P, P, I64, I3, F64, F64, P, I64, P, P, P, P, I64, P, I32, P, P,
+                              F64, F64, F64, F64, D3, F64, P]),
+    "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),
+    "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, P, P]),
+    "abm_deposit_morphogens": (I32, [P, P, I64, P, L3, F64, P]),
+}
+
+
+class AbmError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built -- there is no other path."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AbmError(
+            f"{LIB_PATH} is missing: build it with `python python-hipsc-abm_b200/build.py` "
+            "(nvcc, sm_100a). This package has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.abm_abi_version() != 1:
+        raise AbmError("libabm_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> int:
+    """Raise on negative return codes; positive ones (capacity overflow) are returned to the caller."""
+    if rc < 0:
+        msg = load().abm_last_error().decode("utf-8", "replace")
+        raise AbmError(f"{what} failed with code {rc}: {msg}")
+    return rc
+
+
+def d3(values):
+    return (C.c_double * 3)(*[float(v) for v in values])
+
+
+def i3(values):
+    return (C.c_int32 * 3)(*[int(v) for v in values])
+
+
+def l3(values):
+    return (C.c_int64 * 3)(*[int(v) for v in values])

@@ -1,0 +1,49 @@
+"""Builds libabm_b200.so in-tree with nvcc for sm_100a (the only target).  No torch involvement:
+the library is a plain C-ABI shared object loaded with ctypes."""
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libabm_b200.so")
+SOURCES = ["lib.cu", "sort.cu", "search.cu", "jkr.cu", "diffusion.cu"]
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: libabm_b200.so cannot be built")
+
+
+def needs_build():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "abm_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc_path(), "-shared", "-o", LIB, "-O3", "-std=c++17", "-lineinfo",
+           "-gencode", "arch=compute_100a,code=sm_100a",
+           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+           "-Xptxas", "-v" if verbose else "-warn-spills"] + [os.path.join(CSRC, s) for s in SOURCES]
+    # the image's CC wrapper lacks pieces nvcc's host pass wants; use the distro g++ explicitly
+    if os.path.exists("/usr/bin/g++"):
+        cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout + res.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose="-v" in sys.argv))

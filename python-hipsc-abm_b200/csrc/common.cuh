@@ -1,0 +1,165 @@
+// common.cuh -- shared device/host helpers for libabm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "abm_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libabm_b200 is written for sm_100a (B200) only"
+#endif
+
+#define ABM_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace abm {
+
+constexpr int kSMsB200 = 148;
+
+void set_error(const char *fmt, ...);
+int check_cuda(cudaError_t e, const char *what);   // 0 or -(1000+e), records the text
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+#define ABM_CHECK_LAUNCH(what)                                   \
+    do {                                                         \
+        int _rc = abm::check_cuda(cudaGetLastError(), what);     \
+        if (_rc) return _rc;                                     \
+    } while (0)
+
+#define ABM_REQUIRE(cond, msg)                                   \
+    do {                                                         \
+        if (!(cond)) {                                           \
+            abm::set_error("%s: %s", __func__, msg);             \
+            return -1;                                           \
+        }                                                        \
+    } while (0)
+
+// ---- bin geometry --------------------------------------------------------------------------------
+struct BinGeom {
+    double distance;
+    int dims[3];      // ceil(size/distance)+3 per axis (reference simulation.py:202)
+};
+
+// Exact floor(a/b) for b > 0: numpy's float floor_divide (npy_divmod) returns the mathematically
+// exact floor, which is what bin_locations uses (reference simulation.py:210).  q = floor(a/b) can be
+// one too large when a/b rounds up to an integer; the FMA remainder a - q*b is exact and fixes it.
+__device__ __forceinline__ double exact_floor_div(double a, double b) {
+    double q = floor(a / b);
+    double r = fma(-q, b, a);
+    if (r < 0.0) q -= 1.0;
+    else if (r >= b) q += 1.0;
+    return q;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// bin coordinate of one axis, clamped into the allocated lattice
+__device__ __forceinline__ int bin_coord(double x, double distance, int dim) {
+    return clampi((int)exact_floor_div(x, distance) + 1, 0, dim - 1);
+}
+
+__device__ __forceinline__ int lin_bin(int bx, int by, int bz, const int dims[3]) {
+    return (bz * dims[1] + by) * dims[0] + bx;
+}
+
+// ---- the distance predicate ------------------------------------------------------------------------
+// Sum of squares without FMA contraction, in the oracle's order ((dx*dx + dy*dy) + dz*dz).
+__device__ __forceinline__ double sumsq_nofma(double dx, double dy, double dz) {
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// Thresholds so that "sqrt(s) <= d" (the reference predicate, backend.py:143) is decided without
+// a square root except in a 2^-50-wide band around d*d.
+struct Radius {
+    double d, lo, hi;
+    __host__ __device__ explicit Radius(double dist) : d(dist) {
+        double d2 = dist * dist;
+        lo = d2 * (1.0 - 0x1p-50);
+        hi = d2 * (1.0 + 0x1p-50);
+    }
+    __device__ __forceinline__ bool within(double s) const {
+        if (s <= lo) return true;
+        if (s > hi) return false;
+        return __dsqrt_rn(s) <= d;
+    }
+};
+
+// ---- warp helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane_id() >= o) v += t;
+    }
+    return v;
+}
+
+// ascending insertion sort of a short int row
+__device__ __forceinline__ void insertion_sort(int *a, int n) {
+    for (int i = 1; i < n; ++i) {
+        int v = a[i];
+        int j = i - 1;
+        while (j >= 0 && a[j] > v) {
+            a[j + 1] = a[j];
+            --j;
+        }
+        a[j + 1] = v;
+    }
+}
+
+// ---- JKR contact model (reference cell_backend.py:79-98) ------------------------------------------
+struct JkrConst {
+    double k23;        // ((pi*adhesion)/e_hat)^(2/3)
+    double pi_adh;     // pi*adhesion is applied as (f*pi)*adhesion in the reference; kept separate below
+    double adhesion;
+};
+
+__host__ JkrConst make_jkr_const(double poisson, double youngs, double adhesion);
+
+// Returns true if the bond survives; fx,fy,fz = force on the cell at p from the cell at q.
+// v = p - q, s = |v|^2 (no-FMA sum of squares), rp/rq radii in um.
+__device__ __forceinline__ bool jkr_bond(double vx, double vy, double vz, double s, double rp, double rq,
+                                         const JkrConst &c, double &fx, double &fy, double &fz) {
+    const double kPi = 3.141592653589793;
+    double mag = __dsqrt_rn(s);
+    double overlap = (rp + rq - mag) / 1e6;
+    double r_hat = 1.0 / (1e6 * ((1.0 / rp) + (1.0 / rq)));
+    double overlap_ = c.k23 * cbrt(r_hat);
+    double d = overlap / overlap_;
+    if (d > -0.360562) {
+        double f = (-0.0204 * (d * d * d)) + (0.4942 * (d * d)) + (1.0801 * d) - 1.324;
+        double jkr = f * kPi * c.adhesion * r_hat;
+        if (mag != 0.0) {
+            fx = jkr * (vx / mag);
+            fy = jkr * (vy / mag);
+            fz = jkr * (vz / mag);
+        } else {
+            fx = fy = fz = 0.0;
+        }
+        return true;
+    }
+    return false;
+}
+
+// Stokes integration of one axis (reference cell_backend.py:155-170), operation order preserved.
+__device__ __forceinline__ double stokes_move(double x, double f_mot, double f_jkr, double friction, double dt,
+                                              double size_k) {
+    double velocity = __ddiv_rn(__dadd_rn(f_mot, f_jkr), friction);
+    double moved = __dadd_rn(x, __dmul_rn(dt, __dmul_rn(velocity, 1e6)));
+    if (moved > size_k) return size_k;
+    if (moved < 0.0) return 0.0;
+    return moved;
+}
+
+__device__ __forceinline__ double stokes_friction(double radius, double stokes) {
+    const double kPi = 3.141592653589793;
+    return __dmul_rn(__dmul_rn(__dmul_rn(6.0, kPi), stokes), __ddiv_rn(radius, 1e6));
+}
+
+// block-wide exclusive scan utilities live in scan.cuh
+}  // namespace abm

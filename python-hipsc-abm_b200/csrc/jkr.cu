@@ -1,0 +1,202 @@
+// jkr.cu -- JKR adhesion/repulsion forces, Stokes integration, and the fused mechanics substep.
+// Replaces jkr_forces_cpu/gpu, apply_forces_cpu/gpu and the body of the 11-substep loop of
+// CellMethods.apply_forces (reference cell_backend.py:6-172, cell_methods.py:342-439).
+#include "graph.cuh"
+
+namespace abm {
+
+constexpr int kJkrThreads = 128;
+
+struct Box {
+    double size[3];
+};
+
+// ---- unfused: forces over existing rows, broken bonds compacted away in place ------------------------
+__global__ void __launch_bounds__(kJkrThreads)
+k_jkr_rows(const int *__restrict__ row_start, long long stride, int *__restrict__ row_len, int *__restrict__ cols,
+           const double *__restrict__ loc, const double *__restrict__ radii, double *__restrict__ forces, int n,
+           JkrConst c) {
+    int i = blockIdx.x * kJkrThreads + threadIdx.x;
+    if (i >= n) return;
+    int len = row_len[i];
+    if (len == 0) return;
+    long long s = row_start ? (long long)row_start[i] : (long long)i * stride;
+    double px = loc[3 * (long long)i + 0], py = loc[3 * (long long)i + 1], pz = loc[3 * (long long)i + 2];
+    double pr = radii[i];
+    // continue the running sum held in jkr_forces so the += order equals the serial reference's
+    double fx = forces[3 * (long long)i + 0], fy = forces[3 * (long long)i + 1], fz = forces[3 * (long long)i + 2];
+    int kept = 0;
+    for (int k = 0; k < len; ++k) {
+        int j = cols[s + k];
+        double vx = px - loc[3 * (long long)j + 0], vy = py - loc[3 * (long long)j + 1],
+               vz = pz - loc[3 * (long long)j + 2];
+        double s2 = sumsq_nofma(vx, vy, vz);
+        double gx, gy, gz;
+        if (jkr_bond(vx, vy, vz, s2, pr, radii[j], c, gx, gy, gz)) {
+            fx += gx;
+            fy += gy;
+            fz += gz;
+            cols[s + kept++] = j;
+        }
+    }
+    row_len[i] = kept;
+    forces[3 * (long long)i + 0] = fx;
+    forces[3 * (long long)i + 1] = fy;
+    forces[3 * (long long)i + 2] = fz;
+}
+
+__global__ void __launch_bounds__(256)
+k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, double *__restrict__ loc,
+            const double *__restrict__ radii, int n, double stokes, Box box, double dt,
+            double *__restrict__ zero_me) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double friction = stokes_friction(radii[i], stokes);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        long long a = 3 * (long long)i + k;
+        loc[a] = stokes_move(loc[a], mot[a], jkr[a], friction, dt, box.size[k]);
+    }
+    if (zero_me) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) zero_me[3 * (long long)i + k] = 0.0;
+    }
+}
+
+// ---- fused: search(distance, union with old bonds) + JKR + bond breaking + integration ---------------
+template <bool kSortRows>
+__global__ void __launch_bounds__(kJkrThreads)
+k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_id,
+              const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
+              double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
+              int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
+              double stokes, Box box, double dt) {
+    int s = blockIdx.x * kJkrThreads + threadIdx.x;
+    int cnt = 0;
+    if (s < n) {
+        int i = sorted_id[s];
+        double4 p = spos[s];
+        int bx, by, bz;
+        st.decode(sorted_bin[s], bx, by, bz);
+        int *row = new_cols + (long long)i * stride;
+        double fx = 0.0, fy = 0.0, fz = 0.0;
+        for (int dz = -1; dz <= 1; ++dz) {
+            int z = bz + dz;
+            if (z < 0 || z >= st.dims[2]) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                int y = by + dy;
+                if (y < 0 || y >= st.dims[1]) continue;
+                int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
+                int rowb = (z * st.dims[1] + y) * st.dims[0];
+                int lo = bin_start[rowb + x0], hi = bin_start[rowb + x1 + 1];
+                for (int t = lo; t < hi; ++t) {
+                    if (t == s) continue;
+                    double4 q = spos[t];
+                    double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
+                    double s2 = sumsq_nofma(vx, vy, vz);
+                    if (s2 > reach2) continue;           // no bond can survive beyond the reach
+                    int j = -1;
+                    if (!rad.within(s2)) {               // thin shell: only pre-existing bonds persist
+                        if (!old.valid()) continue;
+                        j = sorted_id[t];
+                        if (!old.contains(i, j)) continue;
+                    }
+                    double gx, gy, gz;
+                    if (jkr_bond(vx, vy, vz, s2, p.w, q.w, c, gx, gy, gz)) {
+                        fx += gx;
+                        fy += gy;
+                        fz += gz;
+                        if (cnt < stride) row[cnt] = (j >= 0) ? j : sorted_id[t];
+                        ++cnt;
+                    }
+                }
+            }
+        }
+        new_len[i] = min(cnt, stride);
+        if (kSortRows) insertion_sort(row, min(cnt, stride));
+        // integration (reference cell_backend.py:155-170); positions are read from the sorted snapshot only
+        double friction = stokes_friction(p.w, stokes);
+        long long a = 3 * (long long)i;
+        loc[a + 0] = stokes_move(p.x, mot[a + 0], fx, friction, dt, box.size[0]);
+        loc[a + 1] = stokes_move(p.y, mot[a + 1], fy, friction, dt, box.size[1]);
+        loc[a + 2] = stokes_move(p.z, mot[a + 2], fz, friction, dt, box.size[2]);
+    }
+    // overflow report: one atomic per warp, and only when a row did not fit
+    int wmax = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+    if (lane_id() == 0 && wmax > stride) atomicMax(max_len, wmax);
+}
+
+}  // namespace abm
+
+using namespace abm;
+
+ABM_EXPORT int abm_jkr_forces(const int32_t *row_start, int64_t row_stride, int32_t *row_len, int32_t *cols,
+                              const double *locations, const double *radii, double *jkr_forces, int64_t n,
+                              double poisson, double youngs, double adhesion_const, void *stream) {
+    ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
+    if (n == 0) return 0;
+    ABM_REQUIRE(row_len && locations && radii && jkr_forces, "null pointer");
+    JkrConst c = make_jkr_const(poisson, youngs, adhesion_const);
+    k_jkr_rows<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
+        row_start, (long long)row_stride, row_len, cols, locations, radii, jkr_forces, (int)n, c);
+    ABM_CHECK_LAUNCH("k_jkr_rows");
+    return 0;
+}
+
+ABM_EXPORT int abm_apply_forces(const double *jkr_forces, const double *motility_forces, double *locations,
+                                const double *radii, int64_t n, double stokes, const double size_host[3],
+                                double move_dt, double *jkr_forces_to_zero, void *stream) {
+    ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
+    if (n == 0) return 0;
+    ABM_REQUIRE(jkr_forces && motility_forces && locations && radii && size_host, "null pointer");
+    Box box;
+    for (int k = 0; k < 3; ++k) box.size[k] = size_host[k];
+    k_integrate<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(jkr_forces, motility_forces, locations, radii,
+                                                                (int)n, stokes, box, move_dt, jkr_forces_to_zero);
+    ABM_CHECK_LAUNCH("k_integrate");
+    return 0;
+}
+
+ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,
+                               const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
+                               double reach, const int32_t *old_row_start, int64_t old_row_stride,
+                               const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len,
+                               int32_t *new_cols, int64_t row_stride, int32_t *max_len, int sort_rows,
+                               const double *motility_forces, double *locations, double poisson, double youngs,
+                               double adhesion_const, double stokes, const double size_host[3], double move_dt,
+                               void *stream) {
+    ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
+    if (n == 0) return 0;
+    ABM_REQUIRE(bin_start && sorted_id && sorted_pos && sorted_bin && dims_host && new_row_len && new_cols &&
+                    max_len && motility_forces && locations && size_host,
+                "null pointer");
+    ABM_REQUIRE(row_stride > 0 && row_stride < (1 << 20), "bad row_stride");
+    ABM_REQUIRE(reach >= distance && distance > 0, "reach must be >= distance > 0");
+    ABM_REQUIRE(old_cols != new_cols, "old and new bond rows must be different buffers");
+    JkrConst c = make_jkr_const(poisson, youngs, adhesion_const);
+    GraphView old{old_row_start, (long long)old_row_stride, old_row_len, old_cols};
+    Stencil stc;
+    Box box;
+    for (int k = 0; k < 3; ++k) {
+        stc.dims[k] = dims_host[k];
+        box.size[k] = size_host[k];
+    }
+    int blocks = ceil_div(n, kJkrThreads);
+    cudaStream_t st = as_stream(stream);
+    const double4 *sp = reinterpret_cast<const double4 *>(sorted_pos);
+    double reach2 = reach * reach;
+    if (sort_rows)
+        k_jkr_substep<true><<<blocks, kJkrThreads, 0, st>>>(bin_start, sorted_id, sp, sorted_bin, (int)n, stc,
+                                                            Radius(distance), reach2, old, new_row_len, new_cols,
+                                                            (int)row_stride, max_len, motility_forces, locations, c,
+                                                            stokes, box, move_dt);
+    else
+        k_jkr_substep<false><<<blocks, kJkrThreads, 0, st>>>(bin_start, sorted_id, sp, sorted_bin, (int)n, stc,
+                                                             Radius(distance), reach2, old, new_row_len, new_cols,
+                                                             (int)row_stride, max_len, motility_forces, locations, c,
+                                                             stokes, box, move_dt);
+    ABM_CHECK_LAUNCH("k_jkr_substep");
+    return 0;
+}

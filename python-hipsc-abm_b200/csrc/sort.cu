@@ -1,0 +1,167 @@
+// sort.cu -- spatial binning as a counting sort (histogram -> scan -> place -> stable gather).
+// Replaces Simulation.assign_bins / assign_bins_jit (reference simulation.py:190-223, backend.py:31-50):
+// instead of dense fixed-capacity buckets (218 MB at 500k cells) the cells are permuted into bin order
+// and a (nbins+1) offset table indexes them.
+#include "scan.cuh"
+
+namespace abm {
+
+constexpr int kThreads = 256;
+
+struct SortWs {
+    int *rank;        // n   : arrival order of the cell inside its bin (atomic, not stable)
+    int *cell_bin;    // n   : linear bin of cell i
+    int *tmp_id;      // n   : unstable placement
+    int *block_sums;  // scan scratch
+};
+
+static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+
+static SortWs carve(void *ws, int64_t n, int64_t nbins) {
+    char *p = (char *)ws;
+    SortWs w;
+    w.rank = (int *)p;       p += align_up((size_t)n * 4);
+    w.cell_bin = (int *)p;   p += align_up((size_t)n * 4);
+    w.tmp_id = (int *)p;     p += align_up((size_t)n * 4);
+    w.block_sums = (int *)p; p += align_up((size_t)scan_blocks(nbins + 1) * 4 + 4);
+    return w;
+}
+
+__global__ void __launch_bounds__(kThreads) k_bin_count(const double *__restrict__ loc, int n, BinGeom g,
+                                                        int *__restrict__ counts, int *__restrict__ cell_bin,
+                                                        int *__restrict__ rank) {
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    double x = loc[3 * (int64_t)i + 0], y = loc[3 * (int64_t)i + 1], z = loc[3 * (int64_t)i + 2];
+    int b = lin_bin(bin_coord(x, g.distance, g.dims[0]), bin_coord(y, g.distance, g.dims[1]),
+                    bin_coord(z, g.distance, g.dims[2]), g.dims);
+    cell_bin[i] = b;
+    rank[i] = atomicAdd(&counts[b], 1);
+}
+
+__global__ void __launch_bounds__(kThreads) k_place(const int *__restrict__ cell_bin, const int *__restrict__ rank,
+                                                    const int *__restrict__ bin_start, int n,
+                                                    int *__restrict__ tmp_id) {
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    tmp_id[bin_start[cell_bin[i]] + rank[i]] = i;
+}
+
+// One thread per provisional slot: find the stable (ascending id) position inside the bin segment and
+// move the cell's {x,y,z,r} there.  Writes land inside the same short segment -> coalesced sectors.
+__global__ void __launch_bounds__(kThreads) k_gather(const int *__restrict__ tmp_id, const int *__restrict__ cell_bin,
+                                                     const int *__restrict__ bin_start,
+                                                     const double *__restrict__ loc, const double *__restrict__ radii,
+                                                     int n, int *__restrict__ sorted_id,
+                                                     double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin) {
+    int s = blockIdx.x * kThreads + threadIdx.x;
+    if (s >= n) return;
+    int id = tmp_id[s];
+    int b = cell_bin[id];
+    int b0 = bin_start[b], b1 = bin_start[b + 1];
+    int before = 0;
+    for (int t = b0; t < b1; ++t) before += (tmp_id[t] < id);
+    int dest = b0 + before;
+    double4 p;
+    p.x = loc[3 * (int64_t)id + 0];
+    p.y = loc[3 * (int64_t)id + 1];
+    p.z = loc[3 * (int64_t)id + 2];
+    p.w = radii[id];
+    sorted_id[dest] = id;
+    sorted_pos[dest] = p;
+    sorted_bin[dest] = b;
+}
+
+__global__ void __launch_bounds__(kThreads) k_bins_dense(const double *__restrict__ loc, int n, BinGeom g,
+                                                         const int *__restrict__ bin_start,
+                                                         const int *__restrict__ sorted_id, long long max_agents,
+                                                         long long *__restrict__ bins, long long *__restrict__ bins_help,
+                                                         long long *__restrict__ bin_locations) {
+    int s = blockIdx.x * kThreads + threadIdx.x;
+    if (s >= n) return;
+    int id = sorted_id[s];
+    double x = loc[3 * (int64_t)id + 0], y = loc[3 * (int64_t)id + 1], z = loc[3 * (int64_t)id + 2];
+    // reference bin_locations are not clamped (simulation.py:210)
+    long long rx = (long long)exact_floor_div(x, g.distance) + 1;
+    long long ry = (long long)exact_floor_div(y, g.distance) + 1;
+    long long rz = (long long)exact_floor_div(z, g.distance) + 1;
+    bin_locations[3 * (int64_t)id + 0] = rx;
+    bin_locations[3 * (int64_t)id + 1] = ry;
+    bin_locations[3 * (int64_t)id + 2] = rz;
+    int bx = clampi((int)rx, 0, g.dims[0] - 1), by = clampi((int)ry, 0, g.dims[1] - 1),
+        bz = clampi((int)rz, 0, g.dims[2] - 1);
+    int b = lin_bin(bx, by, bz, g.dims);
+    int place = s - bin_start[b];
+    int64_t ref_bin = ((int64_t)bx * g.dims[1] + by) * g.dims[2] + bz;   // reference index order x,y,z
+    if (place < max_agents) bins[ref_bin * max_agents + place] = id;
+    if (place == 0) bins_help[ref_bin] = bin_start[b + 1] - bin_start[b];
+}
+
+static int make_geom(const double size_host[3], double distance, BinGeom &g, int64_t &nbins) {
+    if (!(distance > 0)) return -1;
+    g.distance = distance;
+    nbins = 1;
+    for (int k = 0; k < 3; ++k) {
+        g.dims[k] = (int)ceil(size_host[k] / distance) + 3;
+        nbins *= g.dims[k];
+    }
+    return nbins < (int64_t)0x7fffffff ? 0 : -1;
+}
+
+}  // namespace abm
+
+using namespace abm;
+
+ABM_EXPORT size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins) {
+    if (n < 0 || nbins < 0) return 0;
+    return 3 * align_up((size_t)n * 4) + align_up((size_t)scan_blocks(nbins + 1) * 4 + 4) + 256;
+}
+
+ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_t n, const double size_host[3],
+                            double distance, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
+                            int32_t *sorted_bin, int32_t *max_count, void *workspace, size_t workspace_bytes,
+                            void *stream) {
+    ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
+    ABM_REQUIRE(size_host && bin_start && max_count, "null pointer");
+    BinGeom g;
+    int64_t nbins;
+    ABM_REQUIRE(make_geom(size_host, distance, g, nbins) == 0, "bad geometry (distance <= 0 or too many bins)");
+    ABM_REQUIRE(workspace_bytes >= abm_bin_sort_workspace_bytes(n, nbins), "workspace too small");
+    cudaStream_t st = as_stream(stream);
+    int rc = check_cuda(cudaMemsetAsync(bin_start, 0, (size_t)(nbins + 1) * 4, st), "memset bin_start");
+    if (rc) return rc;
+    rc = check_cuda(cudaMemsetAsync(max_count, 0, 4, st), "memset max_count");
+    if (rc) return rc;
+    if (n == 0) return 0;
+    ABM_REQUIRE(locations && radii && sorted_id && sorted_pos && sorted_bin && workspace, "null pointer");
+    ABM_REQUIRE(((uintptr_t)sorted_pos & 31) == 0, "sorted_pos must be 32-byte aligned");
+    SortWs w = carve(workspace, n, nbins);
+    int blocks = ceil_div(n, kThreads);
+    k_bin_count<<<blocks, kThreads, 0, st>>>(locations, (int)n, g, bin_start, w.cell_bin, w.rank);
+    ABM_CHECK_LAUNCH("k_bin_count");
+    rc = exclusive_scan_inplace(bin_start, nbins + 1, w.block_sums, max_count, nullptr, st);
+    if (rc) return rc;
+    k_place<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.rank, bin_start, (int)n, w.tmp_id);
+    ABM_CHECK_LAUNCH("k_place");
+    k_gather<<<blocks, kThreads, 0, st>>>(w.tmp_id, w.cell_bin, bin_start, locations, radii, (int)n, sorted_id,
+                                          reinterpret_cast<double4 *>(sorted_pos), sorted_bin);
+    ABM_CHECK_LAUNCH("k_gather");
+    return 0;
+}
+
+ABM_EXPORT int abm_bins_dense(const double *locations, int64_t n, const double size_host[3], double distance,
+                              const int32_t *bin_start, const int32_t *sorted_id, int64_t max_agents, int64_t *bins,
+                              int64_t *bins_help, int64_t *bin_locations, void *stream) {
+    ABM_REQUIRE(n >= 0 && n < 0x7fffffff && max_agents >= 0, "bad sizes");
+    if (n == 0) return 0;
+    ABM_REQUIRE(locations && size_host && bin_start && sorted_id && bins && bins_help && bin_locations,
+                "null pointer");
+    BinGeom g;
+    int64_t nbins;
+    ABM_REQUIRE(make_geom(size_host, distance, g, nbins) == 0, "bad geometry");
+    k_bins_dense<<<ceil_div(n, kThreads), kThreads, 0, as_stream(stream)>>>(
+        locations, (int)n, g, bin_start, sorted_id, (long long)max_agents, (long long *)bins,
+        (long long *)bins_help, (long long *)bin_locations);
+    ABM_CHECK_LAUNCH("k_bins_dense");
+    return 0;
+}

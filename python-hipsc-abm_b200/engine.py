@@ -1,0 +1,315 @@
+"""Device-resident state and stage launches of the cell-update hot path.
+
+`ColonyEngine` owns the torch CUDA tensors (torch is used for memory and streams only) and calls the
+kernels of libabm_b200.so through the C-ABI.  The reference-facing classes in simulation.py /
+cell_methods.py sit on top of it; bench.py drives it directly for the HBM-resident measurement.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+# physical constants hard-coded in the reference methods
+JKR_ADHESION = 0.000107    # reference cell_methods.py:347
+JKR_POISSON = 0.5          # reference cell_methods.py:348
+JKR_YOUNGS = 1000.0        # reference cell_methods.py:349
+STOKES = 10000.0           # reference cell_methods.py:392
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+@dataclass
+class SortState:
+    """Result of one counting sort (abm_bin_sort)."""
+    distance: float
+    dims: tuple
+    nbins: int
+    n: int
+    bin_start: torch.Tensor
+    sorted_id: torch.Tensor
+    sorted_pos: torch.Tensor
+    sorted_bin: torch.Tensor
+    max_count: torch.Tensor
+
+
+@dataclass
+class GraphTensors:
+    """A row-CSR graph on the device (include/abm_b200.h, 'row CSR')."""
+    n: int
+    row_start: Optional[torch.Tensor]   # None -> fixed-stride rows
+    row_stride: int
+    row_len: torch.Tensor
+    cols: torch.Tensor
+    sorted_rows: bool = True
+
+    def clone(self) -> "GraphTensors":
+        return GraphTensors(self.n, None if self.row_start is None else self.row_start.clone(), self.row_stride,
+                            self.row_len.clone(), self.cols.clone(), self.sorted_rows)
+
+
+class ColonyEngine:
+    def __init__(self, size, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.AbmError("ColonyEngine needs a CUDA device (B200); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.size = np.asarray(size, dtype=np.float64).reshape(3)
+        self._size_c = _lib.d3(self.size)
+        self.n = 0
+        self.loc = self.radii = self.mot = self.jkr = None
+        self.max_radius = 0.0
+        self._sort_ws = None
+        self._sort_bufs = {}
+        self._edge_ws = None
+        self._bond_bufs = None
+        self.cols_capacity_hint = {}
+        self.launches = 0      # number of kernels of this library enqueued (bench.py's gpu_launches)
+
+    # ------------------------------------------------------------------------------------------------
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    def _zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype, device=self.device)
+
+    # ---- state -------------------------------------------------------------------------------------
+    def upload(self, locations, radii, motility=None, jkr=None, pinned=False):
+        """Host -> device copy of the agent arrays the path reads (reference dtypes: float64)."""
+        loc = np.ascontiguousarray(locations, dtype=np.float64)
+        n = loc.shape[0]
+        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, dtype=np.float64), (n,)))
+        self.n = n
+        self.loc = torch.from_numpy(loc).to(self.device, non_blocking=pinned)
+        self.radii = torch.from_numpy(rad).to(self.device, non_blocking=pinned)
+        self.max_radius = float(rad.max()) if n else 0.0
+        self.mot = (torch.from_numpy(np.ascontiguousarray(motility, dtype=np.float64)).to(self.device)
+                    if motility is not None else self._zeros((n, 3), torch.float64))
+        self.jkr = (torch.from_numpy(np.ascontiguousarray(jkr, dtype=np.float64)).to(self.device)
+                    if jkr is not None else self._zeros((n, 3), torch.float64))
+
+    def set_device_state(self, loc, radii, mot=None, jkr=None, max_radius=None):
+        """Adopt tensors that already live on the device (no copies)."""
+        self.n = int(loc.shape[0])
+        self.loc, self.radii = loc, radii
+        self.mot = mot if mot is not None else self._zeros((self.n, 3), torch.float64)
+        self.jkr = jkr if jkr is not None else self._zeros((self.n, 3), torch.float64)
+        self.max_radius = float(max_radius) if max_radius is not None else float(radii.max().item())
+
+    def locations_host(self) -> np.ndarray:
+        return self.loc.cpu().numpy()
+
+    # ---- a1/a2: binning ------------------------------------------------------------------------------
+    def bin_dims(self, distance):
+        dims = (C.c_int32 * 3)()
+        _lib.check(self.lib.abm_bin_dims_host(self._size_c, float(distance), dims), "abm_bin_dims_host")
+        return tuple(int(d) for d in dims)
+
+    def sort(self, distance) -> SortState:
+        """Counting sort of the current locations into bins of edge `distance` (abm_bin_sort)."""
+        n = self.n
+        dims = self.bin_dims(distance)
+        nbins = dims[0] * dims[1] * dims[2]
+        key = (n, nbins)
+        bufs = self._sort_bufs.get(key)
+        if bufs is None:
+            self._sort_bufs.clear()
+            bufs = dict(bin_start=self._empty(nbins + 1, torch.int32), sorted_id=self._empty(max(n, 1), torch.int32),
+                        sorted_pos=self._empty((max(n, 1), 4), torch.float64),
+                        sorted_bin=self._empty(max(n, 1), torch.int32), max_count=self._empty(1, torch.int32))
+            self._sort_bufs[key] = bufs
+        need = self.lib.abm_bin_sort_workspace_bytes(n, nbins)
+        if self._sort_ws is None or self._sort_ws.numel() < need:
+            self._sort_ws = self._empty(int(need), torch.uint8)
+        _lib.check(self.lib.abm_bin_sort(_ptr(self.loc), _ptr(self.radii), n, self._size_c, float(distance),
+                                         _ptr(bufs["bin_start"]), _ptr(bufs["sorted_id"]), _ptr(bufs["sorted_pos"]),
+                                         _ptr(bufs["sorted_bin"]), _ptr(bufs["max_count"]), _ptr(self._sort_ws),
+                                         self._sort_ws.numel(), self.stream), "abm_bin_sort")
+        self.launches += 5 if n else 0
+        return SortState(float(distance), dims, nbins, n, **bufs)
+
+    def bins_dense(self, sort: SortState, max_agents: int):
+        """Reference-shaped (bins, bins_help, bin_locations) of Simulation.assign_bins."""
+        dims, n = sort.dims, sort.n
+        bins = self._zeros(dims + (int(max_agents),), torch.int64)
+        bins_help = self._zeros(dims, torch.int64)
+        bin_locations = self._zeros((n, 3), torch.int64)
+        _lib.check(self.lib.abm_bins_dense(_ptr(self.loc), n, self._size_c, sort.distance, _ptr(sort.bin_start),
+                                           _ptr(sort.sorted_id), int(max_agents), _ptr(bins), _ptr(bins_help),
+                                           _ptr(bin_locations), self.stream), "abm_bins_dense")
+        self.launches += 1 if n else 0
+        return bins, bins_help, bin_locations
+
+    # ---- a3/a4: search -> row CSR --------------------------------------------------------------------
+    def read_i32(self, t: torch.Tensor) -> int:
+        out = C.c_int32(0)
+        _lib.check(self.lib.abm_read_i32_sync(_ptr(t), C.byref(out), self.stream), "abm_read_i32_sync")
+        return int(out.value)
+
+    def search(self, sort: SortState, distance, old: Optional[GraphTensors] = None,
+               capacity: Optional[int] = None) -> GraphTensors:
+        """Fixed-radius search (abm_neighbor_search); grows the column buffer and retries on overflow,
+        like the reference's max_neighbors loop (simulation.py:277-281)."""
+        n = sort.n
+        if distance > sort.distance * (1 + 1e-12):
+            raise _lib.AbmError("search radius exceeds the bin edge of the sort")
+        row_start = self._empty(max(n, 1), torch.int32)
+        row_len = self._zeros(max(n, 1), torch.int32)
+        cursor = self._empty(1, torch.int32)
+        dims = _lib.i3(sort.dims)
+        hint_key = (round(float(distance), 9), old is not None)
+        cap = int(capacity if capacity is not None else self.cols_capacity_hint.get(hint_key, 8 * max(n, 1)))
+        while True:
+            cols = self._empty(max(cap, 1), torch.int32)
+            _lib.check(self.lib.abm_neighbor_search(
+                _ptr(sort.bin_start), _ptr(sort.sorted_id), _ptr(sort.sorted_pos), _ptr(sort.sorted_bin), n, dims,
+                float(distance), _ptr(self.loc),
+                _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
+                _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
+                _ptr(row_start), _ptr(row_len), _ptr(cols), cap, _ptr(cursor), self.stream), "abm_neighbor_search")
+            self.launches += 1 if n else 0
+            used = self.read_i32(cursor)
+            if used <= cap:
+                break
+            cap = int(used * 1.25) + 1024
+        self.cols_capacity_hint[hint_key] = max(int(used * 1.25) + 1024, 1024)
+        g = GraphTensors(n, row_start, 0, row_len, cols, True)
+        g.entries = used
+        return g
+
+    def edge_list(self, g: GraphTensors) -> np.ndarray:
+        """Canonical (i<j) int64 edge array of a graph (abm_graph_edge_list), downloaded."""
+        n = g.n
+        if n == 0:
+            return np.zeros((0, 2), dtype=np.int64)
+        if not g.sorted_rows:
+            raise _lib.AbmError("edge_list needs ascending rows")
+        need = self.lib.abm_graph_edge_list_workspace_bytes(n)
+        ws = self._empty(int(need), torch.uint8)
+        n_edges = self._empty(1, torch.int32)
+        cap = int(g.cols.numel() // 2 + 1)
+        edges = self._empty((cap, 2), torch.int64)
+        _lib.check(self.lib.abm_graph_edge_list(_ptr(g.row_start), g.row_stride, _ptr(g.row_len), _ptr(g.cols), n,
+                                                _ptr(ws), ws.numel(), _ptr(edges), cap, _ptr(n_edges), self.stream),
+                   "abm_graph_edge_list")
+        self.launches += 4
+        e = self.read_i32(n_edges)
+        if e > cap:
+            raise _lib.AbmError("edge list capacity underestimated")
+        return edges[:e].cpu().numpy()
+
+    # ---- a6/a7/a9: unfused mechanics -------------------------------------------------------------------
+    def jkr_forces(self, g: GraphTensors):
+        """calculate_jkr on the device: accumulates into self.jkr, removes broken bonds from g in place."""
+        _lib.check(self.lib.abm_jkr_forces(_ptr(g.row_start), g.row_stride, _ptr(g.row_len), _ptr(g.cols),
+                                           _ptr(self.loc), _ptr(self.radii), _ptr(self.jkr), g.n, JKR_POISSON,
+                                           JKR_YOUNGS, JKR_ADHESION, self.stream), "abm_jkr_forces")
+        self.launches += 1 if g.n else 0
+
+    def integrate(self, move_dt, zero_jkr=True, stokes=STOKES):
+        _lib.check(self.lib.abm_apply_forces(_ptr(self.jkr), _ptr(self.mot), _ptr(self.loc), _ptr(self.radii),
+                                             self.n, float(stokes), self._size_c, float(move_dt),
+                                             _ptr(self.jkr) if zero_jkr else 0, self.stream), "abm_apply_forces")
+        self.launches += 1 if self.n else 0
+
+    # ---- a8: fused mechanics loop ------------------------------------------------------------------------
+    def jkr_reach(self, distance) -> float:
+        return float(self.lib.abm_jkr_reach(float(distance), float(self.max_radius), JKR_POISSON, JKR_YOUNGS,
+                                            JKR_ADHESION))
+
+    def _bond_buffers(self, n, stride):
+        b = self._bond_bufs
+        if b is None or b["n"] != n or b["stride"] != stride:
+            b = dict(n=n, stride=stride,
+                     len=[self._zeros(max(n, 1), torch.int32) for _ in range(3)],
+                     cols=[self._empty((max(n, 1), stride), torch.int32) for _ in range(3)],
+                     max_len=self._zeros(1, torch.int32))
+            self._bond_bufs = b
+        return b
+
+    def enqueue_mechanics(self, old: Optional[GraphTensors], distance, dts, stride, stokes=STOKES):
+        """Enqueue len(dts) fused substeps (sort + abm_jkr_substep each).  No host sync.  Returns the
+        fixed-stride graph holding the final bonds; overflow is reported through bufs['max_len']."""
+        n = self.n
+        b = self._bond_buffers(n, stride)
+        b["max_len"].zero_()
+        reach = self.jkr_reach(distance)
+        cur = old
+        out = None
+        # three row buffers: the two that do not hold `old` ping-pong, so `old` survives a retry
+        held = [i for i in range(3) if old is not None and old.cols.data_ptr() == b["cols"][i].data_ptr()]
+        pair = [i for i in range(3) if i not in held][:2]
+        for k, dt in enumerate(dts):
+            srt = self.sort(reach)
+            last = k == len(dts) - 1
+            new_len, new_cols = b["len"][pair[k & 1]], b["cols"][pair[k & 1]]
+            _lib.check(self.lib.abm_jkr_substep(
+                _ptr(srt.bin_start), _ptr(srt.sorted_id), _ptr(srt.sorted_pos), _ptr(srt.sorted_bin), n,
+                _lib.i3(srt.dims), float(distance), reach,
+                _ptr(cur.row_start) if cur is not None else 0, cur.row_stride if cur is not None else 0,
+                _ptr(cur.row_len) if cur is not None else 0, _ptr(cur.cols) if cur is not None else 0,
+                _ptr(new_len), _ptr(new_cols), stride, _ptr(b["max_len"]), 1 if last else 0, _ptr(self.mot),
+                _ptr(self.loc), JKR_POISSON, JKR_YOUNGS, JKR_ADHESION, float(stokes), self._size_c, float(dt),
+                self.stream), "abm_jkr_substep")
+            self.launches += 1 if n else 0
+            out = GraphTensors(n, None, stride, new_len, new_cols, last)
+            cur = out
+        return out
+
+    def mechanics(self, old: Optional[GraphTensors], distance, dts, stride=16, stokes=STOKES):
+        """The whole substep loop of CellMethods.apply_forces on the device, with the reference's
+        grow-and-retry on row overflow.  Returns (bond graph, stride used)."""
+        if self.n == 0 or len(dts) == 0:
+            return old, stride
+        start = self.loc.clone()
+        while True:
+            g = self.enqueue_mechanics(old, distance, dts, stride, stokes)
+            worst = self.read_i32(self._bond_bufs["max_len"])
+            if worst <= stride:
+                return g, stride
+            stride = 2 * worst          # reference simulation.py:281 doubles the needed capacity
+            self.loc.copy_(start)
+
+    # ---- a10-a13: morphogen field ---------------------------------------------------------------------------
+    def diffuse(self, field: torch.Tensor, steps, diffuse_dt, last_dt, diffuse_const, spat_res2, max_concentration,
+                degradation, use_tma=None, scratch=None) -> torch.Tensor:
+        """update_diffusion on a (gx,gy) float64 device plane; returns the plane holding the result
+        (either `field` or the scratch plane -- no copy back)."""
+        gx, gy = int(field.shape[0]), int(field.shape[1])
+        if use_tma is None:
+            use_tma = (gy % 2 == 0)
+        if scratch is None:
+            scratch = torch.empty_like(field)
+        where = C.c_int(0)
+        _lib.check(self.lib.abm_diffusion(_ptr(field), _ptr(scratch), gx, gy, int(steps), float(diffuse_dt),
+                                          float(last_dt), float(diffuse_const), float(spat_res2),
+                                          float(max_concentration), float(degradation), 1 if use_tma else 0,
+                                          C.byref(where), self.stream), "abm_diffusion")
+        self.launches += int(steps)
+        return scratch if where.value else field
+
+    def sample(self, field: torch.Tensor, spat_res) -> torch.Tensor:
+        gs = tuple(field.shape) + (1,) * (3 - field.dim())
+        out = self._empty(max(self.n, 1), torch.float64)
+        _lib.check(self.lib.abm_sample_concentrations(_ptr(self.loc), self.n, _ptr(field), _lib.l3(gs),
+                                                      float(spat_res), _ptr(out), self.stream),
+                   "abm_sample_concentrations")
+        self.launches += 1 if self.n else 0
+        return out[:self.n]
+
+    def deposit(self, field: torch.Tensor, amounts: torch.Tensor, spat_res):
+        gs = tuple(field.shape) + (1,) * (3 - field.dim())
+        _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc), _ptr(amounts), self.n, _ptr(field), _lib.l3(gs),
+                                                   float(spat_res), self.stream), "abm_deposit_morphogens")
+        self.launches += 1 if self.n else 0
