@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/sec of the neighbor+force+diffusion step (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+
+One "step" = one reference simulation step of the hot path on a synthetic seeded colony
+(SURVEY 8d): 1 x search(r=15) + 11 x [sort + fused search(r=10)/JKR/integrate substep] + deposit +
+S_d diffusion substeps + sample.  Prints ONE JSON line (rank 0).
+
+  value     whole-job throughput with everything resident in HBM (CUDA-graph replay, device-timed)
+  e2e       same metric through the reference-facing Python API with HOST numpy arrays (H2D/D2H inside)
+  roofline  dominant kernel (k_jkr_substep): compulsory bytes per launch / event-timed launch duration
+  cpu_baseline / --impl reference : the oracle port (oracle/abm_oracle.c, OpenMP) on the host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell-updates/sec (neighbor+force+diffusion step)"
+UNIT = "cell-updates/s"
+
+WORKLOADS = {
+    # name: (cells, dim, density, grid spec)          SURVEY 8(d) / BASELINE.json configs[1..4]
+    "c2": dict(n=50_000, dim=2, density=0.01, h=7.07106, diffuse_dt=0.24, sd=10,
+               desc="configs[1]: 50,000-cell 2D colony, JKR adhesion + FGF4 diffusion (318^2 grid, 10 substeps)"),
+    "c3": dict(n=500_000, dim=2, density=0.01, h=7.07106, diffuse_dt=0.24, sd=10,
+               desc="configs[2]: 500,000-cell 2D colony + FGF4 diffusion (1002^2 grid, 10 substeps)"),
+    "c4": dict(n=4_000_000, dim=3, density=0.001, h=None, diffuse_dt=None, sd=0,
+               desc="configs[3]: 4,000,000-cell 3D colony (no 3D diffusion in the reference)"),
+    "c5": dict(n=100_000, dim=2, density=0.01, h=1.5441, diffuse_dt=0.011445, sd=10,
+               desc="configs[4]: 100,000 cells on a fine 2048^2 morphogen grid, 10 diffusion substeps"),
+}
+W = 8  # bytes per real: the path computes in float64, the reference's dtype
+
+
+def make_workload(name, seed=0, n_override=None):
+    spec = dict(WORKLOADS[name])
+    n = int(n_override or spec["n"])
+    rng = np.random.default_rng(seed)
+    if spec["dim"] == 2:
+        side = (n / spec["density"]) ** 0.5
+        size = np.array([side, side, 0.0])
+    else:
+        side = (n / spec["density"]) ** (1.0 / 3.0)
+        size = np.array([side, side, side])
+    loc = rng.random((n, 3)) * size
+    theta = rng.random(n) * 2 * np.pi
+    mot = np.zeros((n, 3))
+    if spec["dim"] == 2:
+        mot[:, 0], mot[:, 1] = np.cos(theta), np.sin(theta)
+    else:
+        phi = rng.random(n) * 2 * np.pi
+        mot[:, 0], mot[:, 1], mot[:, 2] = np.cos(phi) * np.cos(theta), np.cos(phi) * np.sin(theta), np.sin(phi)
+    mot *= 2e-9                                     # motility force, reference cell_methods.py:252
+    grid = None
+    if spec["h"]:
+        g = int(np.ceil(side / spec["h"])) + 1      # gradient_size, reference cell_simulation.py:67
+        g += g % 2                                  # even row length (TMA row pitch multiple of 16 B)
+        grid = (g, g)
+    return dict(name=name, n=n, size=size, loc=loc, radii=np.full(n, 5.0), mot=mot, grid=grid, spec=spec)
+
+
+# ---- clocks -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.rows = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- byte accounting -----------------------------------------------------------------------------
+def step_bytes(n, b15, b10, e15, e10, ej, g, sm, sd):
+    search15 = 7 * W * n + 4 * n + 8 * b15 + 4 * W * n + 4 * b15 + 8 * e15
+    substep = (7 * W * n + 4 * n + 8 * b10) + (4 * W * n + 4 * b10 + 8 * e10) + 8 * (2 * ej + e10) + \
+              (9 * ej + 4 * W * n) + 6 * W * n
+    return search15 + sm * substep + sd * 2 * W * g + 5 * W * n
+
+
+def substep_kernel_bytes(n, b10, ej):
+    """Compulsory traffic of ONE k_jkr_substep launch (DESIGN.md 'kernels'): read sorted {x,y,z,r} 4wN,
+    sorted_id+sorted_bin 8N, bin offsets 4B, motility 3wN; write locations 3wN, bond rows 2*4*E_j, row_len 4N.
+    (The stages it fuses would move 14wN + 4B + 16E + 25E_j under SURVEY 8d's per-stage formulas.)"""
+    return 10 * W * n + 12 * n + 4 * b10 + 8 * ej
+
+
+# ---- the CPU arm (oracle port) ----------------------------------------------------------------------------------
+def oracle_step_fn(wl, threads):
+    from oracle import oracle as orc
+    orc.set_threads(threads)
+    sim = orc.OracleSim(wl["loc"], wl["radii"], wl["size"])
+    sim.multithread = threads > 1
+    spec = wl["spec"]
+    if wl["grid"]:
+        h = spec["h"]
+        sim.spat_res, sim.spat_res2, sim.diffuse_const = h, h * h, 50.0
+        sim.diffuse_dt = spec["diffuse_dt"]
+        sim.max_concentration, sim.degradation = 2.0, 0.1
+        sim.fgf4_values = np.zeros(wl["grid"] + (1,))
+
+    def step():
+        sim.get_neighbors("neighbor_graph", 15)
+        sim.motility_forces[:] = wl["mot"]
+        sim.apply_forces()
+        if wl["grid"]:
+            orc.adjust_morphogens(sim.locations, 1.0, sim.fgf4_values, sim.spat_res)
+            sim.fgf4_values[:, :, 0] = orc.diffuse_field(sim.fgf4_values[:, :, 0], spec["sd"], sim.diffuse_dt,
+                                                         sim.diffuse_dt, sim.diffuse_const, sim.spat_res2,
+                                                         sim.max_concentration, sim.degradation)
+            orc.get_concentrations(sim.locations, sim.fgf4_values, sim.spat_res)
+    return step
+
+
+def cpu_sample_workload(name):
+    """Bounded sample of the workload for the CPU legs: the same density/geometry, at most 100k cells."""
+    cap = 100_000
+    return make_workload(name, seed=0, n_override=min(WORKLOADS[name]["n"], cap))
+
+
+def run_cpu(name, steps, warmup):
+    from oracle import oracle as orc
+    wl = cpu_sample_workload(name)
+    threads = orc.max_threads()
+    step = oracle_step_fn(wl, threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    sample = (f"{wl['n']} cells of workload {name} (same density and step recipe), {steps} steps after "
+              f"{warmup} warm-up, oracle/abm_oracle.c with OpenMP")
+    return wl["n"] * steps / dt, dt / steps, threads, sample
+
+
+# ---- the B200 arm -------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import hipsc_abm_b200  # noqa: F401
+    from hipsc_abm_b200.engine import ColonyEngine, GraphTensors
+    from hipsc_abm_b200.pipeline import HotPathStep, StepConfig
+    from hipsc_abm_b200.simulation import ColonySimulation
+    from hipsc_abm_b200.cell_methods import B200CellMethods
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    wl = make_workload(args.workload, seed=rank)          # weak scaling: one workload-sized colony per GPU
+    spec = wl["spec"]
+    n = wl["n"]
+    cfg = StepConfig(grid=wl["grid"], spat_res=spec["h"] or 1.0, diffuse_dt=spec["diffuse_dt"] or 1.0,
+                     diffuse_steps=spec["sd"], bond_stride=16 if spec["dim"] == 2 else 32,
+                     search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
+    eng = ColonyEngine(wl["size"], dev)
+    eng.upload(wl["loc"], wl["radii"], wl["mot"])
+    pipe = HotPathStep(eng, cfg)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    # warm-up (eager), then capture and a couple of replays
+    for _ in range(2):
+        pipe.step()
+    pipe.check()
+    if pipe.parity:
+        pipe.step()
+    pipe.capture()
+    for _ in range(max(args.warmup, 3)):
+        pipe.replay()
+    pipe.check()
+
+    # ---- value: K graph-replayed steps, each bracketed by events, L2 flushed between steps --------------------
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.launches
+    barrier()
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        pipe.replay()
+        b.record()
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_s = sum(step_ms) / 1e3
+    launches = eng.launches - launches0
+    used_cols, worst_row = pipe.check()
+    if dist is not None:
+        t = torch.tensor([total_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_s = float(t.item())
+    value = n * world * args.steps / total_s
+
+    # ---- graph statistics for the byte model -----------------------------------------------------------------------
+    e15 = used_cols // 2
+    bonds = pipe.current_bonds()
+    ej = int(bonds.row_len[:n].sum().item()) // 2
+    b15 = int(np.prod(eng.bin_dims(cfg.search_radius)))
+    reach = eng.jkr_reach(cfg.contact_radius)
+    b10 = int(np.prod(eng.bin_dims(reach)))
+    g = wl["grid"][0] * wl["grid"][1] if wl["grid"] else 0
+    sm = len(pipe.dts)
+    bytes_step = step_bytes(n, b15, b10, e15, ej, ej, g, sm, spec["sd"])
+
+    # ---- roofline of the dominant kernel: event-timed single launches, L2 flushed before each -----------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+    srt = eng.sort(reach)
+    b = eng._bond_bufs
+    old = pipe.current_bonds()
+    spare = [i for i in range(3) if b["cols"][i].data_ptr() != old.cols.data_ptr()][0]
+    loc_save = eng.loc.clone()
+    lib, _l = eng.lib, hipsc_abm_b200._lib
+
+    def launch_substep():
+        _l.check(lib.abm_jkr_substep(
+            srt.bin_start.data_ptr(), srt.sorted_id.data_ptr(), srt.sorted_pos.data_ptr(), srt.sorted_bin.data_ptr(),
+            n, _l.i3(srt.dims), cfg.contact_radius, reach, 0, old.row_stride, old.row_len.data_ptr(),
+            old.cols.data_ptr(), b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride,
+            b["max_len"].data_ptr(), 0, eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0,
+            _l.d3(wl["size"]), 180.0, eng.stream), "abm_jkr_substep")
+
+    def time_launches(cold, reps=20):
+        out = []
+        for _ in range(reps):
+            if cold:
+                flush.zero_()
+            else:
+                launch_substep()
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            launch_substep()
+            z.record()
+            torch.cuda.synchronize(dev)
+            out.append(a.elapsed_time(z) * 1e3)
+        return float(np.median(out))
+
+    for _ in range(3):
+        launch_substep()
+    cold_us = time_launches(True)
+    hot_us = time_launches(False)
+    eng.loc.copy_(loc_save)
+    kbytes = substep_kernel_bytes(n, b10, ej)
+    achieved = kbytes / (cold_us * 1e-6) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload, {}).get("k_jkr_substep")
+    roofline = {"bound": "hbm", "kernel": "k_jkr_substep", "achieved": round(achieved, 1), "peak": peak,
+                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                "bytes_per_launch": kbytes, "launch_us_cold_l2": round(cold_us, 2),
+                "launch_us_warm_l2": round(hot_us, 2), "launches_per_step": sm,
+                "step_algorithmic_bytes": bytes_step,
+                "step_frac": round(bytes_step / (total_s / args.steps) / 1e9 / peak, 4)}
+
+    # ---- e2e: the reference-facing API with host numpy arrays ----------------------------------------------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        class Cells(B200CellMethods, ColonySimulation):
+            pass
+        sim = Cells(wl["size"], dev)
+        sim.add_agents(n)
+        sim.agent_array("locations", override=wl["loc"].copy())
+        sim.agent_array("radii", override=wl["radii"].copy())
+        sim.agent_array("motility_forces", vector=3)
+        sim.agent_array("jkr_forces", vector=3)
+        sim.agent_graph("neighbor_graph")
+        sim.agent_graph("jkr_graph")
+        sim.max_radius, sim.step_dt, sim.move_dt = 5.0, 1800, 180
+        if wl["grid"]:
+            h = spec["h"]
+            sim.spat_res, sim.spat_res2, sim.diffuse_const = h, h * h, 50.0
+            sim.diffuse_dt = spec["diffuse_dt"]
+            sim.step_dt_diffusion = spec["diffuse_dt"] * spec["sd"]
+            sim.max_concentration, sim.degradation = 2.0, 0.1
+            sim.fgf4_values = np.zeros(wl["grid"] + (1,))
+
+        def api_step():
+            sim.get_neighbors("neighbor_graph", 15)
+            sim.motility_forces[:] = wl["mot"]
+            sim.apply_forces()
+            if wl["grid"]:
+                # S_d substeps exactly: step_dt = (S_d-1)*dt + dt (divmod gives S_d-1 full substeps + remainder)
+                keep = sim.step_dt
+                sim.step_dt = spec["diffuse_dt"] * (spec["sd"] - 1) + 0.5 * spec["diffuse_dt"]
+                sim.update_concentrations("fgf4_values", 1.0, sample=False)
+                sim.update_diffusion("fgf4_values")
+                sim.update_concentrations("fgf4_values", None)
+                sim.step_dt = keep
+        e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            api_step()
+        eng2 = sim.b200_engine()
+        h2d0, d2h0, l0 = eng2.h2d_bytes, eng2.d2h_bytes, eng2.launches
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            api_step()
+        torch.cuda.synchronize(dev)
+        e_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_s = float(t.item())
+        e2e = {"value": n * world * e_steps / e_s, "unit": UNIT,
+               "h2d_bytes_per_step": (eng2.h2d_bytes - h2d0) // e_steps,
+               "d2h_bytes_per_step": (eng2.d2h_bytes - d2h0) // e_steps, "steps": e_steps,
+               "ms_per_step": e_s / e_steps * 1e3,
+               "api": "Simulation.get_neighbors + CellMethods.apply_forces + update_diffusion/update_concentrations"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, spp, threads, sample = run_cpu(args.workload, 2, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+               "s_per_step": spp}
+
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {spec['desc']}", "cells_per_gpu": n, "dim": spec["dim"],
+                   "mechanics_substeps": sm, "diffusion_substeps": spec["sd"], "grid": wl["grid"],
+                   "edges_r15": e15, "jkr_bonds": ej, "l2": "flushed between timed steps (256 MiB memset)",
+                   "timing": "CUDA events per step around a CUDA-graph replay, summed; max over ranks",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent colonies (replicas)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+    }
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the Numba reference
+    itself cannot travel to the GPU box), all host threads, on the same workload recipe."""
+    if rank != 0:
+        return None
+    v, spp, threads, sample = run_cpu(args.workload, args.steps, args.warmup)
+    spec = WORKLOADS[args.workload]
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {spec['desc']}"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        line = run_reference(args, rank, world)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU); running 1 GPU", file=sys.stderr)
+        line = run_b200(args, rank, world, local_rank)
+    if line is not None:
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -90,8 +90,12 @@ def canonical_edges(edges) -> np.ndarray:
         return e
     lo, hi = np.minimum(e[:, 0], e[:, 1]), np.maximum(e[:, 0], e[:, 1])
     keep = lo != hi
-    e = np.unique(np.stack([lo[keep], hi[keep]], axis=1), axis=0)
-    return e
+    lo, hi = lo[keep], hi[keep]
+    if len(lo) == 0:
+        return np.zeros((0, 2), dtype=np.int64)
+    m = int(hi.max()) + 1
+    key = np.unique(lo * m + hi)            # 1-D integer sort: (lo,hi) lexicographic order
+    return np.stack([key // m, key % m], axis=1)
 
 
 class HostGraph:

@@ -24,7 +24,7 @@ class B200CellMethods:
         g = graph.device_tensors(eng)
         eng.jkr_forces(g)
         graph.set_device(g, eng)
-        self.jkr_forces = eng.jkr.cpu().numpy()
+        self.jkr_forces = eng.host(eng.jkr)
 
     jkr_neighbor_forces = calculate_jkr
 
@@ -72,10 +72,10 @@ class B200CellMethods:
         steps = int(steps) + 1
         eng = self.b200_engine()
         field = self.__dict__[gradient_name]
-        plane = torch.from_numpy(np.ascontiguousarray(field[:, :, 0], dtype=np.float64)).to(eng.device)
+        plane = eng.to_device(np.ascontiguousarray(field[:, :, 0], dtype=np.float64), "field")
         out = eng.diffuse(plane, steps, self.diffuse_dt, last_dt, self.diffuse_const, self.spat_res2,
                           self.max_concentration, self.degradation)
-        field[:, :, 0] = out.cpu().numpy()
+        field[:, :, 0] = eng.host(out)
 
     # ---- a12/a13 ---------------------------------------------------------------------------------------------
     def get_concentration(self, gradient_name, index):
@@ -91,20 +91,19 @@ class B200CellMethods:
         """Batched get_concentration + adjust_morphogens over `cells` (default: all): every cell first reads
         its nearest grid point, then -- if `amounts` is given -- deposits amounts[i] on its in-range corner
         points.  Returns the sampled concentrations (or None if sample=False)."""
-        import torch
         eng = self.b200_engine()
         field = self.__dict__[gradient_name]
         locations = np.ascontiguousarray(self.locations[cells], dtype=np.float64)
         saved = (eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng.max_radius)
         eng.n = len(locations)
-        eng.loc = torch.from_numpy(locations).to(eng.device)
+        eng.loc = eng.to_device(locations, "loc")
         try:
-            f = torch.from_numpy(np.ascontiguousarray(field, dtype=np.float64)).to(eng.device)
-            sampled = eng.sample(f, self.spat_res).cpu().numpy() if sample else None
+            f = eng.to_device(np.ascontiguousarray(field, dtype=np.float64), "field")
+            sampled = eng.host(eng.sample(f, self.spat_res)) if sample else None
             if amounts is not None:
                 a = np.ascontiguousarray(np.broadcast_to(np.asarray(amounts, dtype=np.float64), (eng.n,)))
-                eng.deposit(f, torch.from_numpy(a).to(eng.device), self.spat_res)
-                field[...] = f.cpu().numpy()
+                eng.deposit(f, eng.to_device(a, "amounts"), self.spat_res)
+                field[...] = eng.host(f)
         finally:
             eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng.max_radius = saved
         return sampled

@@ -64,6 +64,26 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 }
 
 // ---- fused: search(distance, union with old bonds) + JKR + bond breaking + integration ---------------
+// Two phases per thread, to keep the warp converged while it does the expensive fp64 contact math:
+//   1. walk the bin stencil with the cheap test |p-q|^2 <= reach^2 and park the slots that pass in a
+//      per-thread column of shared memory (a few per cell);
+//   2. loop over the parked slots doing the JKR evaluation.  All lanes run this loop together (trip count =
+//      the largest hit count in the warp), instead of each lane doing the heavy math at a different
+//      iteration of the stencil walk.
+constexpr int kMaxHits = 16;
+
+struct BondEval {
+    // radius-dependent part of the contact model, memoised on the partner radius (radii are usually uniform)
+    double memo_r, r_hat, overlap_;
+    __device__ __forceinline__ void refresh(double rp, double rq, const JkrConst &c) {
+        if (rq != memo_r) {
+            memo_r = rq;
+            r_hat = 1.0 / (1e6 * ((1.0 / rp) + (1.0 / rq)));
+            overlap_ = c.k23 * cbrt(r_hat);
+        }
+    }
+};
+
 template <bool kSortRows>
 __global__ void __launch_bounds__(kJkrThreads)
 k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_id,
@@ -71,6 +91,8 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
               double stokes, Box box, double dt) {
+    __shared__ int hit_slot[kMaxHits][kJkrThreads];
+    const double kPi = 3.141592653589793;
     int s = blockIdx.x * kJkrThreads + threadIdx.x;
     int cnt = 0;
     if (s < n) {
@@ -80,6 +102,36 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         st.decode(sorted_bin[s], bx, by, bz);
         int *row = new_cols + (long long)i * stride;
         double fx = 0.0, fy = 0.0, fz = 0.0;
+        BondEval ev;
+        ev.memo_r = -1.0;
+
+        auto evaluate = [&](int t, double4 q) {
+            double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
+            double s2 = sumsq_nofma(vx, vy, vz);
+            int j = sorted_id[t];
+            if (!rad.within(s2)) {                   // thin shell: only pre-existing bonds persist
+                if (!old.valid() || !old.contains(i, j)) return;
+            }
+            ev.refresh(p.w, q.w, c);
+            double mag = __dsqrt_rn(s2);
+            double overlap = (p.w + q.w - mag) / 1e6;
+            double d = overlap / ev.overlap_;
+            if (d > -0.360562) {
+                double f = (-0.0204 * (d * d * d)) + (0.4942 * (d * d)) + (1.0801 * d) - 1.324;
+                double jkr = f * kPi * c.adhesion * ev.r_hat;
+                if (mag != 0.0) {
+                    double w = jkr / mag;
+                    fx += w * vx;
+                    fy += w * vy;
+                    fz += w * vz;
+                }
+                if (cnt < stride) row[cnt] = j;
+                ++cnt;
+            }
+        };
+
+        // phase 1: cheap reach test over the stencil
+        int nh = 0;
         for (int dz = -1; dz <= 1; ++dz) {
             int z = bz + dz;
             if (z < 0 || z >= st.dims[2]) continue;
@@ -90,27 +142,21 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                 int rowb = (z * st.dims[1] + y) * st.dims[0];
                 int lo = bin_start[rowb + x0], hi = bin_start[rowb + x1 + 1];
                 for (int t = lo; t < hi; ++t) {
-                    if (t == s) continue;
                     double4 q = spos[t];
-                    double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
-                    double s2 = sumsq_nofma(vx, vy, vz);
-                    if (s2 > reach2) continue;           // no bond can survive beyond the reach
-                    int j = -1;
-                    if (!rad.within(s2)) {               // thin shell: only pre-existing bonds persist
-                        if (!old.valid()) continue;
-                        j = sorted_id[t];
-                        if (!old.contains(i, j)) continue;
-                    }
-                    double gx, gy, gz;
-                    if (jkr_bond(vx, vy, vz, s2, p.w, q.w, c, gx, gy, gz)) {
-                        fx += gx;
-                        fy += gy;
-                        fz += gz;
-                        if (cnt < stride) row[cnt] = (j >= 0) ? j : sorted_id[t];
-                        ++cnt;
+                    double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
+                    if (s2 <= reach2 && t != s) {        // no bond can survive beyond the reach
+                        if (nh < kMaxHits) hit_slot[nh][threadIdx.x] = t;
+                        else evaluate(t, q);             // crowded cell: evaluate in place
+                        ++nh;
                     }
                 }
             }
+        }
+        // phase 2: contact model on the parked slots
+        int parked = min(nh, kMaxHits);
+        for (int k = 0; k < parked; ++k) {
+            int t = hit_slot[k][threadIdx.x];
+            evaluate(t, spos[t]);
         }
         new_len[i] = min(cnt, stride);
         if (kSortRows) insertion_sort(row, min(cnt, stride));

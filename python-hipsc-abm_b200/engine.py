@@ -72,6 +72,9 @@ class ColonyEngine:
         self._bond_bufs = None
         self.cols_capacity_hint = {}
         self.launches = 0      # number of kernels of this library enqueued (bench.py's gpu_launches)
+        self.h2d_bytes = 0     # bytes moved by upload()/to_device() and host()/locations_host()
+        self.d2h_bytes = 0
+        self._pinned = {}
 
     # ------------------------------------------------------------------------------------------------
     @property
@@ -85,18 +88,42 @@ class ColonyEngine:
         return torch.zeros(shape, dtype=dtype, device=self.device)
 
     # ---- state -------------------------------------------------------------------------------------
-    def upload(self, locations, radii, motility=None, jkr=None, pinned=False):
+    def to_device(self, array, name=None) -> torch.Tensor:
+        """numpy -> device through a reusable pinned staging buffer (the host arrays of the reference API
+        are pageable numpy; staging keeps the DMA asynchronous and at full PCIe rate)."""
+        a = np.ascontiguousarray(array)
+        t = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
+        self.h2d_bytes += a.nbytes
+        if name is None or a.size == 0:
+            return t.to(self.device)
+        stage = self._pinned.get(name)
+        if stage is None or stage.dtype != t.dtype or stage.numel() < t.numel():
+            stage = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
+            self._pinned[name] = stage
+        view = stage[:t.numel()].view(t.shape)
+        view.copy_(t)
+        out = view.to(self.device, non_blocking=True)
+        # the staging buffer may be overwritten by the next upload: order it after this copy
+        torch.cuda.current_stream(self.device).synchronize()
+        return out
+
+    def host(self, t: torch.Tensor) -> np.ndarray:
+        """device -> numpy, counted."""
+        self.d2h_bytes += t.numel() * t.element_size()
+        return t.cpu().numpy()
+
+    def upload(self, locations, radii, motility=None, jkr=None):
         """Host -> device copy of the agent arrays the path reads (reference dtypes: float64)."""
         loc = np.ascontiguousarray(locations, dtype=np.float64)
         n = loc.shape[0]
         rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, dtype=np.float64), (n,)))
         self.n = n
-        self.loc = torch.from_numpy(loc).to(self.device, non_blocking=pinned)
-        self.radii = torch.from_numpy(rad).to(self.device, non_blocking=pinned)
+        self.loc = self.to_device(loc, "loc")
+        self.radii = self.to_device(rad, "radii")
         self.max_radius = float(rad.max()) if n else 0.0
-        self.mot = (torch.from_numpy(np.ascontiguousarray(motility, dtype=np.float64)).to(self.device)
+        self.mot = (self.to_device(np.asarray(motility, dtype=np.float64), "mot")
                     if motility is not None else self._zeros((n, 3), torch.float64))
-        self.jkr = (torch.from_numpy(np.ascontiguousarray(jkr, dtype=np.float64)).to(self.device)
+        self.jkr = (self.to_device(np.asarray(jkr, dtype=np.float64), "jkr")
                     if jkr is not None else self._zeros((n, 3), torch.float64))
 
     def set_device_state(self, loc, radii, mot=None, jkr=None, max_radius=None):
@@ -108,7 +135,7 @@ class ColonyEngine:
         self.max_radius = float(max_radius) if max_radius is not None else float(radii.max().item())
 
     def locations_host(self) -> np.ndarray:
-        return self.loc.cpu().numpy()
+        return self.host(self.loc)
 
     # ---- a1/a2: binning ------------------------------------------------------------------------------
     def bin_dims(self, distance):
@@ -124,7 +151,8 @@ class ColonyEngine:
         key = (n, nbins)
         bufs = self._sort_bufs.get(key)
         if bufs is None:
-            self._sort_bufs.clear()
+            for stale in [k for k in self._sort_bufs if k[0] != n]:
+                del self._sort_bufs[stale]
             bufs = dict(bin_start=self._empty(nbins + 1, torch.int32), sorted_id=self._empty(max(n, 1), torch.int32),
                         sorted_pos=self._empty((max(n, 1), 4), torch.float64),
                         sorted_bin=self._empty(max(n, 1), torch.int32), max_count=self._empty(1, torch.int32))
@@ -162,23 +190,14 @@ class ColonyEngine:
         """Fixed-radius search (abm_neighbor_search); grows the column buffer and retries on overflow,
         like the reference's max_neighbors loop (simulation.py:277-281)."""
         n = sort.n
-        if distance > sort.distance * (1 + 1e-12):
-            raise _lib.AbmError("search radius exceeds the bin edge of the sort")
         row_start = self._empty(max(n, 1), torch.int32)
         row_len = self._zeros(max(n, 1), torch.int32)
         cursor = self._empty(1, torch.int32)
-        dims = _lib.i3(sort.dims)
         hint_key = (round(float(distance), 9), old is not None)
         cap = int(capacity if capacity is not None else self.cols_capacity_hint.get(hint_key, 8 * max(n, 1)))
         while True:
             cols = self._empty(max(cap, 1), torch.int32)
-            _lib.check(self.lib.abm_neighbor_search(
-                _ptr(sort.bin_start), _ptr(sort.sorted_id), _ptr(sort.sorted_pos), _ptr(sort.sorted_bin), n, dims,
-                float(distance), _ptr(self.loc),
-                _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
-                _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
-                _ptr(row_start), _ptr(row_len), _ptr(cols), cap, _ptr(cursor), self.stream), "abm_neighbor_search")
-            self.launches += 1 if n else 0
+            self.enqueue_search(sort, distance, old, row_start, row_len, cols, cursor)
             used = self.read_i32(cursor)
             if used <= cap:
                 break
@@ -187,6 +206,22 @@ class ColonyEngine:
         g = GraphTensors(n, row_start, 0, row_len, cols, True)
         g.entries = used
         return g
+
+    def enqueue_search(self, sort: SortState, distance, old, row_start, row_len, cols, cursor):
+        """One abm_neighbor_search launch into caller-provided buffers; no host sync (the caller checks
+        cursor <= cols.numel() later)."""
+        if distance > sort.distance * (1 + 1e-12):
+            raise _lib.AbmError("search radius exceeds the bin edge of the sort")
+        n = sort.n
+        _lib.check(self.lib.abm_neighbor_search(
+            _ptr(sort.bin_start), _ptr(sort.sorted_id), _ptr(sort.sorted_pos), _ptr(sort.sorted_bin), n,
+            _lib.i3(sort.dims), float(distance), _ptr(self.loc),
+            _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
+            _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
+            _ptr(row_start), _ptr(row_len), _ptr(cols), cols.numel(), _ptr(cursor), self.stream),
+            "abm_neighbor_search")
+        self.launches += 1 if n else 0
+        return GraphTensors(n, row_start, 0, row_len, cols, True)
 
     def edge_list(self, g: GraphTensors) -> np.ndarray:
         """Canonical (i<j) int64 edge array of a graph (abm_graph_edge_list), downloaded."""
@@ -207,7 +242,7 @@ class ColonyEngine:
         e = self.read_i32(n_edges)
         if e > cap:
             raise _lib.AbmError("edge list capacity underestimated")
-        return edges[:e].cpu().numpy()
+        return self.host(edges[:e])
 
     # ---- a6/a7/a9: unfused mechanics -------------------------------------------------------------------
     def jkr_forces(self, g: GraphTensors):
@@ -238,18 +273,21 @@ class ColonyEngine:
             self._bond_bufs = b
         return b
 
-    def enqueue_mechanics(self, old: Optional[GraphTensors], distance, dts, stride, stokes=STOKES):
+    def enqueue_mechanics(self, old: Optional[GraphTensors], distance, dts, stride, stokes=STOKES, pair=None,
+                          zero_flag=True):
         """Enqueue len(dts) fused substeps (sort + abm_jkr_substep each).  No host sync.  Returns the
         fixed-stride graph holding the final bonds; overflow is reported through bufs['max_len']."""
         n = self.n
         b = self._bond_buffers(n, stride)
-        b["max_len"].zero_()
+        if zero_flag:
+            b["max_len"].zero_()
         reach = self.jkr_reach(distance)
         cur = old
         out = None
         # three row buffers: the two that do not hold `old` ping-pong, so `old` survives a retry
         held = [i for i in range(3) if old is not None and old.cols.data_ptr() == b["cols"][i].data_ptr()]
-        pair = [i for i in range(3) if i not in held][:2]
+        if pair is None:
+            pair = [i for i in range(3) if i not in held][:2]
         for k, dt in enumerate(dts):
             srt = self.sort(reach)
             last = k == len(dts) - 1

@@ -41,12 +41,12 @@ class DeviceGraph:
         if self._dev is None or self._dev.n != self.n:
             ptr, cols = self._host()
             dev = engine.device
-            row_start = torch.from_numpy(ptr[:-1].astype(np.int32)).to(dev)
-            row_len = torch.from_numpy(np.diff(ptr).astype(np.int32)).to(dev)
+            row_start = engine.to_device(ptr[:-1].astype(np.int32))
+            row_len = engine.to_device(np.diff(ptr).astype(np.int32))
             if self.n == 0:
                 row_start = torch.zeros(1, dtype=torch.int32, device=dev)
                 row_len = torch.zeros(1, dtype=torch.int32, device=dev)
-            cols_t = torch.from_numpy(np.ascontiguousarray(cols, dtype=np.int32)).to(dev)
+            cols_t = engine.to_device(np.ascontiguousarray(cols, dtype=np.int32))
             if cols_t.numel() == 0:
                 cols_t = torch.zeros(1, dtype=torch.int32, device=dev)
             self._dev = GraphTensors(self.n, row_start, 0, row_len, cols_t, True)
@@ -56,7 +56,8 @@ class DeviceGraph:
         """Host CSR (ptr int64[n+1], cols int32), downloading the device copy if needed."""
         if not self._host_valid:
             g = self._dev
-            row_len = g.row_len[:g.n].cpu().numpy().astype(np.int64)
+            dl = self._engine.host if self._engine is not None else (lambda t: t.cpu().numpy())
+            row_len = dl(g.row_len[:g.n]).astype(np.int64)
             ptr = np.zeros(g.n + 1, dtype=np.int64)
             np.cumsum(row_len, out=ptr[1:])
             total = int(ptr[-1])
@@ -64,16 +65,16 @@ class DeviceGraph:
                 start = np.arange(g.n, dtype=np.int64) * g.row_stride
                 flat = g.cols.reshape(-1)
             else:
-                start = g.row_start[:g.n].cpu().numpy().astype(np.int64)
+                start = dl(g.row_start[:g.n]).astype(np.int64)
                 flat = g.cols
             if total:
                 # position of every entry inside its row + the row's start in the device layout
                 src = np.repeat(start - ptr[:-1], row_len) + np.arange(total, dtype=np.int64)
                 if g.row_start is None:
-                    cols = flat.cpu().numpy()[src]
+                    cols = dl(flat)[src]
                 else:
                     hi = int(src.max()) + 1
-                    cols = flat[:hi].cpu().numpy()[src]
+                    cols = dl(flat[:hi])[src]
             else:
                 cols = np.zeros(0, dtype=np.int32)
             if not g.sorted_rows and total:

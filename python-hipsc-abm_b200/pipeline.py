@@ -1,0 +1,154 @@
+"""Device-resident simulation step: the whole hot path of one reference step enqueued without any host
+synchronisation, optionally captured in a CUDA graph.
+
+One step =
+    1 x neighbour search at r_search (get_neighbors("neighbor_graph", 15), cell_simulation.py:90)
+  + S_m x fused mechanics substep (CellMethods.apply_forces, cell_methods.py:399-436)
+  + deposit -> S_d diffusion substeps -> sample (update_diffusion + the per-cell coupling, cell_methods.py:441-521)
+
+Capacities (column buffer of the search, bond-row stride) are fixed while a captured graph is alive; the
+kernels report the size they needed and `check()` raises if anything was truncated, so a run is never
+silently wrong.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import ColonyEngine, GraphTensors, STOKES
+
+
+@dataclass
+class StepConfig:
+    search_radius: float = 15.0          # cell_simulation.py:90
+    contact_radius: float = 10.0         # 2 * max_radius, cell_methods.py:401
+    step_dt: float = 1800.0              # cell_simulation.py:34
+    move_dt: float = 180.0               # cell_simulation.py:35
+    # morphogen field (None -> no diffusion stage)
+    grid: Optional[tuple] = None         # (gx, gy)
+    spat_res: float = 7.07106
+    diffuse_const: float = 50.0
+    diffuse_dt: float = 0.24
+    diffuse_steps: int = 10
+    diffuse_last_dt: Optional[float] = None
+    max_concentration: float = 2.0
+    degradation: float = 0.1
+    deposit_amount: float = 1.0
+    bond_stride: int = 16
+    search_cols_per_cell: float = 12.0   # column-buffer capacity of the r_search graph, entries per cell
+    use_tma: Optional[bool] = None
+
+    def substep_dts(self):
+        steps, last_dt = divmod(self.step_dt, self.move_dt)     # cell_methods.py:395-396
+        return [self.move_dt] * int(steps) + [last_dt]
+
+
+class HotPathStep:
+    def __init__(self, engine: ColonyEngine, cfg: StepConfig):
+        self.eng = engine
+        self.cfg = cfg
+        n = engine.n
+        dev = engine.device
+        self.dts = cfg.substep_dts()
+        cap = int(cfg.search_cols_per_cell * max(n, 1)) + 1024
+        self.nbr = dict(row_start=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
+                        row_len=torch.zeros(max(n, 1), dtype=torch.int32, device=dev),
+                        cols=torch.empty(cap, dtype=torch.int32, device=dev),
+                        cursor=torch.zeros(1, dtype=torch.int32, device=dev),
+                        worst=torch.zeros(1, dtype=torch.int32, device=dev))
+        self.neighbor_graph: Optional[GraphTensors] = None
+        self.bonds: Optional[GraphTensors] = None
+        self.parity = 0
+        self.field = self.scratch = self.amounts = self.sampled = None
+        if cfg.grid is not None:
+            gx, gy = cfg.grid
+            self.field = torch.zeros((gx, gy), dtype=torch.float64, device=dev)
+            self.scratch = torch.empty_like(self.field)
+            self.amounts = torch.full((max(n, 1),), cfg.deposit_amount, dtype=torch.float64, device=dev)
+            if cfg.diffuse_steps % 2:
+                raise ValueError("HotPathStep keeps the field in place: use an even number of diffusion substeps")
+        self.graphs = None
+        self.launches_per_step = 0
+        # start with an empty bond graph living in row buffer 0
+        b = engine._bond_buffers(n, cfg.bond_stride)
+        b["len"][0].zero_()
+        b["max_len"].zero_()
+        self.bonds = GraphTensors(n, None, cfg.bond_stride, b["len"][0], b["cols"][0], True)
+
+    # ---- one step, enqueue only ---------------------------------------------------------------------------
+    def enqueue(self):
+        eng, cfg = self.eng, self.cfg
+        before = eng.launches
+        # neighbour graph (what the rule methods consume)
+        srt = eng.sort(cfg.search_radius)
+        self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self.nbr["row_start"],
+                                                 self.nbr["row_len"], self.nbr["cols"], self.nbr["cursor"])
+        torch.maximum(self.nbr["worst"], self.nbr["cursor"], out=self.nbr["worst"])   # sticky overflow record
+        # mechanics: bonds alternate between row buffers 0 and 1, buffer 2 is the intermediate
+        src = self.parity
+        pair = [1 - src, 2]
+        self.bonds = eng.enqueue_mechanics(self.bonds, cfg.contact_radius, self.dts, cfg.bond_stride, STOKES,
+                                           pair=pair, zero_flag=False)
+        self.parity = 1 - src if len(self.dts) % 2 else src
+        if len(self.dts) % 2 == 0:
+            raise ValueError("even substep counts are not wired in HotPathStep")
+        # morphogen: deposit -> diffuse -> sample
+        if self.field is not None:
+            eng.deposit(self.field, self.amounts, cfg.spat_res)
+            last = cfg.diffuse_dt if cfg.diffuse_last_dt is None else cfg.diffuse_last_dt
+            out = eng.diffuse(self.field, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const,
+                              cfg.spat_res ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma,
+                              scratch=self.scratch)
+            assert out.data_ptr() == self.field.data_ptr()
+            self.sampled = eng.sample(self.field, cfg.spat_res)
+        self.launches_per_step = eng.launches - before
+
+    def step(self):
+        """Eager step (no graph)."""
+        self.enqueue()
+
+    # ---- CUDA graphs ------------------------------------------------------------------------------------------
+    def capture(self):
+        """Capture the two alternating step variants (bond rows in buffer 0 -> 1 and 1 -> 0)."""
+        assert self.parity == 0, "capture() must start from an even step"
+        torch.cuda.synchronize(self.eng.device)
+        self.graphs = []
+        launches = self.eng.launches
+        stream = torch.cuda.Stream(device=self.eng.device)
+        for _ in range(2):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                self.enqueue()
+            self.graphs.append(g)
+        # capturing enqueues nothing on the device: undo the launch accounting, and the state did not advance
+        self.eng.launches = launches
+        self.parity = 0
+        b = self.eng._bond_buffers(self.eng.n, self.cfg.bond_stride)
+        self.bonds = GraphTensors(self.eng.n, None, self.cfg.bond_stride, b["len"][0], b["cols"][0], True)
+        self._replays = 0
+
+    def replay(self):
+        self.graphs[self._replays & 1].replay()
+        self._replays += 1
+        self.eng.launches += self.launches_per_step
+
+    # ---- capacity check ------------------------------------------------------------------------------------------
+    def check(self):
+        """Host sync: raise if any fixed-capacity buffer was too small during the steps run so far."""
+        eng = self.eng
+        used = eng.read_i32(self.nbr["worst"])
+        if used > self.nbr["cols"].numel():
+            raise _lib.AbmError(f"neighbour column buffer too small: needed {used}, have {self.nbr['cols'].numel()}")
+        worst = eng.read_i32(eng._bond_bufs["max_len"])
+        if worst > self.cfg.bond_stride:
+            raise _lib.AbmError(f"bond rows too narrow: needed {worst}, have {self.cfg.bond_stride}")
+        return used, worst
+
+    def current_bonds(self) -> GraphTensors:
+        b = self.eng._bond_bufs
+        k = (self._replays & 1) if self.graphs is not None else self.parity
+        return GraphTensors(self.eng.n, None, self.cfg.bond_stride, b["len"][k], b["cols"][k], True)

@@ -79,7 +79,7 @@ class B200Simulation:
         if max_agents < worst:
             max_agents = worst * 2
         bins, bins_help, bin_locations = eng.bins_dense(srt, max_agents)
-        return bins.cpu().numpy(), bins_help.cpu().numpy(), bin_locations.cpu().numpy(), int(max_agents)
+        return eng.host(bins), eng.host(bins_help), eng.host(bin_locations), int(max_agents)
 
     @record_time
     def get_neighbors(self, graph_name, distance, clear=True):
