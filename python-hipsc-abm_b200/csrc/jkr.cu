@@ -71,6 +71,8 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 //      the largest hit count in the warp), instead of each lane doing the heavy math at a different
 //      iteration of the stencil walk.
 constexpr int kMaxHits = 16;
+constexpr int kMaxShell = 4;
+constexpr int kJkrMinBlocks = 6;     // cap registers at 80/thread: the kernel is latency bound, occupancy matters
 
 struct BondEval {
     // radius-dependent part of the contact model, memoised on the partner radius (radii are usually uniform)
@@ -85,13 +87,14 @@ struct BondEval {
 };
 
 template <bool kSortRows>
-__global__ void __launch_bounds__(kJkrThreads)
+__global__ void __launch_bounds__(kJkrThreads, kJkrMinBlocks)
 k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_id,
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
               double stokes, Box box, double dt) {
-    __shared__ int hit_slot[kMaxHits][kJkrThreads];
+    __shared__ int hit_slot[kMaxHits][kJkrThreads];       // partners within `distance`: bonded unless d breaks
+    __shared__ int shell_slot[kMaxShell][kJkrThreads];    // partners in (distance, reach]: bonded only if they were
     const double kPi = 3.141592653589793;
     int s = blockIdx.x * kJkrThreads + threadIdx.x;
     int cnt = 0;
@@ -105,13 +108,10 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         BondEval ev;
         ev.memo_r = -1.0;
 
-        auto evaluate = [&](int t, double4 q) {
+        // contact model for one partner known to be a bond candidate
+        auto bond = [&](int t, double4 q) {
             double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
             double s2 = sumsq_nofma(vx, vy, vz);
-            int j = sorted_id[t];
-            if (!rad.within(s2)) {                   // thin shell: only pre-existing bonds persist
-                if (!old.valid() || !old.contains(i, j)) return;
-            }
             ev.refresh(p.w, q.w, c);
             double mag = __dsqrt_rn(s2);
             double overlap = (p.w + q.w - mag) / 1e6;
@@ -125,38 +125,75 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                     fy += w * vy;
                     fz += w * vz;
                 }
-                if (cnt < stride) row[cnt] = j;
+                if (cnt < stride) row[cnt] = sorted_id[t];
                 ++cnt;
             }
         };
+        // membership of j in this cell's previous bond row; every entry is read (no early exit) so the
+        // loads are independent and overlap
+        auto was_bonded = [&](int j) {
+            long long os = old.start(i);
+            int olen = old.row_len[i];
+            bool found = false;
+            for (int k = 0; k < olen; ++k) found |= (old.cols[os + k] == j);
+            return found;
+        };
 
-        // phase 1: cheap reach test over the stencil
-        int nh = 0;
+        // phase 1: cheap tests over the stencil, park what needs the contact model.
+        // The (lo,hi) slot ranges of the three dy runs of a z-layer are fetched together (6 offset loads in
+        // flight instead of one dependent pair per run), and the next candidate is loaded while the current
+        // one is tested.
+        int nh = 0, ns = 0;
+        const int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
         for (int dz = -1; dz <= 1; ++dz) {
             int z = bz + dz;
             if (z < 0 || z >= st.dims[2]) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                int y = by + dy;
-                if (y < 0 || y >= st.dims[1]) continue;
-                int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
-                int rowb = (z * st.dims[1] + y) * st.dims[0];
+            int run_lo[3], run_n[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                int y = by + r - 1;
+                bool ok = y >= 0 && y < st.dims[1];
+                int rowb = ok ? (z * st.dims[1] + y) * st.dims[0] : 0;
                 int lo = bin_start[rowb + x0], hi = bin_start[rowb + x1 + 1];
-                for (int t = lo; t < hi; ++t) {
-                    double4 q = spos[t];
+                run_lo[r] = lo;
+                run_n[r] = ok ? hi - lo : 0;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                int lo = run_lo[r], cntr = run_n[r];
+                if (cntr <= 0) continue;
+                double4 q = spos[lo];
+                for (int u = 0; u < cntr; ++u) {
+                    int t = lo + u;
+                    double4 qn = q;
+                    if (u + 1 < cntr) qn = spos[t + 1];
                     double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
-                    if (s2 <= reach2 && t != s) {        // no bond can survive beyond the reach
-                        if (nh < kMaxHits) hit_slot[nh][threadIdx.x] = t;
-                        else evaluate(t, q);             // crowded cell: evaluate in place
-                        ++nh;
+                    if (s2 <= reach2 && t != s) {             // no bond can survive beyond the reach
+                        if (rad.within(s2)) {
+                            if (nh < kMaxHits) hit_slot[nh][threadIdx.x] = t;
+                            else bond(t, q);                  // crowded cell: evaluate in place
+                            ++nh;
+                        } else if (old.valid()) {
+                            if (ns < kMaxShell) shell_slot[ns][threadIdx.x] = t;
+                            else if (was_bonded(sorted_id[t])) bond(t, q);
+                            ++ns;
+                        }
                     }
+                    q = qn;
                 }
             }
         }
-        // phase 2: contact model on the parked slots
+        // phase 2: contact model on the parked partners, all lanes together
         int parked = min(nh, kMaxHits);
         for (int k = 0; k < parked; ++k) {
             int t = hit_slot[k][threadIdx.x];
-            evaluate(t, spos[t]);
+            bond(t, spos[t]);
+        }
+        // phase 3: the thin shell -- hysteresis lookups, only the lanes that have any
+        int shelled = min(ns, kMaxShell);
+        for (int k = 0; k < shelled; ++k) {
+            int t = shell_slot[k][threadIdx.x];
+            if (was_bonded(sorted_id[t])) bond(t, spos[t]);
         }
         new_len[i] = min(cnt, stride);
         if (kSortRows) insertion_sort(row, min(cnt, stride));
