@@ -207,6 +207,11 @@ def run_b200(args, rank, world, local_rank):
     cfg = StepConfig(grid=wl["grid"], spat_res=spec["h"] or 1.0, diffuse_dt=spec["diffuse_dt"] or 1.0,
                      diffuse_steps=spec["sd"], bond_stride=16 if spec["dim"] == 2 else 32,
                      search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
+    if world > 1:
+        line = run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg)
+        dist.barrier()
+        dist.destroy_process_group()
+        return line
     eng = ColonyEngine(wl["size"], dev)
     eng.upload(wl["loc"], wl["radii"], wl["mot"])
     pipe = HotPathStep(eng, cfg)
@@ -387,6 +392,107 @@ def run_b200(args, rank, world, local_rank):
                    "timing": "CUDA events per step around a CUDA-graph replay, summed; max over ranks",
                    "parallelism": "single GPU" if world == 1 else f"{world} independent colonies (replicas)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+    }
+
+
+def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
+    """N > 1: ONE colony of world x workload cells, slab-decomposed along x (hipsc_abm_b200/slab.py): per step
+    a halo exchange, the whole step on owned+halo cells without further communication, a morphogen-row
+    exchange and a migration exchange, all over NCCL send/recv."""
+    import torch
+    from hipsc_abm_b200 import slab
+    from hipsc_abm_b200.pipeline import SlabPipeline
+
+    spec, n = wl["spec"], wl["n"]
+    side = wl["size"][0]
+    gsize = wl["size"].copy()
+    gsize[0] = side * world
+    probe = SlabPipeline(slab.SlabGeometry.uniform(gsize, world, rank, 1.0), cfg, dev)
+    reach = probe.eng.jkr_reach(cfg.contact_radius)
+    halo = slab.required_halo(len(cfg.substep_dts()), reach, slack=4.0) + (spec["h"] or 0.0)
+    geom = slab.SlabGeometry.uniform(gsize, world, rank, halo)
+    pipe = SlabPipeline(geom, cfg, dev)
+    loc = wl["loc"].copy()
+    loc[:, 0] += geom.x_lo
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    state = slab.SlabState(t(loc), t(wl["radii"]), t(wl["mot"]), t(np.arange(n, dtype=np.int64) + rank * n),
+                           cfg.bond_stride)
+    field = None
+    if wl["grid"]:
+        gx = int(np.ceil(gsize[0] / spec["h"])) + 1
+        field = slab.FieldSlab(geom, (gx, wl["grid"][1]), spec["h"], spec["sd"] + 1, dev)
+    fabric = slab.DistFabric(rank, world, dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    worst = slab.halo_violation(state, geom).item()
+    sampler = ClockSampler(dev.index or 0)
+    launches0, bytes0, ex0 = pipe.eng.launches, fabric.bytes_sent, fabric.exchanges
+    barrier()
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        step()
+        b.record()
+    barrier()
+    clocks = sampler.stop()
+    total_s = sum(a.elapsed_time(b) for a, b in evs) / 1e3
+    tt = torch.tensor([total_s], device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_s = float(tt.item())
+    cells = torch.tensor([state.n], device=dev)
+    dist.all_reduce(cells)
+    launches = pipe.eng.launches - launches0
+
+    # e2e: the same step with the host in the loop -- the rule methods' inputs (motility forces of the owned
+    # cells) are uploaded from pinned memory and the positions + sampled concentrations downloaded, every step
+    e_steps = max(3, min(args.steps, 10))
+    pin_mot = torch.empty((state.n + 4096, 3), dtype=torch.float64).pin_memory()
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        k = state.n
+        if k > pin_mot.shape[0]:
+            pin_mot = torch.empty((k + 4096, 3), dtype=torch.float64).pin_memory()
+        state.mot = pin_mot[:k].to(dev, non_blocking=True)
+        step()
+        out_loc = state.loc.cpu()
+        out_c = pipe.sampled.cpu() if pipe.sampled is not None else None
+        h2d += k * 24
+        d2h += out_loc.numel() * 8 + (out_c.numel() * 8 if out_c is not None else 0)
+    torch.cuda.synchronize(dev)
+    e_s = time.perf_counter() - t0
+    tt = torch.tensor([e_s], device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    e_s = float(tt.item())
+    if rank != 0:
+        return None
+    value = n * world * args.steps / total_s
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.workload} x {world}: {spec['desc']} per GPU, one colony", "cells_per_gpu": n,
+                   "cells_total": int(cells.item()), "dim": spec["dim"], "mechanics_substeps": len(cfg.substep_dts()),
+                   "diffusion_substeps": spec["sd"], "halo_um": halo, "max_owner_drift_um": worst,
+                   "exchanges_per_step": (fabric.exchanges - ex0) / max(args.steps + e_steps, 1),
+                   "bytes_sent_per_step_rank0": (fabric.bytes_sent - bytes0) // max(args.steps + e_steps, 1),
+                   "l2": "flushed between timed steps (256 MiB memset)",
+                   "timing": "CUDA events per step, summed; max over ranks",
+                   "parallelism": f"slab{world}: 1-D slab decomposition along x, halo + migration + field rows "
+                                  "exchanged once per step over NCCL send/recv"},
+        "clocks": clocks,
+        "e2e": {"value": n * world * e_steps / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e_steps,
+                "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps, "ms_per_step": e_s / e_steps * 1e3,
+                "api": "slab.slab_step with host-resident motility forces in, positions + concentrations out"},
+        "gpu_launches": launches, "roofline": None, "cpu_baseline": None,
     }
 
 

@@ -53,9 +53,12 @@ size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins);
  *                               serial fill order, backend.py:36-48)
  *   sorted_pos (n,4)     f64    {x,y,z,radius} of the cell in that slot (32-byte rows)
  *   sorted_bin (n)       int32  linear bin of the slot
- *   max_count  (1)       int32  largest bin population (what drives the reference's max_agents)   */
+ *   max_count  (1)       int32  largest bin population (what drives the reference's max_agents)
+ * origin_host (may be NULL = 0,0,0) shifts the bin lattice only: bin = floor_divide(x-origin,distance)+1 over
+ * an extent of size_host.  A slab-decomposed colony bins its slab (+halo) this way while positions, the
+ * distance predicate and the [0,size] clamp stay in global coordinates.                              */
 int abm_bin_sort(const double *locations, const double *radii, int64_t n, const double size_host[3],
-                 double distance, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
+                 const double *origin_host, double distance, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
                  int32_t *sorted_bin, int32_t *max_count, void *workspace, size_t workspace_bytes,
                  void *stream);
 
@@ -148,14 +151,18 @@ int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t gy, int64_
                   double degradation, int use_tma, int *result_in_scratch_host, void *stream);
 
 /* Replaces per-cell get_concentration (cell_methods.py:470-483) for all cells: nearest grid point
- * idx = ceil(floor(2x/h)/2); field is (gx,gy,gz) row-major.  sampled (N,) f64.                    */
+ * idx = ceil(floor(2x/h)/2) on the (gx,gy,gz) grid.  `field` holds the global rows [row_lo,row_hi) of that grid,
+ * row-major (the whole grid: row_lo=0,row_hi=gx; a slab of it for a slab-decomposed colony).  sampled (N,) f64. */
 int abm_sample_concentrations(const double *locations, int64_t n, const double *field,
-                              const int64_t gsize_host[3], double spat_res, double *sampled, void *stream);
+                              const int64_t gsize_host[3], double spat_res, int64_t row_lo, int64_t row_hi,
+                              double *sampled, void *stream);
 
 /* Replaces per-cell adjust_morphogens (cell_methods.py:485-521) for all cells: amounts[i] is shared
- * equally by the in-bounds corner points closer than spat_res (fp64 atomic adds).                 */
+ * equally by the in-bounds corner points closer than spat_res (fp64 atomic adds).  Shares that fall on rows
+ * outside [row_lo,row_hi) belong to another slab and are skipped (the share size still counts them).  */
 int abm_deposit_morphogens(const double *locations, const double *amounts, int64_t n, double *field,
-                           const int64_t gsize_host[3], double spat_res, void *stream);
+                           const int64_t gsize_host[3], double spat_res, int64_t row_lo, int64_t row_hi,
+                           void *stream);
 
 #ifdef __cplusplus
 }

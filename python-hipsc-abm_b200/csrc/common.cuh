@@ -40,7 +40,8 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // ---- bin geometry --------------------------------------------------------------------------------
 struct BinGeom {
     double distance;
-    int dims[3];      // ceil(size/distance)+3 per axis (reference simulation.py:202)
+    double origin[3]; // lattice origin (0 for a whole colony; the slab's lower corner for a slab-decomposed one)
+    int dims[3];      // ceil(extent/distance)+3 per axis (reference simulation.py:202)
 };
 
 // Exact floor(a/b) for b > 0: numpy's float floor_divide (npy_divmod) returns the mathematically

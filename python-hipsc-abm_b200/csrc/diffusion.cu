@@ -147,8 +147,11 @@ k_diffuse(const __grid_constant__ CUtensorMap src_map, const double *__restrict_
     }
 }
 
+// `field` holds global rows [row_lo,row_hi) of a (g0,g1,g2) grid (a slab of it, or all of it); indices are computed
+// on the global grid exactly as the reference does and then shifted.
 __global__ void k_sample(const double *__restrict__ loc, int n, const double *__restrict__ field, long long g0,
-                         long long g1, long long g2, double h, double *__restrict__ out) {
+                         long long g1, long long g2, double h, long long row_lo, long long row_hi,
+                         double *__restrict__ out) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     long long g[3] = {g0, g1, g2};
@@ -161,11 +164,13 @@ __global__ void k_sample(const double *__restrict__ loc, int n, const double *__
         v = v < 0 ? 0 : (v >= g[k] ? g[k] - 1 : v);   // the reference would raise IndexError beyond this
         idx[k] = v;
     }
-    out[i] = field[(idx[0] * g1 + idx[1]) * g2 + idx[2]];
+    long long r = idx[0] < row_lo ? row_lo : (idx[0] >= row_hi ? row_hi - 1 : idx[0]);
+    out[i] = field[((r - row_lo) * g1 + idx[1]) * g2 + idx[2]];
 }
 
 __global__ void k_deposit(const double *__restrict__ loc, const double *__restrict__ amounts, int n,
-                          double *__restrict__ field, long long g0, long long g1, long long g2, double h) {
+                          double *__restrict__ field, long long g0, long long g1, long long g2, double h,
+                          long long row_lo, long long row_hi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double lx = loc[3 * (long long)i + 0], ly = loc[3 * (long long)i + 1], lz = loc[3 * (long long)i + 2];
@@ -192,8 +197,8 @@ __global__ void k_deposit(const double *__restrict__ loc, const double *__restri
         long long px = x + (p & 1), py = y + (p >> 1);
         if (px < 0) px += g0;
         if (py < 0) py += g1;
-        if (px < 0 || py < 0) continue;
-        atomicAdd(&field[(px * g1 + py) * g2 + 0], share);
+        if (px < row_lo || px >= row_hi || py < 0) continue;   // rows held by another slab
+        atomicAdd(&field[((px - row_lo) * g1 + py) * g2 + 0], share);
     }
 }
 
@@ -301,26 +306,31 @@ ABM_EXPORT int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t
 }
 
 ABM_EXPORT int abm_sample_concentrations(const double *locations, int64_t n, const double *field,
-                                         const int64_t gsize_host[3], double spat_res, double *sampled,
-                                         void *stream) {
+                                         const int64_t gsize_host[3], double spat_res, int64_t row_lo,
+                                         int64_t row_hi, double *sampled, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(locations && field && gsize_host && sampled, "null pointer");
     ABM_REQUIRE(spat_res > 0 && gsize_host[0] > 0 && gsize_host[1] > 0 && gsize_host[2] > 0, "bad grid");
+    ABM_REQUIRE(row_lo >= 0 && row_hi <= gsize_host[0] && row_lo < row_hi, "bad row window");
     k_sample<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(locations, (int)n, field, gsize_host[0],
-                                                              gsize_host[1], gsize_host[2], spat_res, sampled);
+                                                              gsize_host[1], gsize_host[2], spat_res, row_lo,
+                                                              row_hi, sampled);
     ABM_CHECK_LAUNCH("k_sample");
     return 0;
 }
 
 ABM_EXPORT int abm_deposit_morphogens(const double *locations, const double *amounts, int64_t n, double *field,
-                                      const int64_t gsize_host[3], double spat_res, void *stream) {
+                                      const int64_t gsize_host[3], double spat_res, int64_t row_lo, int64_t row_hi,
+                                      void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(locations && amounts && field && gsize_host, "null pointer");
     ABM_REQUIRE(spat_res > 0 && gsize_host[0] > 0 && gsize_host[1] > 0 && gsize_host[2] > 0, "bad grid");
+    ABM_REQUIRE(row_lo >= 0 && row_hi <= gsize_host[0] && row_lo < row_hi, "bad row window");
     k_deposit<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(locations, amounts, (int)n, field, gsize_host[0],
-                                                               gsize_host[1], gsize_host[2], spat_res);
+                                                               gsize_host[1], gsize_host[2], spat_res, row_lo,
+                                                               row_hi);
     ABM_CHECK_LAUNCH("k_deposit");
     return 0;
 }

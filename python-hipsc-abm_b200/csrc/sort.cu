@@ -33,8 +33,8 @@ __global__ void __launch_bounds__(kThreads) k_bin_count(const double *__restrict
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     double x = loc[3 * (int64_t)i + 0], y = loc[3 * (int64_t)i + 1], z = loc[3 * (int64_t)i + 2];
-    int b = lin_bin(bin_coord(x, g.distance, g.dims[0]), bin_coord(y, g.distance, g.dims[1]),
-                    bin_coord(z, g.distance, g.dims[2]), g.dims);
+    int b = lin_bin(bin_coord(x - g.origin[0], g.distance, g.dims[0]), bin_coord(y - g.origin[1], g.distance, g.dims[1]),
+                    bin_coord(z - g.origin[2], g.distance, g.dims[2]), g.dims);
     cell_bin[i] = b;
     rank[i] = atomicAdd(&counts[b], 1);
 }
@@ -97,11 +97,13 @@ __global__ void __launch_bounds__(kThreads) k_bins_dense(const double *__restric
     if (place == 0) bins_help[ref_bin] = bin_start[b + 1] - bin_start[b];
 }
 
-static int make_geom(const double size_host[3], double distance, BinGeom &g, int64_t &nbins) {
+static int make_geom(const double size_host[3], const double *origin_host, double distance, BinGeom &g,
+                     int64_t &nbins) {
     if (!(distance > 0)) return -1;
     g.distance = distance;
     nbins = 1;
     for (int k = 0; k < 3; ++k) {
+        g.origin[k] = origin_host ? origin_host[k] : 0.0;
         g.dims[k] = (int)ceil(size_host[k] / distance) + 3;
         nbins *= g.dims[k];
     }
@@ -118,14 +120,15 @@ ABM_EXPORT size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins) {
 }
 
 ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_t n, const double size_host[3],
-                            double distance, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
+                            const double *origin_host, double distance, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
                             int32_t *sorted_bin, int32_t *max_count, void *workspace, size_t workspace_bytes,
                             void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     ABM_REQUIRE(size_host && bin_start && max_count, "null pointer");
     BinGeom g;
     int64_t nbins;
-    ABM_REQUIRE(make_geom(size_host, distance, g, nbins) == 0, "bad geometry (distance <= 0 or too many bins)");
+    ABM_REQUIRE(make_geom(size_host, origin_host, distance, g, nbins) == 0,
+                "bad geometry (distance <= 0 or too many bins)");
     ABM_REQUIRE(workspace_bytes >= abm_bin_sort_workspace_bytes(n, nbins), "workspace too small");
     cudaStream_t st = as_stream(stream);
     int rc = check_cuda(cudaMemsetAsync(bin_start, 0, (size_t)(nbins + 1) * 4, st), "memset bin_start");
@@ -158,7 +161,7 @@ ABM_EXPORT int abm_bins_dense(const double *locations, int64_t n, const double s
                 "null pointer");
     BinGeom g;
     int64_t nbins;
-    ABM_REQUIRE(make_geom(size_host, distance, g, nbins) == 0, "bad geometry");
+    ABM_REQUIRE(make_geom(size_host, nullptr, distance, g, nbins) == 0, "bad geometry");
     k_bins_dense<<<ceil_div(n, kThreads), kThreads, 0, as_stream(stream)>>>(
         locations, (int)n, g, bin_start, sorted_id, (long long)max_agents, (long long *)bins,
         (long long *)bins_help, (long long *)bin_locations);

@@ -61,8 +61,9 @@ class ColonyEngine:
             raise _lib.AbmError("ColonyEngine needs a CUDA device (B200); there is no CPU path")
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-        self.size = np.asarray(size, dtype=np.float64).reshape(3)
+        self.size = np.asarray(size, dtype=np.float64).reshape(3)     # the [0,size] box positions are clamped to
         self._size_c = _lib.d3(self.size)
+        self.set_bin_lattice(None, None)
         self.n = 0
         self.loc = self.radii = self.mot = self.jkr = None
         self.max_radius = 0.0
@@ -138,9 +139,16 @@ class ColonyEngine:
         return self.host(self.loc)
 
     # ---- a1/a2: binning ------------------------------------------------------------------------------
+    def set_bin_lattice(self, origin, extent):
+        """Bin only the sub-box [origin, origin+extent) (a slab and its halo); None = the whole [0,size] box."""
+        self.bin_origin = np.zeros(3) if origin is None else np.asarray(origin, dtype=np.float64).reshape(3)
+        self.bin_extent = self.size.copy() if extent is None else np.asarray(extent, dtype=np.float64).reshape(3)
+        self._origin_c = _lib.d3(self.bin_origin)
+        self._extent_c = _lib.d3(self.bin_extent)
+
     def bin_dims(self, distance):
         dims = (C.c_int32 * 3)()
-        _lib.check(self.lib.abm_bin_dims_host(self._size_c, float(distance), dims), "abm_bin_dims_host")
+        _lib.check(self.lib.abm_bin_dims_host(self._extent_c, float(distance), dims), "abm_bin_dims_host")
         return tuple(int(d) for d in dims)
 
     def sort(self, distance) -> SortState:
@@ -160,7 +168,8 @@ class ColonyEngine:
         need = self.lib.abm_bin_sort_workspace_bytes(n, nbins)
         if self._sort_ws is None or self._sort_ws.numel() < need:
             self._sort_ws = self._empty(int(need), torch.uint8)
-        _lib.check(self.lib.abm_bin_sort(_ptr(self.loc), _ptr(self.radii), n, self._size_c, float(distance),
+        _lib.check(self.lib.abm_bin_sort(_ptr(self.loc), _ptr(self.radii), n, self._extent_c, self._origin_c,
+                                         float(distance),
                                          _ptr(bufs["bin_start"]), _ptr(bufs["sorted_id"]), _ptr(bufs["sorted_pos"]),
                                          _ptr(bufs["sorted_bin"]), _ptr(bufs["max_count"]), _ptr(self._sort_ws),
                                          self._sort_ws.numel(), self.stream), "abm_bin_sort")
@@ -337,17 +346,26 @@ class ColonyEngine:
         self.launches += int(steps)
         return scratch if where.value else field
 
-    def sample(self, field: torch.Tensor, spat_res) -> torch.Tensor:
-        gs = tuple(field.shape) + (1,) * (3 - field.dim())
+    def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None) -> torch.Tensor:
+        """get_concentration for every cell.  `field` is the whole (gx,gy[,gz]) grid, or -- with rows=(lo,hi) and
+        grid_rows=gx -- the slab of global rows [lo,hi) of it."""
+        gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
+        lo, hi = (0, gs[0]) if rows is None else rows
+        if grid_rows is not None:
+            gs[0] = int(grid_rows)
         out = self._empty(max(self.n, 1), torch.float64)
         _lib.check(self.lib.abm_sample_concentrations(_ptr(self.loc), self.n, _ptr(field), _lib.l3(gs),
-                                                      float(spat_res), _ptr(out), self.stream),
+                                                      float(spat_res), int(lo), int(hi), _ptr(out), self.stream),
                    "abm_sample_concentrations")
         self.launches += 1 if self.n else 0
         return out[:self.n]
 
-    def deposit(self, field: torch.Tensor, amounts: torch.Tensor, spat_res):
-        gs = tuple(field.shape) + (1,) * (3 - field.dim())
+    def deposit(self, field: torch.Tensor, amounts: torch.Tensor, spat_res, rows=None, grid_rows=None):
+        gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
+        lo, hi = (0, gs[0]) if rows is None else rows
+        if grid_rows is not None:
+            gs[0] = int(grid_rows)
         _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc), _ptr(amounts), self.n, _ptr(field), _lib.l3(gs),
-                                                   float(spat_res), self.stream), "abm_deposit_morphogens")
+                                                   float(spat_res), int(lo), int(hi), self.stream),
+                   "abm_deposit_morphogens")
         self.launches += 1 if self.n else 0

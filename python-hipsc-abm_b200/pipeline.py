@@ -152,3 +152,70 @@ class HotPathStep:
         b = self.eng._bond_bufs
         k = (self._replays & 1) if self.graphs is not None else self.parity
         return GraphTensors(self.eng.n, None, self.cfg.bond_stride, b["len"][k], b["cols"][k], True)
+
+
+class SlabPipeline:
+    """The device-side work of ONE rank of a slab-decomposed colony (slab.py): the single-GPU kernels run on
+    the rank's owned + halo cells, binned over the slab's own box.  Use with slab.slab_step / loopback_step:
+    `compute` is the mechanics callback, and the object itself is the `field_ops` for the morphogen slab."""
+
+    def __init__(self, geom, cfg: StepConfig, device, max_radius=5.0):
+        self.geom, self.cfg = geom, cfg
+        self.eng = ColonyEngine(geom.size, device)
+        self.eng.set_bin_lattice(*geom.local_box())
+        self.dts = cfg.substep_dts()
+        self.max_radius = float(max_radius)
+        self.stride = cfg.bond_stride
+        self._nbr = None
+        self.neighbor_graph = None
+        self.sampled = None
+
+    def compute(self, local):
+        eng, cfg = self.eng, self.cfg
+        n = int(local.loc.shape[0])
+        eng.set_device_state(local.loc, local.radii, local.mot, max_radius=self.max_radius)
+        # neighbour graph of the step (rows of owned cells are complete: the halo is deeper than the radius)
+        cap = int(cfg.search_cols_per_cell * max(n, 1)) + 1024
+        if self._nbr is None or self._nbr["row_start"].numel() < n or self._nbr["cols"].numel() < cap:
+            dev = eng.device
+            self._nbr = dict(row_start=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
+                             row_len=torch.zeros(max(n, 1), dtype=torch.int32, device=dev),
+                             cols=torch.empty(cap, dtype=torch.int32, device=dev),
+                             cursor=torch.zeros(1, dtype=torch.int32, device=dev))
+        srt = eng.sort(cfg.search_radius)
+        self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self._nbr["row_start"],
+                                                 self._nbr["row_len"], self._nbr["cols"], self._nbr["cursor"])
+        # mechanics with the bonds carried in from the previous step (fixed-stride rows of local indices)
+        stride = max(self.stride, int(local.bond_cols.shape[1]))
+        cols = local.bond_cols
+        if cols.shape[1] < stride:
+            cols = torch.nn.functional.pad(cols, (0, stride - cols.shape[1]), value=-1)
+        old = GraphTensors(n, None, stride, local.bond_len.contiguous(), cols.contiguous(), True)
+        bonds, self.stride = eng.mechanics(old, cfg.contact_radius, self.dts, stride, STOKES)
+        used = eng.read_i32(self._nbr["cursor"])
+        if used > self._nbr["cols"].numel():
+            raise _lib.AbmError(f"neighbour column buffer too small: needed {used}")
+        return eng.loc, bonds.row_len, bonds.cols
+
+    # ---- field_ops protocol of slab.rank_step ---------------------------------------------------------------------
+    def deposit(self, local, field):
+        n = self.eng.n
+        amounts = torch.full((max(n, 1),), self.cfg.deposit_amount, dtype=torch.float64, device=self.eng.device)
+        self.eng.deposit(field.data, amounts, field.h, rows=(field.ext_lo, field.ext_hi), grid_rows=field.gx)
+
+    def diffuse(self, field):
+        cfg = self.cfg
+        last = cfg.diffuse_dt if cfg.diffuse_last_dt is None else cfg.diffuse_last_dt
+        out = self.eng.diffuse(field.data, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const,
+                               field.h ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma)
+        if out.data_ptr() != field.data.data_ptr():
+            field.data.copy_(out)
+
+    def sample(self, local, field):
+        eng = self.eng
+        n_all = eng.n
+        eng.n = local.n_own                       # only owned cells read the field (their rows are exact)
+        try:
+            self.sampled = eng.sample(field.data, field.h, rows=(field.ext_lo, field.ext_hi), grid_rows=field.gx)
+        finally:
+            eng.n = n_all
