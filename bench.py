@@ -194,6 +194,8 @@ def run_b200(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"           # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -281,7 +283,7 @@ def run_b200(args, rank, world, local_rank):
             n, _l.i3(srt.dims), cfg.contact_radius, reach, 0, old.row_stride, old.row_len.data_ptr(),
             old.cols.data_ptr(), b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride,
             b["max_len"].data_ptr(), 0, eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0,
-            _l.d3(wl["size"]), 180.0, eng.stream), "abm_jkr_substep")
+            _l.d3(wl["size"]), 180.0, 0, eng.stream), "abm_jkr_substep")
 
     def time_launches(cold, reps=20):
         out = []
@@ -397,8 +399,8 @@ def run_b200(args, rank, world, local_rank):
 
 def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     """N > 1: ONE colony of world x workload cells, slab-decomposed along x (hipsc_abm_b200/slab.py): per step
-    a halo exchange, the whole step on owned+halo cells without further communication, a morphogen-row
-    exchange and a migration exchange, all over NCCL send/recv."""
+    one cell-halo exchange (which also carries the migrating cells), the whole step on owned+halo cells
+    without further communication, and one morphogen-row exchange, over NCCL send/recv."""
     import torch
     from hipsc_abm_b200 import slab
     from hipsc_abm_b200.pipeline import SlabPipeline
@@ -429,7 +431,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
 
     for _ in range(max(args.warmup, 3)):
         step()
-    worst = slab.halo_violation(state, geom).item()
+    pipe.check()
     sampler = ClockSampler(dev.index or 0)
     launches0, bytes0, ex0 = pipe.eng.launches, fabric.bytes_sent, fabric.exchanges
     barrier()
@@ -442,6 +444,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         b.record()
     barrier()
     clocks = sampler.stop()
+    pipe.check()
     total_s = sum(a.elapsed_time(b) for a, b in evs) / 1e3
     tt = torch.tensor([total_s], device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -481,13 +484,13 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{args.workload} x {world}: {spec['desc']} per GPU, one colony", "cells_per_gpu": n,
                    "cells_total": int(cells.item()), "dim": spec["dim"], "mechanics_substeps": len(cfg.substep_dts()),
-                   "diffusion_substeps": spec["sd"], "halo_um": halo, "max_owner_drift_um": worst,
+                   "diffusion_substeps": spec["sd"], "halo_um": halo,
                    "exchanges_per_step": (fabric.exchanges - ex0) / max(args.steps + e_steps, 1),
                    "bytes_sent_per_step_rank0": (fabric.bytes_sent - bytes0) // max(args.steps + e_steps, 1),
                    "l2": "flushed between timed steps (256 MiB memset)",
                    "timing": "CUDA events per step, summed; max over ranks",
-                   "parallelism": f"slab{world}: 1-D slab decomposition along x, halo + migration + field rows "
-                                  "exchanged once per step over NCCL send/recv"},
+                   "parallelism": f"slab{world}: 1-D slab decomposition along x; per step one cell-halo exchange "
+                                  "(migration rides on it) and one morphogen-row exchange over NCCL send/recv"},
         "clocks": clocks,
         "e2e": {"value": n * world * e_steps / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e_steps,
                 "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps, "ms_per_step": e_s / e_steps * 1e3,

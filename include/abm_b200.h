@@ -123,6 +123,9 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  * (row i at new_cols[i*row_stride], length new_row_len[i], ascending if sort_rows) and the moved
  * locations (written in place; the kernel only reads positions from sorted_pos).
  * A bond (i,j) exists afterwards iff (dist <= distance or it existed before) and d > -0.360562.
+ *   global_id        : NULL, or (n) int32 ids to write into / look up in the bond rows instead of the cell
+ *                      index (a slab-decomposed colony keeps its bonds by global id; rows still belong to the
+ *                      local cell index).
  *   reach            : bin edge of the sort, >= abm_jkr_reach(distance, max(radii), ...).
  *   max_len (1) int32: raised (atomicMax) by rows that needed more than row_stride entries; a value
  *   > row_stride afterwards means those rows were truncated: grow row_stride and redo the substep
@@ -135,7 +138,22 @@ int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const do
                     const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len, int32_t *new_cols,
                     int64_t row_stride, int32_t *max_len, int sort_rows, const double *motility_forces,
                     double *locations, double poisson, double youngs, double adhesion_const, double stokes,
-                    const double size_host[3], double move_dt, void *stream);
+                    const double size_host[3], double move_dt, const int32_t *global_id, void *stream);
+
+/* The whole substep loop of CellMethods.apply_forces (cell_methods.py:399-436) enqueued by ONE call:
+ * n_substeps x [abm_bin_sort at bin edge `reach` over (origin, extent) + abm_jkr_substep with dts_host[k]].
+ * Substep 0 reads the bonds old_*; substep k writes row buffer a (k even) or b (k odd), so the final bonds are in
+ * buffer a when n_substeps is odd, else in b (rows ascending if sort_last_rows).  The sort outputs are scratch.
+ * No host synchronisation; overflow is reported through max_len as in abm_jkr_substep.              */
+int abm_mechanics_loop(const double *radii, double *locations, const double *motility_forces, int64_t n,
+                       const double extent_host[3], const double *origin_host, const double size_host[3],
+                       double distance, double reach, int n_substeps, const double *dts_host,
+                       int32_t *bin_start, int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin,
+                       int32_t *max_count, void *sort_workspace, size_t sort_workspace_bytes,
+                       const int32_t *old_row_start, int64_t old_row_stride, const int32_t *old_row_len,
+                       const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
+                       int64_t row_stride, int32_t *max_len, int sort_last_rows, const int32_t *global_id,
+                       double poisson, double youngs, double adhesion_const, double stokes, void *stream);
 
 /* ---- morphogen diffusion ---------------------------------------------------------------------------
  * Replaces CellMethods.update_diffusion + update_diffusion_jit (cell_methods.py:441-468,

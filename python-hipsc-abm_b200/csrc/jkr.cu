@@ -92,7 +92,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
-              double stokes, Box box, double dt) {
+              double stokes, Box box, double dt, const int *__restrict__ gid_of) {
     __shared__ int hit_slot[kMaxHits][kJkrThreads];       // partners within `distance`: bonded unless d breaks
     __shared__ int shell_slot[kMaxShell][kJkrThreads];    // partners in (distance, reach]: bonded only if they were
     const double kPi = 3.141592653589793;
@@ -108,6 +108,11 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         BondEval ev;
         ev.memo_r = -1.0;
 
+        // the id bond rows are written in: the cell index, or its global id when the colony is slab-decomposed
+        auto partner_id = [&](int t) {
+            int j = sorted_id[t];
+            return gid_of ? gid_of[j] : j;
+        };
         // contact model for one partner known to be a bond candidate
         auto bond = [&](int t, double4 q) {
             double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
@@ -125,7 +130,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                     fy += w * vy;
                     fz += w * vz;
                 }
-                if (cnt < stride) row[cnt] = sorted_id[t];
+                if (cnt < stride) row[cnt] = partner_id(t);
                 ++cnt;
             }
         };
@@ -175,7 +180,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                             ++nh;
                         } else if (old.valid()) {
                             if (ns < kMaxShell) shell_slot[ns][threadIdx.x] = t;
-                            else if (was_bonded(sorted_id[t])) bond(t, q);
+                            else if (was_bonded(partner_id(t))) bond(t, q);
                             ++ns;
                         }
                     }
@@ -193,7 +198,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         int shelled = min(ns, kMaxShell);
         for (int k = 0; k < shelled; ++k) {
             int t = shell_slot[k][threadIdx.x];
-            if (was_bonded(sorted_id[t])) bond(t, spos[t]);
+            if (was_bonded(partner_id(t))) bond(t, spos[t]);
         }
         new_len[i] = min(cnt, stride);
         if (kSortRows) insertion_sort(row, min(cnt, stride));
@@ -249,7 +254,7 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
                                int32_t *new_cols, int64_t row_stride, int32_t *max_len, int sort_rows,
                                const double *motility_forces, double *locations, double poisson, double youngs,
                                double adhesion_const, double stokes, const double size_host[3], double move_dt,
-                               void *stream) {
+                               const int32_t *global_id, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(bin_start && sorted_id && sorted_pos && sorted_bin && dims_host && new_row_len && new_cols &&
@@ -274,12 +279,52 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
         k_jkr_substep<true><<<blocks, kJkrThreads, 0, st>>>(bin_start, sorted_id, sp, sorted_bin, (int)n, stc,
                                                             Radius(distance), reach2, old, new_row_len, new_cols,
                                                             (int)row_stride, max_len, motility_forces, locations, c,
-                                                            stokes, box, move_dt);
+                                                            stokes, box, move_dt, global_id);
     else
         k_jkr_substep<false><<<blocks, kJkrThreads, 0, st>>>(bin_start, sorted_id, sp, sorted_bin, (int)n, stc,
                                                              Radius(distance), reach2, old, new_row_len, new_cols,
                                                              (int)row_stride, max_len, motility_forces, locations, c,
-                                                             stokes, box, move_dt);
+                                                             stokes, box, move_dt, global_id);
     ABM_CHECK_LAUNCH("k_jkr_substep");
+    return 0;
+}
+
+// The whole substep loop of CellMethods.apply_forces (reference cell_methods.py:399-436) enqueued by one call:
+// n_substeps x [counting sort at bin edge `reach` + fused substep].  Substep k reads the bonds written by
+// substep k-1 (substep 0 reads old_*) and writes row buffer a (k even) or b (k odd); the final bonds are in
+// buffer a when n_substeps is odd, else in b.  Pure convenience over abm_bin_sort + abm_jkr_substep: it removes
+// the per-launch host overhead of a scripting-language caller.
+ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const double *motility_forces, int64_t n,
+                                  const double extent_host[3], const double *origin_host, const double size_host[3],
+                                  double distance, double reach, int n_substeps, const double *dts_host,
+                                  int32_t *bin_start, int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin,
+                                  int32_t *max_count, void *sort_workspace, size_t sort_workspace_bytes,
+                                  const int32_t *old_row_start, int64_t old_row_stride, const int32_t *old_row_len,
+                                  const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b,
+                                  int32_t *cols_b, int64_t row_stride, int32_t *max_len, int sort_last_rows,
+                                  const int32_t *global_id, double poisson, double youngs, double adhesion_const,
+                                  double stokes, void *stream) {
+    ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
+    ABM_REQUIRE(extent_host && size_host, "null pointer");
+    int32_t dims[3];
+    int rc = abm_bin_dims_host(extent_host, reach, dims);
+    if (rc) return rc;
+    const int32_t *cur_start = old_row_start, *cur_len = old_row_len, *cur_cols = old_cols;
+    int64_t cur_stride = old_row_stride;
+    for (int k = 0; k < n_substeps; ++k) {
+        rc = abm_bin_sort(locations, radii, n, extent_host, origin_host, reach, bin_start, sorted_id, sorted_pos,
+                          sorted_bin, max_count, sort_workspace, sort_workspace_bytes, stream);
+        if (rc) return rc;
+        int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
+        rc = abm_jkr_substep(bin_start, sorted_id, sorted_pos, sorted_bin, n, dims, distance, reach, cur_start,
+                             cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len,
+                             (sort_last_rows && k == n_substeps - 1) ? 1 : 0, motility_forces, locations, poisson,
+                             youngs, adhesion_const, stokes, size_host, dts_host[k], global_id, stream);
+        if (rc) return rc;
+        cur_start = nullptr;
+        cur_stride = row_stride;
+        cur_len = nl;
+        cur_cols = nc;
+    }
     return 0;
 }

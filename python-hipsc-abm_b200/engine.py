@@ -67,20 +67,24 @@ class ColonyEngine:
         self.n = 0
         self.loc = self.radii = self.mot = self.jkr = None
         self.max_radius = 0.0
+        self.global_id = None   # int32 (n,) when bond rows are kept by global id (slab decomposition)
         self._sort_ws = None
         self._sort_bufs = {}
         self._edge_ws = None
         self._bond_bufs = None
         self.cols_capacity_hint = {}
         self.launches = 0      # number of kernels of this library enqueued (bench.py's gpu_launches)
+        self.stream = 0
+        self.use_current_stream()
         self.h2d_bytes = 0     # bytes moved by upload()/to_device() and host()/locations_host()
         self.d2h_bytes = 0
         self._pinned = {}
 
     # ------------------------------------------------------------------------------------------------
-    @property
-    def stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+    def use_current_stream(self):
+        """Bind the engine to torch's current stream (looked up once per step / capture, not per launch)."""
+        self.stream = torch.cuda.current_stream(self.device).cuda_stream
+        return self.stream
 
     def _empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -115,6 +119,7 @@ class ColonyEngine:
 
     def upload(self, locations, radii, motility=None, jkr=None):
         """Host -> device copy of the agent arrays the path reads (reference dtypes: float64)."""
+        self.use_current_stream()
         loc = np.ascontiguousarray(locations, dtype=np.float64)
         n = loc.shape[0]
         rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, dtype=np.float64), (n,)))
@@ -129,6 +134,7 @@ class ColonyEngine:
 
     def set_device_state(self, loc, radii, mot=None, jkr=None, max_radius=None):
         """Adopt tensors that already live on the device (no copies)."""
+        self.use_current_stream()
         self.n = int(loc.shape[0])
         self.loc, self.radii = loc, radii
         self.mot = mot if mot is not None else self._zeros((self.n, 3), torch.float64)
@@ -151,30 +157,35 @@ class ColonyEngine:
         _lib.check(self.lib.abm_bin_dims_host(self._extent_c, float(distance), dims), "abm_bin_dims_host")
         return tuple(int(d) for d in dims)
 
-    def sort(self, distance) -> SortState:
-        """Counting sort of the current locations into bins of edge `distance` (abm_bin_sort)."""
+    def _sort_buffers(self, distance):
         n = self.n
         dims = self.bin_dims(distance)
         nbins = dims[0] * dims[1] * dims[2]
-        key = (n, nbins)
-        bufs = self._sort_bufs.get(key)
-        if bufs is None:
-            for stale in [k for k in self._sort_bufs if k[0] != n]:
-                del self._sort_bufs[stale]
-            bufs = dict(bin_start=self._empty(nbins + 1, torch.int32), sorted_id=self._empty(max(n, 1), torch.int32),
-                        sorted_pos=self._empty((max(n, 1), 4), torch.float64),
-                        sorted_bin=self._empty(max(n, 1), torch.int32), max_count=self._empty(1, torch.int32))
-            self._sort_bufs[key] = bufs
+        b = self._sort_bufs.get(nbins)
+        if b is None or b["cap"] < n:
+            cap = max(int(1.1 * n) + 1024, 1)
+            b = dict(cap=cap, bin_start=self._empty(nbins + 1, torch.int32), sorted_id=self._empty(cap, torch.int32),
+                     sorted_pos=self._empty((cap, 4), torch.float64), sorted_bin=self._empty(cap, torch.int32),
+                     max_count=self._empty(1, torch.int32))
+            if len(self._sort_bufs) > 4:
+                self._sort_bufs.clear()
+            self._sort_bufs[nbins] = b
         need = self.lib.abm_bin_sort_workspace_bytes(n, nbins)
         if self._sort_ws is None or self._sort_ws.numel() < need:
-            self._sort_ws = self._empty(int(need), torch.uint8)
+            self._sort_ws = self._empty(int(1.1 * need) + 4096, torch.uint8)
+        return dims, nbins, b
+
+    def sort(self, distance) -> SortState:
+        """Counting sort of the current locations into bins of edge `distance` (abm_bin_sort)."""
+        n = self.n
+        dims, nbins, b = self._sort_buffers(distance)
         _lib.check(self.lib.abm_bin_sort(_ptr(self.loc), _ptr(self.radii), n, self._extent_c, self._origin_c,
-                                         float(distance),
-                                         _ptr(bufs["bin_start"]), _ptr(bufs["sorted_id"]), _ptr(bufs["sorted_pos"]),
-                                         _ptr(bufs["sorted_bin"]), _ptr(bufs["max_count"]), _ptr(self._sort_ws),
-                                         self._sort_ws.numel(), self.stream), "abm_bin_sort")
+                                         float(distance), _ptr(b["bin_start"]), _ptr(b["sorted_id"]),
+                                         _ptr(b["sorted_pos"]), _ptr(b["sorted_bin"]), _ptr(b["max_count"]),
+                                         _ptr(self._sort_ws), self._sort_ws.numel(), self.stream), "abm_bin_sort")
         self.launches += 5 if n else 0
-        return SortState(float(distance), dims, nbins, n, **bufs)
+        return SortState(float(distance), dims, nbins, n, b["bin_start"], b["sorted_id"], b["sorted_pos"],
+                         b["sorted_bin"], b["max_count"])
 
     def bins_dense(self, sort: SortState, max_agents: int):
         """Reference-shaped (bins, bins_help, bin_locations) of Simulation.assign_bins."""
@@ -273,13 +284,20 @@ class ColonyEngine:
                                             JKR_ADHESION))
 
     def _bond_buffers(self, n, stride):
+        """Three rotating fixed-stride row buffers (+ the overflow flag).  Allocated with some headroom so a
+        slab whose cell count drifts from step to step does not reallocate."""
         b = self._bond_bufs
-        if b is None or b["n"] != n or b["stride"] != stride:
-            b = dict(n=n, stride=stride,
-                     len=[self._zeros(max(n, 1), torch.int32) for _ in range(3)],
-                     cols=[self._empty((max(n, 1), stride), torch.int32) for _ in range(3)],
+        if b is None or b["cap"] < n or b["stride"] != stride:
+            cap = max(int(1.1 * n) + 1024, 1)
+            b = dict(cap=cap, stride=stride,
+                     len_full=[self._zeros(cap, torch.int32) for _ in range(3)],
+                     cols_full=[self._empty((cap, stride), torch.int32) for _ in range(3)],
                      max_len=self._zeros(1, torch.int32))
             self._bond_bufs = b
+        if b.get("n") != n:
+            b["n"] = n
+            b["len"] = [t[:max(n, 1)] for t in b["len_full"]]
+            b["cols"] = [t[:max(n, 1)] for t in b["cols_full"]]
         return b
 
     def enqueue_mechanics(self, old: Optional[GraphTensors], distance, dts, stride, stokes=STOKES, pair=None,
@@ -290,29 +308,28 @@ class ColonyEngine:
         b = self._bond_buffers(n, stride)
         if zero_flag:
             b["max_len"].zero_()
+        if len(dts) == 0:
+            return old
         reach = self.jkr_reach(distance)
-        cur = old
-        out = None
         # three row buffers: the two that do not hold `old` ping-pong, so `old` survives a retry
         held = [i for i in range(3) if old is not None and old.cols.data_ptr() == b["cols"][i].data_ptr()]
         if pair is None:
             pair = [i for i in range(3) if i not in held][:2]
-        for k, dt in enumerate(dts):
-            srt = self.sort(reach)
-            last = k == len(dts) - 1
-            new_len, new_cols = b["len"][pair[k & 1]], b["cols"][pair[k & 1]]
-            _lib.check(self.lib.abm_jkr_substep(
-                _ptr(srt.bin_start), _ptr(srt.sorted_id), _ptr(srt.sorted_pos), _ptr(srt.sorted_bin), n,
-                _lib.i3(srt.dims), float(distance), reach,
-                _ptr(cur.row_start) if cur is not None else 0, cur.row_stride if cur is not None else 0,
-                _ptr(cur.row_len) if cur is not None else 0, _ptr(cur.cols) if cur is not None else 0,
-                _ptr(new_len), _ptr(new_cols), stride, _ptr(b["max_len"]), 1 if last else 0, _ptr(self.mot),
-                _ptr(self.loc), JKR_POISSON, JKR_YOUNGS, JKR_ADHESION, float(stokes), self._size_c, float(dt),
-                self.stream), "abm_jkr_substep")
-            self.launches += 1 if n else 0
-            out = GraphTensors(n, None, stride, new_len, new_cols, last)
-            cur = out
-        return out
+        dims, nbins, sb = self._sort_buffers(reach)
+        dts_c = (C.c_double * len(dts))(*[float(d) for d in dts])
+        _lib.check(self.lib.abm_mechanics_loop(
+            _ptr(self.radii), _ptr(self.loc), _ptr(self.mot), n, self._extent_c, self._origin_c, self._size_c,
+            float(distance), reach, len(dts), dts_c,
+            _ptr(sb["bin_start"]), _ptr(sb["sorted_id"]), _ptr(sb["sorted_pos"]), _ptr(sb["sorted_bin"]),
+            _ptr(sb["max_count"]), _ptr(self._sort_ws), self._sort_ws.numel(),
+            _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
+            _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
+            _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),
+            stride, _ptr(b["max_len"]), 1, _ptr(self.global_id), JKR_POISSON, JKR_YOUNGS, JKR_ADHESION,
+            float(stokes), self.stream), "abm_mechanics_loop")
+        self.launches += 6 * len(dts) if n else 0
+        last = pair[(len(dts) - 1) & 1]
+        return GraphTensors(n, None, stride, b["len"][last], b["cols"][last], True)
 
     def mechanics(self, old: Optional[GraphTensors], distance, dts, stride=16, stokes=STOKES):
         """The whole substep loop of CellMethods.apply_forces on the device, with the reference's

@@ -82,6 +82,7 @@ class HotPathStep:
     # ---- one step, enqueue only ---------------------------------------------------------------------------
     def enqueue(self):
         eng, cfg = self.eng, self.cfg
+        eng.use_current_stream()              # under torch.cuda.graph() this is the capture stream
         before = eng.launches
         # neighbour graph (what the rule methods consume)
         srt = eng.sort(cfg.search_radius)
@@ -171,31 +172,45 @@ class SlabPipeline:
         self.sampled = None
 
     def compute(self, local):
+        """Mechanics of one step on the rank's owned + halo cells (slab.LocalProblem): positions are advanced
+        in place, the new bond rows (global ids) are returned.  Nothing here waits for the device: buffer
+        overflows are recorded on the device and raised by check(), which the caller runs at its next natural
+        synchronisation point."""
         eng, cfg = self.eng, self.cfg
         n = int(local.loc.shape[0])
         eng.set_device_state(local.loc, local.radii, local.mot, max_radius=self.max_radius)
+        eng.global_id = local.gid
         # neighbour graph of the step (rows of owned cells are complete: the halo is deeper than the radius)
         cap = int(cfg.search_cols_per_cell * max(n, 1)) + 1024
         if self._nbr is None or self._nbr["row_start"].numel() < n or self._nbr["cols"].numel() < cap:
             dev = eng.device
-            self._nbr = dict(row_start=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
-                             row_len=torch.zeros(max(n, 1), dtype=torch.int32, device=dev),
-                             cols=torch.empty(cap, dtype=torch.int32, device=dev),
-                             cursor=torch.zeros(1, dtype=torch.int32, device=dev))
+            grow = int(1.1 * n) + 1024
+            self._nbr = dict(row_start=torch.empty(grow, dtype=torch.int32, device=dev),
+                             row_len=torch.zeros(grow, dtype=torch.int32, device=dev),
+                             cols=torch.empty(int(1.1 * cap), dtype=torch.int32, device=dev),
+                             cursor=torch.zeros(1, dtype=torch.int32, device=dev),
+                             worst=torch.zeros(1, dtype=torch.int32, device=dev))
         srt = eng.sort(cfg.search_radius)
         self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self._nbr["row_start"],
                                                  self._nbr["row_len"], self._nbr["cols"], self._nbr["cursor"])
-        # mechanics with the bonds carried in from the previous step (fixed-stride rows of local indices)
-        stride = max(self.stride, int(local.bond_cols.shape[1]))
-        cols = local.bond_cols
-        if cols.shape[1] < stride:
-            cols = torch.nn.functional.pad(cols, (0, stride - cols.shape[1]), value=-1)
-        old = GraphTensors(n, None, stride, local.bond_len.contiguous(), cols.contiguous(), True)
-        bonds, self.stride = eng.mechanics(old, cfg.contact_radius, self.dts, stride, STOKES)
-        used = eng.read_i32(self._nbr["cursor"])
-        if used > self._nbr["cols"].numel():
-            raise _lib.AbmError(f"neighbour column buffer too small: needed {used}")
-        return eng.loc, bonds.row_len, bonds.cols
+        torch.maximum(self._nbr["worst"], self._nbr["cursor"], out=self._nbr["worst"])
+        # mechanics with the bonds carried in from the previous step (fixed-stride rows of global ids)
+        stride = int(local.bond_gid.shape[1])
+        old = GraphTensors(n, None, stride, local.bond_len, local.bond_gid, True)
+        bonds = eng.enqueue_mechanics(old, cfg.contact_radius, self.dts, stride, STOKES, zero_flag=False)
+        return bonds.row_len, bonds.cols
+
+    def check(self):
+        """Host sync: raise if a fixed-capacity buffer overflowed in any step since the last check."""
+        eng = self.eng
+        if self._nbr is not None:
+            used = eng.read_i32(self._nbr["worst"])
+            if used > self._nbr["cols"].numel():
+                raise _lib.AbmError(f"neighbour column buffer too small: needed {used}")
+        if eng._bond_bufs is not None:
+            worst = eng.read_i32(eng._bond_bufs["max_len"])
+            if worst > eng._bond_bufs["stride"]:
+                raise _lib.AbmError(f"bond rows too narrow: needed {worst}, have {eng._bond_bufs['stride']}")
 
     # ---- field_ops protocol of slab.rank_step ---------------------------------------------------------------------
     def deposit(self, local, field):

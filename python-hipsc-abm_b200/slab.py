@@ -4,20 +4,24 @@ The reference has no multi-device path; this is the partitioning the north star 
 the B200 pipeline rather than ported from anything:
 
   * rank k owns the cells with x in [bounds[k], bounds[k+1]);
-  * ONCE per simulation step it receives, from each x-neighbour, a halo of the neighbour's cells (position,
-    radius, motility force, global id and JKR bond row) lying within `halo` of the interface;
+  * ONCE per simulation step every rank sends each x-neighbour the cells it holds within `halo` of their
+    common interface -- on either side of it -- as one packed message (position, radius, motility force,
+    global id, JKR bond row).  A receiver keeps the cells that now lie inside its own slab as OWNED (that is the
+    migration: ownership is a function of position, evaluated on the same bits by both sides) and the rest as
+    read-only halo cells; the sender demotes the cells that left its slab to halo cells for this step;
   * the whole step (neighbour search + the 11 fused mechanics substeps) then runs on owned + halo cells with
-    the unmodified single-GPU kernels and NO communication: a halo cell is simulated redundantly, and the
-    error that creeps in from the outer edge of the halo travels at most (reach + displacement) per substep,
-    so with halo >= substeps * (reach + slack) it never reaches an owned cell;
-  * after the step the halo is dropped, and owned cells that crossed an interface migrate with their state.
+    the unmodified single-GPU kernels and NO communication.  A halo cell is simulated redundantly; the error
+    that creeps in from the outer edge of the halo travels at most (reach + displacement) per substep, so
+    with halo >= substeps * (reach + slack) it never reaches an owned cell;
+  * the morphogen rows next to the interface are exchanged once, after the deposit and before the S_d
+    diffusion substeps (same argument, one grid row per substep).
 
-So a step costs three neighbour exchanges (halo, migration, and the morphogen rows) instead of one per
-substep; over NVLink they are latency-bound messages of a few hundred KB.
+So a step costs two neighbour exchanges instead of one per substep; over NVLink they are latency-bound
+messages of a few hundred KB.  JKR bond rows are kept by GLOBAL id everywhere (the fused kernel takes the id
+table, include/abm_b200.h `global_id`), so nothing is translated when cells change rank.
 
-Everything here is device-agnostic torch tensor plumbing (it runs on CPU with gloo in the tests and on CUDA
-with NCCL in bench.py); the compute callback is the CUDA pipeline.
-Bond rows cross rank boundaries as GLOBAL ids and are translated to local indices for the kernels.
+Everything here is device-agnostic torch tensor plumbing (CPU + gloo in the tests, CUDA + NCCL in bench.py);
+the compute callback is the CUDA pipeline (pipeline.SlabPipeline).
 """
 from __future__ import annotations
 
@@ -49,13 +53,28 @@ class SlabGeometry:
     def x_hi(self):
         return float(self.bounds[self.rank + 1])
 
+    @property
+    def has_left(self):
+        return self.rank > 0
+
+    @property
+    def has_right(self):
+        return self.rank < self.world - 1
+
+    def inside(self, x: torch.Tensor) -> torch.Tensor:
+        """Ownership predicate: the outermost slabs also own whatever lies beyond the box."""
+        m = torch.ones_like(x, dtype=torch.bool)
+        if self.has_left:
+            m &= x >= self.x_lo
+        if self.has_right:
+            m &= x < self.x_hi
+        return m
+
     def local_box(self):
         """(origin, extent) of the region the local bins must cover: the slab plus its halos."""
-        lo = max(self.x_lo - self.halo, 0.0) if self.rank > 0 else 0.0
-        hi = min(self.x_hi + self.halo, self.size[0]) if self.rank < self.world - 1 else float(self.size[0])
-        origin = np.array([lo, 0.0, 0.0])
-        extent = np.array([hi - lo, self.size[1], self.size[2]])
-        return origin, extent
+        lo = max(self.x_lo - self.halo, 0.0) if self.has_left else 0.0
+        hi = min(self.x_hi + self.halo, self.size[0]) if self.has_right else float(self.size[0])
+        return np.array([lo, 0.0, 0.0]), np.array([hi - lo, self.size[1], self.size[2]])
 
 
 def required_halo(substeps, reach, slack=2.0):
@@ -65,16 +84,20 @@ def required_halo(substeps, reach, slack=2.0):
     return float(substeps) * (float(reach) + float(slack))
 
 
-class SlabState:
-    """Cells owned by one rank.  Bond rows hold global ids (-1 padded)."""
+FIELDS = ("loc", "radii", "mot", "gid", "bond_len", "bond_gid")
 
-    FIELDS = ("loc", "radii", "mot", "gid", "bond_len", "bond_gid")
+
+class SlabState:
+    """Cells owned by one rank, in the kernels' own formats: float64 positions / radii / motility forces,
+    int32 global ids, and fixed-stride int32 bond rows holding global ids."""
 
     def __init__(self, loc, radii, mot, gid, stride=16):
         n = loc.shape[0]
-        self.loc, self.radii, self.mot, self.gid = loc, radii, mot, gid
-        self.bond_len = torch.zeros(n, dtype=torch.int64, device=loc.device)
-        self.bond_gid = torch.full((n, stride), -1, dtype=torch.int64, device=loc.device)
+        dev = loc.device
+        self.loc, self.radii, self.mot = loc.contiguous(), radii.contiguous(), mot.contiguous()
+        self.gid = gid.to(torch.int32).contiguous()
+        self.bond_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.bond_gid = torch.full((n, stride), -1, dtype=torch.int32, device=dev)
 
     @property
     def n(self):
@@ -84,42 +107,40 @@ class SlabState:
     def stride(self):
         return int(self.bond_gid.shape[1])
 
-    def grow_stride(self, stride):
-        if stride > self.stride:
-            pad = torch.full((self.n, stride - self.stride), -1, dtype=torch.int64, device=self.loc.device)
-            self.bond_gid = torch.cat([self.bond_gid, pad], dim=1)
+    def record_bytes(self):
+        return 24 + 8 + 24 + 4 + 4 + 4 * self.stride
 
-    # ---- packing: one float64 matrix per message (ids are exact in float64 below 2^53) -----------------------
-    def pack(self, mask) -> torch.Tensor:
-        idx = torch.nonzero(mask, as_tuple=False).flatten()
-        cols = [self.loc[idx], self.radii[idx, None], self.mot[idx], self.gid[idx, None].double(),
-                self.bond_len[idx, None].double(), self.bond_gid[idx].double()]
-        return torch.cat(cols, dim=1).contiguous()
+    def fields(self):
+        return {f: getattr(self, f) for f in FIELDS}
 
-    @staticmethod
-    def unpack(msg: torch.Tensor, stride):
-        if msg.numel() == 0:
-            msg = msg.reshape(0, 9 + stride)
-        return dict(loc=msg[:, 0:3].contiguous(), radii=msg[:, 3].contiguous(), mot=msg[:, 4:7].contiguous(),
-                    gid=msg[:, 7].long(), bond_len=msg[:, 8].long(), bond_gid=msg[:, 9:9 + stride].long())
+    def set_fields(self, d):
+        for f in FIELDS:
+            setattr(self, f, d[f])
 
-    def width(self):
-        return 9 + self.stride
+    def pack(self, idx) -> torch.Tensor:
+        """One byte record per selected cell: loc | radius | motility | gid | bond_len | bond row."""
+        k = idx.numel()
+        parts = [self.loc[idx].view(torch.uint8).reshape(k, 24), self.radii[idx].view(torch.uint8).reshape(k, 8),
+                 self.mot[idx].view(torch.uint8).reshape(k, 24), self.gid[idx].view(torch.uint8).reshape(k, 4),
+                 self.bond_len[idx].view(torch.uint8).reshape(k, 4),
+                 self.bond_gid[idx].contiguous().view(torch.uint8).reshape(k, 4 * self.stride)]
+        return torch.cat(parts, dim=1)
 
-    def keep(self, mask):
-        idx = torch.nonzero(mask, as_tuple=False).flatten()
-        for f in self.FIELDS:
-            setattr(self, f, getattr(self, f)[idx].contiguous())
 
-    def append(self, part):
-        for f in self.FIELDS:
-            setattr(self, f, torch.cat([getattr(self, f), part[f]], dim=0))
+def unpack(msg: torch.Tensor, stride: int):
+    k = msg.shape[0]
+
+    def take(a, b, dtype, shape):
+        return msg[:, a:b].contiguous().view(dtype).reshape(shape)
+    return dict(loc=take(0, 24, torch.float64, (k, 3)), radii=take(24, 32, torch.float64, (k,)),
+                mot=take(32, 56, torch.float64, (k, 3)), gid=take(56, 60, torch.int32, (k,)),
+                bond_len=take(60, 64, torch.int32, (k,)), bond_gid=take(64, 64 + 4 * stride, torch.int32, (k, stride)))
 
 
 # ---- exchange fabrics ---------------------------------------------------------------------------------------------
 class DistFabric:
-    """Neighbour exchange over torch.distributed (NCCL on GPUs, gloo on CPU): sizes first, then one packed
-    float64 message per neighbour and direction, all four transfers posted together."""
+    """Neighbour exchange over torch.distributed (NCCL on GPUs, gloo on CPU): the row counts first, then one
+    packed message per neighbour and direction, all transfers of a phase posted together."""
 
     def __init__(self, rank, world, device):
         import torch.distributed as dist
@@ -127,43 +148,49 @@ class DistFabric:
         self.bytes_sent = 0
         self.exchanges = 0
 
-    def exchange(self, to_left: Optional[torch.Tensor], to_right: Optional[torch.Tensor], width: int):
-        dist = self.dist
+    def _post(self, ops):
+        for w in self.dist.batch_isend_irecv(ops) if ops else []:
+            w.wait()
+
+    def exchange(self, to_left, to_right, width, dtype=torch.float64, fixed_rows=None):
+        """Send `to_left` / `to_right` (2-D, `width` columns) to the x-neighbours, return what they sent.
+        fixed_rows: both sides know the row count (field rows) -> no size handshake."""
+        dist, dev = self.dist, self.device
         left, right = self.rank - 1, self.rank + 1
         has_l, has_r = left >= 0, right < self.world
-        counts_out = torch.tensor([to_left.shape[0] if has_l else 0, to_right.shape[0] if has_r else 0],
-                                  dtype=torch.int64, device=self.device)
-        counts_in = torch.zeros(2, dtype=torch.int64, device=self.device)
+        if fixed_rows is None:
+            counts_out = torch.tensor([to_left.shape[0] if has_l else 0, to_right.shape[0] if has_r else 0],
+                                      dtype=torch.int64, device=dev)
+            counts_in = torch.zeros(2, dtype=torch.int64, device=dev)
+            ops = []
+            if has_l:
+                ops += [dist.P2POp(dist.isend, counts_out[0:1], left), dist.P2POp(dist.irecv, counts_in[0:1], left)]
+            if has_r:
+                ops += [dist.P2POp(dist.isend, counts_out[1:2], right),
+                        dist.P2POp(dist.irecv, counts_in[1:2], right)]
+            self._post(ops)
+            n_l, n_r = (int(v) for v in counts_in.tolist())
+        else:
+            n_l, n_r = (fixed_rows if has_l else 0), (fixed_rows if has_r else 0)
+        from_left = torch.empty((n_l, width), dtype=dtype, device=dev)
+        from_right = torch.empty((n_r, width), dtype=dtype, device=dev)
         ops = []
-        if has_l:
-            ops += [dist.P2POp(dist.isend, counts_out[0:1], left), dist.P2POp(dist.irecv, counts_in[0:1], left)]
-        if has_r:
-            ops += [dist.P2POp(dist.isend, counts_out[1:2], right), dist.P2POp(dist.irecv, counts_in[1:2], right)]
-        for w in dist.batch_isend_irecv(ops) if ops else []:
-            w.wait()
-        n_l, n_r = (int(v) for v in counts_in.tolist())
-        from_left = torch.empty((n_l, width), dtype=torch.float64, device=self.device)
-        from_right = torch.empty((n_r, width), dtype=torch.float64, device=self.device)
-        ops = []
-        if has_l:
-            if to_left.shape[0]:
-                ops.append(dist.P2POp(dist.isend, to_left, left))
-            if n_l:
-                ops.append(dist.P2POp(dist.irecv, from_left, left))
-        if has_r:
-            if to_right.shape[0]:
-                ops.append(dist.P2POp(dist.isend, to_right, right))
-            if n_r:
-                ops.append(dist.P2POp(dist.irecv, from_right, right))
-        for w in dist.batch_isend_irecv(ops) if ops else []:
-            w.wait()
-        self.bytes_sent += sum(t.numel() * 8 for t, ok in ((to_left, has_l), (to_right, has_r)) if ok)
+        if has_l and to_left.shape[0]:
+            ops.append(dist.P2POp(dist.isend, to_left, left))
+        if has_l and n_l:
+            ops.append(dist.P2POp(dist.irecv, from_left, left))
+        if has_r and to_right.shape[0]:
+            ops.append(dist.P2POp(dist.isend, to_right, right))
+        if has_r and n_r:
+            ops.append(dist.P2POp(dist.irecv, from_right, right))
+        self._post(ops)
+        self.bytes_sent += sum(t.numel() * t.element_size() for t, ok in ((to_left, has_l), (to_right, has_r)) if ok)
         self.exchanges += 1
         return from_left, from_right
 
 
 class LoopbackWorld:
-    """All ranks in one process (tests / single-GPU emulation): exchange is a list shuffle."""
+    """All ranks in one process (tests / several slabs emulated on one GPU): exchange is a list shuffle."""
 
     def __init__(self, world):
         self.world = world
@@ -178,100 +205,7 @@ class LoopbackWorld:
         return incoming
 
 
-# ---- per-step operations of one rank -----------------------------------------------------------------------------------
-@dataclass
-class LocalProblem:
-    """Owned + halo cells of one rank for one step; what the single-GPU pipeline runs on."""
-    n_own: int
-    loc: torch.Tensor
-    radii: torch.Tensor
-    mot: torch.Tensor
-    gid: torch.Tensor
-    bond_len: torch.Tensor      # int32 (n_local,)
-    bond_cols: torch.Tensor     # int32 (n_local, stride) local indices
-
-
-def halo_messages(state: SlabState, geom: SlabGeometry):
-    x = state.loc[:, 0]
-    to_left = state.pack(x < geom.x_lo + geom.halo) if geom.rank > 0 else None
-    to_right = state.pack(x >= geom.x_hi - geom.halo) if geom.rank < geom.world - 1 else None
-    return to_left, to_right
-
-
-def assemble_local(state: SlabState, from_left, from_right) -> LocalProblem:
-    parts = [dict(loc=state.loc, radii=state.radii, mot=state.mot, gid=state.gid, bond_len=state.bond_len,
-                  bond_gid=state.bond_gid)]
-    for msg in (from_left, from_right):
-        if msg is not None and msg.shape[0]:
-            parts.append(SlabState.unpack(msg, state.stride))
-    cat = {f: torch.cat([p[f] for p in parts], dim=0) for f in SlabState.FIELDS}
-    gid = cat["gid"]
-    n_local, stride = gid.shape[0], state.stride
-    # global id -> local index (absent partners -> -1, their bonds are dropped for this step)
-    order = torch.argsort(gid)
-    sorted_gid = gid[order]
-    want = cat["bond_gid"]
-    pos = torch.searchsorted(sorted_gid, want.clamp(min=0).reshape(-1)).reshape(n_local, stride)
-    pos = pos.clamp(max=max(n_local - 1, 0))
-    hit = (sorted_gid[pos] == want) & (want >= 0) if n_local else torch.zeros_like(want, dtype=torch.bool)
-    k = torch.arange(stride, device=gid.device)[None, :]
-    hit &= k < cat["bond_len"][:, None]
-    local = torch.where(hit, order[pos], torch.full_like(want, -1))
-    # compact each row: valid entries first (stable), count them
-    rank_key = torch.argsort((~hit).to(torch.int8), dim=1, stable=True)
-    cols = torch.gather(local, 1, rank_key)
-    return LocalProblem(state.n, cat["loc"].contiguous(), cat["radii"].contiguous(), cat["mot"].contiguous(), gid,
-                        hit.sum(dim=1).to(torch.int32), cols.to(torch.int32).contiguous())
-
-
-def adopt_results(state: SlabState, local: LocalProblem, new_loc, bond_len, bond_cols):
-    """Copy the owned cells' results of a step back: positions, and bond rows translated to global ids."""
-    n = local.n_own
-    state.loc = new_loc[:n].contiguous()
-    stride = bond_cols.shape[1]
-    state.grow_stride(stride)
-    blen = bond_len[:n].long()
-    cols = bond_cols[:n].long()
-    k = torch.arange(stride, device=cols.device)[None, :]
-    valid = k < blen[:, None]
-    cols = torch.where(valid, cols, torch.zeros_like(cols))       # entries past the row length are undefined
-    g = local.gid[cols]
-    state.bond_gid = torch.where(valid, g, torch.full_like(g, -1))
-    if state.bond_gid.shape[1] < state.stride:
-        state.grow_stride(state.stride)
-    state.bond_len = blen
-
-
-def migration_messages(state: SlabState, geom: SlabGeometry):
-    x = state.loc[:, 0]
-    go_left = (x < geom.x_lo) if geom.rank > 0 else torch.zeros_like(x, dtype=torch.bool)
-    go_right = (x >= geom.x_hi) if geom.rank < geom.world - 1 else torch.zeros_like(x, dtype=torch.bool)
-    to_left = state.pack(go_left) if geom.rank > 0 else None
-    to_right = state.pack(go_right) if geom.rank < geom.world - 1 else None
-    state.keep(~(go_left | go_right))
-    return to_left, to_right
-
-
-def absorb_migrants(state: SlabState, from_left, from_right):
-    for msg in (from_left, from_right):
-        if msg is not None and msg.shape[0]:
-            state.append(SlabState.unpack(msg, state.stride))
-
-
-def halo_violation(state: SlabState, geom: SlabGeometry):
-    """Largest distance an owned cell sits outside its slab (device scalar).  The halo argument needs it to
-    stay below the slack the halo was sized with; callers check it once per step."""
-    x = state.loc[:, 0]
-    worst = torch.zeros((), dtype=torch.float64, device=x.device)
-    if x.numel() == 0:
-        return worst
-    if geom.rank > 0:
-        worst = torch.maximum(worst, (geom.x_lo - x).max())
-    if geom.rank < geom.world - 1:
-        worst = torch.maximum(worst, (x - geom.x_hi).max())
-    return worst
-
-
+# ---- morphogen rows -----------------------------------------------------------------------------------------------------
 class FieldSlab:
     """Rows [row_lo,row_hi) of the global (gx,gy) morphogen grid owned by one rank, stored with `halo_rows`
     extra rows on each interior side.  Grid row r sits at x = r*h and belongs to the slab containing it.
@@ -282,13 +216,13 @@ class FieldSlab:
         gx, gy = int(grid[0]), int(grid[1])
         h = float(spat_res)
         self.gx, self.gy, self.h, self.halo_rows = gx, gy, h, int(halo_rows)
-        self.row_lo = int(np.ceil(geom.x_lo / h)) if geom.rank > 0 else 0
-        self.row_hi = min(int(np.ceil(geom.x_hi / h)), gx) if geom.rank < geom.world - 1 else gx
-        self.ext_lo = max(self.row_lo - self.halo_rows, 0) if geom.rank > 0 else 0
-        self.ext_hi = min(self.row_hi + self.halo_rows, gx) if geom.rank < geom.world - 1 else gx
+        self.row_lo = int(np.ceil(geom.x_lo / h)) if geom.has_left else 0
+        self.row_hi = min(int(np.ceil(geom.x_hi / h)), gx) if geom.has_right else gx
+        self.ext_lo = max(self.row_lo - self.halo_rows, 0) if geom.has_left else 0
+        self.ext_hi = min(self.row_hi + self.halo_rows, gx) if geom.has_right else gx
         if self.row_hi - self.row_lo < self.halo_rows:
             raise ValueError("slab narrower than the diffusion halo")
-        self.has_left, self.has_right = geom.rank > 0, geom.rank < geom.world - 1
+        self.has_left, self.has_right = geom.has_left, geom.has_right
         self.data = torch.zeros((self.ext_hi - self.ext_lo, gy), dtype=torch.float64, device=device)
 
     def owned(self) -> torch.Tensor:
@@ -309,25 +243,68 @@ class FieldSlab:
             self.data[self.data.shape[0] - k:] = from_right[:k]
 
 
+# ---- one step of one rank ---------------------------------------------------------------------------------------------------
+@dataclass
+class LocalProblem:
+    """Owned (first n_own) + halo cells of one rank for one step; what the single-GPU pipeline runs on."""
+    n_own: int
+    loc: torch.Tensor
+    radii: torch.Tensor
+    mot: torch.Tensor
+    gid: torch.Tensor           # int32 (n_local,)
+    bond_len: torch.Tensor      # int32 (n_local,)
+    bond_gid: torch.Tensor      # int32 (n_local, stride) global ids
+
+
 def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProblem], tuple],
               field: Optional[FieldSlab] = None, field_ops=None):
-    """One simulation step of one rank, written as a generator: it yields (tag, (to_left, to_right), width)
-    whenever it needs a neighbour exchange and is sent (from_left, from_right) back.  `compute(local)` runs the
-    mechanics on the local problem and returns (new_loc, bond_len, bond_cols).  `field_ops`, if a morphogen
-    field is carried, is an object with deposit(local, field), diffuse(field) and sample(local, field)."""
-    from_l, from_r = yield ("halo", halo_messages(state, geom), state.width())
-    local = assemble_local(state, from_l, from_r)
-    new_loc, blen, bcols = compute(local)
-    local.loc = new_loc
+    """One simulation step of one rank, written as a generator: it yields
+    (tag, (to_left, to_right), width, dtype, fixed_rows) whenever it needs a neighbour exchange and is sent
+    (from_left, from_right) back.  `compute(local)` runs the mechanics in place on local.loc and returns the new
+    (bond_len, bond_gid) of all local cells.  `field_ops` (if a morphogen field is carried) provides
+    deposit(local, field), diffuse(field) and sample(local, field)."""
+    stride = state.stride
+    x = state.loc[:, 0]
+    empty = torch.zeros(0, dtype=torch.int64, device=x.device)
+    idx_l = torch.nonzero(x < geom.x_lo + geom.halo).flatten() if geom.has_left else empty
+    idx_r = torch.nonzero(x >= geom.x_hi - geom.halo).flatten() if geom.has_right else empty
+    msgs = (state.pack(idx_l) if geom.has_left else None, state.pack(idx_r) if geom.has_right else None)
+    from_l, from_r = yield ("cells", msgs, state.record_bytes(), torch.uint8, None)
+
+    parts = [m for m in (from_l, from_r) if m is not None and m.shape[0]]
+    recv = unpack(torch.cat(parts, dim=0), stride) if parts else None
+    stay = geom.inside(x)
+    if recv is not None:
+        mine = geom.inside(recv["loc"][:, 0])
+        n_leave, n_arrive = (int(v) for v in torch.stack([(~stay).sum(), mine.sum()]).tolist())
+    else:
+        mine, n_leave, n_arrive = None, int((~stay).sum()), 0
+    own = state.fields()
+    if n_leave == 0 and n_arrive == 0:
+        groups = [own] + ([recv] if recv is not None else [])
+        n_own = state.n
+    else:
+        # migration: arrivals become owned, departures stay around as halo cells for this step
+        keep, gone = torch.nonzero(stay).flatten(), torch.nonzero(~stay).flatten()
+        groups = [{f: own[f][keep] for f in FIELDS}]
+        n_own = keep.numel() + n_arrive
+        if recv is not None:
+            arr, rest = torch.nonzero(mine).flatten(), torch.nonzero(~mine).flatten()
+            groups += [{f: recv[f][arr] for f in FIELDS}, {f: recv[f][rest] for f in FIELDS}]
+        groups.append({f: own[f][gone] for f in FIELDS})
+    cat = {f: (torch.cat([g[f] for g in groups], dim=0) if len(groups) > 1 else groups[0][f]) for f in FIELDS}
+    local = LocalProblem(n_own, cat["loc"], cat["radii"], cat["mot"], cat["gid"], cat["bond_len"], cat["bond_gid"])
+
+    blen, bgid = compute(local)
     if field is not None:
         field_ops.deposit(local, field)                       # owned + halo cells at their new positions
-        from_l, from_r = yield ("rows", field.messages(), field.gy)
+        from_l, from_r = yield ("rows", field.messages(), field.gy, torch.float64, field.halo_rows)
         field.absorb(from_l, from_r)
         field_ops.diffuse(field)                              # S_d substeps, no communication
         field_ops.sample(local, field)
-    adopt_results(state, local, new_loc, blen, bcols)
-    from_l, from_r = yield ("migrate", migration_messages(state, geom), state.width())
-    absorb_migrants(state, from_l, from_r)
+    n = local.n_own
+    state.set_fields(dict(loc=local.loc[:n], radii=local.radii[:n], mot=local.mot[:n], gid=local.gid[:n],
+                          bond_len=blen[:n], bond_gid=bgid[:n]))
     return local
 
 
@@ -337,8 +314,8 @@ def slab_step(state: SlabState, geom: SlabGeometry, fabric: DistFabric, compute,
     incoming = None
     try:
         while True:
-            tag, (to_l, to_r), width = gen.send(incoming) if incoming is not None else next(gen)
-            incoming = fabric.exchange(to_l, to_r, width)
+            tag, (to_l, to_r), width, dtype, fixed = gen.send(incoming) if incoming is not None else next(gen)
+            incoming = fabric.exchange(to_l, to_r, width, dtype, fixed)
     except StopIteration as done:
         return done.value
 
@@ -354,6 +331,7 @@ def loopback_step(states, geoms, computes, fields=None, field_ops=None):
     requests = [next(g) for g in gens]
     results = [None] * len(gens)
     while any(r is not None for r in requests):
+        assert all(r is not None for r in requests), "ranks fell out of lock-step"
         incoming = world.exchange_all([r[1] for r in requests])
         nxt = []
         for k, (g, inc) in enumerate(zip(gens, incoming)):
@@ -363,6 +341,4 @@ def loopback_step(states, geoms, computes, fields=None, field_ops=None):
                 results[k] = done.value
                 nxt.append(None)
         requests = nxt
-        if any(r is None for r in requests):
-            assert all(r is None for r in requests), "ranks fell out of lock-step"
     return results

@@ -62,6 +62,8 @@ def test_emulated_slabs_match_single_domain(world, dim):
     for _ in range(steps):
         slab.loopback_step(states, geoms, [p.compute for p in pipes], fields if grid else None,
                            pipes if grid else None)
+    for p in pipes:
+        p.check()
     gid = torch.cat([s.gid for s in states]).cpu().numpy()
     got_loc = torch.cat([s.loc for s in states]).cpu().numpy()[np.argsort(gid)]
     assert np.array_equal(np.sort(gid), np.arange(n))
