@@ -3,6 +3,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
 
+Default workload c3 = BASELINE.json configs[2] (500,000-cell 2-D colony + FGF4 diffusion): the README's headline
+scale and the only config the metric is quoted on at both 1 and 8 B200; c2 (50k cells, ~5 MB of state) cannot
+load a B200 -- every kernel there is launch-latency bound.
+
 One "step" = one reference simulation step of the hot path on a synthetic seeded colony
 (SURVEY 8d): 1 x search(r=15) + 11 x [sort + fused search(r=10)/JKR/integrate substep] + deposit +
 S_d diffusion substeps + sample.  Prints ONE JSON line (rank 0).
@@ -520,7 +524,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="c3 = BASELINE configs[2], the 500k-cell headline colony quoted at 1 and 8 B200 (default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
