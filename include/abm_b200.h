@@ -30,6 +30,11 @@ extern "C" {
 
 #define ABM_B200_ABI_VERSION 1
 
+/* flags of abm_bin_dims_host / abm_bin_sort */
+#define ABM_SORT_STABLE 1     /* ascending cell id inside a bin (the reference's fill order) */
+#define ABM_SORT_REFERENCE 2  /* keep the reference's 3 z-layers in a flat (size_z == 0) world */
+#define ABM_SORT_PREBINNED 4  /* histogram + per-cell (bin, rank) already written by abm_jkr_substep */
+
 /* ---- library ----------------------------------------------------------------------------------- */
 int abm_abi_version(void);          /* == ABM_B200_ABI_VERSION */
 int abm_compiled_arch(void);        /* 100 : built for sm_100a only */
@@ -41,8 +46,12 @@ int abm_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * Replaces Simulation.assign_bins + assign_bins_jit (simulation.py:190-223, backend.py:31-50).
  * dims[k] = ceil(size[k]/distance)+3 and bin = floor_divide(x,distance)+1 exactly as the reference;
  * coordinates are clamped into [0,dims-1] (the reference wraps negative indices to an always-empty
- * bin; the edge sets agree, DESIGN.md "bins").  Linear bin id = (bz*dims[1]+by)*dims[0]+bx.         */
-int abm_bin_dims_host(const double size_host[3], double distance, int32_t dims_host[3]);
+ * bin; the edge sets agree, DESIGN.md "bins").  Linear bin id = (bz*dims[1]+by)*dims[0]+bx.
+ * Unless ABM_SORT_REFERENCE is set, a flat world (size[2] == 0) gets one z layer instead of three (the other
+ * two are always empty; candidates are a superset and the predicate is exact, so results are unchanged).
+ * Unless ABM_SORT_STABLE is set, the order of the cells INSIDE a bin is unspecified (every consumer in this
+ * library orders rows and force sums by cell id, so results do not depend on it).                    */
+int abm_bin_dims_host(const double size_host[3], double distance, int flags, int32_t dims_host[3]);
 
 /* bytes of scratch abm_bin_sort needs for n cells and nbins bins */
 size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins);
@@ -58,7 +67,7 @@ size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins);
  * an extent of size_host.  A slab-decomposed colony bins its slab (+halo) this way while positions, the
  * distance predicate and the [0,size] clamp stay in global coordinates.                              */
 int abm_bin_sort(const double *locations, const double *radii, int64_t n, const double size_host[3],
-                 const double *origin_host, double distance, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
+                 const double *origin_host, double distance, int flags, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
                  int32_t *sorted_bin, int32_t *max_count, void *workspace, size_t workspace_bytes,
                  void *stream);
 
@@ -120,12 +129,16 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  * Input: a sort of the CURRENT locations made with bin edge >= abm_jkr_reach() (so every bond that
  * can survive lies inside the 27-bin stencil), the bond graph from the previous substep (old_*; rows
  * may be unsorted) and the motility forces.  Output: the new bond graph in fixed-stride rows
- * (row i at new_cols[i*row_stride], length new_row_len[i], ascending if sort_rows) and the moved
- * locations (written in place; the kernel only reads positions from sorted_pos).
+ * (row i at new_cols[i*row_stride], length new_row_len[i], ascending) and the moved locations (written in
+ * place; the kernel only reads positions from sorted_pos).  The force on a cell is summed in ascending
+ * partner id, the serial reference's order, so it does not depend on the order inside the bins.
  * A bond (i,j) exists afterwards iff (dist <= distance or it existed before) and d > -0.360562.
  *   global_id        : NULL, or (n) int32 ids to write into / look up in the bond rows instead of the cell
  *                      index (a slab-decomposed colony keeps its bonds by global id; rows still belong to the
  *                      local cell index).
+ *   next_bin_counts  : NULL, or a zeroed (nbins+1) table (not bin_start): the kernel then also bins every moved
+ *                      cell on the lattice (next_origin, next_extent, edge `reach`) and leaves histogram,
+ *                      bin and rank where abm_bin_sort(ABM_SORT_PREBINNED, same workspace) expects them.
  *   reach            : bin edge of the sort, >= abm_jkr_reach(distance, max(radii), ...).
  *   max_len (1) int32: raised (atomicMax) by rows that needed more than row_stride entries; a value
  *   > row_stride afterwards means those rows were truncated: grow row_stride and redo the substep
@@ -136,24 +149,27 @@ int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const do
                     const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
                     double reach, const int32_t *old_row_start, int64_t old_row_stride,
                     const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len, int32_t *new_cols,
-                    int64_t row_stride, int32_t *max_len, int sort_rows, const double *motility_forces,
-                    double *locations, double poisson, double youngs, double adhesion_const, double stokes,
-                    const double size_host[3], double move_dt, const int32_t *global_id, void *stream);
+                    int64_t row_stride, int32_t *max_len, const double *motility_forces, double *locations,
+                    double poisson, double youngs, double adhesion_const, double stokes,
+                    const double size_host[3], double move_dt, const int32_t *global_id,
+                    const double *next_extent_host, const double *next_origin_host, int32_t *next_bin_counts,
+                    void *next_sort_workspace, void *stream);
 
 /* The whole substep loop of CellMethods.apply_forces (cell_methods.py:399-436) enqueued by ONE call:
  * n_substeps x [abm_bin_sort at bin edge `reach` over (origin, extent) + abm_jkr_substep with dts_host[k]].
  * Substep 0 reads the bonds old_*; substep k writes row buffer a (k even) or b (k odd), so the final bonds are in
- * buffer a when n_substeps is odd, else in b (rows ascending if sort_last_rows).  The sort outputs are scratch.
+ * buffer a when n_substeps is odd, else in b.  Every substep pre-bins the moved cells for the next sort
+ * (ABM_SORT_PREBINNED), alternating between the two offset tables; the sort outputs are scratch.
  * No host synchronisation; overflow is reported through max_len as in abm_jkr_substep.              */
 int abm_mechanics_loop(const double *radii, double *locations, const double *motility_forces, int64_t n,
                        const double extent_host[3], const double *origin_host, const double size_host[3],
                        double distance, double reach, int n_substeps, const double *dts_host,
-                       int32_t *bin_start, int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin,
-                       int32_t *max_count, void *sort_workspace, size_t sort_workspace_bytes,
+                       int32_t *bin_start_a, int32_t *bin_start_b, int32_t *sorted_id, double *sorted_pos,
+                       int32_t *sorted_bin, int32_t *max_count, void *sort_workspace, size_t sort_workspace_bytes,
                        const int32_t *old_row_start, int64_t old_row_stride, const int32_t *old_row_len,
                        const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
-                       int64_t row_stride, int32_t *max_len, int sort_last_rows, const int32_t *global_id,
-                       double poisson, double youngs, double adhesion_const, double stokes, void *stream);
+                       int64_t row_stride, int32_t *max_len, const int32_t *global_id, double poisson,
+                       double youngs, double adhesion_const, double stokes, void *stream);
 
 /* ---- morphogen diffusion ---------------------------------------------------------------------------
  * Replaces CellMethods.update_diffusion + update_diffusion_jit (cell_methods.py:441-468,

@@ -25,9 +25,9 @@ SIGNATURES = {
     "abm_compiled_arch": (I32, []),
     "abm_last_error": (C.c_char_p, []),
     "abm_device_info": (I32, [C.POINTER(I32), C.POINTER(I32), C.POINTER(I32)]),
-    "abm_bin_dims_host": (I32, [D3, F64, I3]),
+    "abm_bin_dims_host": (I32, [D3, F64, I32, I3]),
     "abm_bin_sort_workspace_bytes": (SZ, [I64, I64]),
-    "abm_bin_sort": (I32, [P, P, I64, D3, D3, F64, P, P, P, P, P, P, SZ, P]),
+    "abm_bin_sort": (I32, [P, P, I64, D3, D3, F64, I32, P, P, P, P, P, P, SZ, P]),
     "abm_bins_dense": (I32, [P, I64, D3, F64, P, P, I64, P, P, P, P]),
     "abm_neighbor_search": (I32, [P, P, P, P, I64, I3, F64, P, P, I64, P, P, P, P, P, I64, P, P]),
     "abm_read_i32_sync": (I32, [P, C.POINTER(C.c_int32), P]),
@@ -36,10 +36,10 @@ SIGNATURES = {
     "abm_jkr_forces": (I32, [P, I64, P, P, P, P, P, I64, F64, F64, F64, P]),
     "abm_apply_forces": (I32, [P, P, P, P, I64, F64, D3, F64, P, P]),
     "abm_jkr_reach": (F64, [F64, F64, F64, F64, F64]),
-    "abm_jkr_substep": (I32, [P, P, P, P, I64, I3, F64, F64, P, I64, P, P, P, P, I64, P, I32, P, P,
-                              F64, F64, F64, F64, D3, F64, P, P]),
+    "abm_jkr_substep": (I32, [P, P, P, P, I64, I3, F64, F64, P, I64, P, P, P, P, I64, P, P, P,
+                              F64, F64, F64, F64, D3, F64, P, D3, D3, P, P, P]),
     "abm_mechanics_loop": (I32, [P, P, P, I64, D3, D3, D3, F64, F64, I32, C.POINTER(C.c_double),
-                                 P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, I32, P,
+                                 P, P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, P,
                                  F64, F64, F64, F64, P]),
     "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),
     "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P]),
@@ -80,6 +80,9 @@ def check(rc: int, what: str) -> int:
         msg = load().abm_last_error().decode("utf-8", "replace")
         raise AbmError(f"{what} failed with code {rc}: {msg}")
     return rc
+
+
+SORT_STABLE, SORT_REFERENCE, SORT_PREBINNED = 1, 2, 4
 
 
 def d3(values):

@@ -1,7 +1,10 @@
 // jkr.cu -- JKR adhesion/repulsion forces, Stokes integration, and the fused mechanics substep.
 // Replaces jkr_forces_cpu/gpu, apply_forces_cpu/gpu and the body of the 11-substep loop of
 // CellMethods.apply_forces (reference cell_backend.py:6-172, cell_methods.py:342-439).
+#include <string.h>
+
 #include "graph.cuh"
+#include "sortws.cuh"
 
 namespace abm {
 
@@ -65,38 +68,53 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 
 // ---- fused: search(distance, union with old bonds) + JKR + bond breaking + integration ---------------
 // Two phases per thread, to keep the warp converged while it does the expensive fp64 contact math:
-//   1. walk the bin stencil with the cheap test |p-q|^2 <= reach^2 and park the slots that pass in a
-//      per-thread column of shared memory (a few per cell);
-//   2. loop over the parked slots doing the JKR evaluation.  All lanes run this loop together (trip count =
-//      the largest hit count in the warp), instead of each lane doing the heavy math at a different
-//      iteration of the stencil walk.
+//   1. walk the bin stencil with the cheap test |p-q|^2 <= reach^2 and park what passes -- partner id and
+//      slot, the partners of the thin hysteresis shell flagged -- in per-thread columns of shared memory;
+//   2. order the parked partners by id and run the contact model over them.  All lanes run this loop together
+//      (trip count = the largest hit count in the warp) instead of each lane doing the heavy math at a different
+//      iteration of the stencil walk; and because the sum runs in ascending partner id -- the serial
+//      reference's += order -- the result does not depend on how the sort happened to order a bin.
+// While it integrates a cell the kernel can also pre-bin it for the NEXT substep's sort (histogram + rank).
 constexpr int kMaxHits = 16;
-constexpr int kMaxShell = 4;
 constexpr int kJkrMinBlocks = 6;     // cap registers at 80/thread: the kernel is latency bound, occupancy matters
+constexpr int kShellFlag = 0x40000000;
 
 struct BondEval {
-    // radius-dependent part of the contact model, memoised on the partner radius (radii are usually uniform)
-    double memo_r, r_hat, overlap_;
+    // radius-dependent part of the contact model, memoised on the partner radius (radii are usually uniform).
+    // The two divisions of the reference's  d = ((r1+r2-mag)/1e6)/overlap_  and the force scale
+    // pi*adhesion*r_hat are folded into two factors here, so the per-pair work is one rsqrt and a few FMAs.
+    // This moves d by ~2 ulp: forces stay within 1e-15 relative, and the bond test d > -0.360562 can differ
+    // from the reference only for |d + 0.360562| < 1e-15 (never observed; both ends of a pair use the same
+    // expression, so the two rows of a bond always agree).
+    double memo_r, inv_scale, force_scale, rsum;
     __device__ __forceinline__ void refresh(double rp, double rq, const JkrConst &c) {
         if (rq != memo_r) {
+            const double kPi = 3.141592653589793;
             memo_r = rq;
-            r_hat = 1.0 / (1e6 * ((1.0 / rp) + (1.0 / rq)));
-            overlap_ = c.k23 * cbrt(r_hat);
+            double r_hat = 1.0 / (1e6 * ((1.0 / rp) + (1.0 / rq)));
+            double overlap_ = c.k23 * cbrt(r_hat);
+            inv_scale = 1.0 / (1e6 * overlap_);
+            force_scale = kPi * c.adhesion * r_hat;
+            rsum = rp + rq;
         }
     }
 };
 
-template <bool kSortRows>
+struct NextSort {          // where to pre-bin the moved cells for the following substep (counts == nullptr: off)
+    BinGeom geom;
+    int *counts, *cell_bin, *rank;
+};
+
 __global__ void __launch_bounds__(kJkrThreads, kJkrMinBlocks)
 k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_id,
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
-              double stokes, Box box, double dt, const int *__restrict__ gid_of) {
-    __shared__ int hit_slot[kMaxHits][kJkrThreads];       // partners within `distance`: bonded unless d breaks
-    __shared__ int shell_slot[kMaxShell][kJkrThreads];    // partners in (distance, reach]: bonded only if they were
-    const double kPi = 3.141592653589793;
-    int s = blockIdx.x * kJkrThreads + threadIdx.x;
+              double stokes, Box box, double dt, const int *__restrict__ gid_of, NextSort next) {
+    __shared__ int hit_slot[kMaxHits][kJkrThreads];     // sorted slot of a parked partner (| kShellFlag)
+    __shared__ int hit_id[kMaxHits][kJkrThreads];       // its id as written into bond rows
+    const int tid = threadIdx.x;
+    int s = blockIdx.x * kJkrThreads + tid;
     int cnt = 0;
     if (s < n) {
         int i = sorted_id[s];
@@ -113,27 +131,6 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
             int j = sorted_id[t];
             return gid_of ? gid_of[j] : j;
         };
-        // contact model for one partner known to be a bond candidate
-        auto bond = [&](int t, double4 q) {
-            double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
-            double s2 = sumsq_nofma(vx, vy, vz);
-            ev.refresh(p.w, q.w, c);
-            double mag = __dsqrt_rn(s2);
-            double overlap = (p.w + q.w - mag) / 1e6;
-            double d = overlap / ev.overlap_;
-            if (d > -0.360562) {
-                double f = (-0.0204 * (d * d * d)) + (0.4942 * (d * d)) + (1.0801 * d) - 1.324;
-                double jkr = f * kPi * c.adhesion * ev.r_hat;
-                if (mag != 0.0) {
-                    double w = jkr / mag;
-                    fx += w * vx;
-                    fy += w * vy;
-                    fz += w * vz;
-                }
-                if (cnt < stride) row[cnt] = partner_id(t);
-                ++cnt;
-            }
-        };
         // membership of j in this cell's previous bond row; every entry is read (no early exit) so the
         // loads are independent and overlap
         auto was_bonded = [&](int j) {
@@ -143,12 +140,31 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
             for (int k = 0; k < olen; ++k) found |= (old.cols[os + k] == j);
             return found;
         };
+        // contact model for one bond candidate
+        auto bond = [&](double4 q, int j) {
+            double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
+            double s2 = sumsq_nofma(vx, vy, vz);
+            ev.refresh(p.w, q.w, c);
+            double inv_mag = rsqrt(s2);                     // +inf for coincident cells, handled below
+            double mag = s2 > 0.0 ? s2 * inv_mag : 0.0;
+            double d = (ev.rsum - mag) * ev.inv_scale;
+            if (d > -0.360562) {
+                double f = (-0.0204 * (d * d * d)) + (0.4942 * (d * d)) + (1.0801 * d) - 1.324;
+                if (s2 > 0.0) {
+                    double w = f * ev.force_scale * inv_mag;
+                    fx += w * vx;
+                    fy += w * vy;
+                    fz += w * vz;
+                }
+                if (cnt < stride) row[cnt] = j;
+                ++cnt;
+            }
+        };
 
-        // phase 1: cheap tests over the stencil, park what needs the contact model.
-        // The (lo,hi) slot ranges of the three dy runs of a z-layer are fetched together (6 offset loads in
-        // flight instead of one dependent pair per run), and the next candidate is loaded while the current
-        // one is tested.
-        int nh = 0, ns = 0;
+        // phase 1: cheap tests over the stencil.  The (lo,hi) slot ranges of the three dy runs of a z-layer are
+        // fetched together, and the next candidate is loaded while the current one is tested.
+        int nh = 0;
+        bool crowded = false;
         const int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
         for (int dz = -1; dz <= 1; ++dz) {
             int z = bz + dz;
@@ -174,40 +190,61 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                     if (u + 1 < cntr) qn = spos[t + 1];
                     double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
                     if (s2 <= reach2 && t != s) {             // no bond can survive beyond the reach
-                        if (rad.within(s2)) {
-                            if (nh < kMaxHits) hit_slot[nh][threadIdx.x] = t;
-                            else bond(t, q);                  // crowded cell: evaluate in place
-                            ++nh;
-                        } else if (old.valid()) {
-                            if (ns < kMaxShell) shell_slot[ns][threadIdx.x] = t;
-                            else if (was_bonded(partner_id(t))) bond(t, q);
-                            ++ns;
+                        bool inside = rad.within(s2);
+                        if (inside || old.valid()) {
+                            int j = partner_id(t);
+                            if (nh < kMaxHits) {
+                                hit_slot[nh][tid] = inside ? t : (t | kShellFlag);
+                                hit_id[nh][tid] = j;
+                                ++nh;
+                            } else {                          // crowded cell: evaluate in place
+                                crowded = true;
+                                if (inside || was_bonded(j)) bond(q, j);
+                            }
                         }
                     }
                     q = qn;
                 }
             }
         }
-        // phase 2: contact model on the parked partners, all lanes together
-        int parked = min(nh, kMaxHits);
-        for (int k = 0; k < parked; ++k) {
-            int t = hit_slot[k][threadIdx.x];
-            bond(t, spos[t]);
+        // order the parked partners by id (a handful of entries in this thread's shared-memory columns)
+        for (int a = 1; a < nh; ++a) {
+            int key = hit_id[a][tid], val = hit_slot[a][tid];
+            int b = a - 1;
+            while (b >= 0 && hit_id[b][tid] > key) {
+                hit_id[b + 1][tid] = hit_id[b][tid];
+                hit_slot[b + 1][tid] = hit_slot[b][tid];
+                --b;
+            }
+            hit_id[b + 1][tid] = key;
+            hit_slot[b + 1][tid] = val;
         }
-        // phase 3: the thin shell -- hysteresis lookups, only the lanes that have any
-        int shelled = min(ns, kMaxShell);
-        for (int k = 0; k < shelled; ++k) {
-            int t = shell_slot[k][threadIdx.x];
-            if (was_bonded(partner_id(t))) bond(t, spos[t]);
+        // phase 2: contact model, all lanes together, ascending partner id
+        for (int k = 0; k < nh; ++k) {
+            int t = hit_slot[k][tid], j = hit_id[k][tid];
+            if (t & kShellFlag) {                             // thin shell: only pre-existing bonds persist
+                if (!was_bonded(j)) continue;
+                t &= ~kShellFlag;
+            }
+            bond(spos[t], j);
         }
-        new_len[i] = min(cnt, stride);
-        if (kSortRows) insertion_sort(row, min(cnt, stride));
+        int kept = min(cnt, stride);
+        new_len[i] = kept;
+        if (crowded) insertion_sort(row, kept);               // rows are ascending in every case
         // integration (reference cell_backend.py:155-170); positions are read from the sorted snapshot only
         double friction = stokes_friction(p.w, stokes);
-        long long a = 3 * (long long)i;
-        loc[a + 0] = stokes_move(p.x, mot[a + 0], fx, friction, dt, box.size[0]);
-        loc[a + 1] = stokes_move(p.y, mot[a + 1], fy, friction, dt, box.size[1]);
-        loc[a + 2] = stokes_move(p.z, mot[a + 2], fz, friction, dt, box.size[2]);
+        long long a3 = 3 * (long long)i;
+        double nx = stokes_move(p.x, mot[a3 + 0], fx, friction, dt, box.size[0]);
+        double ny = stokes_move(p.y, mot[a3 + 1], fy, friction, dt, box.size[1]);
+        double nz = stokes_move(p.z, mot[a3 + 2], fz, friction, dt, box.size[2]);
+        loc[a3 + 0] = nx;
+        loc[a3 + 1] = ny;
+        loc[a3 + 2] = nz;
+        if (next.counts) {                                    // histogram + rank for the next substep's sort
+            int b = cell_bin_of(nx, ny, nz, next.geom);
+            next.cell_bin[i] = b;
+            next.rank[i] = atomicAdd(&next.counts[b], 1);
+        }
     }
     // overflow report: one atomic per warp, and only when a row did not fit
     int wmax = cnt;
@@ -251,10 +288,12 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
                                const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
                                double reach, const int32_t *old_row_start, int64_t old_row_stride,
                                const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len,
-                               int32_t *new_cols, int64_t row_stride, int32_t *max_len, int sort_rows,
+                               int32_t *new_cols, int64_t row_stride, int32_t *max_len,
                                const double *motility_forces, double *locations, double poisson, double youngs,
                                double adhesion_const, double stokes, const double size_host[3], double move_dt,
-                               const int32_t *global_id, void *stream) {
+                               const int32_t *global_id, const double *next_extent_host,
+                               const double *next_origin_host, int32_t *next_bin_counts, void *next_sort_workspace,
+                               void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(bin_start && sorted_id && sorted_pos && sorted_bin && dims_host && new_row_len && new_cols &&
@@ -271,20 +310,23 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
         stc.dims[k] = dims_host[k];
         box.size[k] = size_host[k];
     }
-    int blocks = ceil_div(n, kJkrThreads);
-    cudaStream_t st = as_stream(stream);
-    const double4 *sp = reinterpret_cast<const double4 *>(sorted_pos);
-    double reach2 = reach * reach;
-    if (sort_rows)
-        k_jkr_substep<true><<<blocks, kJkrThreads, 0, st>>>(bin_start, sorted_id, sp, sorted_bin, (int)n, stc,
-                                                            Radius(distance), reach2, old, new_row_len, new_cols,
-                                                            (int)row_stride, max_len, motility_forces, locations, c,
-                                                            stokes, box, move_dt, global_id);
-    else
-        k_jkr_substep<false><<<blocks, kJkrThreads, 0, st>>>(bin_start, sorted_id, sp, sorted_bin, (int)n, stc,
-                                                             Radius(distance), reach2, old, new_row_len, new_cols,
-                                                             (int)row_stride, max_len, motility_forces, locations, c,
-                                                             stokes, box, move_dt, global_id);
+    NextSort next;
+    memset(&next, 0, sizeof(next));
+    if (next_bin_counts) {
+        ABM_REQUIRE(next_extent_host && next_sort_workspace && next_bin_counts != bin_start,
+                    "pre-binning needs the next sort's extent, workspace and a second offset table");
+        int64_t nbins;
+        ABM_REQUIRE(make_bin_geom(next_extent_host, next_origin_host, reach, 0, next.geom, nbins) == 0,
+                    "bad next-sort geometry");
+        SortWs w = sort_ws_carve(next_sort_workspace, n, nbins);
+        next.counts = next_bin_counts;
+        next.cell_bin = w.cell_bin;
+        next.rank = w.rank;
+    }
+    k_jkr_substep<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
+        bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
+        Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
+        locations, c, stokes, box, move_dt, global_id, next);
     ABM_CHECK_LAUNCH("k_jkr_substep");
     return 0;
 }
@@ -292,34 +334,44 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
 // The whole substep loop of CellMethods.apply_forces (reference cell_methods.py:399-436) enqueued by one call:
 // n_substeps x [counting sort at bin edge `reach` + fused substep].  Substep k reads the bonds written by
 // substep k-1 (substep 0 reads old_*) and writes row buffer a (k even) or b (k odd); the final bonds are in
-// buffer a when n_substeps is odd, else in b.  Pure convenience over abm_bin_sort + abm_jkr_substep: it removes
-// the per-launch host overhead of a scripting-language caller.
+// buffer a when n_substeps is odd, else in b.  Every substep pre-bins the moved cells, so only the first sort
+// of the loop runs the histogram kernel; the two offset tables alternate.
 ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const double *motility_forces, int64_t n,
                                   const double extent_host[3], const double *origin_host, const double size_host[3],
                                   double distance, double reach, int n_substeps, const double *dts_host,
-                                  int32_t *bin_start, int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin,
-                                  int32_t *max_count, void *sort_workspace, size_t sort_workspace_bytes,
-                                  const int32_t *old_row_start, int64_t old_row_stride, const int32_t *old_row_len,
-                                  const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b,
-                                  int32_t *cols_b, int64_t row_stride, int32_t *max_len, int sort_last_rows,
-                                  const int32_t *global_id, double poisson, double youngs, double adhesion_const,
-                                  double stokes, void *stream) {
+                                  int32_t *bin_start_a, int32_t *bin_start_b, int32_t *sorted_id, double *sorted_pos,
+                                  int32_t *sorted_bin, int32_t *max_count, void *sort_workspace,
+                                  size_t sort_workspace_bytes, const int32_t *old_row_start, int64_t old_row_stride,
+                                  const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a,
+                                  int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
+                                  int32_t *max_len, const int32_t *global_id, double poisson, double youngs,
+                                  double adhesion_const, double stokes, void *stream) {
     ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
-    ABM_REQUIRE(extent_host && size_host, "null pointer");
-    int32_t dims[3];
-    int rc = abm_bin_dims_host(extent_host, reach, dims);
-    if (rc) return rc;
+    ABM_REQUIRE(extent_host && size_host && bin_start_a && bin_start_b && bin_start_a != bin_start_b,
+                "need two distinct offset tables");
+    BinGeom g;
+    int64_t nbins;
+    ABM_REQUIRE(make_bin_geom(extent_host, origin_host, reach, 0, g, nbins) == 0, "bad geometry");
+    cudaStream_t st = as_stream(stream);
     const int32_t *cur_start = old_row_start, *cur_len = old_row_len, *cur_cols = old_cols;
     int64_t cur_stride = old_row_stride;
     for (int k = 0; k < n_substeps; ++k) {
-        rc = abm_bin_sort(locations, radii, n, extent_host, origin_host, reach, bin_start, sorted_id, sorted_pos,
-                          sorted_bin, max_count, sort_workspace, sort_workspace_bytes, stream);
+        int32_t *table = (k & 1) ? bin_start_b : bin_start_a, *other = (k & 1) ? bin_start_a : bin_start_b;
+        int rc = abm_bin_sort(locations, radii, n, extent_host, origin_host, reach, k ? ABM_SORT_PREBINNED : 0, table,
+                              sorted_id, sorted_pos, sorted_bin, max_count, sort_workspace, sort_workspace_bytes,
+                              stream);
         if (rc) return rc;
+        const bool prebin = k + 1 < n_substeps && n > 0;
+        if (prebin) {
+            rc = check_cuda(cudaMemsetAsync(other, 0, (size_t)(nbins + 1) * 4, st), "memset next offset table");
+            if (rc) return rc;
+        }
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
-        rc = abm_jkr_substep(bin_start, sorted_id, sorted_pos, sorted_bin, n, dims, distance, reach, cur_start,
-                             cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len,
-                             (sort_last_rows && k == n_substeps - 1) ? 1 : 0, motility_forces, locations, poisson,
-                             youngs, adhesion_const, stokes, size_host, dts_host[k], global_id, stream);
+        rc = abm_jkr_substep(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
+                             cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, motility_forces, locations,
+                             poisson, youngs, adhesion_const, stokes, size_host, dts_host[k], global_id,
+                             prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
+                             prebin ? sort_workspace : nullptr, stream);
         if (rc) return rc;
         cur_start = nullptr;
         cur_stride = row_stride;

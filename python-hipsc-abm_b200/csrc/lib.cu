@@ -62,13 +62,6 @@ ABM_EXPORT int abm_read_i32_sync(const int32_t *device_value, int32_t *value_hos
     return abm::check_cuda(cudaStreamSynchronize(abm::as_stream(stream)), "cudaStreamSynchronize");
 }
 
-ABM_EXPORT int abm_bin_dims_host(const double size_host[3], double distance, int32_t dims_host[3]) {
-    ABM_REQUIRE(size_host && dims_host, "null pointer");
-    ABM_REQUIRE(distance > 0, "distance must be positive");
-    for (int k = 0; k < 3; ++k) dims_host[k] = (int32_t)ceil(size_host[k] / distance) + 3;
-    return 0;
-}
-
 ABM_EXPORT double abm_jkr_reach(double distance, double max_radius, double poisson, double youngs,
                                 double adhesion_const) {
     // Largest centre distance at which a bond can survive: d > -0.360562 <=> mag < r1+r2+0.360562e6*overlap_

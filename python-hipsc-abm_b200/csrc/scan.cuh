@@ -8,7 +8,7 @@
 namespace abm {
 
 constexpr int kScanThreads = 512;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 8;      // k_scan_apply moves them as two int4
 constexpr int kScanChunk = kScanThreads * kScanItems;
 
 inline int scan_blocks(int64_t n) { return ceil_div(n, kScanChunk); }
@@ -64,16 +64,25 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restr
     for (int b = threadIdx.x; b < (int)blockIdx.x; b += kScanThreads) part += block_sums[b];
     int offset = block_reduce_sum(part, smem);
 
-    // each thread owns kScanItems CONSECUTIVE elements
+    // each thread owns kScanItems CONSECUTIVE elements, moved as two 16-byte vectors when the chunk is full
     int64_t first = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
     int v[kScanItems];
     int tsum = 0;
+    const bool full = first + kScanItems <= n && ((reinterpret_cast<uintptr_t>(data + first) & 15) == 0);
+    if (full) {
+        int4 a = *reinterpret_cast<const int4 *>(data + first);
+        int4 b = *reinterpret_cast<const int4 *>(data + first + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < kScanItems; ++k) {
-        int64_t i = first + k;
-        v[k] = (i < n) ? data[i] : 0;
-        tsum += v[k];
+        for (int k = 0; k < kScanItems; ++k) {
+            int64_t i = first + k;
+            v[k] = (i < n) ? data[i] : 0;
+        }
     }
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) tsum += v[k];
     int incl = warp_inclusive_scan(tsum);
     if (lane_id() == 31) warp_tot[threadIdx.x >> 5] = incl;
     __syncthreads();
@@ -84,11 +93,19 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restr
     }
     __syncthreads();
     int run = offset + warp_tot[threadIdx.x >> 5] + (incl - tsum);
+    int o[kScanItems];
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        int64_t i = first + k;
-        if (i < n) data[i] = run;
+        o[k] = run;
         run += v[k];
+    }
+    if (full) {
+        *reinterpret_cast<int4 *>(data + first) = make_int4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<int4 *>(data + first + 4) = make_int4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k)
+            if (first + k < n) data[first + k] = o[k];
     }
     if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
 }

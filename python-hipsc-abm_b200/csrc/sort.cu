@@ -1,42 +1,50 @@
-// sort.cu -- spatial binning as a counting sort (histogram -> scan -> place -> stable gather).
+// sort.cu -- spatial binning as a counting sort (histogram -> scan -> scatter).
 // Replaces Simulation.assign_bins / assign_bins_jit (reference simulation.py:190-223, backend.py:31-50):
 // instead of dense fixed-capacity buckets (218 MB at 500k cells) the cells are permuted into bin order
 // and a (nbins+1) offset table indexes them.
-#include "scan.cuh"
+//
+// Two placements:
+//   fast (default)      : slot = bin_start[bin] + arrival rank.  The order inside a bin is whatever the atomics
+//                         produced; every consumer is order-independent (rows and force sums are ordered by
+//                         cell id downstream), so results stay run-to-run identical.
+//   ABM_SORT_STABLE     : ascending cell id inside a bin -- the reference's serial fill order, needed only to
+//                         hand out the reference-shaped dense buckets of assign_bins().
+// ABM_SORT_PREBINNED skips the histogram: bin_start already holds the bin populations and the scratch buffer
+// the (bin, rank) of every cell, written by the fused mechanics kernel of the previous substep.
+#include "sortws.cuh"
 
 namespace abm {
 
 constexpr int kThreads = 256;
-
-struct SortWs {
-    int *rank;        // n   : arrival order of the cell inside its bin (atomic, not stable)
-    int *cell_bin;    // n   : linear bin of cell i
-    int *tmp_id;      // n   : unstable placement
-    int *block_sums;  // scan scratch
-};
-
-static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
-
-static SortWs carve(void *ws, int64_t n, int64_t nbins) {
-    char *p = (char *)ws;
-    SortWs w;
-    w.rank = (int *)p;       p += align_up((size_t)n * 4);
-    w.cell_bin = (int *)p;   p += align_up((size_t)n * 4);
-    w.tmp_id = (int *)p;     p += align_up((size_t)n * 4);
-    w.block_sums = (int *)p; p += align_up((size_t)scan_blocks(nbins + 1) * 4 + 4);
-    return w;
-}
 
 __global__ void __launch_bounds__(kThreads) k_bin_count(const double *__restrict__ loc, int n, BinGeom g,
                                                         int *__restrict__ counts, int *__restrict__ cell_bin,
                                                         int *__restrict__ rank) {
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
-    double x = loc[3 * (int64_t)i + 0], y = loc[3 * (int64_t)i + 1], z = loc[3 * (int64_t)i + 2];
-    int b = lin_bin(bin_coord(x - g.origin[0], g.distance, g.dims[0]), bin_coord(y - g.origin[1], g.distance, g.dims[1]),
-                    bin_coord(z - g.origin[2], g.distance, g.dims[2]), g.dims);
+    int b = cell_bin_of(loc[3 * (int64_t)i + 0], loc[3 * (int64_t)i + 1], loc[3 * (int64_t)i + 2], g);
     cell_bin[i] = b;
     rank[i] = atomicAdd(&counts[b], 1);
+}
+
+// fast placement: coalesced reads by cell id, one 32-byte row + two ints scattered per cell
+__global__ void __launch_bounds__(kThreads) k_scatter(const int *__restrict__ cell_bin, const int *__restrict__ rank,
+                                                      const int *__restrict__ bin_start,
+                                                      const double *__restrict__ loc, const double *__restrict__ radii,
+                                                      int n, int *__restrict__ sorted_id,
+                                                      double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin) {
+    int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    int b = cell_bin[i];
+    int dest = bin_start[b] + rank[i];
+    double4 p;
+    p.x = loc[3 * (int64_t)i + 0];
+    p.y = loc[3 * (int64_t)i + 1];
+    p.z = loc[3 * (int64_t)i + 2];
+    p.w = radii[i];
+    sorted_id[dest] = i;
+    sorted_pos[dest] = p;
+    sorted_bin[dest] = b;
 }
 
 __global__ void __launch_bounds__(kThreads) k_place(const int *__restrict__ cell_bin, const int *__restrict__ rank,
@@ -47,8 +55,7 @@ __global__ void __launch_bounds__(kThreads) k_place(const int *__restrict__ cell
     tmp_id[bin_start[cell_bin[i]] + rank[i]] = i;
 }
 
-// One thread per provisional slot: find the stable (ascending id) position inside the bin segment and
-// move the cell's {x,y,z,r} there.  Writes land inside the same short segment -> coalesced sectors.
+// stable placement: one thread per provisional slot finds its ascending-id position inside the bin segment
 __global__ void __launch_bounds__(kThreads) k_gather(const int *__restrict__ tmp_id, const int *__restrict__ cell_bin,
                                                      const int *__restrict__ bin_start,
                                                      const double *__restrict__ loc, const double *__restrict__ radii,
@@ -97,58 +104,68 @@ __global__ void __launch_bounds__(kThreads) k_bins_dense(const double *__restric
     if (place == 0) bins_help[ref_bin] = bin_start[b + 1] - bin_start[b];
 }
 
-static int make_geom(const double size_host[3], const double *origin_host, double distance, BinGeom &g,
-                     int64_t &nbins) {
-    if (!(distance > 0)) return -1;
-    g.distance = distance;
-    nbins = 1;
-    for (int k = 0; k < 3; ++k) {
-        g.origin[k] = origin_host ? origin_host[k] : 0.0;
-        g.dims[k] = (int)ceil(size_host[k] / distance) + 3;
-        nbins *= g.dims[k];
-    }
-    return nbins < (int64_t)0x7fffffff ? 0 : -1;
-}
-
 }  // namespace abm
 
 using namespace abm;
 
+ABM_EXPORT int abm_bin_dims_host(const double size_host[3], double distance, int flags, int32_t dims_host[3]) {
+    ABM_REQUIRE(size_host && dims_host, "null pointer");
+    ABM_REQUIRE(distance > 0, "distance must be positive");
+    BinGeom g;
+    int64_t nbins;
+    ABM_REQUIRE(make_bin_geom(size_host, nullptr, distance, flags, g, nbins) == 0, "too many bins");
+    for (int k = 0; k < 3; ++k) dims_host[k] = g.dims[k];
+    return 0;
+}
+
 ABM_EXPORT size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins) {
     if (n < 0 || nbins < 0) return 0;
-    return 3 * align_up((size_t)n * 4) + align_up((size_t)scan_blocks(nbins + 1) * 4 + 4) + 256;
+    return sort_ws_bytes(n, nbins);
 }
 
 ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_t n, const double size_host[3],
-                            const double *origin_host, double distance, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
-                            int32_t *sorted_bin, int32_t *max_count, void *workspace, size_t workspace_bytes,
-                            void *stream) {
+                            const double *origin_host, double distance, int flags, int32_t *bin_start,
+                            int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
+                            void *workspace, size_t workspace_bytes, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     ABM_REQUIRE(size_host && bin_start && max_count, "null pointer");
     BinGeom g;
     int64_t nbins;
-    ABM_REQUIRE(make_geom(size_host, origin_host, distance, g, nbins) == 0,
+    ABM_REQUIRE(make_bin_geom(size_host, origin_host, distance, flags, g, nbins) == 0,
                 "bad geometry (distance <= 0 or too many bins)");
-    ABM_REQUIRE(workspace_bytes >= abm_bin_sort_workspace_bytes(n, nbins), "workspace too small");
+    ABM_REQUIRE(workspace_bytes >= sort_ws_bytes(n, nbins), "workspace too small");
     cudaStream_t st = as_stream(stream);
-    int rc = check_cuda(cudaMemsetAsync(bin_start, 0, (size_t)(nbins + 1) * 4, st), "memset bin_start");
-    if (rc) return rc;
+    const bool prebinned = flags & ABM_SORT_PREBINNED;
+    int rc;
+    if (!prebinned) {
+        rc = check_cuda(cudaMemsetAsync(bin_start, 0, (size_t)(nbins + 1) * 4, st), "memset bin_start");
+        if (rc) return rc;
+    }
     rc = check_cuda(cudaMemsetAsync(max_count, 0, 4, st), "memset max_count");
     if (rc) return rc;
     if (n == 0) return 0;
     ABM_REQUIRE(locations && radii && sorted_id && sorted_pos && sorted_bin && workspace, "null pointer");
     ABM_REQUIRE(((uintptr_t)sorted_pos & 31) == 0, "sorted_pos must be 32-byte aligned");
-    SortWs w = carve(workspace, n, nbins);
+    SortWs w = sort_ws_carve(workspace, n, nbins);
     int blocks = ceil_div(n, kThreads);
-    k_bin_count<<<blocks, kThreads, 0, st>>>(locations, (int)n, g, bin_start, w.cell_bin, w.rank);
-    ABM_CHECK_LAUNCH("k_bin_count");
+    if (!prebinned) {
+        k_bin_count<<<blocks, kThreads, 0, st>>>(locations, (int)n, g, bin_start, w.cell_bin, w.rank);
+        ABM_CHECK_LAUNCH("k_bin_count");
+    }
     rc = exclusive_scan_inplace(bin_start, nbins + 1, w.block_sums, max_count, nullptr, st);
     if (rc) return rc;
-    k_place<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.rank, bin_start, (int)n, w.tmp_id);
-    ABM_CHECK_LAUNCH("k_place");
-    k_gather<<<blocks, kThreads, 0, st>>>(w.tmp_id, w.cell_bin, bin_start, locations, radii, (int)n, sorted_id,
-                                          reinterpret_cast<double4 *>(sorted_pos), sorted_bin);
-    ABM_CHECK_LAUNCH("k_gather");
+    double4 *sp = reinterpret_cast<double4 *>(sorted_pos);
+    if (flags & ABM_SORT_STABLE) {
+        k_place<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.rank, bin_start, (int)n, w.tmp_id);
+        ABM_CHECK_LAUNCH("k_place");
+        k_gather<<<blocks, kThreads, 0, st>>>(w.tmp_id, w.cell_bin, bin_start, locations, radii, (int)n, sorted_id, sp,
+                                              sorted_bin);
+        ABM_CHECK_LAUNCH("k_gather");
+    } else {
+        k_scatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.rank, bin_start, locations, radii, (int)n, sorted_id, sp,
+                                               sorted_bin);
+        ABM_CHECK_LAUNCH("k_scatter");
+    }
     return 0;
 }
 
@@ -161,7 +178,7 @@ ABM_EXPORT int abm_bins_dense(const double *locations, int64_t n, const double s
                 "null pointer");
     BinGeom g;
     int64_t nbins;
-    ABM_REQUIRE(make_geom(size_host, nullptr, distance, g, nbins) == 0, "bad geometry");
+    ABM_REQUIRE(make_bin_geom(size_host, nullptr, distance, ABM_SORT_REFERENCE, g, nbins) == 0, "bad geometry");
     k_bins_dense<<<ceil_div(n, kThreads), kThreads, 0, as_stream(stream)>>>(
         locations, (int)n, g, bin_start, sorted_id, (long long)max_agents, (long long *)bins,
         (long long *)bins_help, (long long *)bin_locations);

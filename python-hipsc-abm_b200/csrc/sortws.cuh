@@ -1,0 +1,55 @@
+// sortws.cuh -- layout of the counting-sort scratch buffer, shared by sort.cu and the fused mechanics kernel
+// (which can pre-bin the cells for the NEXT sort while it integrates them).
+#pragma once
+#include "scan.cuh"
+
+namespace abm {
+
+struct SortWs {
+    int *rank;        // n   : arrival order of the cell inside its bin (atomicAdd return value, not stable)
+    int *cell_bin;    // n   : linear bin of cell i
+    int *tmp_id;      // n   : unstable placement (stable mode only)
+    int *block_sums;  // scan scratch
+};
+
+inline size_t sort_align(size_t v) { return (v + 255) & ~size_t(255); }
+
+inline size_t sort_ws_bytes(int64_t n, int64_t nbins) {
+    return 3 * sort_align((size_t)n * 4) + sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4) + 256;
+}
+
+inline SortWs sort_ws_carve(void *ws, int64_t n, int64_t nbins) {
+    char *p = (char *)ws;
+    SortWs w;
+    w.rank = (int *)p;       p += sort_align((size_t)n * 4);
+    w.cell_bin = (int *)p;   p += sort_align((size_t)n * 4);
+    w.tmp_id = (int *)p;     p += sort_align((size_t)n * 4);
+    w.block_sums = (int *)p;
+    (void)nbins;
+    return w;
+}
+
+// Bin lattice of a sort.  A flat world (extent_z == 0, the reference's 2-D runs) gets ONE z layer instead of the
+// reference's three (two of which are always empty): every cell is a stencil candidate of its (x,y) neighbours
+// whatever its z, and the distance predicate is exact, so the result is unchanged and the offset table is 3x
+// shorter.  ABM_SORT_REFERENCE keeps the reference's lattice (what assign_bins() returns).
+inline int make_bin_geom(const double extent[3], const double *origin, double distance, int flags, BinGeom &g,
+                         int64_t &nbins) {
+    if (!(distance > 0)) return -1;
+    g.distance = distance;
+    nbins = 1;
+    for (int k = 0; k < 3; ++k) {
+        g.origin[k] = origin ? origin[k] : 0.0;
+        g.dims[k] = (int)ceil(extent[k] / distance) + 3;
+        if (k == 2 && extent[2] == 0.0 && !(flags & ABM_SORT_REFERENCE)) g.dims[k] = 1;
+        nbins *= g.dims[k];
+    }
+    return nbins < (int64_t)0x7fffffff ? 0 : -1;
+}
+
+__device__ __forceinline__ int cell_bin_of(double x, double y, double z, const BinGeom &g) {
+    return lin_bin(bin_coord(x - g.origin[0], g.distance, g.dims[0]), bin_coord(y - g.origin[1], g.distance, g.dims[1]),
+                   bin_coord(z - g.origin[2], g.distance, g.dims[2]), g.dims);
+}
+
+}  // namespace abm

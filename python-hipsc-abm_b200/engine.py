@@ -152,19 +152,21 @@ class ColonyEngine:
         self._origin_c = _lib.d3(self.bin_origin)
         self._extent_c = _lib.d3(self.bin_extent)
 
-    def bin_dims(self, distance):
+    def bin_dims(self, distance, flags=0):
         dims = (C.c_int32 * 3)()
-        _lib.check(self.lib.abm_bin_dims_host(self._extent_c, float(distance), dims), "abm_bin_dims_host")
+        _lib.check(self.lib.abm_bin_dims_host(self._extent_c, float(distance), int(flags), dims),
+                   "abm_bin_dims_host")
         return tuple(int(d) for d in dims)
 
-    def _sort_buffers(self, distance):
+    def _sort_buffers(self, distance, flags=0):
         n = self.n
-        dims = self.bin_dims(distance)
+        dims = self.bin_dims(distance, flags)
         nbins = dims[0] * dims[1] * dims[2]
         b = self._sort_bufs.get(nbins)
         if b is None or b["cap"] < n:
             cap = max(int(1.1 * n) + 1024, 1)
-            b = dict(cap=cap, bin_start=self._empty(nbins + 1, torch.int32), sorted_id=self._empty(cap, torch.int32),
+            b = dict(cap=cap, bin_start=self._empty(nbins + 1, torch.int32),
+                     bin_start_b=self._empty(nbins + 1, torch.int32), sorted_id=self._empty(cap, torch.int32),
                      sorted_pos=self._empty((cap, 4), torch.float64), sorted_bin=self._empty(cap, torch.int32),
                      max_count=self._empty(1, torch.int32))
             if len(self._sort_bufs) > 4:
@@ -175,15 +177,16 @@ class ColonyEngine:
             self._sort_ws = self._empty(int(1.1 * need) + 4096, torch.uint8)
         return dims, nbins, b
 
-    def sort(self, distance) -> SortState:
-        """Counting sort of the current locations into bins of edge `distance` (abm_bin_sort)."""
+    def sort(self, distance, flags=0) -> SortState:
+        """Counting sort of the current locations into bins of edge `distance` (abm_bin_sort).
+        flags: _lib.SORT_STABLE | _lib.SORT_REFERENCE for the reference-shaped assign_bins() output."""
         n = self.n
-        dims, nbins, b = self._sort_buffers(distance)
+        dims, nbins, b = self._sort_buffers(distance, flags)
         _lib.check(self.lib.abm_bin_sort(_ptr(self.loc), _ptr(self.radii), n, self._extent_c, self._origin_c,
-                                         float(distance), _ptr(b["bin_start"]), _ptr(b["sorted_id"]),
+                                         float(distance), int(flags), _ptr(b["bin_start"]), _ptr(b["sorted_id"]),
                                          _ptr(b["sorted_pos"]), _ptr(b["sorted_bin"]), _ptr(b["max_count"]),
                                          _ptr(self._sort_ws), self._sort_ws.numel(), self.stream), "abm_bin_sort")
-        self.launches += 5 if n else 0
+        self.launches += (5 if flags & _lib.SORT_STABLE else 4) if n else 0
         return SortState(float(distance), dims, nbins, n, b["bin_start"], b["sorted_id"], b["sorted_pos"],
                          b["sorted_bin"], b["max_count"])
 
@@ -320,14 +323,14 @@ class ColonyEngine:
         _lib.check(self.lib.abm_mechanics_loop(
             _ptr(self.radii), _ptr(self.loc), _ptr(self.mot), n, self._extent_c, self._origin_c, self._size_c,
             float(distance), reach, len(dts), dts_c,
-            _ptr(sb["bin_start"]), _ptr(sb["sorted_id"]), _ptr(sb["sorted_pos"]), _ptr(sb["sorted_bin"]),
-            _ptr(sb["max_count"]), _ptr(self._sort_ws), self._sort_ws.numel(),
+            _ptr(sb["bin_start"]), _ptr(sb["bin_start_b"]), _ptr(sb["sorted_id"]), _ptr(sb["sorted_pos"]),
+            _ptr(sb["sorted_bin"]), _ptr(sb["max_count"]), _ptr(self._sort_ws), self._sort_ws.numel(),
             _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
             _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),
-            stride, _ptr(b["max_len"]), 1, _ptr(self.global_id), JKR_POISSON, JKR_YOUNGS, JKR_ADHESION,
+            stride, _ptr(b["max_len"]), _ptr(self.global_id), JKR_POISSON, JKR_YOUNGS, JKR_ADHESION,
             float(stokes), self.stream), "abm_mechanics_loop")
-        self.launches += 6 * len(dts) if n else 0
+        self.launches += (4 * len(dts) + 1) if n else 0      # [scan x2, scatter, substep] per substep + 1 histogram
         last = pair[(len(dts) - 1) & 1]
         return GraphTensors(n, None, stride, b["len"][last], b["cols"][last], True)
 

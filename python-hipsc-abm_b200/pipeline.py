@@ -126,6 +126,7 @@ class HotPathStep:
                 self.enqueue()
             self.graphs.append(g)
         # capturing enqueues nothing on the device: undo the launch accounting, and the state did not advance
+        self.eng.use_current_stream()         # leave the capture stream
         self.eng.launches = launches
         self.parity = 0
         b = self.eng._bond_buffers(self.eng.n, self.cfg.bond_stride)

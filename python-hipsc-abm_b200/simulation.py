@@ -73,8 +73,9 @@ class B200Simulation:
     def assign_bins(self, max_agents, distance):
         """reference simulation.py:190-223.  Returns the reference-shaped (bins, bins_help, bin_locations,
         max_agents) as numpy arrays; capacity follows the reference's rule (double the worst bin)."""
+        from . import _lib
         eng = self.b200_upload()
-        srt = eng.sort(distance)
+        srt = eng.sort(distance, _lib.SORT_STABLE | _lib.SORT_REFERENCE)
         worst = eng.read_i32(srt.max_count)
         if max_agents < worst:
             max_agents = worst * 2

@@ -50,14 +50,16 @@ def test_host_helpers_need_no_gpu(built):
     from hipsc_abm_b200 import _lib
     lib = _lib.load()
     dims = (ctypes.c_int32 * 3)()
-    assert lib.abm_bin_dims_host(_lib.d3([2000, 2000, 0]), 15.0, dims) == 0
+    assert lib.abm_bin_dims_host(_lib.d3([2000, 2000, 0]), 15.0, _lib.SORT_REFERENCE, dims) == 0
     assert list(dims) == list(np.ceil(np.array([2000, 2000, 0]) / 15).astype(int) + 3)   # simulation.py:202
+    assert lib.abm_bin_dims_host(_lib.d3([2000, 2000, 0]), 15.0, 0, dims) == 0
+    assert list(dims) == [137, 137, 1]             # a flat world needs one z layer, not the reference's three
     # bond reach for two r=5 cells = the break distance probed in SURVEY 3.3 (10.31001 um)
     reach = lib.abm_jkr_reach(10.0, 5.0, 0.5, 1000.0, 0.000107)
     assert abs(reach - 10.31001) < 1e-4
     assert lib.abm_jkr_reach(15.0, 5.0, 0.5, 1000.0, 0.000107) >= 15.0
     # invalid arguments come back as negative codes with a message, never as exceptions from C
-    assert lib.abm_bin_dims_host(_lib.d3([1, 1, 1]), -1.0, dims) == -1
+    assert lib.abm_bin_dims_host(_lib.d3([1, 1, 1]), -1.0, 0, dims) == -1
     assert b"distance" in lib.abm_last_error()
     assert lib.abm_bin_sort_workspace_bytes(1000, 5000) > 3 * 4000
 

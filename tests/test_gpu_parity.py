@@ -72,7 +72,8 @@ def test_sort_is_a_stable_permutation():
     loc, radii, size = colony(3, 20000, 2)
     eng = ColonyEngine(size)
     eng.upload(loc, radii)
-    s = eng.sort(10.0)
+    from hipsc_abm_b200 import _lib
+    s = eng.sort(10.0, _lib.SORT_STABLE)
     n = len(loc)
     sid = s.sorted_id[:n].cpu().numpy()
     assert np.array_equal(np.sort(sid), np.arange(n))
@@ -85,6 +86,13 @@ def test_sort_is_a_stable_permutation():
     pos = s.sorted_pos[:n].cpu().numpy()
     assert np.array_equal(pos[:, :3], loc[sid]) and np.array_equal(pos[:, 3], radii[sid])
     assert eng.read_i32(s.max_count) == np.diff(start).max()
+    # the fast placement is the same permutation up to the order inside a bin
+    f = eng.sort(10.0)
+    fid = f.sorted_id[:n].cpu().numpy()
+    assert np.array_equal(np.sort(fid), np.arange(n))
+    assert np.array_equal(f.bin_start.cpu().numpy(), start)
+    assert np.array_equal(f.sorted_bin[:n].cpu().numpy(), sbin)
+    assert np.array_equal(f.sorted_pos[:n].cpu().numpy()[:, :3], loc[fid])
 
 
 # ---- a3/a4/a5 ---------------------------------------------------------------------------------------------
