@@ -288,7 +288,7 @@ def run_b200(args, rank, world, local_rank):
             n, _l.i3(srt.dims), cfg.contact_radius, reach, 0, old.row_stride, old.row_len.data_ptr(),
             old.cols.data_ptr(), b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride,
             b["max_len"].data_ptr(), eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0,
-            _l.d3(wl["size"]), 180.0, 0, None, None, 0, 0, eng.stream), "abm_jkr_substep")
+            _l.d3(wl["size"]), 180.0, 0, eng.uniform_radius, None, None, 0, 0, eng.stream), "abm_jkr_substep")
 
     def time_launches(cold, reps=20):
         out = []
@@ -408,7 +408,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     without further communication, and one morphogen-row exchange, over NCCL send/recv."""
     import torch
     from hipsc_abm_b200 import slab
-    from hipsc_abm_b200.pipeline import SlabPipeline
+    from hipsc_abm_b200.pipeline import NativeSlabOps, SlabPipeline
 
     spec, n = wl["spec"], wl["n"]
     side = wl["size"][0]
@@ -431,8 +431,10 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     fabric = slab.DistFabric(rank, world, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    ops = NativeSlabOps(pipe.eng)
+
     def step():
-        slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None)
+        slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None, ops)
 
     for _ in range(max(args.warmup, 3)):
         step()

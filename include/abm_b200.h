@@ -136,6 +136,8 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  *   global_id        : NULL, or (n) int32 ids to write into / look up in the bond rows instead of the cell
  *                      index (a slab-decomposed colony keeps its bonds by global id; rows still belong to the
  *                      local cell index).
+ *   uniform_radius   : the common radius if all radii are equal (the contact constants are then evaluated once
+ *                      on the host), else 0.
  *   next_bin_counts  : NULL, or a zeroed (nbins+1) table (not bin_start): the kernel then also bins every moved
  *                      cell on the lattice (next_origin, next_extent, edge `reach`) and leaves histogram,
  *                      bin and rank where abm_bin_sort(ABM_SORT_PREBINNED, same workspace) expects them.
@@ -151,7 +153,7 @@ int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const do
                     const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len, int32_t *new_cols,
                     int64_t row_stride, int32_t *max_len, const double *motility_forces, double *locations,
                     double poisson, double youngs, double adhesion_const, double stokes,
-                    const double size_host[3], double move_dt, const int32_t *global_id,
+                    const double size_host[3], double move_dt, const int32_t *global_id, double uniform_radius,
                     const double *next_extent_host, const double *next_origin_host, int32_t *next_bin_counts,
                     void *next_sort_workspace, void *stream);
 
@@ -168,8 +170,8 @@ int abm_mechanics_loop(const double *radii, double *locations, const double *mot
                        int32_t *sorted_bin, int32_t *max_count, void *sort_workspace, size_t sort_workspace_bytes,
                        const int32_t *old_row_start, int64_t old_row_stride, const int32_t *old_row_len,
                        const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
-                       int64_t row_stride, int32_t *max_len, const int32_t *global_id, double poisson,
-                       double youngs, double adhesion_const, double stokes, void *stream);
+                       int64_t row_stride, int32_t *max_len, const int32_t *global_id, double uniform_radius,
+                       double poisson, double youngs, double adhesion_const, double stokes, void *stream);
 
 /* ---- morphogen diffusion ---------------------------------------------------------------------------
  * Replaces CellMethods.update_diffusion + update_diffusion_jit (cell_methods.py:441-468,
@@ -197,6 +199,31 @@ int abm_sample_concentrations(const double *locations, int64_t n, const double *
 int abm_deposit_morphogens(const double *locations, const double *amounts, int64_t n, double *field,
                            const int64_t gsize_host[3], double spat_res, int64_t row_lo, int64_t row_hi,
                            void *stream);
+
+/* ---- slab decomposition plumbing (no reference counterpart; see hipsc_abm_b200/slab.py) -------------------
+ * A cell travels between ranks as one byte record:
+ *   [0,24) position  [24,32) radius  [32,56) motility force  [56,60) global id  [60,64) bond_len
+ *   [64,64+4*row_stride) bond row (global ids).
+ * abm_slab_pack writes, in cell order, the records of the owned cells with x < x_send_left (to the left
+ * neighbour) and with x >= x_send_right (to the right one); counts (2) int32 receives the two record counts
+ * (records beyond a capacity are dropped: the caller compares and retries with larger buffers).
+ * abm_slab_merge partitions the n_own owned cells followed by the n_received records into
+ * [cells owned after the exchange | halo cells] -- owned iff x in [x_lo,x_hi) (open towards a missing
+ * neighbour) -- keeping input order inside each part, and writes them to the out_* arrays (capacity
+ * n_own + n_received); n_owned_out (1) int32 receives the size of the first part.
+ * workspace: abm_slab_workspace_bytes(n) with n = n_own resp. n_own + n_received.  No host synchronisation. */
+size_t abm_slab_workspace_bytes(int64_t n);
+int abm_slab_pack(const double *locations, const double *radii, const double *motility_forces,
+                  const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t n_own,
+                  int64_t row_stride, double x_send_left, double x_send_right, int has_left, int has_right,
+                  uint8_t *records_left, int64_t capacity_left, uint8_t *records_right, int64_t capacity_right,
+                  int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
+int abm_slab_merge(const double *locations, const double *radii, const double *motility_forces,
+                   const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t n_own,
+                   const uint8_t *received, int64_t n_received, int64_t row_stride, double x_lo, double x_hi,
+                   int has_left, int has_right, double *out_locations, double *out_radii, double *out_motility,
+                   int32_t *out_global_id, int32_t *out_bond_len, int32_t *out_bond_rows, int32_t *n_owned_out,
+                   void *workspace, size_t workspace_bytes, void *stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libabm_b200.so")
+LIB_PATH = os.environ.get("ABM_B200_LIB") or os.path.join(_HERE, "libabm_b200.so")   # env: kernel A/B builds
 
 P = C.c_void_p          # device pointer / stream
 I64 = C.c_int64
@@ -37,12 +37,15 @@ SIGNATURES = {
     "abm_apply_forces": (I32, [P, P, P, P, I64, F64, D3, F64, P, P]),
     "abm_jkr_reach": (F64, [F64, F64, F64, F64, F64]),
     "abm_jkr_substep": (I32, [P, P, P, P, I64, I3, F64, F64, P, I64, P, P, P, P, I64, P, P, P,
-                              F64, F64, F64, F64, D3, F64, P, D3, D3, P, P, P]),
+                              F64, F64, F64, F64, D3, F64, P, F64, D3, D3, P, P, P]),
     "abm_mechanics_loop": (I32, [P, P, P, I64, D3, D3, D3, F64, F64, I32, C.POINTER(C.c_double),
                                  P, P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, P,
-                                 F64, F64, F64, F64, P]),
+                                 F64, F64, F64, F64, F64, P]),
     "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),
     "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P]),
+    "abm_slab_workspace_bytes": (SZ, [I64]),
+    "abm_slab_pack": (I32, [P, P, P, P, P, P, I64, I64, F64, F64, I32, I32, P, I64, P, I64, P, P, SZ, P]),
+    "abm_slab_merge": (I32, [P, P, P, P, P, P, I64, P, I64, I64, F64, F64, I32, I32, P, P, P, P, P, P, P, P, SZ, P]),
     "abm_deposit_morphogens": (I32, [P, P, I64, P, L3, F64, I64, I64, P]),
 }
 

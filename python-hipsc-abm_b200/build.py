@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabm_b200.so")
-SOURCES = ["lib.cu", "sort.cu", "search.cu", "jkr.cu", "diffusion.cu"]
+SOURCES = ["lib.cu", "sort.cu", "search.cu", "jkr.cu", "diffusion.cu", "slab.cu"]
 
 
 def nvcc_path():
@@ -27,14 +27,16 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines/out: build a variant library with -D switches (kernel A/B experiments, scripts/ab_substep.py)."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), "-shared", "-o", LIB, "-O3", "-std=c++17", "-lineinfo",
+    cmd = [nvcc_path(), "-shared", "-o", out or LIB, "-O3", "-std=c++17", "-lineinfo",
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-Xptxas", "-v" if verbose else "-warn-spills"] + [os.path.join(CSRC, s) for s in SOURCES]
     # the image's CC wrapper lacks pieces nvcc's host pass wants; use the distro g++ explicitly
+    cmd += ["-D" + d for d in defines]
     if os.path.exists("/usr/bin/g++"):
         cmd[1:1] = ["-ccbin", "/usr/bin/g++"]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -42,7 +44,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

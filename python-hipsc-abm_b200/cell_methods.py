@@ -46,7 +46,7 @@ class B200CellMethods:
                  getattr(type(self).get_neighbors, "__wrapped__", None) is
                  getattr(B200Simulation.get_neighbors, "__wrapped__", None))
         if fused:
-            eng = self.b200_upload(with_forces=True)
+            eng = self.b200_upload(with_forces="motility")
             graph = self.jkr_graph
             old = graph.device_tensors(eng)
             bonds, graph.row_stride_hint = eng.mechanics(old, distance, dts, graph.row_stride_hint, STOKES)

@@ -40,6 +40,7 @@ inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 // ---- bin geometry --------------------------------------------------------------------------------
 struct BinGeom {
     double distance;
+    double inv_distance;
     double origin[3]; // lattice origin (0 for a whole colony; the slab's lower corner for a slab-decomposed one)
     int dims[3];      // ceil(extent/distance)+3 per axis (reference simulation.py:202)
 };
@@ -55,11 +56,27 @@ __device__ __forceinline__ double exact_floor_div(double a, double b) {
     return q;
 }
 
+// Same result without the division: the estimate floor(a * (1/b)) is off by at most one for the magnitudes that
+// occur (|a/b| < 2^31), and the exact FMA remainder corrects it in either direction.
+__device__ __forceinline__ double exact_floor_mul(double a, double b, double inv_b) {
+    double q = floor(a * inv_b);
+    double r = fma(-q, b, a);
+    if (r < 0.0) q -= 1.0;
+    else if (r >= b) q += 1.0;
+    return q;
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 // bin coordinate of one axis, clamped into the allocated lattice
 __device__ __forceinline__ int bin_coord(double x, double distance, int dim) {
     return clampi((int)exact_floor_div(x, distance) + 1, 0, dim - 1);
+}
+__device__ __forceinline__ int bin_coord_fast(double x, double distance, double inv_distance, int dim) {
+    // |x/distance| beyond int range cannot occur for finite colonies; clamp first to keep the cast defined
+    double q = exact_floor_mul(x, distance, inv_distance);
+    q = fmin(fmax(q, -2.0), 2147483000.0);
+    return clampi((int)q + 1, 0, dim - 1);
 }
 
 __device__ __forceinline__ int lin_bin(int bx, int by, int bz, const int dims[3]) {
@@ -84,8 +101,10 @@ struct Radius {
     __device__ __forceinline__ bool within(double s) const {
         if (s <= lo) return true;
         if (s > hi) return false;
-        return __dsqrt_rn(s) <= d;
+        return tie(s, d);
     }
+    // out of line on purpose: inlined, the compiler if-converts it and every candidate pays for the square root
+    static __device__ __noinline__ bool tie(double s, double dist) { return __dsqrt_rn(s) <= dist; }
 };
 
 // ---- warp helpers ----------------------------------------------------------------------------------
@@ -118,9 +137,11 @@ struct JkrConst {
     double k23;        // ((pi*adhesion)/e_hat)^(2/3)
     double pi_adh;     // pi*adhesion is applied as (f*pi)*adhesion in the reference; kept separate below
     double adhesion;
+    // the radius-dependent factors for a colony whose radii all equal uni_r (0 = radii differ)
+    double uni_r, uni_inv_scale, uni_force_scale;
 };
 
-__host__ JkrConst make_jkr_const(double poisson, double youngs, double adhesion);
+__host__ JkrConst make_jkr_const(double poisson, double youngs, double adhesion, double uniform_radius);
 
 // Returns true if the bond survives; fx,fy,fz = force on the cell at p from the cell at q.
 // v = p - q, s = |v|^2 (no-FMA sum of squares), rp/rq radii in um.

@@ -68,6 +68,7 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 
 // ---- fused: search(distance, union with old bonds) + JKR + bond breaking + integration ---------------
 // Two phases per thread, to keep the warp converged while it does the expensive fp64 contact math:
+//   0. the block stages the bin tiles its 128 cells can touch (3 or 9 contiguous slot ranges) in shared memory;
 //   1. walk the bin stencil with the cheap test |p-q|^2 <= reach^2 and park what passes -- partner id and
 //      slot, the partners of the thin hysteresis shell flagged -- in per-thread columns of shared memory;
 //   2. order the parked partners by id and run the contact model over them.  All lanes run this loop together
@@ -75,9 +76,22 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 //      iteration of the stencil walk; and because the sum runs in ascending partner id -- the serial
 //      reference's += order -- the result does not depend on how the sort happened to order a bin.
 // While it integrates a cell the kernel can also pre-bin it for the NEXT substep's sort (histogram + rank).
+#ifndef ABM_JKR_TILES
+#define ABM_JKR_TILES 0          // stage the candidate bin tiles in shared memory
+#endif
+#ifndef ABM_JKR_PREFETCH_OLD
+#define ABM_JKR_PREFETCH_OLD 0   // copy the previous bond row to shared memory before the stencil walk
+#endif
+#ifndef ABM_JKR_PREFETCH_MOT
+#define ABM_JKR_PREFETCH_MOT 1   // load the motility force before the stencil walk
+#endif
+#ifndef ABM_JKR_MINBLOCKS
+#define ABM_JKR_MINBLOCKS 6      // register cap: 6 -> 80/thread, 5 -> 96, 8 -> 64
+#endif
 constexpr int kMaxHits = 16;
-constexpr int kJkrMinBlocks = 6;     // cap registers at 80/thread: the kernel is latency bound, occupancy matters
+constexpr int kJkrMinBlocks = ABM_JKR_MINBLOCKS;
 constexpr int kShellFlag = 0x40000000;
+constexpr int kMaxOld = 8;
 
 struct BondEval {
     // radius-dependent part of the contact model, memoised on the partner radius (radii are usually uniform).
@@ -87,6 +101,15 @@ struct BondEval {
     // from the reference only for |d + 0.360562| < 1e-15 (never observed; both ends of a pair use the same
     // expression, so the two rows of a bond always agree).
     double memo_r, inv_scale, force_scale, rsum;
+    __device__ __forceinline__ void preset(const JkrConst &c, double rp) {
+        memo_r = -1.0;
+        if (rp == c.uni_r) {                 // colony of equal radii: the host evaluated the model once
+            memo_r = c.uni_r;
+            inv_scale = c.uni_inv_scale;
+            force_scale = c.uni_force_scale;
+            rsum = c.uni_r + c.uni_r;
+        }
+    }
     __device__ __forceinline__ void refresh(double rp, double rq, const JkrConst &c) {
         if (rq != memo_r) {
             const double kPi = 3.141592653589793;
@@ -110,12 +133,44 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
-              double stokes, Box box, double dt, const int *__restrict__ gid_of, NextSort next) {
+              double stokes, Box box, double dt, const int *__restrict__ gid_of, NextSort next, int tile_cap) {
     __shared__ int hit_slot[kMaxHits][kJkrThreads];     // sorted slot of a parked partner (| kShellFlag)
     __shared__ int hit_id[kMaxHits][kJkrThreads];       // its id as written into bond rows
+    __shared__ int old_row[ABM_JKR_PREFETCH_OLD ? kMaxOld : 1][kJkrThreads];   // previous bond row (hysteresis lookups)
+    __shared__ int tile_lo[9], tile_n[9];               // slot range staged for each (dz,dy) row of the stencil
+    extern __shared__ double4 tile[];                   // rows x tile_cap candidate {x,y,z,r}
     const int tid = threadIdx.x;
     int s = blockIdx.x * kJkrThreads + tid;
     int cnt = 0;
+
+    // ---- stage the bin tiles: the 128 consecutive slots of this block span the linear bins [b_first, b_last];
+    // every candidate of every thread lies in one of the rows (dz,dy) of bins [b_first-1, b_last+1] shifted by the
+    // row offset -- a contiguous slot range each, copied once, coalesced, into shared memory.
+    const int nz = st.dims[2] == 1 ? 1 : 3;
+    const int rows = 3 * nz;
+    if (ABM_JKR_TILES) {
+        const int s_last = min(blockIdx.x * kJkrThreads + kJkrThreads, n) - 1;
+        if (tid < rows) {
+            int b_first = sorted_bin[blockIdx.x * kJkrThreads], b_last = sorted_bin[s_last];
+            int dz = nz == 1 ? 0 : tid / 3 - 1, dy = tid % 3 - 1;
+            long long off = ((long long)dz * st.dims[1] + dy) * st.dims[0];
+            long long nbins = (long long)st.dims[0] * st.dims[1] * st.dims[2];
+            long long lo_bin = max(b_first + off - 1, 0LL), hi_bin = min(b_last + off + 1, nbins - 1);
+            int lo = 0, cntb = 0;
+            if (lo_bin <= hi_bin) {
+                lo = bin_start[lo_bin];
+                cntb = min(bin_start[hi_bin + 1] - lo, tile_cap);
+            }
+            tile_lo[tid] = lo;
+            tile_n[tid] = cntb;
+        }
+        __syncthreads();
+        for (int r = 0; r < rows; ++r) {
+            int lo = tile_lo[r], cntb = tile_n[r];
+            for (int k = tid; k < cntb; k += kJkrThreads) tile[r * tile_cap + k] = spos[lo + k];
+        }
+        __syncthreads();
+    }
     if (s < n) {
         int i = sorted_id[s];
         double4 p = spos[s];
@@ -124,7 +179,19 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         int *row = new_cols + (long long)i * stride;
         double fx = 0.0, fy = 0.0, fz = 0.0;
         BondEval ev;
-        ev.memo_r = -1.0;
+        ev.preset(c, p.w);
+        // loads whose latency the stencil walk will hide: the motility force and the previous bond row
+        long long a3 = 3 * (long long)i;
+#if ABM_JKR_PREFETCH_MOT
+        const double mx = mot[a3 + 0], my = mot[a3 + 1], mz = mot[a3 + 2];
+#endif
+        int olen = 0;
+        if (ABM_JKR_PREFETCH_OLD && old.valid()) {
+            long long os = old.start(i);
+            olen = old.row_len[i];
+            int keep = min(olen, kMaxOld);
+            for (int k = 0; k < keep; ++k) old_row[k][tid] = old.cols[os + k];
+        }
 
         // the id bond rows are written in: the cell index, or its global id when the colony is slab-decomposed
         auto partner_id = [&](int t) {
@@ -134,10 +201,19 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         // membership of j in this cell's previous bond row; every entry is read (no early exit) so the
         // loads are independent and overlap
         auto was_bonded = [&](int j) {
-            long long os = old.start(i);
-            int olen = old.row_len[i];
             bool found = false;
-            for (int k = 0; k < olen; ++k) found |= (old.cols[os + k] == j);
+            if (ABM_JKR_PREFETCH_OLD) {
+                int keep = min(olen, kMaxOld);
+                for (int k = 0; k < keep; ++k) found |= (old_row[k][tid] == j);
+                if (olen > kMaxOld) {                          // very long row: the tail stays in global memory
+                    long long os = old.start(i);
+                    for (int k = kMaxOld; k < olen; ++k) found |= (old.cols[os + k] == j);
+                }
+            } else {
+                long long os = old.start(i);
+                int len = old.row_len[i];
+                for (int k = 0; k < len; ++k) found |= (old.cols[os + k] == j);
+            }
             return found;
         };
         // contact model for one bond candidate
@@ -183,11 +259,13 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
             for (int r = 0; r < 3; ++r) {
                 int lo = run_lo[r], cntr = run_n[r];
                 if (cntr <= 0) continue;
-                double4 q = spos[lo];
+                const int row = (nz == 1 ? 0 : (dz + 1) * 3) + r;
+                const double4 *trow = tile + row * tile_cap;
+                const int base = ABM_JKR_TILES ? tile_lo[row] : 0, staged = ABM_JKR_TILES ? tile_n[row] : 0;
                 for (int u = 0; u < cntr; ++u) {
                     int t = lo + u;
-                    double4 qn = q;
-                    if (u + 1 < cntr) qn = spos[t + 1];
+                    int o = t - base;
+                    double4 q = (ABM_JKR_TILES && o >= 0 && o < staged) ? trow[o] : spos[t];   // else: global
                     double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
                     if (s2 <= reach2 && t != s) {             // no bond can survive beyond the reach
                         bool inside = rad.within(s2);
@@ -203,7 +281,6 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                             }
                         }
                     }
-                    q = qn;
                 }
             }
         }
@@ -232,11 +309,13 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         new_len[i] = kept;
         if (crowded) insertion_sort(row, kept);               // rows are ascending in every case
         // integration (reference cell_backend.py:155-170); positions are read from the sorted snapshot only
+#if !ABM_JKR_PREFETCH_MOT
+        const double mx = mot[a3 + 0], my = mot[a3 + 1], mz = mot[a3 + 2];
+#endif
         double friction = stokes_friction(p.w, stokes);
-        long long a3 = 3 * (long long)i;
-        double nx = stokes_move(p.x, mot[a3 + 0], fx, friction, dt, box.size[0]);
-        double ny = stokes_move(p.y, mot[a3 + 1], fy, friction, dt, box.size[1]);
-        double nz = stokes_move(p.z, mot[a3 + 2], fz, friction, dt, box.size[2]);
+        double nx = stokes_move(p.x, mx, fx, friction, dt, box.size[0]);
+        double ny = stokes_move(p.y, my, fy, friction, dt, box.size[1]);
+        double nz = stokes_move(p.z, mz, fz, friction, dt, box.size[2]);
         loc[a3 + 0] = nx;
         loc[a3 + 1] = ny;
         loc[a3 + 2] = nz;
@@ -263,7 +342,7 @@ ABM_EXPORT int abm_jkr_forces(const int32_t *row_start, int64_t row_stride, int3
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(row_len && locations && radii && jkr_forces, "null pointer");
-    JkrConst c = make_jkr_const(poisson, youngs, adhesion_const);
+    JkrConst c = make_jkr_const(poisson, youngs, adhesion_const, 0.0);
     k_jkr_rows<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
         row_start, (long long)row_stride, row_len, cols, locations, radii, jkr_forces, (int)n, c);
     ABM_CHECK_LAUNCH("k_jkr_rows");
@@ -291,7 +370,7 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
                                int32_t *new_cols, int64_t row_stride, int32_t *max_len,
                                const double *motility_forces, double *locations, double poisson, double youngs,
                                double adhesion_const, double stokes, const double size_host[3], double move_dt,
-                               const int32_t *global_id, const double *next_extent_host,
+                               const int32_t *global_id, double uniform_radius, const double *next_extent_host,
                                const double *next_origin_host, int32_t *next_bin_counts, void *next_sort_workspace,
                                void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
@@ -302,7 +381,7 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
     ABM_REQUIRE(row_stride > 0 && row_stride < (1 << 20), "bad row_stride");
     ABM_REQUIRE(reach >= distance && distance > 0, "reach must be >= distance > 0");
     ABM_REQUIRE(old_cols != new_cols, "old and new bond rows must be different buffers");
-    JkrConst c = make_jkr_const(poisson, youngs, adhesion_const);
+    JkrConst c = make_jkr_const(poisson, youngs, adhesion_const, uniform_radius);
     GraphView old{old_row_start, (long long)old_row_stride, old_row_len, old_cols};
     Stencil stc;
     Box box;
@@ -323,10 +402,22 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
         next.cell_bin = w.cell_bin;
         next.rank = w.rank;
     }
-    k_jkr_substep<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
+    // candidate tiles: 3 stencil rows in a flat world, 9 in 3-D; ~1.5x the mean population of a row
+    const int rows = dims_host[2] == 1 ? 3 : 9;
+    const int tile_cap = rows == 3 ? 192 : 160;
+    const size_t tile_bytes = ABM_JKR_TILES ? (size_t)rows * tile_cap * sizeof(double4) : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        int rc = check_cuda(cudaFuncSetAttribute(k_jkr_substep, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 9 * 160 * (int)sizeof(double4)),
+                            "cudaFuncSetAttribute(k_jkr_substep)");
+        if (rc) return rc;
+        attr_set = true;
+    }
+    k_jkr_substep<<<ceil_div(n, kJkrThreads), kJkrThreads, tile_bytes, as_stream(stream)>>>(
         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
         Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
-        locations, c, stokes, box, move_dt, global_id, next);
+        locations, c, stokes, box, move_dt, global_id, next, tile_cap);
     ABM_CHECK_LAUNCH("k_jkr_substep");
     return 0;
 }
@@ -344,8 +435,8 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                                   size_t sort_workspace_bytes, const int32_t *old_row_start, int64_t old_row_stride,
                                   const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a,
                                   int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
-                                  int32_t *max_len, const int32_t *global_id, double poisson, double youngs,
-                                  double adhesion_const, double stokes, void *stream) {
+                                  int32_t *max_len, const int32_t *global_id, double uniform_radius, double poisson,
+                                  double youngs, double adhesion_const, double stokes, void *stream) {
     ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
     ABM_REQUIRE(extent_host && size_host && bin_start_a && bin_start_b && bin_start_a != bin_start_b,
                 "need two distinct offset tables");
@@ -369,7 +460,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
         rc = abm_jkr_substep(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
                              cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, motility_forces, locations,
-                             poisson, youngs, adhesion_const, stokes, size_host, dts_host[k], global_id,
+                             poisson, youngs, adhesion_const, stokes, size_host, dts_host[k], global_id, uniform_radius,
                              prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
                              prebin ? sort_workspace : nullptr, stream);
         if (rc) return rc;

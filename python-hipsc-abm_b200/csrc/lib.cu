@@ -22,13 +22,22 @@ int check_cuda(cudaError_t e, const char *what) {
     return -(1000 + (int)e);
 }
 
-JkrConst make_jkr_const(double poisson, double youngs, double adhesion) {
+JkrConst make_jkr_const(double poisson, double youngs, double adhesion, double uniform_radius) {
     // reference cell_backend.py:84,88 -- e_hat and the radius-independent factor of overlap_
     double e_hat = 1.0 / (((1 - poisson * poisson) / youngs) + ((1 - poisson * poisson) / youngs));
     JkrConst c;
     c.k23 = pow((M_PI * adhesion) / e_hat, 2.0 / 3.0);
     c.pi_adh = M_PI * adhesion;
     c.adhesion = adhesion;
+    c.uni_r = c.uni_inv_scale = c.uni_force_scale = 0.0;
+    if (uniform_radius > 0) {
+        // reference cell_backend.py:85,88 for r1 == r2 == uniform_radius
+        double r_hat = 1.0 / (1e6 * ((1.0 / uniform_radius) + (1.0 / uniform_radius)));
+        double overlap_ = c.k23 * cbrt(r_hat);
+        c.uni_r = uniform_radius;
+        c.uni_inv_scale = 1.0 / (1e6 * overlap_);
+        c.uni_force_scale = M_PI * adhesion * r_hat;
+    }
     return c;
 }
 
@@ -66,7 +75,7 @@ ABM_EXPORT double abm_jkr_reach(double distance, double max_radius, double poiss
                                 double adhesion_const) {
     // Largest centre distance at which a bond can survive: d > -0.360562 <=> mag < r1+r2+0.360562e6*overlap_
     // with overlap_ = k23*cbrt(r_hat) and r_hat <= max_radius/2e6 (reference cell_backend.py:81-94).
-    abm::JkrConst c = abm::make_jkr_const(poisson, youngs, adhesion_const);
+    abm::JkrConst c = abm::make_jkr_const(poisson, youngs, adhesion_const, 0.0);
     double brk = 2.0 * max_radius + 0.360562e6 * c.k23 * cbrt(max_radius / 2e6);
     double reach = distance > brk ? distance : brk;
     return reach * (1.0 + 1e-9);

@@ -37,6 +37,7 @@ inline int make_bin_geom(const double extent[3], const double *origin, double di
                          int64_t &nbins) {
     if (!(distance > 0)) return -1;
     g.distance = distance;
+    g.inv_distance = 1.0 / distance;
     nbins = 1;
     for (int k = 0; k < 3; ++k) {
         g.origin[k] = origin ? origin[k] : 0.0;
@@ -48,8 +49,9 @@ inline int make_bin_geom(const double extent[3], const double *origin, double di
 }
 
 __device__ __forceinline__ int cell_bin_of(double x, double y, double z, const BinGeom &g) {
-    return lin_bin(bin_coord(x - g.origin[0], g.distance, g.dims[0]), bin_coord(y - g.origin[1], g.distance, g.dims[1]),
-                   bin_coord(z - g.origin[2], g.distance, g.dims[2]), g.dims);
+    return lin_bin(bin_coord_fast(x - g.origin[0], g.distance, g.inv_distance, g.dims[0]),
+                   bin_coord_fast(y - g.origin[1], g.distance, g.inv_distance, g.dims[1]),
+                   bin_coord_fast(z - g.origin[2], g.distance, g.inv_distance, g.dims[2]), g.dims);
 }
 
 }  // namespace abm

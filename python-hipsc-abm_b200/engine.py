@@ -7,6 +7,7 @@ cell_methods.py sit on top of it; bench.py drives it directly for the HBM-reside
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import Optional
 
@@ -67,6 +68,7 @@ class ColonyEngine:
         self.n = 0
         self.loc = self.radii = self.mot = self.jkr = None
         self.max_radius = 0.0
+        self.uniform_radius = 0.0   # common radius when all radii are equal (contact constants evaluated once)
         self.global_id = None   # int32 (n,) when bond rows are kept by global id (slab decomposition)
         self._sort_ws = None
         self._sort_bufs = {}
@@ -79,6 +81,7 @@ class ColonyEngine:
         self.h2d_bytes = 0     # bytes moved by upload()/to_device() and host()/locations_host()
         self.d2h_bytes = 0
         self._pinned = {}
+        self._handed_out = weakref.WeakValueDictionary()   # data pointer -> pinned tensor backing a numpy array
 
     # ------------------------------------------------------------------------------------------------
     def use_current_stream(self):
@@ -94,28 +97,46 @@ class ColonyEngine:
 
     # ---- state -------------------------------------------------------------------------------------
     def to_device(self, array, name=None) -> torch.Tensor:
-        """numpy -> device through a reusable pinned staging buffer (the host arrays of the reference API
-        are pageable numpy; staging keeps the DMA asynchronous and at full PCIe rate)."""
+        """numpy -> device.  The host arrays of the reference API are pageable numpy, so the copy is staged
+        through a reusable pinned buffer (asynchronous DMA at full PCIe rate); arrays this engine handed out
+        itself (host()) already live in pinned memory and are sent as they are."""
         a = np.ascontiguousarray(array)
-        t = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
         self.h2d_bytes += a.nbytes
-        if name is None or a.size == 0:
+        if a.size == 0:
+            return torch.from_numpy(a.copy()).to(self.device)
+        backing = self._handed_out.get(a.ctypes.data)
+        if backing is not None and backing.numel() * backing.element_size() == a.nbytes and \
+                backing.dtype == torch.from_numpy(a[:0].copy()).dtype:
+            return backing.view(a.shape).to(self.device, non_blocking=True)
+        t = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
+        if name is None:
             return t.to(self.device)
-        stage = self._pinned.get(name)
+        stage, busy = self._pinned.get(name, (None, None))
         if stage is None or stage.dtype != t.dtype or stage.numel() < t.numel():
-            stage = torch.empty(max(t.numel(), 1), dtype=t.dtype).pin_memory()
-            self._pinned[name] = stage
+            stage = torch.empty(max(int(1.1 * t.numel()), 1), dtype=t.dtype).pin_memory()
+            busy = None
+        if busy is not None:
+            busy.synchronize()                # the previous DMA out of this staging buffer has finished
         view = stage[:t.numel()].view(t.shape)
         view.copy_(t)
         out = view.to(self.device, non_blocking=True)
-        # the staging buffer may be overwritten by the next upload: order it after this copy
-        torch.cuda.current_stream(self.device).synchronize()
+        busy = torch.cuda.Event()
+        busy.record(torch.cuda.current_stream(self.device))
+        self._pinned[name] = (stage, busy)
         return out
 
     def host(self, t: torch.Tensor) -> np.ndarray:
-        """device -> numpy, counted."""
+        """device -> numpy (counted).  The array is backed by pinned memory, so handing it back to to_device()
+        later needs no staging copy."""
         self.d2h_bytes += t.numel() * t.element_size()
-        return t.cpu().numpy()
+        if t.numel() == 0:
+            return t.cpu().numpy()
+        dst = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        dst.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        arr = dst.numpy()
+        self._handed_out[arr.ctypes.data] = dst
+        return arr
 
     def upload(self, locations, radii, motility=None, jkr=None):
         """Host -> device copy of the agent arrays the path reads (reference dtypes: float64)."""
@@ -127,12 +148,13 @@ class ColonyEngine:
         self.loc = self.to_device(loc, "loc")
         self.radii = self.to_device(rad, "radii")
         self.max_radius = float(rad.max()) if n else 0.0
+        self.uniform_radius = self.max_radius if n and float(rad.min()) == self.max_radius else 0.0
         self.mot = (self.to_device(np.asarray(motility, dtype=np.float64), "mot")
                     if motility is not None else self._zeros((n, 3), torch.float64))
         self.jkr = (self.to_device(np.asarray(jkr, dtype=np.float64), "jkr")
                     if jkr is not None else self._zeros((n, 3), torch.float64))
 
-    def set_device_state(self, loc, radii, mot=None, jkr=None, max_radius=None):
+    def set_device_state(self, loc, radii, mot=None, jkr=None, max_radius=None, uniform_radius=0.0):
         """Adopt tensors that already live on the device (no copies)."""
         self.use_current_stream()
         self.n = int(loc.shape[0])
@@ -140,6 +162,7 @@ class ColonyEngine:
         self.mot = mot if mot is not None else self._zeros((self.n, 3), torch.float64)
         self.jkr = jkr if jkr is not None else self._zeros((self.n, 3), torch.float64)
         self.max_radius = float(max_radius) if max_radius is not None else float(radii.max().item())
+        self.uniform_radius = float(uniform_radius)
 
     def locations_host(self) -> np.ndarray:
         return self.host(self.loc)
@@ -328,8 +351,8 @@ class ColonyEngine:
             _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
             _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),
-            stride, _ptr(b["max_len"]), _ptr(self.global_id), JKR_POISSON, JKR_YOUNGS, JKR_ADHESION,
-            float(stokes), self.stream), "abm_mechanics_loop")
+            stride, _ptr(b["max_len"]), _ptr(self.global_id), float(self.uniform_radius), JKR_POISSON, JKR_YOUNGS,
+            JKR_ADHESION, float(stokes), self.stream), "abm_mechanics_loop")
         self.launches += (4 * len(dts) + 1) if n else 0      # [scan x2, scatter, substep] per substep + 1 histogram
         last = pair[(len(dts) - 1) & 1]
         return GraphTensors(n, None, stride, b["len"][last], b["cols"][last], True)

@@ -235,3 +235,78 @@ class SlabPipeline:
             self.sampled = eng.sample(field.data, field.h, rows=(field.ext_lo, field.ext_hi), grid_rows=field.gx)
         finally:
             eng.n = n_all
+
+
+class NativeSlabOps:
+    """slab.rank_step's select/pack/merge on the device (csrc/slab.cu): two C calls and two small host reads per
+    step instead of a few dozen tensor ops."""
+
+    def __init__(self, engine: ColonyEngine, send_fraction=0.12):
+        self.eng = engine
+        self.lib = engine.lib
+        self.send_cap = 0
+        self.send_fraction = send_fraction
+        self.counts = torch.zeros(2, dtype=torch.int32, device=engine.device)
+        self.n_owned = torch.zeros(1, dtype=torch.int32, device=engine.device)
+        self.ws = None
+
+    def _workspace(self, n):
+        need = int(self.lib.abm_slab_workspace_bytes(int(n)))
+        if self.ws is None or self.ws.numel() < need:
+            self.ws = torch.empty(int(1.2 * need) + 4096, dtype=torch.uint8, device=self.eng.device)
+        return self.ws
+
+    def outgoing(self, state, geom):
+        eng, dev = self.eng, self.eng.device
+        eng.use_current_stream()
+        n, stride, rec = state.n, state.stride, state.record_bytes()
+        ws = self._workspace(n)
+        if self.send_cap == 0:
+            self.send_cap = int(self.send_fraction * n) + 4096
+        while True:
+            cap = self.send_cap
+            out_l = torch.empty((cap, rec), dtype=torch.uint8, device=dev)
+            out_r = torch.empty((cap, rec), dtype=torch.uint8, device=dev)
+            _lib.check(self.lib.abm_slab_pack(
+                state.loc.data_ptr(), state.radii.data_ptr(), state.mot.data_ptr(), state.gid.data_ptr(),
+                state.bond_len.data_ptr(), state.bond_gid.data_ptr(), n, stride, geom.x_lo + geom.halo,
+                geom.x_hi - geom.halo, int(geom.has_left), int(geom.has_right), out_l.data_ptr(), cap,
+                out_r.data_ptr(), cap, self.counts.data_ptr(), ws.data_ptr(), ws.numel(), eng.stream),
+                "abm_slab_pack")
+            eng.launches += 6
+            cl, cr = (int(v) for v in self.counts.tolist())
+            if max(cl, cr) <= cap:
+                break
+            self.send_cap = int(1.25 * max(cl, cr)) + 4096
+        return (out_l[:cl] if geom.has_left else None, out_r[:cr] if geom.has_right else None)
+
+    def merge(self, state, geom, from_l, from_r):
+        from .slab import LocalProblem
+        eng, dev = self.eng, self.eng.device
+        n, stride, rec = state.n, state.stride, state.record_bytes()
+        parts = [m for m in (from_l, from_r) if m is not None and m.shape[0]]
+        if len(parts) == 2:
+            recv = torch.cat(parts, dim=0)
+        elif parts:
+            recv = parts[0].contiguous()
+        else:
+            recv = torch.empty((0, rec), dtype=torch.uint8, device=dev)
+        k = int(recv.shape[0])
+        total = n + k
+        ws = self._workspace(total)
+        f64, i32 = torch.float64, torch.int32
+        loc = torch.empty((total, 3), dtype=f64, device=dev)
+        radii = torch.empty(total, dtype=f64, device=dev)
+        mot = torch.empty((total, 3), dtype=f64, device=dev)
+        gid = torch.empty(total, dtype=i32, device=dev)
+        blen = torch.empty(total, dtype=i32, device=dev)
+        rows = torch.empty((total, stride), dtype=i32, device=dev)
+        _lib.check(self.lib.abm_slab_merge(
+            state.loc.data_ptr(), state.radii.data_ptr(), state.mot.data_ptr(), state.gid.data_ptr(),
+            state.bond_len.data_ptr(), state.bond_gid.data_ptr(), n, recv.data_ptr(), k, stride, geom.x_lo, geom.x_hi,
+            int(geom.has_left), int(geom.has_right), loc.data_ptr(), radii.data_ptr(), mot.data_ptr(),
+            gid.data_ptr(), blen.data_ptr(), rows.data_ptr(), self.n_owned.data_ptr(), ws.data_ptr(), ws.numel(),
+            eng.stream), "abm_slab_merge")
+        eng.launches += 4
+        n_own = eng.read_i32(self.n_owned)
+        return LocalProblem(n_own, loc, radii, mot, gid, blen, rows)

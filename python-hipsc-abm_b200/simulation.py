@@ -53,9 +53,10 @@ class B200Simulation:
         (np.delete, np.concatenate, in-place +=; reference cell_methods.py:39-44, 86-105), so the arrays the
         path reads are re-sent at the start of every public hot-path call."""
         eng = self.b200_engine()
+        want_jkr = with_forces is True            # with_forces="motility": the fused loop never reads jkr_forces
         eng.upload(self.locations, self.radii,
                    self.motility_forces if with_forces and hasattr(self, "motility_forces") else None,
-                   self.jkr_forces if with_forces and hasattr(self, "jkr_forces") else None)
+                   self.jkr_forces if want_jkr and hasattr(self, "jkr_forces") else None)
         return eng
 
     def __getstate__(self):

@@ -256,44 +256,58 @@ class LocalProblem:
     bond_gid: torch.Tensor      # int32 (n_local, stride) global ids
 
 
+class TorchSlabOps:
+    """Selecting / packing / merging with plain torch tensor ops: runs anywhere (the CPU + gloo tests use it) but
+    costs a few dozen small kernels per step; on a GPU use pipeline.NativeSlabOps (csrc/slab.cu)."""
+
+    def outgoing(self, state: SlabState, geom: SlabGeometry):
+        x = state.loc[:, 0]
+        empty = torch.zeros(0, dtype=torch.int64, device=x.device)
+        idx_l = torch.nonzero(x < geom.x_lo + geom.halo).flatten() if geom.has_left else empty
+        idx_r = torch.nonzero(x >= geom.x_hi - geom.halo).flatten() if geom.has_right else empty
+        return (state.pack(idx_l) if geom.has_left else None, state.pack(idx_r) if geom.has_right else None)
+
+    def merge(self, state: SlabState, geom: SlabGeometry, from_l, from_r) -> LocalProblem:
+        stride = state.stride
+        x = state.loc[:, 0]
+        parts = [m for m in (from_l, from_r) if m is not None and m.shape[0]]
+        recv = unpack(torch.cat(parts, dim=0), stride) if parts else None
+        stay = geom.inside(x)
+        if recv is not None:
+            mine = geom.inside(recv["loc"][:, 0])
+            n_leave, n_arrive = (int(v) for v in torch.stack([(~stay).sum(), mine.sum()]).tolist())
+        else:
+            mine, n_leave, n_arrive = None, int((~stay).sum()), 0
+        own = state.fields()
+        if n_leave == 0 and n_arrive == 0:
+            groups = [own] + ([recv] if recv is not None else [])
+            n_own = state.n
+        else:
+            # migration: arrivals become owned, departures stay around as halo cells for this step
+            keep, gone = torch.nonzero(stay).flatten(), torch.nonzero(~stay).flatten()
+            groups = [{f: own[f][keep] for f in FIELDS}]
+            n_own = keep.numel() + n_arrive
+            if recv is not None:
+                arr, rest = torch.nonzero(mine).flatten(), torch.nonzero(~mine).flatten()
+                groups += [{f: recv[f][arr] for f in FIELDS}, {f: recv[f][rest] for f in FIELDS}]
+            groups.append({f: own[f][gone] for f in FIELDS})
+        cat = {f: (torch.cat([g[f] for g in groups], dim=0) if len(groups) > 1 else groups[0][f]) for f in FIELDS}
+        return LocalProblem(n_own, cat["loc"], cat["radii"], cat["mot"], cat["gid"], cat["bond_len"],
+                            cat["bond_gid"])
+
+
 def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProblem], tuple],
-              field: Optional[FieldSlab] = None, field_ops=None):
+              field: Optional[FieldSlab] = None, field_ops=None, ops=None):
     """One simulation step of one rank, written as a generator: it yields
     (tag, (to_left, to_right), width, dtype, fixed_rows) whenever it needs a neighbour exchange and is sent
     (from_left, from_right) back.  `compute(local)` runs the mechanics in place on local.loc and returns the new
     (bond_len, bond_gid) of all local cells.  `field_ops` (if a morphogen field is carried) provides
-    deposit(local, field), diffuse(field) and sample(local, field)."""
-    stride = state.stride
-    x = state.loc[:, 0]
-    empty = torch.zeros(0, dtype=torch.int64, device=x.device)
-    idx_l = torch.nonzero(x < geom.x_lo + geom.halo).flatten() if geom.has_left else empty
-    idx_r = torch.nonzero(x >= geom.x_hi - geom.halo).flatten() if geom.has_right else empty
-    msgs = (state.pack(idx_l) if geom.has_left else None, state.pack(idx_r) if geom.has_right else None)
+    deposit(local, field), diffuse(field) and sample(local, field).  `ops` selects/packs/merges the cells
+    (TorchSlabOps by default, pipeline.NativeSlabOps on a GPU)."""
+    ops = ops or TorchSlabOps()
+    msgs = ops.outgoing(state, geom)
     from_l, from_r = yield ("cells", msgs, state.record_bytes(), torch.uint8, None)
-
-    parts = [m for m in (from_l, from_r) if m is not None and m.shape[0]]
-    recv = unpack(torch.cat(parts, dim=0), stride) if parts else None
-    stay = geom.inside(x)
-    if recv is not None:
-        mine = geom.inside(recv["loc"][:, 0])
-        n_leave, n_arrive = (int(v) for v in torch.stack([(~stay).sum(), mine.sum()]).tolist())
-    else:
-        mine, n_leave, n_arrive = None, int((~stay).sum()), 0
-    own = state.fields()
-    if n_leave == 0 and n_arrive == 0:
-        groups = [own] + ([recv] if recv is not None else [])
-        n_own = state.n
-    else:
-        # migration: arrivals become owned, departures stay around as halo cells for this step
-        keep, gone = torch.nonzero(stay).flatten(), torch.nonzero(~stay).flatten()
-        groups = [{f: own[f][keep] for f in FIELDS}]
-        n_own = keep.numel() + n_arrive
-        if recv is not None:
-            arr, rest = torch.nonzero(mine).flatten(), torch.nonzero(~mine).flatten()
-            groups += [{f: recv[f][arr] for f in FIELDS}, {f: recv[f][rest] for f in FIELDS}]
-        groups.append({f: own[f][gone] for f in FIELDS})
-    cat = {f: (torch.cat([g[f] for g in groups], dim=0) if len(groups) > 1 else groups[0][f]) for f in FIELDS}
-    local = LocalProblem(n_own, cat["loc"], cat["radii"], cat["mot"], cat["gid"], cat["bond_len"], cat["bond_gid"])
+    local = ops.merge(state, geom, from_l, from_r)
 
     blen, bgid = compute(local)
     if field is not None:
@@ -308,9 +322,10 @@ def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProb
     return local
 
 
-def slab_step(state: SlabState, geom: SlabGeometry, fabric: DistFabric, compute, field=None, field_ops=None):
+def slab_step(state: SlabState, geom: SlabGeometry, fabric: DistFabric, compute, field=None, field_ops=None,
+              ops=None):
     """Drive rank_step over torch.distributed."""
-    gen = rank_step(state, geom, compute, field, field_ops)
+    gen = rank_step(state, geom, compute, field, field_ops, ops)
     incoming = None
     try:
         while True:
@@ -320,14 +335,15 @@ def slab_step(state: SlabState, geom: SlabGeometry, fabric: DistFabric, compute,
         return done.value
 
 
-def loopback_step(states, geoms, computes, fields=None, field_ops=None):
+def loopback_step(states, geoms, computes, fields=None, field_ops=None, ops=None):
     """The same step for all ranks emulated in one process (tests; several slabs on one GPU)."""
     world = LoopbackWorld(len(states))
     if callable(computes):
         computes = [computes] * len(states)
     fields = fields or [None] * len(states)
     field_ops = field_ops or [None] * len(states)
-    gens = [rank_step(s, g, c, f, o) for s, g, c, f, o in zip(states, geoms, computes, fields, field_ops)]
+    ops = ops or [None] * len(states)
+    gens = [rank_step(s, g, c, f, o, p) for s, g, c, f, o, p in zip(states, geoms, computes, fields, field_ops, ops)]
     requests = [next(g) for g in gens]
     results = [None] * len(gens)
     while any(r is not None for r in requests):

@@ -1,0 +1,54 @@
+"""A/B timing of k_jkr_substep variants: builds variant libraries (local, needs nvcc) or times one (GPU box).
+  build:  python scripts/ab_substep.py build
+  time:   ABM_B200_LIB=<so> python scripts/ab_substep.py time <workload>"""
+import importlib.util, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VARIANTS = {
+    "base80": ["ABM_JKR_MINBLOCKS=6"],
+    "regs64": ["ABM_JKR_MINBLOCKS=8"],
+    "regs96": ["ABM_JKR_MINBLOCKS=5"],
+    "nomot": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_PREFETCH_MOT=0"],
+    "old80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_PREFETCH_OLD=1"],
+    "tiles80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_TILES=1"],
+    "tiles96": ["ABM_JKR_MINBLOCKS=5", "ABM_JKR_TILES=1", "ABM_JKR_PREFETCH_OLD=1"],
+}
+if sys.argv[1] == "build":
+    spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "python-hipsc-abm_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec); spec.loader.exec_module(b)
+    os.makedirs(os.path.join(ROOT, "build_ab"), exist_ok=True)
+    for name, defs in VARIANTS.items():
+        print(name, b.build(defines=defs, out=os.path.join(ROOT, "build_ab", f"libabm_{name}.so")))
+else:
+    import numpy as np, torch, bench
+    from hipsc_abm_b200 import _lib as _l
+    from hipsc_abm_b200.engine import ColonyEngine
+    from hipsc_abm_b200.pipeline import HotPathStep, StepConfig
+    name = sys.argv[2]
+    wl = bench.make_workload(name); spec = wl["spec"]; n = wl["n"]
+    cfg = StepConfig(grid=None, bond_stride=16 if spec["dim"] == 2 else 32, search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
+    eng = ColonyEngine(wl["size"]); eng.upload(wl["loc"], wl["radii"], wl["mot"])
+    pipe = HotPathStep(eng, cfg)
+    for _ in range(int(sys.argv[3]) if len(sys.argv) > 3 else 4):
+        pipe.step()
+    pipe.check()
+    reach = eng.jkr_reach(10.0); srt = eng.sort(reach); b = eng._bond_bufs; old = pipe.current_bonds()
+    spare = [i for i in range(3) if b["cols"][i].data_ptr() != old.cols.data_ptr()][0]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    def launch():
+        _l.check(eng.lib.abm_jkr_substep(
+            srt.bin_start.data_ptr(), srt.sorted_id.data_ptr(), srt.sorted_pos.data_ptr(), srt.sorted_bin.data_ptr(),
+            n, _l.i3(srt.dims), 10.0, reach, 0, old.row_stride, old.row_len.data_ptr(), old.cols.data_ptr(),
+            b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride, b["max_len"].data_ptr(),
+            eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0, _l.d3(wl["size"]), 180.0, 0,
+            eng.uniform_radius, None, None, 0, 0, eng.stream), "abm_jkr_substep")
+    res = {}
+    for cold in (True, False):
+        ts = []
+        for _ in range(15):
+            flush.zero_() if cold else launch()
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); launch(); z.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(z) * 1e3)
+        res["cold" if cold else "warm"] = float(np.median(ts))
+    print(os.path.basename(os.environ.get("ABM_B200_LIB", "default")), name, res)

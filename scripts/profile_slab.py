@@ -25,8 +25,10 @@ for r, (wl, g) in enumerate(zip(wls, geoms)):
     states.append(slab.SlabState(t(loc), t(wl["radii"]), t(wl["mot"]), t(np.arange(n) + r * n), 16))
 gx = int(np.ceil(gsize[0] / spec["h"])) + 1
 fields = [slab.FieldSlab(g, (gx, wls[0]["grid"][1]), spec["h"], spec["sd"] + 1, dev) for g in geoms]
+from hipsc_abm_b200.pipeline import NativeSlabOps
+ops = [NativeSlabOps(p.eng) for p in pipes] if os.environ.get("NATIVE", "1") == "1" else None
 def step():
-    slab.loopback_step(states, geoms, [p.compute for p in pipes], fields, pipes)
+    slab.loopback_step(states, geoms, [p.compute for p in pipes], fields, pipes, ops)
 for _ in range(3):
     step()
 torch.cuda.synchronize()

@@ -19,8 +19,9 @@ def bonds_as_gid_edges(gid, row_len, cols):
     return orc.canonical_edges(np.stack([np.repeat(gid, row_len), cols[k]], axis=1))
 
 
+@pytest.mark.parametrize("native", [False, True], ids=["torch_ops", "native_ops"])
 @pytest.mark.parametrize("world,dim", [(3, 2), (2, 3)])
-def test_emulated_slabs_match_single_domain(world, dim):
+def test_emulated_slabs_match_single_domain(world, dim, native):
     rng = np.random.default_rng(4)
     if dim == 2:
         size, n = np.array([1500.0, 400.0, 0.0]), 6000
@@ -59,9 +60,11 @@ def test_emulated_slabs_match_single_domain(world, dim):
         states.append(slab.SlabState(t(loc), t(radii), t(mot), torch.from_numpy(np.arange(n)[m]).to(dev), 32))
         pipes.append(SlabPipeline(g, cfg, dev))
         fields.append(slab.FieldSlab(g, grid, h, sd + 1, dev) if grid else None)
+    from hipsc_abm_b200.pipeline import NativeSlabOps
+    ops = [NativeSlabOps(p.eng) for p in pipes] if native else None
     for _ in range(steps):
         slab.loopback_step(states, geoms, [p.compute for p in pipes], fields if grid else None,
-                           pipes if grid else None)
+                           pipes if grid else None, ops)
     for p in pipes:
         p.check()
     gid = torch.cat([s.gid for s in states]).cpu().numpy()
