@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -211,7 +211,7 @@ def run_b200(args, rank, world, local_rank):
     spec = wl["spec"]
     n = wl["n"]
     cfg = StepConfig(grid=wl["grid"], spat_res=spec["h"] or 1.0, diffuse_dt=spec["diffuse_dt"] or 1.0,
-                     diffuse_steps=spec["sd"], bond_stride=16 if spec["dim"] == 2 else 32,
+                     diffuse_steps=spec["sd"], bond_stride=args.bond_stride or (16 if spec["dim"] == 2 else 32),
                      search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
     if world > 1:
         line = run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg)
@@ -230,15 +230,17 @@ def run_b200(args, rank, world, local_rank):
     if pipe.parity:
         pipe.step()
     pipe.capture()
-    for _ in range(max(args.warmup, 3)):
+    sampler = ClockSampler(local_rank)
+    sampler.start()                       # sampled from the warm-up replays to the end of the timed steps
+    for _ in range(max(args.warmup, 3) + 40):           # 40 extra replays: a few 20 ms clock samples under load
         pipe.replay()
     pipe.check()
+    if pipe._replays & 1:
+        pipe.replay()
 
     # ---- value: K graph-replayed steps, each bracketed by events, L2 flushed between steps --------------------
-    sampler = ClockSampler(local_rank)
     launches0 = eng.launches
     barrier()
-    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in evs:
         flush.zero_()
@@ -440,9 +442,11 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         step()
     pipe.check()
     sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    for _ in range(40):                   # a few clock samples under load (a fixed count: ranks stay in lock-step)
+        step()
     launches0, bytes0, ex0 = pipe.eng.launches, fabric.bytes_sent, fabric.exchanges
     barrier()
-    sampler.start()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in evs:
         flush.zero_()
@@ -531,6 +535,7 @@ def main():
                     help="c3 = BASELINE configs[2], the 500k-cell headline colony quoted at 1 and 8 B200 (default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--bond-stride", type=int, default=0, help="fixed width of the JKR bond rows (0 = 16 / 32)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -540,7 +545,16 @@ def main():
     else:
         if world != args.gpus and world == 1 and args.gpus > 1:
             print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU); running 1 GPU", file=sys.stderr)
-        line = run_b200(args, rank, world, local_rank)
+        try:
+            line = run_b200(args, rank, world, local_rank)
+        except Exception as err:
+            # a captured step has fixed buffer sizes; a colony that needs wider bond rows is re-run once with them
+            if world == 1 and "bond rows too narrow" in str(err) and not args.bond_stride:
+                args.bond_stride = 32 if WORKLOADS[args.workload]["dim"] == 2 else 64
+                print(f"bench.py: {err}; re-running with --bond-stride {args.bond_stride}", file=sys.stderr)
+                line = run_b200(args, rank, world, local_rank)
+            else:
+                raise
     if line is not None:
         print(json.dumps(line))
 
