@@ -85,6 +85,9 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 #ifndef ABM_JKR_PREFETCH_MOT
 #define ABM_JKR_PREFETCH_MOT 1   // load the motility force before the stencil walk
 #endif
+#ifndef ABM_JKR_FLATTEN
+#define ABM_JKR_FLATTEN 1        // walk the three runs of a stencil layer in one loop
+#endif
 #ifndef ABM_JKR_MINBLOCKS
 #define ABM_JKR_MINBLOCKS 6      // register cap: 6 -> 80/thread, 5 -> 96, 8 -> 64
 #endif
@@ -255,6 +258,31 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                 run_lo[r] = lo;
                 run_n[r] = ok ? hi - lo : 0;
             }
+            auto test = [&](int t, const double4 &q) {
+                double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
+                if (s2 <= reach2 && t != s) {                 // no bond can survive beyond the reach
+                    bool inside = rad.within(s2);
+                    if (inside || old.valid()) {
+                        int j = partner_id(t);
+                        if (nh < kMaxHits) {
+                            hit_slot[nh][tid] = inside ? t : (t | kShellFlag);
+                            hit_id[nh][tid] = j;
+                            ++nh;
+                        } else {                              // crowded cell: evaluate in place
+                            crowded = true;
+                            if (inside || was_bonded(j)) bond(q, j);
+                        }
+                    }
+                }
+            };
+#if ABM_JKR_FLATTEN
+            // one loop over the three runs of the layer: the warp iterates max(total) times, not sum(max(run))
+            const int n0 = run_n[0], n01 = n0 + run_n[1], tot = n01 + run_n[2];
+            for (int u = 0; u < tot; ++u) {
+                int t = u < n0 ? run_lo[0] + u : (u < n01 ? run_lo[1] + (u - n0) : run_lo[2] + (u - n01));
+                test(t, spos[t]);
+            }
+#else
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 int lo = run_lo[r], cntr = run_n[r];
@@ -265,24 +293,10 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                 for (int u = 0; u < cntr; ++u) {
                     int t = lo + u;
                     int o = t - base;
-                    double4 q = (ABM_JKR_TILES && o >= 0 && o < staged) ? trow[o] : spos[t];   // else: global
-                    double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
-                    if (s2 <= reach2 && t != s) {             // no bond can survive beyond the reach
-                        bool inside = rad.within(s2);
-                        if (inside || old.valid()) {
-                            int j = partner_id(t);
-                            if (nh < kMaxHits) {
-                                hit_slot[nh][tid] = inside ? t : (t | kShellFlag);
-                                hit_id[nh][tid] = j;
-                                ++nh;
-                            } else {                          // crowded cell: evaluate in place
-                                crowded = true;
-                                if (inside || was_bonded(j)) bond(q, j);
-                            }
-                        }
-                    }
+                    test(t, (ABM_JKR_TILES && o >= 0 && o < staged) ? trow[o] : spos[t]);   // else: global
                 }
             }
+#endif
         }
         // order the parked partners by id (a handful of entries in this thread's shared-memory columns)
         for (int a = 1; a < nh; ++a) {

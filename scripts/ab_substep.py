@@ -5,13 +5,10 @@ import importlib.util, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "base80": ["ABM_JKR_MINBLOCKS=6"],
-    "regs64": ["ABM_JKR_MINBLOCKS=8"],
-    "regs96": ["ABM_JKR_MINBLOCKS=5"],
-    "nomot": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_PREFETCH_MOT=0"],
-    "old80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_PREFETCH_OLD=1"],
-    "tiles80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_TILES=1"],
-    "tiles96": ["ABM_JKR_MINBLOCKS=5", "ABM_JKR_TILES=1", "ABM_JKR_PREFETCH_OLD=1"],
+    "base80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=0"],
+    "flat80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=1"],
+    "flat64": ["ABM_JKR_MINBLOCKS=8", "ABM_JKR_FLATTEN=1"],
+    "flatnomot": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=1", "ABM_JKR_PREFETCH_MOT=0"],
 }
 if sys.argv[1] == "build":
     spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "python-hipsc-abm_b200", "build.py"))
