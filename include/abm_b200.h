@@ -129,9 +129,9 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  * Input: a sort of the CURRENT locations made with bin edge >= abm_jkr_reach() (so every bond that
  * can survive lies inside the 27-bin stencil), the bond graph from the previous substep (old_*; rows
  * may be unsorted) and the motility forces.  Output: the new bond graph in fixed-stride rows
- * (row i at new_cols[i*row_stride], length new_row_len[i], ascending) and the moved locations (written in
- * place; the kernel only reads positions from sorted_pos).  The force on a cell is summed in ascending
- * partner id, the serial reference's order, so it does not depend on the order inside the bins.
+ * (row i at new_cols[i*row_stride], length new_row_len[i], ascending if sort_rows) and the moved locations
+ * (written in place; the kernel only reads positions from sorted_pos).  The force on a cell is summed in
+ * 2^-76 N fixed point (integer adds are associative), so it does not depend on the order inside the bins.
  * A bond (i,j) exists afterwards iff (dist <= distance or it existed before) and d > -0.360562.
  *   global_id        : NULL, or (n) int32 ids to write into / look up in the bond rows instead of the cell
  *                      index (a slab-decomposed colony keeps its bonds by global id; rows still belong to the
@@ -151,7 +151,8 @@ int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const do
                     const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
                     double reach, const int32_t *old_row_start, int64_t old_row_stride,
                     const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len, int32_t *new_cols,
-                    int64_t row_stride, int32_t *max_len, const double *motility_forces, double *locations,
+                    int64_t row_stride, int32_t *max_len, int sort_rows, const double *motility_forces,
+                    double *locations,
                     double poisson, double youngs, double adhesion_const, double stokes,
                     const double size_host[3], double move_dt, const int32_t *global_id, double uniform_radius,
                     const double *next_extent_host, const double *next_origin_host, int32_t *next_bin_counts,
@@ -160,7 +161,7 @@ int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const do
 /* The whole substep loop of CellMethods.apply_forces (cell_methods.py:399-436) enqueued by ONE call:
  * n_substeps x [abm_bin_sort at bin edge `reach` over (origin, extent) + abm_jkr_substep with dts_host[k]].
  * Substep 0 reads the bonds old_*; substep k writes row buffer a (k even) or b (k odd), so the final bonds are in
- * buffer a when n_substeps is odd, else in b.  Every substep pre-bins the moved cells for the next sort
+ * buffer a when n_substeps is odd, else in b (the last substep writes ascending rows).  Every substep pre-bins the moved cells for the next sort
  * (ABM_SORT_PREBINNED), alternating between the two offset tables; the sort outputs are scratch.
  * No host synchronisation; overflow is reported through max_len as in abm_jkr_substep.              */
 int abm_mechanics_loop(const double *radii, double *locations, const double *motility_forces, int64_t n,

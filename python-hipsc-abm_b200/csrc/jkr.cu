@@ -71,10 +71,10 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 //   0. the block stages the bin tiles its 128 cells can touch (3 or 9 contiguous slot ranges) in shared memory;
 //   1. walk the bin stencil with the cheap test |p-q|^2 <= reach^2 and park what passes -- partner id and
 //      slot, the partners of the thin hysteresis shell flagged -- in per-thread columns of shared memory;
-//   2. order the parked partners by id and run the contact model over them.  All lanes run this loop together
-//      (trip count = the largest hit count in the warp) instead of each lane doing the heavy math at a different
-//      iteration of the stencil walk; and because the sum runs in ascending partner id -- the serial
-//      reference's += order -- the result does not depend on how the sort happened to order a bin.
+//   2. run the contact model over the parked partners.  All lanes run this loop together (trip count = the
+//      largest hit count in the warp) instead of each lane doing the heavy math at a different iteration of the
+//      stencil walk.  The force is summed in fixed point, so the result does not depend on how the sort happened
+//      to order a bin (nor on the order of the partners).
 // While it integrates a cell the kernel can also pre-bin it for the NEXT substep's sort (histogram + rank).
 #ifndef ABM_JKR_TILES
 #define ABM_JKR_TILES 0          // stage the candidate bin tiles in shared memory
@@ -85,6 +85,9 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 #ifndef ABM_JKR_PREFETCH_MOT
 #define ABM_JKR_PREFETCH_MOT 1   // load the motility force before the stencil walk
 #endif
+#ifndef ABM_JKR_EXP
+#define ABM_JKR_EXP 0            // timing experiments only (results are wrong): 1 = no contact math, 2 = no parking,
+#endif                           // 4 = outputs written by sorted slot instead of by cell id
 #ifndef ABM_JKR_FLATTEN
 #define ABM_JKR_FLATTEN 1        // walk the three runs of a stencil layer in one loop
 #endif
@@ -94,6 +97,7 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 constexpr int kMaxHits = 16;
 constexpr int kJkrMinBlocks = ABM_JKR_MINBLOCKS;
 constexpr int kShellFlag = 0x40000000;
+constexpr double kForceUnit = 0x1p-76, kForceUnitInv = 0x1p76;   // fixed-point force accumulation (N)
 constexpr int kMaxOld = 8;
 
 struct BondEval {
@@ -136,9 +140,9 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
-              double stokes, Box box, double dt, const int *__restrict__ gid_of, NextSort next, int tile_cap) {
+              double stokes, Box box, double dt, const int *__restrict__ gid_of, NextSort next, int tile_cap,
+              int sort_rows) {
     __shared__ int hit_slot[kMaxHits][kJkrThreads];     // sorted slot of a parked partner (| kShellFlag)
-    __shared__ int hit_id[kMaxHits][kJkrThreads];       // its id as written into bond rows
     __shared__ int old_row[ABM_JKR_PREFETCH_OLD ? kMaxOld : 1][kJkrThreads];   // previous bond row (hysteresis lookups)
     __shared__ int tile_lo[9], tile_n[9];               // slot range staged for each (dz,dy) row of the stencil
     extern __shared__ double4 tile[];                   // rows x tile_cap candidate {x,y,z,r}
@@ -179,12 +183,15 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         double4 p = spos[s];
         int bx, by, bz;
         st.decode(sorted_bin[s], bx, by, bz);
-        int *row = new_cols + (long long)i * stride;
-        double fx = 0.0, fy = 0.0, fz = 0.0;
+        int *row = new_cols + (long long)((ABM_JKR_EXP & 4) ? s : i) * stride;
+        // The force is accumulated in 2^-76 N fixed point: integer addition is associative, so the sum -- and with it
+        // the whole trajectory -- is bit-identical whatever order the sort left the cells of a bin in, without
+        // ordering the partners first.  One unit is 1.3e-23 N (typical contact forces are 1e-9 N, int64 holds 1e-4 N).
+        long long fxi = 0, fyi = 0, fzi = 0;
         BondEval ev;
         ev.preset(c, p.w);
         // loads whose latency the stencil walk will hide: the motility force and the previous bond row
-        long long a3 = 3 * (long long)i;
+        long long a3 = 3 * (long long)((ABM_JKR_EXP & 4) ? s : i);
 #if ABM_JKR_PREFETCH_MOT
         const double mx = mot[a3 + 0], my = mot[a3 + 1], mz = mot[a3 + 2];
 #endif
@@ -221,6 +228,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         };
         // contact model for one bond candidate
         auto bond = [&](double4 q, int j) {
+            if (ABM_JKR_EXP & 1) return;
             double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
             double s2 = sumsq_nofma(vx, vy, vz);
             ev.refresh(p.w, q.w, c);
@@ -230,10 +238,10 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
             if (d > -0.360562) {
                 double f = (-0.0204 * (d * d * d)) + (0.4942 * (d * d)) + (1.0801 * d) - 1.324;
                 if (s2 > 0.0) {
-                    double w = f * ev.force_scale * inv_mag;
-                    fx += w * vx;
-                    fy += w * vy;
-                    fz += w * vz;
+                    double w = f * ev.force_scale * inv_mag * kForceUnitInv;
+                    fxi += __double2ll_rn(w * vx);
+                    fyi += __double2ll_rn(w * vy);
+                    fzi += __double2ll_rn(w * vz);
                 }
                 if (cnt < stride) row[cnt] = j;
                 ++cnt;
@@ -243,7 +251,6 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         // phase 1: cheap tests over the stencil.  The (lo,hi) slot ranges of the three dy runs of a z-layer are
         // fetched together, and the next candidate is loaded while the current one is tested.
         int nh = 0;
-        bool crowded = false;
         const int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
         for (int dz = -1; dz <= 1; ++dz) {
             int z = bz + dz;
@@ -262,14 +269,12 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                 double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
                 if (s2 <= reach2 && t != s) {                 // no bond can survive beyond the reach
                     bool inside = rad.within(s2);
-                    if (inside || old.valid()) {
-                        int j = partner_id(t);
+                    if ((inside || old.valid()) && !(ABM_JKR_EXP & 2)) {
                         if (nh < kMaxHits) {
                             hit_slot[nh][tid] = inside ? t : (t | kShellFlag);
-                            hit_id[nh][tid] = j;
                             ++nh;
                         } else {                              // crowded cell: evaluate in place
-                            crowded = true;
+                            int j = partner_id(t);
                             if (inside || was_bonded(j)) bond(q, j);
                         }
                     }
@@ -298,38 +303,27 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
             }
 #endif
         }
-        // order the parked partners by id (a handful of entries in this thread's shared-memory columns)
-        for (int a = 1; a < nh; ++a) {
-            int key = hit_id[a][tid], val = hit_slot[a][tid];
-            int b = a - 1;
-            while (b >= 0 && hit_id[b][tid] > key) {
-                hit_id[b + 1][tid] = hit_id[b][tid];
-                hit_slot[b + 1][tid] = hit_slot[b][tid];
-                --b;
-            }
-            hit_id[b + 1][tid] = key;
-            hit_slot[b + 1][tid] = val;
-        }
-        // phase 2: contact model, all lanes together, ascending partner id
+        // phase 2: contact model over the parked partners, all lanes together.  The partner's id is only fetched
+        // here, in the converged loop, where the loads of the whole warp overlap.
         for (int k = 0; k < nh; ++k) {
-            int t = hit_slot[k][tid], j = hit_id[k][tid];
-            if (t & kShellFlag) {                             // thin shell: only pre-existing bonds persist
-                if (!was_bonded(j)) continue;
-                t &= ~kShellFlag;
-            }
+            int t = hit_slot[k][tid];
+            bool shell = t & kShellFlag;
+            t &= ~kShellFlag;
+            int j = partner_id(t);
+            if (shell && !was_bonded(j)) continue;            // thin shell: only pre-existing bonds persist
             bond(spos[t], j);
         }
         int kept = min(cnt, stride);
-        new_len[i] = kept;
-        if (crowded) insertion_sort(row, kept);               // rows are ascending in every case
+        new_len[(ABM_JKR_EXP & 4) ? s : i] = kept;
+        if (sort_rows) insertion_sort(row, kept);             // ascending rows for the host-visible graph
         // integration (reference cell_backend.py:155-170); positions are read from the sorted snapshot only
 #if !ABM_JKR_PREFETCH_MOT
         const double mx = mot[a3 + 0], my = mot[a3 + 1], mz = mot[a3 + 2];
 #endif
         double friction = stokes_friction(p.w, stokes);
-        double nx = stokes_move(p.x, mx, fx, friction, dt, box.size[0]);
-        double ny = stokes_move(p.y, my, fy, friction, dt, box.size[1]);
-        double nz = stokes_move(p.z, mz, fz, friction, dt, box.size[2]);
+        double nx = stokes_move(p.x, mx, (double)fxi * kForceUnit, friction, dt, box.size[0]);
+        double ny = stokes_move(p.y, my, (double)fyi * kForceUnit, friction, dt, box.size[1]);
+        double nz = stokes_move(p.z, mz, (double)fzi * kForceUnit, friction, dt, box.size[2]);
         loc[a3 + 0] = nx;
         loc[a3 + 1] = ny;
         loc[a3 + 2] = nz;
@@ -381,7 +375,7 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
                                const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
                                double reach, const int32_t *old_row_start, int64_t old_row_stride,
                                const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len,
-                               int32_t *new_cols, int64_t row_stride, int32_t *max_len,
+                               int32_t *new_cols, int64_t row_stride, int32_t *max_len, int sort_rows,
                                const double *motility_forces, double *locations, double poisson, double youngs,
                                double adhesion_const, double stokes, const double size_host[3], double move_dt,
                                const int32_t *global_id, double uniform_radius, const double *next_extent_host,
@@ -431,7 +425,7 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
     k_jkr_substep<<<ceil_div(n, kJkrThreads), kJkrThreads, tile_bytes, as_stream(stream)>>>(
         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
         Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
-        locations, c, stokes, box, move_dt, global_id, next, tile_cap);
+        locations, c, stokes, box, move_dt, global_id, next, tile_cap, sort_rows);
     ABM_CHECK_LAUNCH("k_jkr_substep");
     return 0;
 }
@@ -473,7 +467,8 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
         }
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
         rc = abm_jkr_substep(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
-                             cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, motility_forces, locations,
+                             cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, k == n_substeps - 1,
+                             motility_forces, locations,
                              poisson, youngs, adhesion_const, stokes, size_host, dts_host[k], global_id, uniform_radius,
                              prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
                              prebin ? sort_workspace : nullptr, stream);

@@ -7,6 +7,7 @@ sys.path.insert(0, ROOT)
 VARIANTS = {
     "base80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=0"],
     "flat80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=1"],
+    "exp1": ["ABM_JKR_EXP=1"], "exp3": ["ABM_JKR_EXP=3"], "exp4": ["ABM_JKR_EXP=4"], "exp7": ["ABM_JKR_EXP=7"],
     "flat64": ["ABM_JKR_MINBLOCKS=8", "ABM_JKR_FLATTEN=1"],
     "flatnomot": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=1", "ABM_JKR_PREFETCH_MOT=0"],
 }
@@ -36,7 +37,7 @@ else:
         _l.check(eng.lib.abm_jkr_substep(
             srt.bin_start.data_ptr(), srt.sorted_id.data_ptr(), srt.sorted_pos.data_ptr(), srt.sorted_bin.data_ptr(),
             n, _l.i3(srt.dims), 10.0, reach, 0, old.row_stride, old.row_len.data_ptr(), old.cols.data_ptr(),
-            b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride, b["max_len"].data_ptr(),
+            b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride, b["max_len"].data_ptr(), 0,
             eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0, _l.d3(wl["size"]), 180.0, 0,
             eng.uniform_radius, None, None, 0, 0, eng.stream), "abm_jkr_substep")
     res = {}
