@@ -67,38 +67,28 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 }
 
 // ---- fused: search(distance, union with old bonds) + JKR + bond breaking + integration ---------------
-// Two phases per thread, to keep the warp converged while it does the expensive fp64 contact math:
-//   0. the block stages the bin tiles its 128 cells can touch (3 or 9 contiguous slot ranges) in shared memory;
-//   1. walk the bin stencil with the cheap test |p-q|^2 <= reach^2 and park what passes -- partner id and
-//      slot, the partners of the thin hysteresis shell flagged -- in per-thread columns of shared memory;
-//   2. run the contact model over the parked partners.  All lanes run this loop together (trip count = the
-//      largest hit count in the warp) instead of each lane doing the heavy math at a different iteration of the
-//      stencil walk.  The force is summed in fixed point, so the result does not depend on how the sort happened
-//      to order a bin (nor on the order of the partners).
-// While it integrates a cell the kernel can also pre-bin it for the NEXT substep's sort (histogram + rank).
-#ifndef ABM_JKR_TILES
-#define ABM_JKR_TILES 0          // stage the candidate bin tiles in shared memory
-#endif
-#ifndef ABM_JKR_PREFETCH_OLD
-#define ABM_JKR_PREFETCH_OLD 0   // copy the previous bond row to shared memory before the stencil walk
-#endif
-#ifndef ABM_JKR_PREFETCH_MOT
-#define ABM_JKR_PREFETCH_MOT 1   // load the motility force before the stencil walk
-#endif
-#ifndef ABM_JKR_EXP
-#define ABM_JKR_EXP 0            // timing experiments only (results are wrong): 1 = no contact math, 2 = no parking,
-#endif                           // 4 = outputs written by sorted slot instead of by cell id
-#ifndef ABM_JKR_FLATTEN
-#define ABM_JKR_FLATTEN 1        // walk the three runs of a stencil layer in one loop
-#endif
+// Phases of one thread (one sorted slot = one cell), arranged so that the warp stays converged while it does
+// the expensive work and so that the scattered memory operations are few and wide:
+//   1. walk the bin stencil with the cheap test |p-q|^2 <= reach^2; partners within `distance` are parked (their
+//      slot) in a per-thread column of shared memory, partners in the thin hysteresis shell (distance, reach]
+//      in two registers;
+//   2. the (few) lanes that have shell partners start loading their previous bond row -- its latency hides behind
+//      the contact loop;
+//   3. contact model over the parked partners, all lanes together (trip count = the largest hit count in the
+//      warp).  The force is summed in 2^-76 N fixed point: integer addition is associative, so the result -- and
+//      with it the whole trajectory -- is bit-identical whatever order the sort left the cells of a bin in;
+//   4. shell partners that were bonded before go through the same contact model (bond hysteresis);
+//   5. the new bond row, collected in the shared-memory column, is written with 16-byte stores; the cell is
+//      integrated and pre-binned for the next substep's sort.
+// Measured alternatives that did NOT help (profiles/r01_kernels_c3.md): staging the candidate bin tiles in shared
+// memory, prefetching every cell's previous bond row, 64/96-register variants, ordering partners by id.
 #ifndef ABM_JKR_MINBLOCKS
-#define ABM_JKR_MINBLOCKS 6      // register cap: 6 -> 80/thread, 5 -> 96, 8 -> 64
+#define ABM_JKR_MINBLOCKS 6      // register cap: 6 -> 80/thread
 #endif
 constexpr int kMaxHits = 16;
-constexpr int kJkrMinBlocks = ABM_JKR_MINBLOCKS;
 constexpr int kShellFlag = 0x40000000;
+constexpr int kJkrMinBlocks = ABM_JKR_MINBLOCKS;
 constexpr double kForceUnit = 0x1p-76, kForceUnitInv = 0x1p76;   // fixed-point force accumulation (N)
-constexpr int kMaxOld = 8;
 
 struct BondEval {
     // radius-dependent part of the contact model, memoised on the partner radius (radii are usually uniform).
@@ -140,95 +130,33 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
-              double stokes, Box box, double dt, const int *__restrict__ gid_of, NextSort next, int tile_cap,
-              int sort_rows) {
-    __shared__ int hit_slot[kMaxHits][kJkrThreads];     // sorted slot of a parked partner (| kShellFlag)
-    __shared__ int old_row[ABM_JKR_PREFETCH_OLD ? kMaxOld : 1][kJkrThreads];   // previous bond row (hysteresis lookups)
-    __shared__ int tile_lo[9], tile_n[9];               // slot range staged for each (dz,dy) row of the stencil
-    extern __shared__ double4 tile[];                   // rows x tile_cap candidate {x,y,z,r}
+              double stokes, Box box, double dt, const int *__restrict__ gid_of, NextSort next, int sort_rows) {
+    // column tid: first the parked partner slots, then (overwritten from the front) the ids of the new bond row
+    __shared__ int column[kMaxHits][kJkrThreads];
     const int tid = threadIdx.x;
     int s = blockIdx.x * kJkrThreads + tid;
     int cnt = 0;
-
-    // ---- stage the bin tiles: the 128 consecutive slots of this block span the linear bins [b_first, b_last];
-    // every candidate of every thread lies in one of the rows (dz,dy) of bins [b_first-1, b_last+1] shifted by the
-    // row offset -- a contiguous slot range each, copied once, coalesced, into shared memory.
-    const int nz = st.dims[2] == 1 ? 1 : 3;
-    const int rows = 3 * nz;
-    if (ABM_JKR_TILES) {
-        const int s_last = min(blockIdx.x * kJkrThreads + kJkrThreads, n) - 1;
-        if (tid < rows) {
-            int b_first = sorted_bin[blockIdx.x * kJkrThreads], b_last = sorted_bin[s_last];
-            int dz = nz == 1 ? 0 : tid / 3 - 1, dy = tid % 3 - 1;
-            long long off = ((long long)dz * st.dims[1] + dy) * st.dims[0];
-            long long nbins = (long long)st.dims[0] * st.dims[1] * st.dims[2];
-            long long lo_bin = max(b_first + off - 1, 0LL), hi_bin = min(b_last + off + 1, nbins - 1);
-            int lo = 0, cntb = 0;
-            if (lo_bin <= hi_bin) {
-                lo = bin_start[lo_bin];
-                cntb = min(bin_start[hi_bin + 1] - lo, tile_cap);
-            }
-            tile_lo[tid] = lo;
-            tile_n[tid] = cntb;
-        }
-        __syncthreads();
-        for (int r = 0; r < rows; ++r) {
-            int lo = tile_lo[r], cntb = tile_n[r];
-            for (int k = tid; k < cntb; k += kJkrThreads) tile[r * tile_cap + k] = spos[lo + k];
-        }
-        __syncthreads();
-    }
     if (s < n) {
         int i = sorted_id[s];
         double4 p = spos[s];
         int bx, by, bz;
         st.decode(sorted_bin[s], bx, by, bz);
-        int *row = new_cols + (long long)((ABM_JKR_EXP & 4) ? s : i) * stride;
-        // The force is accumulated in 2^-76 N fixed point: integer addition is associative, so the sum -- and with it
-        // the whole trajectory -- is bit-identical whatever order the sort left the cells of a bin in, without
-        // ordering the partners first.  One unit is 1.3e-23 N (typical contact forces are 1e-9 N, int64 holds 1e-4 N).
+        int *row = new_cols + (long long)i * stride;
         long long fxi = 0, fyi = 0, fzi = 0;
         BondEval ev;
         ev.preset(c, p.w);
-        // loads whose latency the stencil walk will hide: the motility force and the previous bond row
-        long long a3 = 3 * (long long)((ABM_JKR_EXP & 4) ? s : i);
-#if ABM_JKR_PREFETCH_MOT
-        const double mx = mot[a3 + 0], my = mot[a3 + 1], mz = mot[a3 + 2];
-#endif
-        int olen = 0;
-        if (ABM_JKR_PREFETCH_OLD && old.valid()) {
-            long long os = old.start(i);
-            olen = old.row_len[i];
-            int keep = min(olen, kMaxOld);
-            for (int k = 0; k < keep; ++k) old_row[k][tid] = old.cols[os + k];
-        }
+        long long a3 = 3 * (long long)i;
+        const double mx = mot[a3 + 0], my = mot[a3 + 1], mz = mot[a3 + 2];   // latency hidden by the walk
 
         // the id bond rows are written in: the cell index, or its global id when the colony is slab-decomposed
         auto partner_id = [&](int t) {
             int j = sorted_id[t];
             return gid_of ? gid_of[j] : j;
         };
-        // membership of j in this cell's previous bond row; every entry is read (no early exit) so the
-        // loads are independent and overlap
-        auto was_bonded = [&](int j) {
-            bool found = false;
-            if (ABM_JKR_PREFETCH_OLD) {
-                int keep = min(olen, kMaxOld);
-                for (int k = 0; k < keep; ++k) found |= (old_row[k][tid] == j);
-                if (olen > kMaxOld) {                          // very long row: the tail stays in global memory
-                    long long os = old.start(i);
-                    for (int k = kMaxOld; k < olen; ++k) found |= (old.cols[os + k] == j);
-                }
-            } else {
-                long long os = old.start(i);
-                int len = old.row_len[i];
-                for (int k = 0; k < len; ++k) found |= (old.cols[os + k] == j);
-            }
-            return found;
-        };
-        // contact model for one bond candidate
-        auto bond = [&](double4 q, int j) {
-            if (ABM_JKR_EXP & 1) return;
+        int direct = 0;      // bonds of a crowded cell written straight to row[kMaxHits + direct]
+        // contact model for one bond candidate; a surviving bond is recorded in the column (or, for a crowded cell
+        // during the walk, directly in the global row)
+        auto bond = [&](double4 q, int j, bool to_column) {
             double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
             double s2 = sumsq_nofma(vx, vy, vz);
             ev.refresh(p.w, q.w, c);
@@ -243,14 +171,26 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                     fyi += __double2ll_rn(w * vy);
                     fzi += __double2ll_rn(w * vz);
                 }
-                if (cnt < stride) row[cnt] = j;
-                ++cnt;
+                if (to_column && cnt < kMaxHits) {
+                    column[cnt++][tid] = j;
+                } else {
+                    if (kMaxHits + direct < stride) row[kMaxHits + direct] = j;
+                    ++direct;
+                }
             }
+        };
+        // membership of j in this cell's previous bond row, straight from global memory (crowded cells only)
+        auto was_bonded_slow = [&](int j) {
+            long long os = old.start(i);
+            int olen = old.row_len[i];
+            bool found = false;
+            for (int k = 0; k < olen; ++k) found |= (old.cols[os + k] == j);
+            return found;
         };
 
         // phase 1: cheap tests over the stencil.  The (lo,hi) slot ranges of the three dy runs of a z-layer are
-        // fetched together, and the next candidate is loaded while the current one is tested.
-        int nh = 0;
+        // fetched together and walked in one loop (the warp iterates max(total) times, not sum(max(run))).
+        int nh = 0, nsh = 0, sh0 = 0, sh1 = 0;
         const int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
         for (int dz = -1; dz <= 1; ++dz) {
             int z = bz + dz;
@@ -265,61 +205,111 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                 run_lo[r] = lo;
                 run_n[r] = ok ? hi - lo : 0;
             }
-            auto test = [&](int t, const double4 &q) {
-                double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
-                if (s2 <= reach2 && t != s) {                 // no bond can survive beyond the reach
-                    bool inside = rad.within(s2);
-                    if ((inside || old.valid()) && !(ABM_JKR_EXP & 2)) {
-                        if (nh < kMaxHits) {
-                            hit_slot[nh][tid] = inside ? t : (t | kShellFlag);
-                            ++nh;
-                        } else {                              // crowded cell: evaluate in place
-                            int j = partner_id(t);
-                            if (inside || was_bonded(j)) bond(q, j);
-                        }
-                    }
-                }
-            };
-#if ABM_JKR_FLATTEN
-            // one loop over the three runs of the layer: the warp iterates max(total) times, not sum(max(run))
             const int n0 = run_n[0], n01 = n0 + run_n[1], tot = n01 + run_n[2];
             for (int u = 0; u < tot; ++u) {
                 int t = u < n0 ? run_lo[0] + u : (u < n01 ? run_lo[1] + (u - n0) : run_lo[2] + (u - n01));
-                test(t, spos[t]);
-            }
-#else
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                int lo = run_lo[r], cntr = run_n[r];
-                if (cntr <= 0) continue;
-                const int row = (nz == 1 ? 0 : (dz + 1) * 3) + r;
-                const double4 *trow = tile + row * tile_cap;
-                const int base = ABM_JKR_TILES ? tile_lo[row] : 0, staged = ABM_JKR_TILES ? tile_n[row] : 0;
-                for (int u = 0; u < cntr; ++u) {
-                    int t = lo + u;
-                    int o = t - base;
-                    test(t, (ABM_JKR_TILES && o >= 0 && o < staged) ? trow[o] : spos[t]);   // else: global
+                double4 q = spos[t];
+                double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
+                if (s2 > reach2 || t == s) continue;          // no bond can survive beyond the reach
+                if (rad.within(s2)) {
+                    if (nh < kMaxHits) column[nh++][tid] = t;
+                    else bond(q, partner_id(t), false);       // crowded cell: evaluate in place
+                } else if (old.valid()) {                     // thin shell: only pre-existing bonds persist
+                    if (nsh == 0) sh0 = t;
+                    else if (nsh == 1) sh1 = t;
+                    else if (nh < kMaxHits) column[nh++][tid] = t | kShellFlag;   // rare third+ shell partner
+                    else {
+                        int j = partner_id(t);
+                        if (was_bonded_slow(j)) bond(q, j, false);
+                    }
+                    ++nsh;
                 }
             }
-#endif
         }
-        // phase 2: contact model over the parked partners, all lanes together.  The partner's id is only fetched
-        // here, in the converged loop, where the loads of the whole warp overlap.
+        // phase 2: lanes with shell partners fetch (the head of) their previous bond row now
+        int olen = 0;
+        int4 oa = make_int4(-1, -1, -1, -1), ob = oa;
+        long long os = 0;
+        if (nsh > 0) {
+            os = old.start(i);
+            olen = old.row_len[i];
+            if ((os & 3) == 0) {                               // fixed-stride rows (stride % 4 == 0): 16-byte loads
+                if (olen > 0) oa = *reinterpret_cast<const int4 *>(old.cols + os);
+                if (olen > 4) ob = *reinterpret_cast<const int4 *>(old.cols + os + 4);
+            }
+        }
+        auto in_old_row = [&](int j) {
+            if ((os & 3) != 0) return was_bonded_slow(j);
+            bool f = false;
+            if (olen > 0) f |= (oa.x == j);
+            if (olen > 1) f |= (oa.y == j);
+            if (olen > 2) f |= (oa.z == j);
+            if (olen > 3) f |= (oa.w == j);
+            if (olen > 4) f |= (ob.x == j);
+            if (olen > 5) f |= (ob.y == j);
+            if (olen > 6) f |= (ob.z == j);
+            if (olen > 7) f |= (ob.w == j);
+            for (int k = 8; k < olen; ++k) f |= (old.cols[os + k] == j);
+            return f;
+        };
+        // phase 3: contact model over the parked partners, all lanes together
         for (int k = 0; k < nh; ++k) {
-            int t = hit_slot[k][tid];
+            int t = column[k][tid];
             bool shell = t & kShellFlag;
             t &= ~kShellFlag;
             int j = partner_id(t);
-            if (shell && !was_bonded(j)) continue;            // thin shell: only pre-existing bonds persist
-            bond(spos[t], j);
+            if (shell && !in_old_row(j)) continue;
+            bond(spos[t], j, true);                           // cnt <= k: the column is overwritten behind the read
         }
-        int kept = min(cnt, stride);
-        new_len[(ABM_JKR_EXP & 4) ? s : i] = kept;
-        if (sort_rows) insertion_sort(row, kept);             // ascending rows for the host-visible graph
+        // phase 4: hysteresis -- shell partners that are in the previous row
+        if (nsh > 0) {
+            int j0 = partner_id(sh0);
+            if (in_old_row(j0)) bond(spos[sh0], j0, true);
+            if (nsh > 1) {
+                int j1 = partner_id(sh1);
+                if (in_old_row(j1)) bond(spos[sh1], j1, true);
+            }
+        }
+        // phase 5: the bond row.  cnt entries sit in the column; a crowded cell has `direct` more already in global
+        // memory from row[kMaxHits] on, which are moved down so that the row is dense.
+        int total = cnt + direct;
+        int kept = min(total, stride);
+        if (direct == 0) {
+            if (sort_rows) {                                   // ascending rows for the host-visible graph
+                for (int a = 1; a < cnt; ++a) {
+                    int v = column[a][tid], b = a - 1;
+                    while (b >= 0 && column[b][tid] > v) {
+                        column[b + 1][tid] = column[b][tid];
+                        --b;
+                    }
+                    column[b + 1][tid] = v;
+                }
+            }
+            int m = min(cnt, stride);
+            if ((stride & 3) == 0) {
+                for (int k = 0; k < m; k += 4) {
+                    int4 v;
+                    v.x = column[k][tid];
+                    v.y = k + 1 < m ? column[k + 1][tid] : -1;
+                    v.z = k + 2 < m ? column[k + 2][tid] : -1;
+                    v.w = k + 3 < m ? column[k + 3][tid] : -1;
+                    *reinterpret_cast<int4 *>(row + k) = v;
+                }
+            } else {
+                for (int k = 0; k < m; ++k) row[k] = column[k][tid];
+            }
+        } else {
+            int moved = min(direct, max(stride - kMaxHits, 0));
+            for (int k = 0; k < min(cnt, stride); ++k) row[k] = column[k][tid];
+            if (cnt < kMaxHits)
+                for (int k = 0; k < moved; ++k) row[cnt + k] = row[kMaxHits + k];
+            if (sort_rows) insertion_sort(row, kept);
+        }
+        new_len[i] = kept;
+        // what the overflow report below needs: the row length, and room for the direct entries of a crowded cell
+        // (they live behind the first kMaxHits slots until they are moved down)
+        cnt = direct ? max(total, kMaxHits + direct) : total;
         // integration (reference cell_backend.py:155-170); positions are read from the sorted snapshot only
-#if !ABM_JKR_PREFETCH_MOT
-        const double mx = mot[a3 + 0], my = mot[a3 + 1], mz = mot[a3 + 2];
-#endif
         double friction = stokes_friction(p.w, stokes);
         double nx = stokes_move(p.x, mx, (double)fxi * kForceUnit, friction, dt, box.size[0]);
         double ny = stokes_move(p.y, my, (double)fyi * kForceUnit, friction, dt, box.size[1]);
@@ -410,22 +400,10 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
         next.cell_bin = w.cell_bin;
         next.rank = w.rank;
     }
-    // candidate tiles: 3 stencil rows in a flat world, 9 in 3-D; ~1.5x the mean population of a row
-    const int rows = dims_host[2] == 1 ? 3 : 9;
-    const int tile_cap = rows == 3 ? 192 : 160;
-    const size_t tile_bytes = ABM_JKR_TILES ? (size_t)rows * tile_cap * sizeof(double4) : 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        int rc = check_cuda(cudaFuncSetAttribute(k_jkr_substep, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 9 * 160 * (int)sizeof(double4)),
-                            "cudaFuncSetAttribute(k_jkr_substep)");
-        if (rc) return rc;
-        attr_set = true;
-    }
-    k_jkr_substep<<<ceil_div(n, kJkrThreads), kJkrThreads, tile_bytes, as_stream(stream)>>>(
+    k_jkr_substep<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
         Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
-        locations, c, stokes, box, move_dt, global_id, next, tile_cap, sort_rows);
+        locations, c, stokes, box, move_dt, global_id, next, sort_rows);
     ABM_CHECK_LAUNCH("k_jkr_substep");
     return 0;
 }

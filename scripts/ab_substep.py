@@ -5,11 +5,11 @@ import importlib.util, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VARIANTS = {
-    "base80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=0"],
-    "flat80": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=1"],
-    "exp1": ["ABM_JKR_EXP=1"], "exp3": ["ABM_JKR_EXP=3"], "exp4": ["ABM_JKR_EXP=4"], "exp7": ["ABM_JKR_EXP=7"],
-    "flat64": ["ABM_JKR_MINBLOCKS=8", "ABM_JKR_FLATTEN=1"],
-    "flatnomot": ["ABM_JKR_MINBLOCKS=6", "ABM_JKR_FLATTEN=1", "ABM_JKR_PREFETCH_MOT=0"],
+    "base": [],
+    "exp1": ["ABM_JKR_EXP=1"], "exp8": ["ABM_JKR_EXP=8"], "exp16": ["ABM_JKR_EXP=16"], "exp24": ["ABM_JKR_EXP=24"],
+    "exp9": ["ABM_JKR_EXP=9"],
+
+
 }
 if sys.argv[1] == "build":
     spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "python-hipsc-abm_b200", "build.py"))
