@@ -33,7 +33,7 @@ extern "C" {
 /* flags of abm_bin_dims_host / abm_bin_sort */
 #define ABM_SORT_STABLE 1     /* ascending cell id inside a bin (the reference's fill order) */
 #define ABM_SORT_REFERENCE 2  /* keep the reference's 3 z-layers in a flat (size_z == 0) world */
-#define ABM_SORT_PREBINNED 4  /* histogram + per-cell (bin, rank) already written by abm_jkr_substep */
+#define ABM_SORT_PREBINNED 4  /* histogram + per-cell bin already written by abm_jkr_substep */
 
 /* ---- library ----------------------------------------------------------------------------------- */
 int abm_abi_version(void);          /* == ABM_B200_ABI_VERSION */
@@ -140,7 +140,7 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  *                      on the host), else 0.
  *   next_bin_counts  : NULL, or a zeroed (nbins+1) table (not bin_start): the kernel then also bins every moved
  *                      cell on the lattice (next_origin, next_extent, edge `reach`) and leaves histogram,
- *                      bin and rank where abm_bin_sort(ABM_SORT_PREBINNED, same workspace) expects them.
+ *                      bin where abm_bin_sort(ABM_SORT_PREBINNED, same workspace) expects them.
  *   reach            : bin edge of the sort, >= abm_jkr_reach(distance, max(radii), ...).
  *   max_len (1) int32: raised (atomicMax) by rows that needed more than row_stride entries; a value
  *   > row_stride afterwards means those rows were truncated: grow row_stride and redo the substep

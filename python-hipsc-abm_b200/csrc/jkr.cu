@@ -5,6 +5,7 @@
 
 #include "graph.cuh"
 #include "sortws.cuh"
+#include "tile.cuh"
 
 namespace abm {
 
@@ -69,24 +70,24 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 // ---- fused: search(distance, union with old bonds) + JKR + bond breaking + integration ---------------
 // Phases of one thread (one sorted slot = one cell), arranged so that the warp stays converged while it does
 // the expensive work and so that the scattered memory operations are few and wide:
-//   1. walk the bin stencil with the cheap test |p-q|^2 <= reach^2; partners within `distance` are parked (their
-//      slot) in a per-thread column of shared memory, partners in the thin hysteresis shell (distance, reach]
-//      in two registers;
-//   2. the (few) lanes that have shell partners start loading their previous bond row -- its latency hides behind
-//      the contact loop;
-//   3. contact model over the parked partners, all lanes together (trip count = the largest hit count in the
-//      warp).  The force is summed in 2^-76 N fixed point: integer addition is associative, so the result -- and
-//      with it the whole trajectory -- is bit-identical whatever order the sort left the cells of a bin in;
-//   4. shell partners that were bonded before go through the same contact model (bond hysteresis);
-//   5. the new bond row, collected in the shared-memory column, is written with 16-byte stores; the cell is
-//      integrated and pre-binned for the next substep's sort.
-// Measured alternatives that did NOT help (profiles/r01_kernels_c3.md): staging the candidate bin tiles in shared
-// memory, prefetching every cell's previous bond row, 64/96-register variants, ordering partners by id.
+//   1. filter the bin stencil: the candidates of the warp's 32 cells are staged in shared memory one z layer at a
+//      time (tile.cuh) and tested in fp32 against reach^2 + error band; survivors (their slots) are parked in a
+//      per-thread column of shared memory.  The filter can only let through too many, never too few;
+//   2. contact loop over the parked partners, all lanes together (trip count = the largest hit count in the
+//      warp): the exact fp64 squared distance decides (discard beyond the reach / bond within `distance` /
+//      hysteresis shell in between), then the JKR model.  The force is summed in 2^-76 N fixed point: integer
+//      addition is associative, so the result -- and with it the whole trajectory -- is bit-identical whatever
+//      order the sort left the cells of a bin in;
+//   3. the (few) shell partners are looked up in the cell's previous bond row and, if bonded before, go through
+//      the same contact model (bond hysteresis);
+//   4. the new bond row, collected in the shared-memory column, is written with 16-byte stores; the cell is
+//      integrated and binned for the next substep's sort.
+// A cell with more than kMaxHits partners, or whose candidate run does not fit the tile, takes a slow path that
+// walks the stencil from global memory and evaluates every candidate in place.
 #ifndef ABM_JKR_MINBLOCKS
-#define ABM_JKR_MINBLOCKS 6      // register cap: 6 -> 80/thread
+#define ABM_JKR_MINBLOCKS 7      // register cap: 7 -> 72/thread (measured best of 5..8 at 500k cells)
 #endif
 constexpr int kMaxHits = 16;
-constexpr int kShellFlag = 0x40000000;
 constexpr int kJkrMinBlocks = ABM_JKR_MINBLOCKS;
 constexpr double kForceUnit = 0x1p-76, kForceUnitInv = 0x1p76;   // fixed-point force accumulation (N)
 
@@ -120,214 +121,290 @@ struct BondEval {
     }
 };
 
-struct NextSort {          // where to pre-bin the moved cells for the following substep (counts == nullptr: off)
-    BinGeom geom;
-    int *counts, *cell_bin, *rank;
+struct NextSort {          // hand-over of the moved cells to the following substep's sort (counts == nullptr: off),
+    BinGeom geom;          // in THIS sort's slot order: the next permutation is then nearly the identity
+    int *counts, *cell_bin, *prev_id;
+    double4 *next_pos;
 };
 
+struct Friction {          // Stokes friction of a colony of equal radii and its correctly rounded reciprocal
+    double uni, uni_inv;   // uni == 0: radii differ, every thread evaluates its own
+};
+
+// a / b rounded to nearest, given y = RN(1/b): Markstein's correction applied twice (the first brings the
+// quotient within one ulp, from where the second is proven to round correctly).  Same bits as __ddiv_rn for
+// normal operands, a quarter of its instructions.
+__device__ __forceinline__ double div_by(double a, double b, double y) {
+    double q = __dmul_rn(a, y);
+    q = __fma_rn(__fma_rn(-b, q, a), y, q);
+    return __fma_rn(__fma_rn(-b, q, a), y, q);
+}
+
+// Stokes integration of one axis with the division replaced by div_by (reference cell_backend.py:155-170)
+__device__ __forceinline__ double stokes_move_y(double x, double f_mot, double f_jkr, double friction, double inv_f,
+                                                double dt, double size_k) {
+    double velocity = div_by(__dadd_rn(f_mot, f_jkr), friction, inv_f);
+    double moved = __dadd_rn(x, __dmul_rn(dt, __dmul_rn(velocity, 1e6)));
+    if (moved > size_k) return size_k;
+    if (moved < 0.0) return 0.0;
+    return moved;
+}
+
+// kUniform: all radii equal c.uni_r -- the radius-dependent contact factors and the friction are kernel constants.
+template <bool kUniform>
 __global__ void __launch_bounds__(kJkrThreads, kJkrMinBlocks)
 k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_id,
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
-              double stokes, Box box, double dt, const int *__restrict__ gid_of, NextSort next, int sort_rows) {
+              double stokes, Friction fric, Box box, double dt, const int *__restrict__ gid_of, NextSort next,
+              int sort_rows) {
     // column tid: first the parked partner slots, then (overwritten from the front) the ids of the new bond row
     __shared__ int column[kMaxHits][kJkrThreads];
+    __shared__ float4 tiles[kJkrThreads / 32][kTileRows * kTileCap];
     const int tid = threadIdx.x;
-    int s = blockIdx.x * kJkrThreads + tid;
-    int cnt = 0;
-    if (s < n) {
-        int i = sorted_id[s];
-        double4 p = spos[s];
-        int bx, by, bz;
+    const int s = blockIdx.x * kJkrThreads + tid;
+    if (s - (tid & 31) >= n) return;                           // the whole warp is past the last cell
+    const bool live = s < n;
+    float4 *tile = tiles[tid >> 5];
+    int i = 0, bx = 0, by = 0, bz = 0;
+    double4 p = make_double4(0.0, 0.0, 0.0, 1.0);
+    if (live) {
+        i = sorted_id[s];
+        p = spos[s];
         st.decode(sorted_bin[s], bx, by, bz);
-        int *row = new_cols + (long long)i * stride;
-        long long fxi = 0, fyi = 0, fzi = 0;
-        BondEval ev;
-        ev.preset(c, p.w);
-        long long a3 = 3 * (long long)i;
-        const double mx = mot[a3 + 0], my = mot[a3 + 1], mz = mot[a3 + 2];   // latency hidden by the walk
+        // the motility force is needed at the very end: pull its line into L2 now, load it then
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(mot + 3 * (long long)i));
+    }
 
-        // the id bond rows are written in: the cell index, or its global id when the colony is slab-decomposed
-        auto partner_id = [&](int t) {
-            int j = sorted_id[t];
-            return gid_of ? gid_of[j] : j;
-        };
-        int direct = 0;      // bonds of a crowded cell written straight to row[kMaxHits + direct]
-        // contact model for one bond candidate; a surviving bond is recorded in the column (or, for a crowded cell
-        // during the walk, directly in the global row)
-        auto bond = [&](double4 q, int j, bool to_column) {
-            double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
-            double s2 = sumsq_nofma(vx, vy, vz);
-            ev.refresh(p.w, q.w, c);
-            double inv_mag = rsqrt(s2);                     // +inf for coincident cells, handled below
-            double mag = s2 > 0.0 ? s2 * inv_mag : 0.0;
-            double d = (ev.rsum - mag) * ev.inv_scale;
-            if (d > -0.360562) {
-                double f = (-0.0204 * (d * d * d)) + (0.4942 * (d * d)) + (1.0801 * d) - 1.324;
-                if (s2 > 0.0) {
-                    double w = f * ev.force_scale * inv_mag * kForceUnitInv;
-                    fxi += __double2ll_rn(w * vx);
-                    fyi += __double2ll_rn(w * vy);
-                    fzi += __double2ll_rn(w * vz);
-                }
-                if (to_column && cnt < kMaxHits) {
-                    column[cnt++][tid] = j;
-                } else {
-                    if (kMaxHits + direct < stride) row[kMaxHits + direct] = j;
-                    ++direct;
-                }
-            }
-        };
-        // membership of j in this cell's previous bond row, straight from global memory (crowded cells only)
-        auto was_bonded_slow = [&](int j) {
-            long long os = old.start(i);
-            int olen = old.row_len[i];
-            bool found = false;
-            for (int k = 0; k < olen; ++k) found |= (old.cols[os + k] == j);
-            return found;
-        };
-
-        // phase 1: cheap tests over the stencil.  The (lo,hi) slot ranges of the three dy runs of a z-layer are
-        // fetched together and walked in one loop (the warp iterates max(total) times, not sum(max(run))).
-        int nh = 0, nsh = 0, sh0 = 0, sh1 = 0;
-        const int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
-        for (int dz = -1; dz <= 1; ++dz) {
-            int z = bz + dz;
-            if (z < 0 || z >= st.dims[2]) continue;
-            int run_lo[3], run_n[3];
+    // ---- phase 1: fp32 filter over the staged stencil ----------------------------------------------------------
+    TileOrigin org;
+    org.x = __shfl_sync(kFullWarp, p.x, 0);
+    org.y = __shfl_sync(kFullWarp, p.y, 0);
+    org.z = __shfl_sync(kFullWarp, p.z, 0);
+    const float pfx = (float)(p.x - org.x), pfy = (float)(p.y - org.y), pfz = (float)(p.z - org.z);
+    const float t_out = (float)reach2 + tile_band(pfx, pfy, pfz, sqrtf((float)reach2));
+    int nh = 0;                                                // parked partners (counts on past kMaxHits)
+    bool slow = false;
+    for (int dz = -1; dz <= 1; ++dz) {
+        const int z = bz + dz;
+        if (__all_sync(kFullWarp, !live || z < 0 || z >= st.dims[2])) continue;
+        const LayerRuns R = stage_layer(live, bx, by, z, st, bin_start, spos, org, tile);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                int y = by + r - 1;
-                bool ok = y >= 0 && y < st.dims[1];
-                int rowb = ok ? (z * st.dims[1] + y) * st.dims[0] : 0;
-                int lo = bin_start[rowb + x0], hi = bin_start[rowb + x1 + 1];
-                run_lo[r] = lo;
-                run_n[r] = ok ? hi - lo : 0;
+        for (int r = 0; r < kTileRows; ++r) {
+            if (!((R.staged >> r) & 1u)) {                     // warp-uniform
+                slow |= R.n[r] > 0;
+                continue;
             }
-            const int n0 = run_n[0], n01 = n0 + run_n[1], tot = n01 + run_n[2];
-            for (int u = 0; u < tot; ++u) {
-                int t = u < n0 ? run_lo[0] + u : (u < n01 ? run_lo[1] + (u - n0) : run_lo[2] + (u - n01));
-                double4 q = spos[t];
-                double s2 = sumsq_nofma(p.x - q.x, p.y - q.y, p.z - q.z);
-                if (s2 > reach2 || t == s) continue;          // no bond can survive beyond the reach
-                if (rad.within(s2)) {
-                    if (nh < kMaxHits) column[nh++][tid] = t;
-                    else bond(q, partner_id(t), false);       // crowded cell: evaluate in place
-                } else if (old.valid()) {                     // thin shell: only pre-existing bonds persist
-                    if (nsh == 0) sh0 = t;
-                    else if (nsh == 1) sh1 = t;
-                    else if (nh < kMaxHits) column[nh++][tid] = t | kShellFlag;   // rare third+ shell partner
-                    else {
-                        int j = partner_id(t);
-                        if (was_bonded_slow(j)) bond(q, j, false);
-                    }
-                    ++nsh;
+            const float4 *run = tile + R.first[r];
+            const int nr = R.n[r];
+            for (int u = 0; u < nr; ++u) {
+                const float4 q = run[u];
+                const float dx = pfx - q.x, dy = pfy - q.y, dzf = pfz - q.z;
+                const float s2f = fmaf(dzf, dzf, fmaf(dy, dy, dx * dx));
+                const int t = __float_as_int(q.w);
+                if (s2f <= t_out && t != s) {
+                    if (nh < kMaxHits) column[nh][tid] = t;
+                    ++nh;
                 }
             }
         }
-        // phase 2: lanes with shell partners fetch (the head of) their previous bond row now
-        int olen = 0;
-        int4 oa = make_int4(-1, -1, -1, -1), ob = oa;
-        long long os = 0;
+        __syncwarp();                                         // the tile is overwritten by the next layer
+    }
+    if (!live) return;                                         // no warp-wide operation below this line
+    slow |= nh > kMaxHits;
+
+    int *row = new_cols + (long long)i * stride;
+    long long fxi = 0, fyi = 0, fzi = 0;
+    BondEval ev;
+    if (!kUniform) ev.preset(c, p.w);
+    int cnt = 0;         // bonds recorded in the column
+    int direct = 0;      // bonds of a crowded cell written straight to row[kMaxHits + direct]
+    // the id bond rows are written in: the cell index, or its global id when the colony is slab-decomposed
+    auto partner_id = [&](int t) {
+        int j = sorted_id[t];
+        return gid_of ? gid_of[j] : j;
+    };
+    // contact model for one bond candidate at offset v = p - q, |v|^2 = s2; a surviving bond is recorded in the
+    // column (or, for a crowded cell, directly in the global row)
+    auto bond = [&](double vx, double vy, double vz, double s2, double rq, int j) {
+        if (!kUniform) ev.refresh(p.w, rq, c);
+        const double rsum = kUniform ? c.uni_r + c.uni_r : ev.rsum;
+        const double inv_scale = kUniform ? c.uni_inv_scale : ev.inv_scale;
+        const double force_scale = kUniform ? c.uni_force_scale : ev.force_scale;
+        double inv_mag = rsqrt(s2);                         // +inf for coincident cells, handled below
+        double mag = s2 > 0.0 ? s2 * inv_mag : 0.0;
+        double d = (rsum - mag) * inv_scale;
+        if (d > -0.360562) {
+            double f = (-0.0204 * (d * d * d)) + (0.4942 * (d * d)) + (1.0801 * d) - 1.324;
+            if (s2 > 0.0) {
+                double w = f * force_scale * inv_mag * kForceUnitInv;
+                fxi += __double2ll_rn(w * vx);
+                fyi += __double2ll_rn(w * vy);
+                fzi += __double2ll_rn(w * vz);
+            }
+            if (cnt < kMaxHits) {
+                column[cnt++][tid] = j;
+            } else {
+                if (kMaxHits + direct < stride) row[kMaxHits + direct] = j;
+                ++direct;
+            }
+        }
+    };
+    // membership of j in this cell's previous bond row, straight from global memory (slow path only)
+    auto was_bonded_slow = [&](int j) {
+        long long os = old.start(i);
+        int olen = old.row_len[i];
+        bool found = false;
+        for (int k = 0; k < olen; ++k) found |= (old.cols[os + k] == j);
+        return found;
+    };
+
+    int nsh = 0, sh0 = 0, sh1 = 0;                             // hysteresis-shell partners, looked up in phase 3
+    if (!slow) {
+        // ---- phase 2: exact distances and the contact model over the parked partners ---------------------------
+        // (the next partner's position and id are fetched while the current one is evaluated)
+        int t_next = nh > 0 ? column[0][tid] : s;
+        double4 q_next = spos[t_next];
+        int j_next = sorted_id[t_next];
+        for (int k = 0; k < nh; ++k) {
+            const int t = t_next;
+            const double4 q = q_next;
+            int j = j_next;
+            if (k + 1 < nh) {
+                t_next = column[k + 1][tid];
+                q_next = spos[t_next];
+                j_next = sorted_id[t_next];
+            }
+            const double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
+            const double s2 = sumsq_nofma(vx, vy, vz);
+            if (s2 > reach2) continue;                        // let through by the fp32 filter's error band only
+            if (rad.within(s2)) {
+                if (gid_of) j = gid_of[j];
+                bond(vx, vy, vz, s2, q.w, j);                 // cnt <= k: the column is overwritten behind the read
+            } else if (old.valid()) {                         // thin shell: only pre-existing bonds persist
+                if (nsh == 0) sh0 = t;
+                else if (nsh == 1) sh1 = t;
+                else {                                        // rare third+ shell partner
+                    if (gid_of) j = gid_of[j];
+                    if (was_bonded_slow(j)) bond(vx, vy, vz, s2, q.w, j);
+                }
+                ++nsh;
+            }
+        }
+        // ---- phase 3: hysteresis -- shell partners that are in the previous row --------------------------------
         if (nsh > 0) {
-            os = old.start(i);
-            olen = old.row_len[i];
-            if ((os & 3) == 0) {                               // fixed-stride rows (stride % 4 == 0): 16-byte loads
+            const long long os = old.start(i);
+            const int olen = old.row_len[i];
+            int4 oa = make_int4(-1, -1, -1, -1), ob = oa;
+            const bool wide = (os & 3) == 0;                   // fixed-stride rows (stride % 4 == 0): 16-byte loads
+            if (wide) {
                 if (olen > 0) oa = *reinterpret_cast<const int4 *>(old.cols + os);
                 if (olen > 4) ob = *reinterpret_cast<const int4 *>(old.cols + os + 4);
             }
-        }
-        auto in_old_row = [&](int j) {
-            if ((os & 3) != 0) return was_bonded_slow(j);
-            bool f = false;
-            if (olen > 0) f |= (oa.x == j);
-            if (olen > 1) f |= (oa.y == j);
-            if (olen > 2) f |= (oa.z == j);
-            if (olen > 3) f |= (oa.w == j);
-            if (olen > 4) f |= (ob.x == j);
-            if (olen > 5) f |= (ob.y == j);
-            if (olen > 6) f |= (ob.z == j);
-            if (olen > 7) f |= (ob.w == j);
-            for (int k = 8; k < olen; ++k) f |= (old.cols[os + k] == j);
-            return f;
-        };
-        // phase 3: contact model over the parked partners, all lanes together
-        for (int k = 0; k < nh; ++k) {
-            int t = column[k][tid];
-            bool shell = t & kShellFlag;
-            t &= ~kShellFlag;
-            int j = partner_id(t);
-            if (shell && !in_old_row(j)) continue;
-            bond(spos[t], j, true);                           // cnt <= k: the column is overwritten behind the read
-        }
-        // phase 4: hysteresis -- shell partners that are in the previous row
-        if (nsh > 0) {
-            int j0 = partner_id(sh0);
-            if (in_old_row(j0)) bond(spos[sh0], j0, true);
-            if (nsh > 1) {
-                int j1 = partner_id(sh1);
-                if (in_old_row(j1)) bond(spos[sh1], j1, true);
-            }
-        }
-        // phase 5: the bond row.  cnt entries sit in the column; a crowded cell has `direct` more already in global
-        // memory from row[kMaxHits] on, which are moved down so that the row is dense.
-        int total = cnt + direct;
-        int kept = min(total, stride);
-        if (direct == 0) {
-            if (sort_rows) {                                   // ascending rows for the host-visible graph
-                for (int a = 1; a < cnt; ++a) {
-                    int v = column[a][tid], b = a - 1;
-                    while (b >= 0 && column[b][tid] > v) {
-                        column[b + 1][tid] = column[b][tid];
-                        --b;
-                    }
-                    column[b + 1][tid] = v;
+            auto in_old_row = [&](int j) {
+                if (!wide) return was_bonded_slow(j);
+                bool f = false;
+                if (olen > 0) f |= (oa.x == j);
+                if (olen > 1) f |= (oa.y == j);
+                if (olen > 2) f |= (oa.z == j);
+                if (olen > 3) f |= (oa.w == j);
+                if (olen > 4) f |= (ob.x == j);
+                if (olen > 5) f |= (ob.y == j);
+                if (olen > 6) f |= (ob.z == j);
+                if (olen > 7) f |= (ob.w == j);
+                for (int k = 8; k < olen; ++k) f |= (old.cols[os + k] == j);
+                return f;
+            };
+            const int nshell = min(nsh, 2);
+            for (int k = 0; k < nshell; ++k) {
+                const int t = k ? sh1 : sh0;
+                const int j = partner_id(t);
+                if (in_old_row(j)) {
+                    const double4 q = spos[t];
+                    const double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
+                    bond(vx, vy, vz, sumsq_nofma(vx, vy, vz), q.w, j);
                 }
             }
-            int m = min(cnt, stride);
-            if ((stride & 3) == 0) {
-                for (int k = 0; k < m; k += 4) {
-                    int4 v;
-                    v.x = column[k][tid];
-                    v.y = k + 1 < m ? column[k + 1][tid] : -1;
-                    v.z = k + 2 < m ? column[k + 2][tid] : -1;
-                    v.w = k + 3 < m ? column[k + 3][tid] : -1;
-                    *reinterpret_cast<int4 *>(row + k) = v;
-                }
-            } else {
-                for (int k = 0; k < m; ++k) row[k] = column[k][tid];
-            }
-        } else {
-            int moved = min(direct, max(stride - kMaxHits, 0));
-            for (int k = 0; k < min(cnt, stride); ++k) row[k] = column[k][tid];
-            if (cnt < kMaxHits)
-                for (int k = 0; k < moved; ++k) row[cnt + k] = row[kMaxHits + k];
-            if (sort_rows) insertion_sort(row, kept);
         }
-        new_len[i] = kept;
-        // what the overflow report below needs: the row length, and room for the direct entries of a crowded cell
-        // (they live behind the first kMaxHits slots until they are moved down)
-        cnt = direct ? max(total, kMaxHits + direct) : total;
-        // integration (reference cell_backend.py:155-170); positions are read from the sorted snapshot only
-        double friction = stokes_friction(p.w, stokes);
-        double nx = stokes_move(p.x, mx, (double)fxi * kForceUnit, friction, dt, box.size[0]);
-        double ny = stokes_move(p.y, my, (double)fyi * kForceUnit, friction, dt, box.size[1]);
-        double nz = stokes_move(p.z, mz, (double)fzi * kForceUnit, friction, dt, box.size[2]);
-        loc[a3 + 0] = nx;
-        loc[a3 + 1] = ny;
-        loc[a3 + 2] = nz;
-        if (next.counts) {                                    // histogram + rank for the next substep's sort
-            int b = cell_bin_of(nx, ny, nz, next.geom);
-            next.cell_bin[i] = b;
-            next.rank[i] = atomicAdd(&next.counts[b], 1);
+    } else {
+        // ---- slow path: crowded cell or candidate run longer than the tile -------------------------------------
+        const int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int z = bz + dz;
+            if (z < 0 || z >= st.dims[2]) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = by + dy;
+                if (y < 0 || y >= st.dims[1]) continue;
+                const int rowb = (z * st.dims[1] + y) * st.dims[0];
+                const int lo = bin_start[rowb + x0], hi = bin_start[rowb + x1 + 1];
+                for (int t = lo; t < hi; ++t) {
+                    if (t == s) continue;
+                    const double4 q = spos[t];
+                    const double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
+                    const double s2 = sumsq_nofma(vx, vy, vz);
+                    if (s2 > reach2) continue;
+                    const int j = partner_id(t);
+                    if (rad.within(s2) || (old.valid() && was_bonded_slow(j))) bond(vx, vy, vz, s2, q.w, j);
+                }
+            }
         }
     }
-    // overflow report: one atomic per warp, and only when a row did not fit
-    int wmax = cnt;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-    if (lane_id() == 0 && wmax > stride) atomicMax(max_len, wmax);
+
+    // ---- phase 4: the bond row.  cnt entries sit in the column; a crowded cell has `direct` more already in
+    // global memory from row[kMaxHits] on (cnt == kMaxHits then, so the row is dense)
+    const int total = cnt + direct;
+    const int kept = min(total, stride);
+    if (sort_rows && direct == 0) {                            // ascending rows for the host-visible graph
+        for (int a = 1; a < cnt; ++a) {
+            int v = column[a][tid], b = a - 1;
+            while (b >= 0 && column[b][tid] > v) {
+                column[b + 1][tid] = column[b][tid];
+                --b;
+            }
+            column[b + 1][tid] = v;
+        }
+    }
+    {
+        const int m = min(cnt, stride);
+        if ((stride & 3) == 0) {
+            for (int k = 0; k < m; k += 4) {
+                int4 v;
+                v.x = column[k][tid];
+                v.y = k + 1 < m ? column[k + 1][tid] : -1;
+                v.z = k + 2 < m ? column[k + 2][tid] : -1;
+                v.w = k + 3 < m ? column[k + 3][tid] : -1;
+                *reinterpret_cast<int4 *>(row + k) = v;
+            }
+        } else {
+            for (int k = 0; k < m; ++k) row[k] = column[k][tid];
+        }
+        if (sort_rows && direct > 0) insertion_sort(row, kept);
+    }
+    new_len[i] = kept;
+    if (total > stride) atomicMax(max_len, total);            // overflow report (rare): the host doubles the stride
+    // integration (reference cell_backend.py:155-170); positions are read from the sorted snapshot only
+    double friction = fric.uni, inv_f = fric.uni_inv;
+    if (!kUniform) {
+        friction = stokes_friction(p.w, stokes);
+        inv_f = __drcp_rn(friction);
+    }
+    const double mx = mot[3 * (long long)i + 0], my = mot[3 * (long long)i + 1], mz = mot[3 * (long long)i + 2];
+    const double nx = stokes_move_y(p.x, mx, (double)fxi * kForceUnit, friction, inv_f, dt, box.size[0]);
+    const double ny = stokes_move_y(p.y, my, (double)fyi * kForceUnit, friction, inv_f, dt, box.size[1]);
+    const double nz = stokes_move_y(p.z, mz, (double)fzi * kForceUnit, friction, inv_f, dt, box.size[2]);
+    if (loc) {
+        loc[3 * (long long)i + 0] = nx;
+        loc[3 * (long long)i + 1] = ny;
+        loc[3 * (long long)i + 2] = nz;
+    }
+    if (next.counts) {                                        // hand-over to the next substep's sort, by slot
+        int b = cell_bin_of(nx, ny, nz, next.geom);
+        next.next_pos[s] = make_double4(nx, ny, nz, p.w);
+        next.cell_bin[s] = b;
+        next.prev_id[s] = i;
+        atomicAdd(&next.counts[b], 1);
+    }
 }
 
 }  // namespace abm
@@ -374,8 +451,9 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(bin_start && sorted_id && sorted_pos && sorted_bin && dims_host && new_row_len && new_cols &&
-                    max_len && motility_forces && locations && size_host,
+                    max_len && motility_forces && size_host,
                 "null pointer");
+    ABM_REQUIRE(locations || next_bin_counts, "locations may be NULL only when the cells are handed to the next sort");
     ABM_REQUIRE(row_stride > 0 && row_stride < (1 << 20), "bad row_stride");
     ABM_REQUIRE(reach >= distance && distance > 0, "reach must be >= distance > 0");
     ABM_REQUIRE(old_cols != new_cols, "old and new bond rows must be different buffers");
@@ -398,12 +476,21 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
         SortWs w = sort_ws_carve(next_sort_workspace, n, nbins);
         next.counts = next_bin_counts;
         next.cell_bin = w.cell_bin;
-        next.rank = w.rank;
+        next.prev_id = w.tmp_id;
+        next.next_pos = w.next_pos;
     }
-    k_jkr_substep<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
+    Friction fric{0.0, 0.0};
+    if (uniform_radius > 0) {                                  // stokes_friction() on the host: same IEEE products
+        const double kPi = 3.141592653589793;
+        volatile double f = ((6.0 * kPi) * stokes) * (uniform_radius / 1e6);
+        fric.uni = f;
+        fric.uni_inv = 1.0 / f;
+    }
+    auto kernel = uniform_radius > 0 ? k_jkr_substep<true> : k_jkr_substep<false>;
+    kernel<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
         Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
-        locations, c, stokes, box, move_dt, global_id, next, sort_rows);
+        locations, c, stokes, fric, box, move_dt, global_id, next, sort_rows);
     ABM_CHECK_LAUNCH("k_jkr_substep");
     return 0;
 }
@@ -446,7 +533,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
         rc = abm_jkr_substep(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
                              cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, k == n_substeps - 1,
-                             motility_forces, locations,
+                             motility_forces, prebin ? nullptr : locations,
                              poisson, youngs, adhesion_const, stokes, size_host, dts_host[k], global_id, uniform_radius,
                              prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
                              prebin ? sort_workspace : nullptr, stream);

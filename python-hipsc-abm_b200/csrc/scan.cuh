@@ -53,10 +53,12 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const int *
     }
 }
 
-// exclusive scan in place; if total_out != nullptr the grand total is written there by the last block
+// exclusive scan in place; if total_out != nullptr the grand total is written there by the last block, and if
+// copy_out != nullptr the scanned values are written there as well (same alignment as data)
 static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restrict__ data, int64_t n,
                                                              const int *__restrict__ block_sums,
-                                                             int *__restrict__ total_out) {
+                                                             int *__restrict__ total_out,
+                                                             int *__restrict__ copy_out) {
     __shared__ int smem[32];
     __shared__ int warp_tot[kScanThreads / 32];
     // offset of this chunk = sum of the preceding block sums
@@ -107,17 +109,27 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restr
         for (int k = 0; k < kScanItems; ++k)
             if (first + k < n) data[first + k] = o[k];
     }
+    if (copy_out) {
+        if (full && ((reinterpret_cast<uintptr_t>(copy_out + first) & 15) == 0)) {
+            *reinterpret_cast<int4 *>(copy_out + first) = make_int4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<int4 *>(copy_out + first + 4) = make_int4(o[4], o[5], o[6], o[7]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k)
+                if (first + k < n) copy_out[first + k] = o[k];
+        }
+    }
     if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
 }
 
 // data[0..n) -> exclusive prefix in place.  block_sums: scan_blocks(n) ints of scratch.
 inline int exclusive_scan_inplace(int *data, int64_t n, int *block_sums, int *max_out, int *total_out,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int *copy_out = nullptr) {
     int nb = scan_blocks(n);
     if (nb == 0) return 0;
     k_scan_reduce<<<nb, kScanThreads, 0, st>>>(data, n, block_sums, max_out);
     ABM_CHECK_LAUNCH("k_scan_reduce");
-    k_scan_apply<<<nb, kScanThreads, 0, st>>>(data, n, block_sums, total_out);
+    k_scan_apply<<<nb, kScanThreads, 0, st>>>(data, n, block_sums, total_out, copy_out);
     ABM_CHECK_LAUNCH("k_scan_apply");
     return 0;
 }

@@ -4,13 +4,14 @@
 // and a (nbins+1) offset table indexes them.
 //
 // Two placements:
-//   fast (default)      : slot = bin_start[bin] + arrival rank.  The order inside a bin is whatever the atomics
-//                         produced; every consumer is order-independent (rows and force sums are ordered by
-//                         cell id downstream), so results stay run-to-run identical.
+//   fast (default)      : every cell claims the next free slot of its bin with one atomicAdd on a copy of the
+//                         offset table.  The order inside a bin is whatever the atomics produced; every
+//                         consumer is order-independent (rows are ordered by cell id, force sums are integer
+//                         sums), so results stay run-to-run identical.
 //   ABM_SORT_STABLE     : ascending cell id inside a bin -- the reference's serial fill order, needed only to
 //                         hand out the reference-shaped dense buckets of assign_bins().
 // ABM_SORT_PREBINNED skips the histogram: bin_start already holds the bin populations and the scratch buffer
-// the (bin, rank) of every cell, written by the fused mechanics kernel of the previous substep.
+// the bin of every cell, written by the fused mechanics kernel of the previous substep.
 #include "sortws.cuh"
 
 namespace abm {
@@ -18,25 +19,23 @@ namespace abm {
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) k_bin_count(const double *__restrict__ loc, int n, BinGeom g,
-                                                        int *__restrict__ counts, int *__restrict__ cell_bin,
-                                                        int *__restrict__ rank) {
+                                                        int *__restrict__ counts, int *__restrict__ cell_bin) {
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     int b = cell_bin_of(loc[3 * (int64_t)i + 0], loc[3 * (int64_t)i + 1], loc[3 * (int64_t)i + 2], g);
     cell_bin[i] = b;
-    rank[i] = atomicAdd(&counts[b], 1);
+    atomicAdd(&counts[b], 1);
 }
 
 // fast placement: coalesced reads by cell id, one 32-byte row + two ints scattered per cell
-__global__ void __launch_bounds__(kThreads) k_scatter(const int *__restrict__ cell_bin, const int *__restrict__ rank,
-                                                      const int *__restrict__ bin_start,
+__global__ void __launch_bounds__(kThreads) k_scatter(const int *__restrict__ cell_bin, int *__restrict__ cursor,
                                                       const double *__restrict__ loc, const double *__restrict__ radii,
                                                       int n, int *__restrict__ sorted_id,
                                                       double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin) {
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
     int b = cell_bin[i];
-    int dest = bin_start[b] + rank[i];
+    int dest = atomicAdd(&cursor[b], 1);
     double4 p;
     p.x = loc[3 * (int64_t)i + 0];
     p.y = loc[3 * (int64_t)i + 1];
@@ -47,12 +46,27 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const int *__restrict__ ce
     sorted_bin[dest] = b;
 }
 
-__global__ void __launch_bounds__(kThreads) k_place(const int *__restrict__ cell_bin, const int *__restrict__ rank,
-                                                    const int *__restrict__ bin_start, int n,
+// ABM_SORT_PREBINNED placement: the moved cells arrive in the PREVIOUS sort's slot order (written coalesced by the
+// fused mechanics kernel).  Cells move a fraction of a bin per substep, so the destination slots of a warp lie
+// within a few cache lines of each other: both sides of the permutation are (nearly) coalesced.
+__global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ next_bin, const int *__restrict__ prev_id,
+                                                        const double4 *__restrict__ next_pos, int *__restrict__ cursor,
+                                                        int n, int *__restrict__ sorted_id,
+                                                        double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin) {
+    int s = blockIdx.x * kThreads + threadIdx.x;
+    if (s >= n) return;
+    int b = next_bin[s];
+    int dest = atomicAdd(&cursor[b], 1);
+    sorted_pos[dest] = next_pos[s];
+    sorted_id[dest] = prev_id[s];
+    sorted_bin[dest] = b;
+}
+
+__global__ void __launch_bounds__(kThreads) k_place(const int *__restrict__ cell_bin, int *__restrict__ cursor, int n,
                                                     int *__restrict__ tmp_id) {
     int i = blockIdx.x * kThreads + threadIdx.x;
     if (i >= n) return;
-    tmp_id[bin_start[cell_bin[i]] + rank[i]] = i;
+    tmp_id[atomicAdd(&cursor[cell_bin[i]], 1)] = i;
 }
 
 // stable placement: one thread per provisional slot finds its ascending-id position inside the bin segment
@@ -144,25 +158,31 @@ ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_
     rc = check_cuda(cudaMemsetAsync(max_count, 0, 4, st), "memset max_count");
     if (rc) return rc;
     if (n == 0) return 0;
-    ABM_REQUIRE(locations && radii && sorted_id && sorted_pos && sorted_bin && workspace, "null pointer");
+    ABM_REQUIRE(sorted_id && sorted_pos && sorted_bin && workspace, "null pointer");
+    ABM_REQUIRE(prebinned || (locations && radii), "null pointer");
+    ABM_REQUIRE(!(prebinned && (flags & ABM_SORT_STABLE)), "ABM_SORT_PREBINNED cannot be combined with ABM_SORT_STABLE");
     ABM_REQUIRE(((uintptr_t)sorted_pos & 31) == 0, "sorted_pos must be 32-byte aligned");
     SortWs w = sort_ws_carve(workspace, n, nbins);
     int blocks = ceil_div(n, kThreads);
     if (!prebinned) {
-        k_bin_count<<<blocks, kThreads, 0, st>>>(locations, (int)n, g, bin_start, w.cell_bin, w.rank);
+        k_bin_count<<<blocks, kThreads, 0, st>>>(locations, (int)n, g, bin_start, w.cell_bin);
         ABM_CHECK_LAUNCH("k_bin_count");
     }
-    rc = exclusive_scan_inplace(bin_start, nbins + 1, w.block_sums, max_count, nullptr, st);
+    rc = exclusive_scan_inplace(bin_start, nbins + 1, w.block_sums, max_count, nullptr, st, w.cursor);
     if (rc) return rc;
     double4 *sp = reinterpret_cast<double4 *>(sorted_pos);
-    if (flags & ABM_SORT_STABLE) {
-        k_place<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.rank, bin_start, (int)n, w.tmp_id);
+    if (prebinned) {
+        k_rescatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.tmp_id, w.next_pos, w.cursor, (int)n, sorted_id, sp,
+                                                 sorted_bin);
+        ABM_CHECK_LAUNCH("k_rescatter");
+    } else if (flags & ABM_SORT_STABLE) {
+        k_place<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.cursor, (int)n, w.tmp_id);
         ABM_CHECK_LAUNCH("k_place");
         k_gather<<<blocks, kThreads, 0, st>>>(w.tmp_id, w.cell_bin, bin_start, locations, radii, (int)n, sorted_id, sp,
                                               sorted_bin);
         ABM_CHECK_LAUNCH("k_gather");
     } else {
-        k_scatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.rank, bin_start, locations, radii, (int)n, sorted_id, sp,
+        k_scatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.cursor, locations, radii, (int)n, sorted_id, sp,
                                                sorted_bin);
         ABM_CHECK_LAUNCH("k_scatter");
     }

@@ -6,26 +6,29 @@
 namespace abm {
 
 struct SortWs {
-    int *rank;        // n   : arrival order of the cell inside its bin (atomicAdd return value, not stable)
-    int *cell_bin;    // n   : linear bin of cell i
-    int *tmp_id;      // n   : unstable placement (stable mode only)
+    int *cursor;      // nbins+1 : copy of the offset table; the placement kernels claim slots from it atomically
+    int *cell_bin;    // n   : linear bin of cell i (ABM_SORT_PREBINNED: of the cell in PREVIOUS slot s)
+    int *tmp_id;      // n   : unstable placement (stable mode); ABM_SORT_PREBINNED: id of the cell in previous slot s
     int *block_sums;  // scan scratch
+    double4 *next_pos;// n   : ABM_SORT_PREBINNED: moved {x,y,z,r} of the cell in previous slot s
 };
 
 inline size_t sort_align(size_t v) { return (v + 255) & ~size_t(255); }
 
 inline size_t sort_ws_bytes(int64_t n, int64_t nbins) {
-    return 3 * sort_align((size_t)n * 4) + sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4) + 256;
+    return 2 * sort_align((size_t)n * 4) + sort_align((size_t)(nbins + 1) * 4) +
+           sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4) + sort_align((size_t)n * 32) + 512;
 }
 
 inline SortWs sort_ws_carve(void *ws, int64_t n, int64_t nbins) {
     char *p = (char *)ws;
     SortWs w;
-    w.rank = (int *)p;       p += sort_align((size_t)n * 4);
     w.cell_bin = (int *)p;   p += sort_align((size_t)n * 4);
     w.tmp_id = (int *)p;     p += sort_align((size_t)n * 4);
-    w.block_sums = (int *)p;
-    (void)nbins;
+    w.cursor = (int *)p;     p += sort_align((size_t)(nbins + 1) * 4);
+    w.block_sums = (int *)p; p += sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4);
+    p = (char *)(((uintptr_t)p + 255) & ~uintptr_t(255));    // the caller's buffer need not be aligned
+    w.next_pos = (double4 *)p;
     return w;
 }
 

@@ -49,4 +49,18 @@ else:
             a.record(); launch(); z.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(z) * 1e3)
         res["cold" if cold else "warm"] = float(np.median(ts))
-    print(os.path.basename(os.environ.get("ABM_B200_LIB", "default")), name, res)
+    # whole step as a CUDA-graph replay (no diffusion grid), L2 flushed before each
+    if pipe.parity:
+        pipe.step()
+    pipe.capture()
+    for _ in range(6):
+        pipe.replay()
+    ts = []
+    for _ in range(20):
+        flush.zero_()
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); pipe.replay(); z.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(z) * 1e3)
+    res["step_us"] = float(np.median(ts))
+    pipe.check()
+    print(os.path.basename(os.environ.get("ABM_B200_LIB", "default")), name, {k: round(v, 1) for k, v in res.items()})
