@@ -140,7 +140,10 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  *                      on the host), else 0.
  *   next_bin_counts  : NULL, or a zeroed (nbins+1) table (not bin_start): the kernel then also bins every moved
  *                      cell on the lattice (next_origin, next_extent, edge `reach`) and leaves histogram,
- *                      bin where abm_bin_sort(ABM_SORT_PREBINNED, same workspace) expects them.
+ *                      bin, moved position and id of every cell (in the current slot order) and the histogram's
+ *                      per-chunk sums where abm_bin_sort(ABM_SORT_PREBINNED, same workspace, SAME lattice as the
+ *                      sort that produced the current order) expects them.  `locations` may then be NULL (the
+ *                      moved cells are only handed to the next sort).
  *   reach            : bin edge of the sort, >= abm_jkr_reach(distance, max(radii), ...).
  *   max_len (1) int32: raised (atomicMax) by rows that needed more than row_stride entries; a value
  *   > row_stride afterwards means those rows were truncated: grow row_stride and redo the substep

@@ -87,6 +87,9 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 #ifndef ABM_JKR_MINBLOCKS
 #define ABM_JKR_MINBLOCKS 7      // register cap: 7 -> 72/thread (measured best of 5..8 at 500k cells)
 #endif
+#ifndef ABM_JKR_EXP
+#define ABM_JKR_EXP 0
+#endif
 constexpr int kMaxHits = 16;
 constexpr int kJkrMinBlocks = ABM_JKR_MINBLOCKS;
 constexpr double kForceUnit = 0x1p-76, kForceUnitInv = 0x1p76;   // fixed-point force accumulation (N)
@@ -123,7 +126,7 @@ struct BondEval {
 
 struct NextSort {          // hand-over of the moved cells to the following substep's sort (counts == nullptr: off),
     BinGeom geom;          // in THIS sort's slot order: the next permutation is then nearly the identity
-    int *counts, *cell_bin, *prev_id;
+    int *counts, *cell_bin, *prev_id, *chunk_sums;
     double4 *next_pos;
 };
 
@@ -173,7 +176,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         i = sorted_id[s];
         p = spos[s];
         st.decode(sorted_bin[s], bx, by, bz);
-        // the motility force is needed at the very end: pull its line into L2 now, load it then
+        // the motility force is loaded after the walk (registers) and used at the very end: pull its line in now
         asm volatile("prefetch.global.L2 [%0];" ::"l"(mot + 3 * (long long)i));
     }
 
@@ -214,6 +217,9 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     if (!live) return;                                         // no warp-wide operation below this line
     slow |= nh > kMaxHits;
 
+#if ABM_JKR_EXP & 1
+    const double mx = mot[3 * (long long)i + 0], my = mot[3 * (long long)i + 1], mz = mot[3 * (long long)i + 2];
+#endif
     int *row = new_cols + (long long)i * stride;
     long long fxi = 0, fyi = 0, fzi = 0;
     BondEval ev;
@@ -260,7 +266,12 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         return found;
     };
 
-    int nsh = 0, sh0 = 0, sh1 = 0;                             // hysteresis-shell partners, looked up in phase 3
+    int nsh = 0, sh0 = 0, sh1 = 0, shj0 = 0, shj1 = 0;         // hysteresis-shell partners, looked up in phase 3
+    const long long os = old.valid() ? old.start(i) : 0;
+    // fixed-stride rows of >= 8 entries (stride % 4 == 0): the first 8 ids come as two unconditional 16-byte loads
+    const bool wide = old.valid() && !old.row_start && (old.stride & 3) == 0 && old.stride >= 8;
+    int olen = 0;
+    int4 oa = make_int4(-1, -1, -1, -1), ob = oa;
     if (!slow) {
         // ---- phase 2: exact distances and the contact model over the parked partners ---------------------------
         // (the next partner's position and id are fetched while the current one is evaluated)
@@ -283,25 +294,35 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                 if (gid_of) j = gid_of[j];
                 bond(vx, vy, vz, s2, q.w, j);                 // cnt <= k: the column is overwritten behind the read
             } else if (old.valid()) {                         // thin shell: only pre-existing bonds persist
-                if (nsh == 0) sh0 = t;
-                else if (nsh == 1) sh1 = t;
-                else {                                        // rare third+ shell partner
-                    if (gid_of) j = gid_of[j];
-                    if (was_bonded_slow(j)) bond(vx, vy, vz, s2, q.w, j);
+                if (gid_of) j = gid_of[j];
+                if (nsh == 0) {
+                    sh0 = t;
+                    shj0 = j;
+#if ABM_JKR_EXP & 2
+                    olen = old.row_len[i];                    // the previous row starts its way here now
+                    if (wide) {
+                        oa = *reinterpret_cast<const int4 *>(old.cols + os);
+                        ob = *reinterpret_cast<const int4 *>(old.cols + os + 4);
+                    }
+#endif
+                } else if (nsh == 1) {
+                    sh1 = t;
+                    shj1 = j;
+                } else if (was_bonded_slow(j)) {              // rare third+ shell partner
+                    bond(vx, vy, vz, s2, q.w, j);
                 }
                 ++nsh;
             }
         }
         // ---- phase 3: hysteresis -- shell partners that are in the previous row --------------------------------
         if (nsh > 0) {
-            const long long os = old.start(i);
-            const int olen = old.row_len[i];
-            int4 oa = make_int4(-1, -1, -1, -1), ob = oa;
-            const bool wide = (os & 3) == 0;                   // fixed-stride rows (stride % 4 == 0): 16-byte loads
+#if !(ABM_JKR_EXP & 2)
+            olen = old.row_len[i];
             if (wide) {
-                if (olen > 0) oa = *reinterpret_cast<const int4 *>(old.cols + os);
-                if (olen > 4) ob = *reinterpret_cast<const int4 *>(old.cols + os + 4);
+                oa = *reinterpret_cast<const int4 *>(old.cols + os);
+                ob = *reinterpret_cast<const int4 *>(old.cols + os + 4);
             }
+#endif
             auto in_old_row = [&](int j) {
                 if (!wide) return was_bonded_slow(j);
                 bool f = false;
@@ -319,7 +340,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
             const int nshell = min(nsh, 2);
             for (int k = 0; k < nshell; ++k) {
                 const int t = k ? sh1 : sh0;
-                const int j = partner_id(t);
+                const int j = k ? shj1 : shj0;
                 if (in_old_row(j)) {
                     const double4 q = spos[t];
                     const double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
@@ -389,7 +410,9 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         friction = stokes_friction(p.w, stokes);
         inv_f = __drcp_rn(friction);
     }
+#if !(ABM_JKR_EXP & 1)
     const double mx = mot[3 * (long long)i + 0], my = mot[3 * (long long)i + 1], mz = mot[3 * (long long)i + 2];
+#endif
     const double nx = stokes_move_y(p.x, mx, (double)fxi * kForceUnit, friction, inv_f, dt, box.size[0]);
     const double ny = stokes_move_y(p.y, my, (double)fyi * kForceUnit, friction, inv_f, dt, box.size[1]);
     const double nz = stokes_move_y(p.z, mz, (double)fzi * kForceUnit, friction, inv_f, dt, box.size[2]);
@@ -404,6 +427,11 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         next.cell_bin[s] = b;
         next.prev_id[s] = i;
         atomicAdd(&next.counts[b], 1);
+        // the histogram's sum per scan chunk, so that the next sort needs no reduction pass: one atomic per
+        // distinct chunk among the lanes here (neighbouring slots fall in the same chunk)
+        const int chunk = b / kScanChunk;
+        const unsigned peers = __match_any_sync(__activemask(), chunk);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&next.chunk_sums[chunk], __popc(peers));
     }
 }
 
@@ -477,6 +505,7 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
         next.counts = next_bin_counts;
         next.cell_bin = w.cell_bin;
         next.prev_id = w.tmp_id;
+        next.chunk_sums = w.next_sums;
         next.next_pos = w.next_pos;
     }
     Friction fric{0.0, 0.0};
@@ -521,15 +550,11 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
     int64_t cur_stride = old_row_stride;
     for (int k = 0; k < n_substeps; ++k) {
         int32_t *table = (k & 1) ? bin_start_b : bin_start_a, *other = (k & 1) ? bin_start_a : bin_start_b;
-        int rc = abm_bin_sort(locations, radii, n, extent_host, origin_host, reach, k ? ABM_SORT_PREBINNED : 0, table,
-                              sorted_id, sorted_pos, sorted_bin, max_count, sort_workspace, sort_workspace_bytes,
-                              stream);
-        if (rc) return rc;
         const bool prebin = k + 1 < n_substeps && n > 0;
-        if (prebin) {
-            rc = check_cuda(cudaMemsetAsync(other, 0, (size_t)(nbins + 1) * 4, st), "memset next offset table");
-            if (rc) return rc;
-        }
+        int rc = bin_sort_impl(locations, radii, n, extent_host, origin_host, reach, k ? ABM_SORT_PREBINNED : 0, table,
+                               sorted_id, sorted_pos, sorted_bin, max_count, sort_workspace, sort_workspace_bytes,
+                               prebin ? other : nullptr, stream);     // the idle table is cleared on the way
+        if (rc) return rc;
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
         rc = abm_jkr_substep(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
                              cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, k == n_substeps - 1,

@@ -54,11 +54,15 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const int *
 }
 
 // exclusive scan in place; if total_out != nullptr the grand total is written there by the last block, and if
-// copy_out != nullptr the scanned values are written there as well (same alignment as data)
+// copy_out != nullptr the scanned values are written there as well (same alignment as data).  Optional riders
+// that save separate launches: zero_out (n ints, same alignment as data) is cleared, max_out is raised to the
+// largest input value.
 static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restrict__ data, int64_t n,
                                                              const int *__restrict__ block_sums,
                                                              int *__restrict__ total_out,
-                                                             int *__restrict__ copy_out) {
+                                                             int *__restrict__ copy_out,
+                                                             int *__restrict__ zero_out = nullptr,
+                                                             int *__restrict__ max_out = nullptr) {
     __shared__ int smem[32];
     __shared__ int warp_tot[kScanThreads / 32];
     // offset of this chunk = sum of the preceding block sums
@@ -118,6 +122,24 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restr
             for (int k = 0; k < kScanItems; ++k)
                 if (first + k < n) copy_out[first + k] = o[k];
         }
+    }
+    if (zero_out) {
+        if (full && ((reinterpret_cast<uintptr_t>(zero_out + first) & 15) == 0)) {
+            *reinterpret_cast<int4 *>(zero_out + first) = make_int4(0, 0, 0, 0);
+            *reinterpret_cast<int4 *>(zero_out + first + 4) = make_int4(0, 0, 0, 0);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; ++k)
+                if (first + k < n) zero_out[first + k] = 0;
+        }
+    }
+    if (max_out) {
+        int mx = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; ++k) mx = max(mx, v[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane_id() == 0 && mx > 0) atomicMax(max_out, mx);
     }
     if (total_out && blockIdx.x == gridDim.x - 1 && threadIdx.x == kScanThreads - 1) *total_out = run;
 }

@@ -31,8 +31,10 @@ __global__ void __launch_bounds__(kThreads) k_bin_count(const double *__restrict
 __global__ void __launch_bounds__(kThreads) k_scatter(const int *__restrict__ cell_bin, int *__restrict__ cursor,
                                                       const double *__restrict__ loc, const double *__restrict__ radii,
                                                       int n, int *__restrict__ sorted_id,
-                                                      double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin) {
+                                                      double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
+                                                      int *__restrict__ next_sums, int n_sums) {
     int i = blockIdx.x * kThreads + threadIdx.x;
+    for (int k = i; k < n_sums; k += gridDim.x * kThreads) next_sums[k] = 0;
     if (i >= n) return;
     int b = cell_bin[i];
     int dest = atomicAdd(&cursor[b], 1);
@@ -52,8 +54,11 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const int *__restrict__ ce
 __global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ next_bin, const int *__restrict__ prev_id,
                                                         const double4 *__restrict__ next_pos, int *__restrict__ cursor,
                                                         int n, int *__restrict__ sorted_id,
-                                                        double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin) {
+                                                        double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
+                                                        int *__restrict__ next_sums, int n_sums) {
     int s = blockIdx.x * kThreads + threadIdx.x;
+    // consumed by this sort's scan; the next hand-over adds to it
+    for (int k = s; k < n_sums; k += gridDim.x * kThreads) next_sums[k] = 0;
     if (s >= n) return;
     int b = next_bin[s];
     int dest = atomicAdd(&cursor[b], 1);
@@ -141,6 +146,16 @@ ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_
                             const double *origin_host, double distance, int flags, int32_t *bin_start,
                             int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
                             void *workspace, size_t workspace_bytes, void *stream) {
+    return abm::bin_sort_impl(locations, radii, n, size_host, origin_host, distance, flags, bin_start, sorted_id,
+                              sorted_pos, sorted_bin, max_count, workspace, workspace_bytes, nullptr, stream);
+}
+
+// zero_table: optional second (nbins+1) offset table cleared on the way (the mechanics loop alternates two tables
+// and needs the idle one zeroed for the next histogram).
+int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, const double size_host[3],
+                       const double *origin_host, double distance, int flags, int32_t *bin_start,
+                       int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
+                       void *workspace, size_t workspace_bytes, int32_t *zero_table, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     ABM_REQUIRE(size_host && bin_start && max_count, "null pointer");
     BinGeom g;
@@ -157,7 +172,10 @@ ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_
     }
     rc = check_cuda(cudaMemsetAsync(max_count, 0, 4, st), "memset max_count");
     if (rc) return rc;
-    if (n == 0) return 0;
+    if (n == 0) {
+        if (zero_table) return check_cuda(cudaMemsetAsync(zero_table, 0, (size_t)(nbins + 1) * 4, st), "memset table");
+        return 0;
+    }
     ABM_REQUIRE(sorted_id && sorted_pos && sorted_bin && workspace, "null pointer");
     ABM_REQUIRE(prebinned || (locations && radii), "null pointer");
     ABM_REQUIRE(!(prebinned && (flags & ABM_SORT_STABLE)), "ABM_SORT_PREBINNED cannot be combined with ABM_SORT_STABLE");
@@ -168,14 +186,27 @@ ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_
         k_bin_count<<<blocks, kThreads, 0, st>>>(locations, (int)n, g, bin_start, w.cell_bin);
         ABM_CHECK_LAUNCH("k_bin_count");
     }
-    rc = exclusive_scan_inplace(bin_start, nbins + 1, w.block_sums, max_count, nullptr, st, w.cursor);
-    if (rc) return rc;
+    const int nb = scan_blocks(nbins + 1);
+    if (prebinned) {
+        // the mechanics kernel that binned the cells also summed the histogram per scan chunk: one scan launch
+        k_scan_apply<<<nb, kScanThreads, 0, st>>>(bin_start, nbins + 1, w.next_sums, nullptr, w.cursor, zero_table,
+                                                  max_count);
+        ABM_CHECK_LAUNCH("k_scan_apply");
+    } else {
+        k_scan_reduce<<<nb, kScanThreads, 0, st>>>(bin_start, nbins + 1, w.block_sums, max_count);
+        ABM_CHECK_LAUNCH("k_scan_reduce");
+        k_scan_apply<<<nb, kScanThreads, 0, st>>>(bin_start, nbins + 1, w.block_sums, nullptr, w.cursor, zero_table,
+                                                  nullptr);
+        ABM_CHECK_LAUNCH("k_scan_apply");
+    }
     double4 *sp = reinterpret_cast<double4 *>(sorted_pos);
     if (prebinned) {
         k_rescatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.tmp_id, w.next_pos, w.cursor, (int)n, sorted_id, sp,
-                                                 sorted_bin);
+                                                 sorted_bin, w.next_sums, nb);
         ABM_CHECK_LAUNCH("k_rescatter");
     } else if (flags & ABM_SORT_STABLE) {
+        rc = check_cuda(cudaMemsetAsync(w.next_sums, 0, (size_t)nb * 4, st), "memset next_sums");
+        if (rc) return rc;
         k_place<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.cursor, (int)n, w.tmp_id);
         ABM_CHECK_LAUNCH("k_place");
         k_gather<<<blocks, kThreads, 0, st>>>(w.tmp_id, w.cell_bin, bin_start, locations, radii, (int)n, sorted_id, sp,
@@ -183,7 +214,7 @@ ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_
         ABM_CHECK_LAUNCH("k_gather");
     } else {
         k_scatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.cursor, locations, radii, (int)n, sorted_id, sp,
-                                               sorted_bin);
+                                               sorted_bin, w.next_sums, nb);
         ABM_CHECK_LAUNCH("k_scatter");
     }
     return 0;

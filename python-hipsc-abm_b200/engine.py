@@ -353,7 +353,8 @@ class ColonyEngine:
             _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),
             stride, _ptr(b["max_len"]), _ptr(self.global_id), float(self.uniform_radius), JKR_POISSON, JKR_YOUNGS,
             JKR_ADHESION, float(stokes), self.stream), "abm_mechanics_loop")
-        self.launches += (4 * len(dts) + 1) if n else 0      # [scan x2, scatter, substep] per substep + 1 histogram
+        # first substep: histogram, scan x2, scatter, substep; every later one: scan, rescatter, substep
+        self.launches += (3 * len(dts) + 2) if n else 0
         last = pair[(len(dts) - 1) & 1]
         return GraphTensors(n, None, stride, b["len"][last], b["cols"][last], True)
 
@@ -389,7 +390,7 @@ class ColonyEngine:
         self.launches += int(steps)
         return scratch if where.value else field
 
-    def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None) -> torch.Tensor:
+    def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None) -> torch.Tensor:
         """get_concentration for every cell.  `field` is the whole (gx,gy[,gz]) grid, or -- with rows=(lo,hi) and
         grid_rows=gx -- the slab of global rows [lo,hi) of it."""
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
@@ -397,18 +398,20 @@ class ColonyEngine:
         if grid_rows is not None:
             gs[0] = int(grid_rows)
         out = self._empty(max(self.n, 1), torch.float64)
-        _lib.check(self.lib.abm_sample_concentrations(_ptr(self.loc), self.n, _ptr(field), _lib.l3(gs),
+        _lib.check(self.lib.abm_sample_concentrations(_ptr(self.loc if loc is None else loc), self.n, _ptr(field),
+                                                      _lib.l3(gs),
                                                       float(spat_res), int(lo), int(hi), _ptr(out), self.stream),
                    "abm_sample_concentrations")
         self.launches += 1 if self.n else 0
         return out[:self.n]
 
-    def deposit(self, field: torch.Tensor, amounts: torch.Tensor, spat_res, rows=None, grid_rows=None):
+    def deposit(self, field: torch.Tensor, amounts: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None):
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
         lo, hi = (0, gs[0]) if rows is None else rows
         if grid_rows is not None:
             gs[0] = int(grid_rows)
-        _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc), _ptr(amounts), self.n, _ptr(field), _lib.l3(gs),
+        _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc if loc is None else loc), _ptr(amounts), self.n,
+                                                   _ptr(field), _lib.l3(gs),
                                                    float(spat_res), int(lo), int(hi), self.stream),
                    "abm_deposit_morphogens")
         self.launches += 1 if self.n else 0

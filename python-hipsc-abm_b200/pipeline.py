@@ -41,6 +41,11 @@ class StepConfig:
     bond_stride: int = 16
     search_cols_per_cell: float = 12.0   # column-buffer capacity of the r_search graph, entries per cell
     use_tma: Optional[bool] = None
+    # morphogen stage (deposit -> diffuse -> sample) on the positions the step STARTS with -- where the reference
+    # calls update_diffusion, before cell_motility/apply_forces (cell_simulation.py:101-112) -- so that it is
+    # independent of the step's search + mechanics and runs beside them on a second stream.  False: after the
+    # mechanics, on the moved positions, on the same stream.
+    overlap_morphogen: bool = False
 
     def substep_dts(self):
         steps, last_dt = divmod(self.step_dt, self.move_dt)     # cell_methods.py:395-396
@@ -73,6 +78,10 @@ class HotPathStep:
                 raise ValueError("HotPathStep keeps the field in place: use an even number of diffusion substeps")
         self.graphs = None
         self.launches_per_step = 0
+        self._side = self._loc_snap = None
+        if cfg.grid is not None and cfg.overlap_morphogen:
+            self._side = torch.cuda.Stream(device=dev)
+            self._loc_snap = torch.empty((max(n, 1), 3), dtype=torch.float64, device=dev)
         # start with an empty bond graph living in row buffer 0
         b = engine._bond_buffers(n, cfg.bond_stride)
         b["len"][0].zero_()
@@ -84,6 +93,16 @@ class HotPathStep:
         eng, cfg = self.eng, self.cfg
         eng.use_current_stream()              # under torch.cuda.graph() this is the capture stream
         before = eng.launches
+        overlap = self.field is not None and cfg.overlap_morphogen
+        if overlap:
+            # fork: the morphogen stage works on a snapshot of the positions and runs beside search + mechanics
+            main = torch.cuda.current_stream(eng.device)
+            self._loc_snap[:eng.n].copy_(eng.loc)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                eng.use_current_stream()
+                self._morphogen(self._loc_snap)
+            eng.use_current_stream()
         # neighbour graph (what the rule methods consume)
         srt = eng.sort(cfg.search_radius)
         self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self.nbr["row_start"],
@@ -97,16 +116,22 @@ class HotPathStep:
         self.parity = 1 - src if len(self.dts) % 2 else src
         if len(self.dts) % 2 == 0:
             raise ValueError("even substep counts are not wired in HotPathStep")
-        # morphogen: deposit -> diffuse -> sample
-        if self.field is not None:
-            eng.deposit(self.field, self.amounts, cfg.spat_res)
-            last = cfg.diffuse_dt if cfg.diffuse_last_dt is None else cfg.diffuse_last_dt
-            out = eng.diffuse(self.field, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const,
-                              cfg.spat_res ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma,
-                              scratch=self.scratch)
-            assert out.data_ptr() == self.field.data_ptr()
-            self.sampled = eng.sample(self.field, cfg.spat_res)
+        if overlap:
+            torch.cuda.current_stream(eng.device).wait_stream(self._side)      # join
+        elif self.field is not None:
+            self._morphogen(None)
         self.launches_per_step = eng.launches - before
+
+    def _morphogen(self, loc):
+        """deposit -> diffuse -> sample on the engine's current stream (loc=None: the engine's positions)."""
+        eng, cfg = self.eng, self.cfg
+        eng.deposit(self.field, self.amounts, cfg.spat_res, loc=loc)
+        last = cfg.diffuse_dt if cfg.diffuse_last_dt is None else cfg.diffuse_last_dt
+        out = eng.diffuse(self.field, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const,
+                          cfg.spat_res ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma,
+                          scratch=self.scratch)
+        assert out.data_ptr() == self.field.data_ptr()
+        self.sampled = eng.sample(self.field, cfg.spat_res, loc=loc)
 
     def step(self):
         """Eager step (no graph)."""

@@ -24,7 +24,9 @@ else:
     from hipsc_abm_b200.pipeline import HotPathStep, StepConfig
     name = sys.argv[2]
     wl = bench.make_workload(name); spec = wl["spec"]; n = wl["n"]
-    cfg = StepConfig(grid=None, bond_stride=16 if spec["dim"] == 2 else 32, search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
+    full = os.environ.get("AB_FULL")          # AB_FULL=1: with the morphogen stage, AB_FULL=overlap: on a side stream
+    cfg = StepConfig(grid=wl["grid"] if full else None, spat_res=spec["h"] or 1.0, diffuse_dt=spec["diffuse_dt"] or 1.0,
+                     diffuse_steps=spec["sd"], overlap_morphogen=(full == "overlap"), bond_stride=16 if spec["dim"] == 2 else 32, search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
     eng = ColonyEngine(wl["size"]); eng.upload(wl["loc"], wl["radii"], wl["mot"])
     pipe = HotPathStep(eng, cfg)
     for _ in range(int(sys.argv[3]) if len(sys.argv) > 3 else 4):

@@ -13,7 +13,8 @@ wl = bench.make_workload(name)
 spec = wl["spec"]
 cfg = StepConfig(grid=wl["grid"], spat_res=spec["h"] or 1.0, diffuse_dt=spec["diffuse_dt"] or 1.0,
                  diffuse_steps=spec["sd"], bond_stride=16 if spec["dim"] == 2 else 32,
-                 search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
+                 search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0,
+                 overlap_morphogen=len(sys.argv) > 3 and sys.argv[3] == "overlap")
 eng = ColonyEngine(wl["size"])
 eng.upload(wl["loc"], wl["radii"], wl["mot"])
 pipe = HotPathStep(eng, cfg)
