@@ -212,7 +212,8 @@ def run_b200(args, rank, world, local_rank):
     n = wl["n"]
     cfg = StepConfig(grid=wl["grid"], spat_res=spec["h"] or 1.0, diffuse_dt=spec["diffuse_dt"] or 1.0,
                      diffuse_steps=spec["sd"], bond_stride=args.bond_stride or (16 if spec["dim"] == 2 else 32),
-                     search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
+                     search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0,
+                     overlap_morphogen=not args.no_overlap)
     if world > 1:
         line = run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg)
         dist.barrier()
@@ -398,10 +399,17 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": f"{args.workload}: {spec['desc']}", "cells_per_gpu": n, "dim": spec["dim"],
                    "mechanics_substeps": sm, "diffusion_substeps": spec["sd"], "grid": wl["grid"],
                    "edges_r15": e15, "jkr_bonds": ej, "l2": "flushed between timed steps (256 MiB memset)",
+                   "morphogen_stage": ("reference order (before the mechanics, on the step's starting positions), "
+                                       "on a second stream beside search + mechanics") if cfg.overlap_morphogen and
+                   wl["grid"] else "after the mechanics, same stream",
                    "timing": "CUDA events per step around a CUDA-graph replay, summed; max over ranks",
                    "parallelism": "single GPU" if world == 1 else f"{world} independent colonies (replicas)"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
     }
+
+
+def field_wanted(wl):
+    return bool(wl["grid"])
 
 
 def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
@@ -416,11 +424,12 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     side = wl["size"][0]
     gsize = wl["size"].copy()
     gsize[0] = side * world
-    probe = SlabPipeline(slab.SlabGeometry.uniform(gsize, world, rank, 1.0), cfg, dev)
+    probe = SlabPipeline(slab.SlabGeometry.uniform(gsize, world, rank, 1.0), cfg, dev, side_stream=False)
     reach = probe.eng.jkr_reach(cfg.contact_radius)
     halo = slab.required_halo(len(cfg.substep_dts()), reach, slack=4.0) + (spec["h"] or 0.0)
     geom = slab.SlabGeometry.uniform(gsize, world, rank, halo)
-    pipe = SlabPipeline(geom, cfg, dev)
+    pipe = SlabPipeline(geom, cfg, dev, max_radius=5.0, uniform_radius=5.0)
+    first = cfg.overlap_morphogen and field_wanted(wl)
     loc = wl["loc"].copy()
     loc[:, 0] += geom.x_lo
     t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -433,14 +442,16 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     fabric = slab.DistFabric(rank, world, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    ops = NativeSlabOps(pipe.eng)
+    ops = NativeSlabOps(pipe.eng, send_cap=int(0.12 * n) + 4096)      # the same on every rank
 
     def step():
-        slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None, ops)
+        slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None, ops,
+                       morphogen_first=first)
 
     for _ in range(max(args.warmup, 3)):
         step()
     pipe.check()
+    ops.check()
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     for _ in range(40):                   # a few clock samples under load (a fixed count: ranks stay in lock-step)
@@ -456,6 +467,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     barrier()
     clocks = sampler.stop()
     pipe.check()
+    ops.check()
     total_s = sum(a.elapsed_time(b) for a, b in evs) / 1e3
     tt = torch.tensor([total_s], device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -496,12 +508,15 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         "config": {"workload": f"{args.workload} x {world}: {spec['desc']} per GPU, one colony", "cells_per_gpu": n,
                    "cells_total": int(cells.item()), "dim": spec["dim"], "mechanics_substeps": len(cfg.substep_dts()),
                    "diffusion_substeps": spec["sd"], "halo_um": halo,
+                   "morphogen_stage": ("reference order (before the mechanics), with its row exchange on a second "
+                                       "stream beside search + mechanics") if first else "after the mechanics",
                    "exchanges_per_step": (fabric.exchanges - ex0) / max(args.steps + e_steps, 1),
                    "bytes_sent_per_step_rank0": (fabric.bytes_sent - bytes0) // max(args.steps + e_steps, 1),
                    "l2": "flushed between timed steps (256 MiB memset)",
                    "timing": "CUDA events per step, summed; max over ranks",
                    "parallelism": f"slab{world}: 1-D slab decomposition along x; per step one cell-halo exchange "
-                                  "(migration rides on it) and one morphogen-row exchange over NCCL send/recv"},
+                                  "(migration rides on it; fixed-capacity messages, no size handshake) and one "
+                                  "morphogen-row exchange over NCCL send/recv"},
         "clocks": clocks,
         "e2e": {"value": n * world * e_steps / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e_steps,
                 "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps, "ms_per_step": e_s / e_steps * 1e3,
@@ -535,6 +550,8 @@ def main():
                     help="c3 = BASELINE configs[2], the 500k-cell headline colony quoted at 1 and 8 B200 (default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="run deposit/diffusion/sample after the mechanics on one stream instead of beside them")
     ap.add_argument("--bond-stride", type=int, default=0, help="fixed width of the JKR bond rows (0 = 16 / 32)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -390,28 +390,31 @@ class ColonyEngine:
         self.launches += int(steps)
         return scratch if where.value else field
 
-    def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None) -> torch.Tensor:
+    def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None, n=None) -> torch.Tensor:
         """get_concentration for every cell.  `field` is the whole (gx,gy[,gz]) grid, or -- with rows=(lo,hi) and
         grid_rows=gx -- the slab of global rows [lo,hi) of it."""
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
         lo, hi = (0, gs[0]) if rows is None else rows
         if grid_rows is not None:
             gs[0] = int(grid_rows)
-        out = self._empty(max(self.n, 1), torch.float64)
-        _lib.check(self.lib.abm_sample_concentrations(_ptr(self.loc if loc is None else loc), self.n, _ptr(field),
+        n = self.n if n is None else int(n)
+        out = self._empty(max(n, 1), torch.float64)
+        _lib.check(self.lib.abm_sample_concentrations(_ptr(self.loc if loc is None else loc), n, _ptr(field),
                                                       _lib.l3(gs),
                                                       float(spat_res), int(lo), int(hi), _ptr(out), self.stream),
                    "abm_sample_concentrations")
-        self.launches += 1 if self.n else 0
-        return out[:self.n]
+        self.launches += 1 if n else 0
+        return out[:n]
 
-    def deposit(self, field: torch.Tensor, amounts: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None):
+    def deposit(self, field: torch.Tensor, amounts: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None,
+                n=None):
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
         lo, hi = (0, gs[0]) if rows is None else rows
         if grid_rows is not None:
             gs[0] = int(grid_rows)
-        _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc if loc is None else loc), _ptr(amounts), self.n,
+        n = self.n if n is None else int(n)
+        _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc if loc is None else loc), _ptr(amounts), n,
                                                    _ptr(field), _lib.l3(gs),
                                                    float(spat_res), int(lo), int(hi), self.stream),
                    "abm_deposit_morphogens")
-        self.launches += 1 if self.n else 0
+        self.launches += 1 if n else 0

@@ -186,16 +186,31 @@ class SlabPipeline:
     the rank's owned + halo cells, binned over the slab's own box.  Use with slab.slab_step / loopback_step:
     `compute` is the mechanics callback, and the object itself is the `field_ops` for the morphogen slab."""
 
-    def __init__(self, geom, cfg: StepConfig, device, max_radius=5.0):
+    def __init__(self, geom, cfg: StepConfig, device, max_radius=5.0, uniform_radius=0.0, side_stream=True):
+        """uniform_radius: the common radius if ALL cells of the colony have the same one (selects the kernel
+        variant with the contact constants folded in), else 0.  side_stream: run the morphogen stage of a
+        morphogen_first step on a second stream (off for several slabs emulated on one GPU, whose loopback
+        exchange does not synchronise streams)."""
         self.geom, self.cfg = geom, cfg
         self.eng = ColonyEngine(geom.size, device)
         self.eng.set_bin_lattice(*geom.local_box())
         self.dts = cfg.substep_dts()
         self.max_radius = float(max_radius)
+        self.uniform_radius = float(uniform_radius)
         self.stride = cfg.bond_stride
         self._nbr = None
         self.neighbor_graph = None
-        self.sampled = None
+        self._sampled_all = self._sampled_local = None
+        self._side = torch.cuda.Stream(device=device) if side_stream else None
+        self._snap = None
+        self._amounts = None
+
+    @property
+    def sampled(self):
+        """Concentrations sampled by the OWNED cells in the last step (reads the owned count if still pending)."""
+        if self._sampled_all is None:
+            return None
+        return self._sampled_all[:self._sampled_local.n_own]
 
     def compute(self, local):
         """Mechanics of one step on the rank's owned + halo cells (slab.LocalProblem): positions are advanced
@@ -204,7 +219,8 @@ class SlabPipeline:
         synchronisation point."""
         eng, cfg = self.eng, self.cfg
         n = int(local.loc.shape[0])
-        eng.set_device_state(local.loc, local.radii, local.mot, max_radius=self.max_radius)
+        eng.set_device_state(local.loc, local.radii, local.mot, max_radius=self.max_radius,
+                             uniform_radius=self.uniform_radius)
         eng.global_id = local.gid
         # neighbour graph of the step (rows of owned cells are complete: the halo is deeper than the radius)
         cap = int(cfg.search_cols_per_cell * max(n, 1)) + 1024
@@ -239,13 +255,44 @@ class SlabPipeline:
                 raise _lib.AbmError(f"bond rows too narrow: needed {worst}, have {eng._bond_bufs['stride']}")
 
     # ---- field_ops protocol of slab.rank_step ---------------------------------------------------------------------
+    def begin_side(self, local):
+        """morphogen_first: snapshot the positions (the mechanics will move them) and fork the second stream."""
+        eng = self.eng
+        n = int(local.loc.shape[0])
+        if self._snap is None or self._snap.shape[0] < n:
+            self._snap = torch.empty((int(1.1 * n) + 1024, 3), dtype=torch.float64, device=eng.device)
+        self._snap[:n].copy_(local.loc)
+        self._snap_n = n
+        if self._side is None:
+            return None
+        self._side.wait_stream(torch.cuda.current_stream(eng.device))
+        return self._side
+
+    def end_side(self):
+        self._snap_n = None
+        if self._side is not None:
+            torch.cuda.current_stream(self.eng.device).wait_stream(self._side)
+        self.eng.use_current_stream()
+
+    def _positions(self, local):
+        """(positions, count) the morphogen stage works on: the snapshot inside a morphogen_first step."""
+        if getattr(self, "_snap_n", None) is not None:
+            return self._snap, self._snap_n
+        return local.loc, int(local.loc.shape[0])
+
     def deposit(self, local, field):
-        n = self.eng.n
-        amounts = torch.full((max(n, 1),), self.cfg.deposit_amount, dtype=torch.float64, device=self.eng.device)
-        self.eng.deposit(field.data, amounts, field.h, rows=(field.ext_lo, field.ext_hi), grid_rows=field.gx)
+        eng = self.eng
+        eng.use_current_stream()
+        loc, n = self._positions(local)
+        if self._amounts is None or self._amounts.numel() < n:
+            self._amounts = torch.full((int(1.1 * n) + 1024,), self.cfg.deposit_amount, dtype=torch.float64,
+                                       device=eng.device)
+        eng.deposit(field.data, self._amounts, field.h, rows=(field.ext_lo, field.ext_hi), grid_rows=field.gx,
+                    loc=loc, n=n)
 
     def diffuse(self, field):
         cfg = self.cfg
+        self.eng.use_current_stream()
         last = cfg.diffuse_dt if cfg.diffuse_last_dt is None else cfg.diffuse_last_dt
         out = self.eng.diffuse(field.data, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const,
                                field.h ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma)
@@ -253,26 +300,29 @@ class SlabPipeline:
             field.data.copy_(out)
 
     def sample(self, local, field):
+        # every local cell samples (no owned count needed on the host yet); only the owned ones -- whose rows are
+        # exact -- are handed out by the `sampled` property
         eng = self.eng
-        n_all = eng.n
-        eng.n = local.n_own                       # only owned cells read the field (their rows are exact)
-        try:
-            self.sampled = eng.sample(field.data, field.h, rows=(field.ext_lo, field.ext_hi), grid_rows=field.gx)
-        finally:
-            eng.n = n_all
+        eng.use_current_stream()
+        loc, n = self._positions(local)
+        self._sampled_all = eng.sample(field.data, field.h, rows=(field.ext_lo, field.ext_hi), grid_rows=field.gx,
+                                       loc=loc, n=n)
+        self._sampled_local = local
 
 
 class NativeSlabOps:
     """slab.rank_step's select/pack/merge on the device (csrc/slab.cu): two C calls and two small host reads per
     step instead of a few dozen tensor ops."""
 
-    def __init__(self, engine: ColonyEngine, send_fraction=0.12):
+    def __init__(self, engine: ColonyEngine, send_fraction=0.12, send_cap=None):
+        """send_cap: rows of the fixed-capacity cell messages.  Every rank must use the SAME value (the receiver
+        posts a buffer of that size); None = send_fraction * (cells of the first step) + 4096, which agrees across
+        ranks only if they start with equal cell counts."""
         self.eng = engine
         self.lib = engine.lib
-        self.send_cap = 0
+        self.send_cap = int(send_cap or 0)
         self.send_fraction = send_fraction
-        self.counts = torch.zeros(2, dtype=torch.int32, device=engine.device)
-        self.n_owned = torch.zeros(1, dtype=torch.int32, device=engine.device)
+        self.worst = torch.zeros(2, dtype=torch.int32, device=engine.device)   # largest counts seen (overflow check)
         self.ws = None
 
     def _workspace(self, n):
@@ -288,27 +338,37 @@ class NativeSlabOps:
         ws = self._workspace(n)
         if self.send_cap == 0:
             self.send_cap = int(self.send_fraction * n) + 4096
-        while True:
-            cap = self.send_cap
-            out_l = torch.empty((cap, rec), dtype=torch.uint8, device=dev)
-            out_r = torch.empty((cap, rec), dtype=torch.uint8, device=dev)
-            _lib.check(self.lib.abm_slab_pack(
-                state.loc.data_ptr(), state.radii.data_ptr(), state.mot.data_ptr(), state.gid.data_ptr(),
-                state.bond_len.data_ptr(), state.bond_gid.data_ptr(), n, stride, geom.x_lo + geom.halo,
-                geom.x_hi - geom.halo, int(geom.has_left), int(geom.has_right), out_l.data_ptr(), cap,
-                out_r.data_ptr(), cap, self.counts.data_ptr(), ws.data_ptr(), ws.numel(), eng.stream),
-                "abm_slab_pack")
-            eng.launches += 6
-            cl, cr = (int(v) for v in self.counts.tolist())
-            if max(cl, cr) <= cap:
-                break
-            self.send_cap = int(1.25 * max(cl, cr)) + 4096
-        return (out_l[:cl] if geom.has_left else None, out_r[:cr] if geom.has_right else None)
+        # full-capacity messages + their valid row counts on the device: nothing here waits for the GPU (a count
+        # beyond the capacity truncates the message and is raised by check())
+        cap = self.send_cap
+        out_l = torch.empty((cap, rec), dtype=torch.uint8, device=dev)
+        out_r = torch.empty((cap, rec), dtype=torch.uint8, device=dev)
+        counts = torch.empty(2, dtype=torch.int32, device=dev)
+        _lib.check(self.lib.abm_slab_pack(
+            state.loc.data_ptr(), state.radii.data_ptr(), state.mot.data_ptr(), state.gid.data_ptr(),
+            state.bond_len.data_ptr(), state.bond_gid.data_ptr(), n, stride, geom.x_lo + geom.halo,
+            geom.x_hi - geom.halo, int(geom.has_left), int(geom.has_right), out_l.data_ptr(), cap,
+            out_r.data_ptr(), cap, counts.data_ptr(), ws.data_ptr(), ws.numel(), eng.stream),
+            "abm_slab_pack")
+        eng.launches += 6
+        torch.maximum(self.worst, counts, out=self.worst)
+        return out_l, out_r, counts
 
-    def merge(self, state, geom, from_l, from_r):
+    def check(self):
+        """Host sync: raise if a cell message was ever truncated."""
+        worst = int(self.worst.max().item())
+        if worst > self.send_cap:
+            raise _lib.AbmError(f"cell message capacity too small: needed {worst} rows, have {self.send_cap} "
+                                "(NativeSlabOps(send_cap=...))")
+
+    def merge(self, state, geom, from_l, from_r, counts_in=None):
         from .slab import LocalProblem
         eng, dev = self.eng, self.eng.device
         n, stride, rec = state.n, state.stride, state.record_bytes()
+        if counts_in is not None:                 # the one host synchronisation of the exchange
+            n_l, n_r = (min(int(v), self.send_cap) for v in counts_in.tolist())
+            from_l = from_l[:n_l] if from_l is not None else None
+            from_r = from_r[:n_r] if from_r is not None else None
         parts = [m for m in (from_l, from_r) if m is not None and m.shape[0]]
         if len(parts) == 2:
             recv = torch.cat(parts, dim=0)
@@ -326,12 +386,12 @@ class NativeSlabOps:
         gid = torch.empty(total, dtype=i32, device=dev)
         blen = torch.empty(total, dtype=i32, device=dev)
         rows = torch.empty((total, stride), dtype=i32, device=dev)
+        n_owned = torch.empty(1, dtype=i32, device=dev)
         _lib.check(self.lib.abm_slab_merge(
             state.loc.data_ptr(), state.radii.data_ptr(), state.mot.data_ptr(), state.gid.data_ptr(),
             state.bond_len.data_ptr(), state.bond_gid.data_ptr(), n, recv.data_ptr(), k, stride, geom.x_lo, geom.x_hi,
             int(geom.has_left), int(geom.has_right), loc.data_ptr(), radii.data_ptr(), mot.data_ptr(),
-            gid.data_ptr(), blen.data_ptr(), rows.data_ptr(), self.n_owned.data_ptr(), ws.data_ptr(), ws.numel(),
+            gid.data_ptr(), blen.data_ptr(), rows.data_ptr(), n_owned.data_ptr(), ws.data_ptr(), ws.numel(),
             eng.stream), "abm_slab_merge")
         eng.launches += 4
-        n_own = eng.read_i32(self.n_owned)
-        return LocalProblem(n_own, loc, radii, mot, gid, blen, rows)
+        return LocalProblem(n_owned, loc, radii, mot, gid, blen, rows)      # owned count read when first needed

@@ -25,8 +25,9 @@ the compute callback is the CUDA pipeline (pipeline.SlabPipeline).
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass
-from typing import Callable, Optional
+from typing import Any, Callable, Optional
 
 import numpy as np
 import torch
@@ -138,6 +139,24 @@ def unpack(msg: torch.Tensor, stride: int):
 
 
 # ---- exchange fabrics ---------------------------------------------------------------------------------------------
+@dataclass
+class Exchange:
+    """What rank_step asks its driver for: send to_left / to_right (2-D, `width` columns of `dtype`) to the
+    x-neighbours and hand back what they sent.
+      fixed_rows: both sides know the row count (no size handshake);
+      counts:     int32[2] on the device = rows of to_left / to_right that are valid.  The messages are then
+                  full-capacity buffers (fixed_rows = capacity) and the counts travel in the same transfer group,
+                  so there is neither a handshake nor a host synchronisation; the reply is
+                  (from_left, from_right, counts_in)."""
+    tag: str
+    to_left: Any
+    to_right: Any
+    width: int
+    dtype: Any
+    fixed_rows: Optional[int] = None
+    counts: Any = None
+
+
 class DistFabric:
     """Neighbour exchange over torch.distributed (NCCL on GPUs, gloo on CPU): the row counts first, then one
     packed message per neighbour and direction, all transfers of a phase posted together."""
@@ -152,12 +171,29 @@ class DistFabric:
         for w in self.dist.batch_isend_irecv(ops) if ops else []:
             w.wait()
 
-    def exchange(self, to_left, to_right, width, dtype=torch.float64, fixed_rows=None):
+    def exchange(self, to_left, to_right, width, dtype=torch.float64, fixed_rows=None, counts=None):
         """Send `to_left` / `to_right` (2-D, `width` columns) to the x-neighbours, return what they sent.
-        fixed_rows: both sides know the row count (field rows) -> no size handshake."""
+        fixed_rows: both sides know the row count (field rows) -> no size handshake.
+        counts: see Exchange (full-capacity messages + their valid row counts in one transfer group)."""
         dist, dev = self.dist, self.device
         left, right = self.rank - 1, self.rank + 1
         has_l, has_r = left >= 0, right < self.world
+        if counts is not None:
+            cap = int(fixed_rows)
+            from_left = torch.empty((cap if has_l else 0, width), dtype=dtype, device=dev)
+            from_right = torch.empty((cap if has_r else 0, width), dtype=dtype, device=dev)
+            counts_in = torch.zeros(2, dtype=counts.dtype, device=dev)
+            ops = []
+            if has_l:
+                ops += [dist.P2POp(dist.isend, to_left, left), dist.P2POp(dist.irecv, from_left, left),
+                        dist.P2POp(dist.isend, counts[0:1], left), dist.P2POp(dist.irecv, counts_in[0:1], left)]
+            if has_r:
+                ops += [dist.P2POp(dist.isend, to_right, right), dist.P2POp(dist.irecv, from_right, right),
+                        dist.P2POp(dist.isend, counts[1:2], right), dist.P2POp(dist.irecv, counts_in[1:2], right)]
+            self._post(ops)
+            self.bytes_sent += (int(has_l) + int(has_r)) * cap * width * to_left.element_size() if cap else 0
+            self.exchanges += 1
+            return from_left, from_right, counts_in
         if fixed_rows is None:
             counts_out = torch.tensor([to_left.shape[0] if has_l else 0, to_right.shape[0] if has_r else 0],
                                       dtype=torch.int64, device=dev)
@@ -195,13 +231,21 @@ class LoopbackWorld:
     def __init__(self, world):
         self.world = world
 
-    def exchange_all(self, outgoing):
-        """outgoing[k] = (to_left, to_right) -> incoming[k] = (from_left, from_right)."""
+    def exchange_all(self, requests):
+        """requests[k] = Exchange of rank k -> incoming[k] = (from_left, from_right[, counts_in])."""
         incoming = []
         for k in range(self.world):
-            from_left = outgoing[k - 1][1] if k > 0 else None
-            from_right = outgoing[k + 1][0] if k < self.world - 1 else None
-            incoming.append((from_left, from_right))
+            from_left = requests[k - 1].to_right if k > 0 else None
+            from_right = requests[k + 1].to_left if k < self.world - 1 else None
+            if requests[k].counts is not None:
+                c = torch.zeros_like(requests[k].counts)
+                if k > 0:
+                    c[0] = requests[k - 1].counts[1]
+                if k < self.world - 1:
+                    c[1] = requests[k + 1].counts[0]
+                incoming.append((from_left, from_right, c))
+            else:
+                incoming.append((from_left, from_right))
         return incoming
 
 
@@ -244,16 +288,23 @@ class FieldSlab:
 
 
 # ---- one step of one rank ---------------------------------------------------------------------------------------------------
-@dataclass
 class LocalProblem:
-    """Owned (first n_own) + halo cells of one rank for one step; what the single-GPU pipeline runs on."""
-    n_own: int
-    loc: torch.Tensor
-    radii: torch.Tensor
-    mot: torch.Tensor
-    gid: torch.Tensor           # int32 (n_local,)
-    bond_len: torch.Tensor      # int32 (n_local,)
-    bond_gid: torch.Tensor      # int32 (n_local, stride) global ids
+    """Owned (first n_own) + halo cells of one rank for one step; what the single-GPU pipeline runs on.
+    n_own may be given as a one-element device tensor: it is then read (one host synchronisation) only when
+    somebody asks for it -- at the end of the step, after the whole step has been enqueued."""
+
+    def __init__(self, n_own, loc, radii, mot, gid, bond_len, bond_gid):
+        self._n_own = n_own
+        self.loc, self.radii, self.mot = loc, radii, mot
+        self.gid = gid                  # int32 (n_local,)
+        self.bond_len = bond_len        # int32 (n_local,)
+        self.bond_gid = bond_gid        # int32 (n_local, stride) global ids
+
+    @property
+    def n_own(self) -> int:
+        if not isinstance(self._n_own, int):
+            self._n_own = int(self._n_own.item())
+        return self._n_own
 
 
 class TorchSlabOps:
@@ -297,22 +348,48 @@ class TorchSlabOps:
 
 
 def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProblem], tuple],
-              field: Optional[FieldSlab] = None, field_ops=None, ops=None):
+              field: Optional[FieldSlab] = None, field_ops=None, ops=None, morphogen_first=False):
     """One simulation step of one rank, written as a generator: it yields
     (tag, (to_left, to_right), width, dtype, fixed_rows) whenever it needs a neighbour exchange and is sent
     (from_left, from_right) back.  `compute(local)` runs the mechanics in place on local.loc and returns the new
     (bond_len, bond_gid) of all local cells.  `field_ops` (if a morphogen field is carried) provides
     deposit(local, field), diffuse(field) and sample(local, field).  `ops` selects/packs/merges the cells
-    (TorchSlabOps by default, pipeline.NativeSlabOps on a GPU)."""
-    ops = ops or TorchSlabOps()
-    msgs = ops.outgoing(state, geom)
-    from_l, from_r = yield ("cells", msgs, state.record_bytes(), torch.uint8, None)
-    local = ops.merge(state, geom, from_l, from_r)
+    (TorchSlabOps by default, pipeline.NativeSlabOps on a GPU).
 
-    blen, bgid = compute(local)
+    morphogen_first: the morphogen stage works on the positions the step starts with (after the exchange) --
+    the reference's order, update_diffusion before apply_forces (cell_simulation.py:101-112).  It is then
+    independent of the mechanics: field_ops.begin_side(local) may return a second stream on which the stage
+    (including its row exchange) runs beside them, field_ops.end_side() joins it."""
+    ops = ops or TorchSlabOps()
+    out = ops.outgoing(state, geom)
+    if len(out) == 3:                                         # full-capacity buffers + device counts, no handshake
+        reply = yield Exchange("cells", out[0], out[1], state.record_bytes(), torch.uint8,
+                               fixed_rows=ops.send_cap, counts=out[2])
+        local = ops.merge(state, geom, reply[0], reply[1], reply[2])
+    else:
+        from_l, from_r = yield Exchange("cells", out[0], out[1], state.record_bytes(), torch.uint8)
+        local = ops.merge(state, geom, from_l, from_r)
+
+    if field is not None and morphogen_first:
+        begin = getattr(field_ops, "begin_side", None)
+        side = begin(local) if begin else None
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            field_ops.deposit(local, field)                   # owned + halo cells, where the step starts
+            to_l, to_r = field.messages()
+            from_l, from_r = yield Exchange("rows", to_l, to_r, field.gy, torch.float64, fixed_rows=field.halo_rows)
+            field.absorb(from_l, from_r)
+            field_ops.diffuse(field)
+            field_ops.sample(local, field)
+        blen, bgid = compute(local)
+        if begin:
+            field_ops.end_side()
+        field = None                                          # done
+    else:
+        blen, bgid = compute(local)
     if field is not None:
         field_ops.deposit(local, field)                       # owned + halo cells at their new positions
-        from_l, from_r = yield ("rows", field.messages(), field.gy, torch.float64, field.halo_rows)
+        to_l, to_r = field.messages()
+        from_l, from_r = yield Exchange("rows", to_l, to_r, field.gy, torch.float64, fixed_rows=field.halo_rows)
         field.absorb(from_l, from_r)
         field_ops.diffuse(field)                              # S_d substeps, no communication
         field_ops.sample(local, field)
@@ -323,19 +400,19 @@ def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProb
 
 
 def slab_step(state: SlabState, geom: SlabGeometry, fabric: DistFabric, compute, field=None, field_ops=None,
-              ops=None):
+              ops=None, morphogen_first=False):
     """Drive rank_step over torch.distributed."""
-    gen = rank_step(state, geom, compute, field, field_ops, ops)
+    gen = rank_step(state, geom, compute, field, field_ops, ops, morphogen_first)
     incoming = None
     try:
         while True:
-            tag, (to_l, to_r), width, dtype, fixed = gen.send(incoming) if incoming is not None else next(gen)
-            incoming = fabric.exchange(to_l, to_r, width, dtype, fixed)
+            req = gen.send(incoming) if incoming is not None else next(gen)
+            incoming = fabric.exchange(req.to_left, req.to_right, req.width, req.dtype, req.fixed_rows, req.counts)
     except StopIteration as done:
         return done.value
 
 
-def loopback_step(states, geoms, computes, fields=None, field_ops=None, ops=None):
+def loopback_step(states, geoms, computes, fields=None, field_ops=None, ops=None, morphogen_first=False):
     """The same step for all ranks emulated in one process (tests; several slabs on one GPU)."""
     world = LoopbackWorld(len(states))
     if callable(computes):
@@ -343,12 +420,13 @@ def loopback_step(states, geoms, computes, fields=None, field_ops=None, ops=None
     fields = fields or [None] * len(states)
     field_ops = field_ops or [None] * len(states)
     ops = ops or [None] * len(states)
-    gens = [rank_step(s, g, c, f, o, p) for s, g, c, f, o, p in zip(states, geoms, computes, fields, field_ops, ops)]
+    gens = [rank_step(s, g, c, f, o, p, morphogen_first)
+            for s, g, c, f, o, p in zip(states, geoms, computes, fields, field_ops, ops)]
     requests = [next(g) for g in gens]
     results = [None] * len(gens)
     while any(r is not None for r in requests):
         assert all(r is not None for r in requests), "ranks fell out of lock-step"
-        incoming = world.exchange_all([r[1] for r in requests])
+        incoming = world.exchange_all(requests)
         nxt = []
         for k, (g, inc) in enumerate(zip(gens, incoming)):
             try:

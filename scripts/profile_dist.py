@@ -16,20 +16,21 @@ cfg = StepConfig(grid=wl["grid"], spat_res=spec["h"], diffuse_dt=spec["diffuse_d
 gsize = wl["size"].copy(); gsize[0] *= world
 halo = slab.required_halo(11, 10.3100107, slack=4.0) + spec["h"]
 geom = slab.SlabGeometry.uniform(gsize, world, rank, halo)
-pipe = SlabPipeline(geom, cfg, dev)
+first = len(sys.argv) > 2 and sys.argv[2] == "first"
+pipe = SlabPipeline(geom, cfg, dev, uniform_radius=5.0)
 loc = wl["loc"].copy(); loc[:, 0] += geom.x_lo
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 state = slab.SlabState(t(loc), t(wl["radii"]), t(wl["mot"]), t(np.arange(n) + rank * n), 16)
 gx = int(np.ceil(gsize[0] / spec["h"])) + 1
 field = slab.FieldSlab(geom, (gx, wl["grid"][1]), spec["h"], spec["sd"] + 1, dev)
-fabric = slab.DistFabric(rank, world, dev); ops = NativeSlabOps(pipe.eng)
+fabric = slab.DistFabric(rank, world, dev); ops = NativeSlabOps(pipe.eng, send_cap=int(0.12 * n) + 4096)
 acc = collections.defaultdict(float)
 def timed(name, fn):
     def w(*a, **k):
         torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(*a, **k); torch.cuda.synchronize()
         acc[name] += time.perf_counter() - t0; return r
     return w
-def step(): slab.slab_step(state, geom, fabric, pipe.compute, field, pipe, ops)
+def step(): slab.slab_step(state, geom, fabric, pipe.compute, field, pipe, ops, morphogen_first=first)
 for _ in range(3): step()
 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
 for _ in range(10): step()

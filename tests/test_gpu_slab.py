@@ -19,9 +19,12 @@ def bonds_as_gid_edges(gid, row_len, cols):
     return orc.canonical_edges(np.stack([np.repeat(gid, row_len), cols[k]], axis=1))
 
 
+@pytest.mark.parametrize("first", [False, True], ids=["morphogen_after", "morphogen_first"])
 @pytest.mark.parametrize("native", [False, True], ids=["torch_ops", "native_ops"])
 @pytest.mark.parametrize("world,dim", [(3, 2), (2, 3)])
-def test_emulated_slabs_match_single_domain(world, dim, native):
+def test_emulated_slabs_match_single_domain(world, dim, native, first):
+    if first and dim == 3:
+        pytest.skip("no morphogen field in the 3-D case")
     rng = np.random.default_rng(4)
     if dim == 2:
         size, n = np.array([1500.0, 400.0, 0.0]), 6000
@@ -35,7 +38,7 @@ def test_emulated_slabs_match_single_domain(world, dim, native):
     radii = np.full(n, 5.0)
     steps = 2
     cfg = StepConfig(grid=grid, spat_res=h, diffuse_dt=0.2 * h * h / 50.0, diffuse_steps=sd, bond_stride=32,
-                     search_cols_per_cell=40.0)
+                     search_cols_per_cell=40.0, overlap_morphogen=first)
     dev = torch.device("cuda")
 
     # single domain
@@ -58,15 +61,17 @@ def test_emulated_slabs_match_single_domain(world, dim, native):
         m = (loc[:, 0] >= g.x_lo) & ((loc[:, 0] < g.x_hi) | (g.rank == world - 1))
         t = lambda a: torch.from_numpy(a[m].copy()).to(dev)
         states.append(slab.SlabState(t(loc), t(radii), t(mot), torch.from_numpy(np.arange(n)[m]).to(dev), 32))
-        pipes.append(SlabPipeline(g, cfg, dev))
+        pipes.append(SlabPipeline(g, cfg, dev, uniform_radius=5.0 if native else 0.0, side_stream=False))
         fields.append(slab.FieldSlab(g, grid, h, sd + 1, dev) if grid else None)
     from hipsc_abm_b200.pipeline import NativeSlabOps
     ops = [NativeSlabOps(p.eng) for p in pipes] if native else None
     for _ in range(steps):
         slab.loopback_step(states, geoms, [p.compute for p in pipes], fields if grid else None,
-                           pipes if grid else None, ops)
+                           pipes if grid else None, ops, morphogen_first=first)
     for p in pipes:
         p.check()
+    for o in ops or []:
+        o.check()
     gid = torch.cat([s.gid for s in states]).cpu().numpy()
     got_loc = torch.cat([s.loc for s in states]).cpu().numpy()[np.argsort(gid)]
     assert np.array_equal(np.sort(gid), np.arange(n))

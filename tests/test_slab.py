@@ -191,20 +191,28 @@ class OracleFieldOps:
         self.sampled = orc.get_concentrations(local.loc.numpy()[:local.n_own], full, self.H)
 
 
-def test_field_slabs_reproduce_single_domain():
+@pytest.mark.parametrize("first", [False, True], ids=["morphogen_after", "morphogen_first"])
+def test_field_slabs_reproduce_single_domain(first):
     world, steps = 3, 2
     loc, radii, mot = make_cells()
     ops0 = OracleFieldOps()
     gx, gy = int(np.ceil(SIZE[0] / ops0.H)) + 1, int(np.ceil(SIZE[1] / ops0.H)) + 1
-    # single domain: mechanics -> deposit -> diffuse -> sample, twice
+    # single domain: mechanics -> deposit -> diffuse -> sample, twice (morphogen_first: the morphogen stage
+    # before the mechanics, the reference's order)
     sim = orc.OracleSim(loc, radii, SIZE)
     full = np.zeros((gx, gy, 1))
-    for _ in range(steps):
-        sim.motility_forces = mot.copy()
-        sim.apply_forces()
+
+    def morphogen():
         orc.adjust_morphogens(sim.locations, 1.0, full, ops0.H)
         full[:, :, 0] = orc.diffuse_field(full[:, :, 0], ops0.SD, ops0.dt, ops0.dt, ops0.D, ops0.H ** 2, 2.0, 0.1)
-        ref_sampled = orc.get_concentrations(sim.locations, full, ops0.H)
+        return orc.get_concentrations(sim.locations, full, ops0.H)
+    for _ in range(steps):
+        if first:
+            ref_sampled = morphogen()
+        sim.motility_forces = mot.copy()
+        sim.apply_forces()
+        if not first:
+            ref_sampled = morphogen()
     halo = slab.required_halo(11, 10.3100107, slack=5.0) + ops0.H
     geoms, states = split(loc, radii, mot, world, halo)
     # one more halo row than substeps: a cell next to the interface samples the neighbour's first row
@@ -212,7 +220,7 @@ def test_field_slabs_reproduce_single_domain():
     ops = [OracleFieldOps() for _ in geoms]
     assert [f.row_lo for f in fields[1:]] == [f.row_hi for f in fields[:-1]] and fields[-1].row_hi == gx
     for _ in range(steps):
-        slab.loopback_step(states, geoms, oracle_compute, fields, ops)
+        slab.loopback_step(states, geoms, oracle_compute, fields, ops, morphogen_first=first)
     got = np.concatenate([f.owned().numpy() for f in fields], axis=0)
     assert got.shape == (gx, gy)
     assert np.abs(got - full[:, :, 0]).max() <= 1e-12                 # deposits are summed in a different order
