@@ -211,6 +211,9 @@ int abm_deposit_morphogens(const double *locations, const double *amounts, int64
  * abm_slab_pack writes, in cell order, the records of the owned cells with x < x_send_left (to the left
  * neighbour) and with x >= x_send_right (to the right one); counts (2) int32 receives the two record counts
  * (records beyond a capacity are dropped: the caller compares and retries with larger buffers).
+ * n_own_device (may be NULL): device int32 -- only the first *n_own_device of the n_own rows are owned cells, the
+ * rest (last step's halo cells) are skipped; lets a caller enqueue the pack before the owned count of the
+ * finishing step has reached the host.
  * abm_slab_merge partitions the n_own owned cells followed by the n_received records into
  * [cells owned after the exchange | halo cells] -- owned iff x in [x_lo,x_hi) (open towards a missing
  * neighbour) -- keeping input order inside each part, and writes them to the out_* arrays (capacity
@@ -219,8 +222,8 @@ int abm_deposit_morphogens(const double *locations, const double *amounts, int64
 size_t abm_slab_workspace_bytes(int64_t n);
 int abm_slab_pack(const double *locations, const double *radii, const double *motility_forces,
                   const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t n_own,
-                  int64_t row_stride, double x_send_left, double x_send_right, int has_left, int has_right,
-                  uint8_t *records_left, int64_t capacity_left, uint8_t *records_right, int64_t capacity_right,
+                  const int32_t *n_own_device, int64_t row_stride, double x_send_left, double x_send_right,
+                  int has_left, int has_right, uint8_t *records_left, int64_t capacity_left, uint8_t *records_right, int64_t capacity_right,
                   int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
 int abm_slab_merge(const double *locations, const double *radii, const double *motility_forces,
                    const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t n_own,

@@ -160,8 +160,8 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
               double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
-              double stokes, Friction fric, Box box, double dt, const int *__restrict__ gid_of, NextSort next,
-              int sort_rows) {
+              double stokes, Friction fric, Box box, double dt, const int *__restrict__ gid_of,
+              const int *__restrict__ slot_pid, NextSort next, int sort_rows) {
     // column tid: first the parked partner slots, then (overwritten from the front) the ids of the new bond row
     __shared__ int column[kMaxHits][kJkrThreads];
     __shared__ float4 tiles[kJkrThreads / 32][kTileRows * kTileCap];
@@ -227,10 +227,14 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     int cnt = 0;         // bonds recorded in the column
     int direct = 0;      // bonds of a crowded cell written straight to row[kMaxHits + direct]
     // the id bond rows are written in: the cell index, or its global id when the colony is slab-decomposed
+    // (slot_pid, when given, holds that id by slot: one gather instead of two dependent ones)
     auto partner_id = [&](int t) {
+        if (slot_pid) return slot_pid[t];
         int j = sorted_id[t];
         return gid_of ? gid_of[j] : j;
     };
+    const int *first_hop = slot_pid ? slot_pid : sorted_id;
+    const bool second_hop = !slot_pid && gid_of;
     // contact model for one bond candidate at offset v = p - q, |v|^2 = s2; a surviving bond is recorded in the
     // column (or, for a crowded cell, directly in the global row)
     auto bond = [&](double vx, double vy, double vz, double s2, double rq, int j) {
@@ -277,7 +281,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         // (the next partner's position and id are fetched while the current one is evaluated)
         int t_next = nh > 0 ? column[0][tid] : s;
         double4 q_next = spos[t_next];
-        int j_next = sorted_id[t_next];
+        int j_next = first_hop[t_next];
         for (int k = 0; k < nh; ++k) {
             const int t = t_next;
             const double4 q = q_next;
@@ -285,16 +289,16 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
             if (k + 1 < nh) {
                 t_next = column[k + 1][tid];
                 q_next = spos[t_next];
-                j_next = sorted_id[t_next];
+                j_next = first_hop[t_next];
             }
             const double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
             const double s2 = sumsq_nofma(vx, vy, vz);
             if (s2 > reach2) continue;                        // let through by the fp32 filter's error band only
             if (rad.within(s2)) {
-                if (gid_of) j = gid_of[j];
+                if (second_hop) j = gid_of[j];
                 bond(vx, vy, vz, s2, q.w, j);                 // cnt <= k: the column is overwritten behind the read
             } else if (old.valid()) {                         // thin shell: only pre-existing bonds persist
-                if (gid_of) j = gid_of[j];
+                if (second_hop) j = gid_of[j];
                 if (nsh == 0) {
                     sh0 = t;
                     shj0 = j;
@@ -466,16 +470,17 @@ ABM_EXPORT int abm_apply_forces(const double *jkr_forces, const double *motility
     return 0;
 }
 
-ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,
-                               const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
-                               double reach, const int32_t *old_row_start, int64_t old_row_stride,
-                               const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len,
-                               int32_t *new_cols, int64_t row_stride, int32_t *max_len, int sort_rows,
-                               const double *motility_forces, double *locations, double poisson, double youngs,
-                               double adhesion_const, double stokes, const double size_host[3], double move_dt,
-                               const int32_t *global_id, double uniform_radius, const double *next_extent_host,
-                               const double *next_origin_host, int32_t *next_bin_counts, void *next_sort_workspace,
-                               void *stream) {
+// slot_gid: optional (n) global id of the cell in every slot (written by the sort of the mechanics loop)
+static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,
+                            const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
+                            double reach, const int32_t *old_row_start, int64_t old_row_stride,
+                            const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len,
+                            int32_t *new_cols, int64_t row_stride, int32_t *max_len, int sort_rows,
+                            const double *motility_forces, double *locations, double poisson, double youngs,
+                            double adhesion_const, double stokes, const double size_host[3], double move_dt,
+                            const int32_t *global_id, const int32_t *slot_gid, double uniform_radius,
+                            const double *next_extent_host, const double *next_origin_host,
+                            int32_t *next_bin_counts, void *next_sort_workspace, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(bin_start && sorted_id && sorted_pos && sorted_bin && dims_host && new_row_len && new_cols &&
@@ -519,9 +524,26 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
     kernel<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
         Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
-        locations, c, stokes, fric, box, move_dt, global_id, next, sort_rows);
+        locations, c, stokes, fric, box, move_dt, global_id, global_id ? slot_gid : sorted_id, next, sort_rows);
     ABM_CHECK_LAUNCH("k_jkr_substep");
     return 0;
+}
+
+ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,
+                               const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
+                               double reach, const int32_t *old_row_start, int64_t old_row_stride,
+                               const int32_t *old_row_len, const int32_t *old_cols, int32_t *new_row_len,
+                               int32_t *new_cols, int64_t row_stride, int32_t *max_len, int sort_rows,
+                               const double *motility_forces, double *locations, double poisson, double youngs,
+                               double adhesion_const, double stokes, const double size_host[3], double move_dt,
+                               const int32_t *global_id, double uniform_radius, const double *next_extent_host,
+                               const double *next_origin_host, int32_t *next_bin_counts, void *next_sort_workspace,
+                               void *stream) {
+    return jkr_substep_impl(bin_start, sorted_id, sorted_pos, sorted_bin, n, dims_host, distance, reach,
+                            old_row_start, old_row_stride, old_row_len, old_cols, new_row_len, new_cols, row_stride,
+                            max_len, sort_rows, motility_forces, locations, poisson, youngs, adhesion_const, stokes,
+                            size_host, move_dt, global_id, nullptr, uniform_radius, next_extent_host,
+                            next_origin_host, next_bin_counts, next_sort_workspace, stream);
 }
 
 // The whole substep loop of CellMethods.apply_forces (reference cell_methods.py:399-436) enqueued by one call:
@@ -553,15 +575,16 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
         const bool prebin = k + 1 < n_substeps && n > 0;
         int rc = bin_sort_impl(locations, radii, n, extent_host, origin_host, reach, k ? ABM_SORT_PREBINNED : 0, table,
                                sorted_id, sorted_pos, sorted_bin, max_count, sort_workspace, sort_workspace_bytes,
-                               prebin ? other : nullptr, stream);     // the idle table is cleared on the way
+                               prebin ? other : nullptr, global_id, stream);   // the idle table is cleared on the way
         if (rc) return rc;
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
-        rc = abm_jkr_substep(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
-                             cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, k == n_substeps - 1,
-                             motility_forces, prebin ? nullptr : locations,
-                             poisson, youngs, adhesion_const, stokes, size_host, dts_host[k], global_id, uniform_radius,
-                             prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
-                             prebin ? sort_workspace : nullptr, stream);
+        const int32_t *slot_gid = (global_id && n > 0) ? sort_ws_carve(sort_workspace, n, nbins).slot_gid : nullptr;
+        rc = jkr_substep_impl(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
+                              cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, k == n_substeps - 1,
+                              motility_forces, prebin ? nullptr : locations, poisson, youngs, adhesion_const, stokes,
+                              size_host, dts_host[k], global_id, slot_gid, uniform_radius,
+                              prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
+                              prebin ? sort_workspace : nullptr, stream);
         if (rc) return rc;
         cur_start = nullptr;
         cur_stride = row_stride;

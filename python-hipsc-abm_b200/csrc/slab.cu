@@ -19,13 +19,16 @@ __device__ __forceinline__ bool owns(double x, double x_lo, double x_hi, int has
 }
 
 // flags[i] = 1 if owned cell i goes to the left (side 0) / right (side 1) neighbour
-__global__ void __launch_bounds__(256) k_slab_flags(const double *__restrict__ loc, int n, double x_send_left,
+// n_own_dev (may be nullptr): only the first *n_own_dev of the n rows are owned cells (the rest are last step's
+// halo cells, which are not sent) -- lets the caller enqueue the pack before it knows the owned count itself
+__global__ void __launch_bounds__(256) k_slab_flags(const double *__restrict__ loc, int n,
+                                                    const int *__restrict__ n_own_dev, double x_send_left,
                                                     double x_send_right, int has_left, int has_right,
                                                     int *__restrict__ flag_l, int *__restrict__ flag_r) {
     int i = blockIdx.x * 256 + threadIdx.x;
     if (i > n) return;
     int l = 0, r = 0;
-    if (i < n) {
+    if (i < n && (!n_own_dev || i < *n_own_dev)) {
         double x = loc[3 * (long long)i];
         l = has_left && x < x_send_left;
         r = has_right && x >= x_send_right;
@@ -134,7 +137,8 @@ ABM_EXPORT size_t abm_slab_workspace_bytes(int64_t n) {
 
 ABM_EXPORT int abm_slab_pack(const double *locations, const double *radii, const double *motility_forces,
                              const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows,
-                             int64_t n_own, int64_t row_stride, double x_send_left, double x_send_right, int has_left,
+                             int64_t n_own, const int32_t *n_own_device, int64_t row_stride, double x_send_left,
+                             double x_send_right, int has_left,
                              int has_right, uint8_t *records_left, int64_t capacity_left, uint8_t *records_right,
                              int64_t capacity_right, int32_t *counts, void *workspace, size_t workspace_bytes,
                              void *stream) {
@@ -147,8 +151,8 @@ ABM_EXPORT int abm_slab_pack(const double *locations, const double *radii, const
     size_t half = scan_ws_ints(n_own + 1);
     int *flag_l = (int *)workspace, *flag_r = flag_l + half;
     int *sums_l = flag_l + ((size_t)(n_own + 1) + 63) / 64 * 64, *sums_r = flag_r + ((size_t)(n_own + 1) + 63) / 64 * 64;
-    k_slab_flags<<<ceil_div(n_own + 1, 256), 256, 0, st>>>(locations, (int)n_own, x_send_left, x_send_right, has_left,
-                                                           has_right, flag_l, flag_r);
+    k_slab_flags<<<ceil_div(n_own + 1, 256), 256, 0, st>>>(locations, (int)n_own, n_own_device, x_send_left,
+                                                           x_send_right, has_left, has_right, flag_l, flag_r);
     ABM_CHECK_LAUNCH("k_slab_flags");
     rc = exclusive_scan_inplace(flag_l, n_own + 1, sums_l, nullptr, nullptr, st);
     if (rc) return rc;

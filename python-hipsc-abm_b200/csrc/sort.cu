@@ -32,12 +32,14 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const int *__restrict__ ce
                                                       const double *__restrict__ loc, const double *__restrict__ radii,
                                                       int n, int *__restrict__ sorted_id,
                                                       double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
-                                                      int *__restrict__ next_sums, int n_sums) {
+                                                      int *__restrict__ next_sums, int n_sums,
+                                                      const int *__restrict__ gid_of, int *__restrict__ slot_gid) {
     int i = blockIdx.x * kThreads + threadIdx.x;
     for (int k = i; k < n_sums; k += gridDim.x * kThreads) next_sums[k] = 0;
     if (i >= n) return;
     int b = cell_bin[i];
     int dest = atomicAdd(&cursor[b], 1);
+    if (gid_of) slot_gid[dest] = gid_of[i];
     double4 p;
     p.x = loc[3 * (int64_t)i + 0];
     p.y = loc[3 * (int64_t)i + 1];
@@ -55,16 +57,19 @@ __global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ 
                                                         const double4 *__restrict__ next_pos, int *__restrict__ cursor,
                                                         int n, int *__restrict__ sorted_id,
                                                         double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
-                                                        int *__restrict__ next_sums, int n_sums) {
+                                                        int *__restrict__ next_sums, int n_sums,
+                                                        const int *__restrict__ gid_of, int *__restrict__ slot_gid) {
     int s = blockIdx.x * kThreads + threadIdx.x;
     // consumed by this sort's scan; the next hand-over adds to it
     for (int k = s; k < n_sums; k += gridDim.x * kThreads) next_sums[k] = 0;
     if (s >= n) return;
     int b = next_bin[s];
     int dest = atomicAdd(&cursor[b], 1);
+    int id = prev_id[s];
     sorted_pos[dest] = next_pos[s];
-    sorted_id[dest] = prev_id[s];
+    sorted_id[dest] = id;
     sorted_bin[dest] = b;
+    if (gid_of) slot_gid[dest] = gid_of[id];
 }
 
 __global__ void __launch_bounds__(kThreads) k_place(const int *__restrict__ cell_bin, int *__restrict__ cursor, int n,
@@ -147,15 +152,17 @@ ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_
                             int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
                             void *workspace, size_t workspace_bytes, void *stream) {
     return abm::bin_sort_impl(locations, radii, n, size_host, origin_host, distance, flags, bin_start, sorted_id,
-                              sorted_pos, sorted_bin, max_count, workspace, workspace_bytes, nullptr, stream);
+                              sorted_pos, sorted_bin, max_count, workspace, workspace_bytes, nullptr, nullptr, stream);
 }
 
 // zero_table: optional second (nbins+1) offset table cleared on the way (the mechanics loop alternates two tables
-// and needs the idle one zeroed for the next histogram).
+// and needs the idle one zeroed for the next histogram).  global_id: optional (n) id table; the workspace's
+// slot_gid then receives the global id of the cell in every slot (fast placements only).
 int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, const double size_host[3],
                        const double *origin_host, double distance, int flags, int32_t *bin_start,
                        int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
-                       void *workspace, size_t workspace_bytes, int32_t *zero_table, void *stream) {
+                       void *workspace, size_t workspace_bytes, int32_t *zero_table, const int32_t *global_id,
+                       void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     ABM_REQUIRE(size_host && bin_start && max_count, "null pointer");
     BinGeom g;
@@ -202,7 +209,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
     double4 *sp = reinterpret_cast<double4 *>(sorted_pos);
     if (prebinned) {
         k_rescatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.tmp_id, w.next_pos, w.cursor, (int)n, sorted_id, sp,
-                                                 sorted_bin, w.next_sums, nb);
+                                                 sorted_bin, w.next_sums, nb, global_id, w.slot_gid);
         ABM_CHECK_LAUNCH("k_rescatter");
     } else if (flags & ABM_SORT_STABLE) {
         rc = check_cuda(cudaMemsetAsync(w.next_sums, 0, (size_t)nb * 4, st), "memset next_sums");
@@ -214,7 +221,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
         ABM_CHECK_LAUNCH("k_gather");
     } else {
         k_scatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.cursor, locations, radii, (int)n, sorted_id, sp,
-                                               sorted_bin, w.next_sums, nb);
+                                               sorted_bin, w.next_sums, nb, global_id, w.slot_gid);
         ABM_CHECK_LAUNCH("k_scatter");
     }
     return 0;

@@ -13,13 +13,14 @@ struct SortWs {
     int *next_sums;   // ABM_SORT_PREBINNED: per-scan-chunk sums of the histogram, accumulated by the mechanics kernel
                       // (the placement kernel of every sort leaves them zeroed for the next one)
     double4 *next_pos;// n   : ABM_SORT_PREBINNED: moved {x,y,z,r} of the cell in previous slot s
+    int *slot_gid;    // n   : global id of the cell in slot s (mechanics loop of a slab-decomposed colony)
 };
 
 inline size_t sort_align(size_t v) { return (v + 255) & ~size_t(255); }
 
 inline size_t sort_ws_bytes(int64_t n, int64_t nbins) {
     return 2 * sort_align((size_t)n * 4) + sort_align((size_t)(nbins + 1) * 4) +
-           2 * sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4) + sort_align((size_t)n * 32) + 512;
+           2 * sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4) + sort_align((size_t)n * 32) + sort_align((size_t)n * 4) + 512;
 }
 
 inline SortWs sort_ws_carve(void *ws, int64_t n, int64_t nbins) {
@@ -31,7 +32,8 @@ inline SortWs sort_ws_carve(void *ws, int64_t n, int64_t nbins) {
     w.block_sums = (int *)p; p += sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4);
     w.next_sums = (int *)p;  p += sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4);
     p = (char *)(((uintptr_t)p + 255) & ~uintptr_t(255));    // the caller's buffer need not be aligned
-    w.next_pos = (double4 *)p;
+    w.next_pos = (double4 *)p; p += sort_align((size_t)n * 32);
+    w.slot_gid = (int *)p;
     return w;
 }
 
@@ -58,7 +60,7 @@ inline int make_bin_geom(const double extent[3], const double *origin, double di
 int bin_sort_impl(const double *locations, const double *radii, int64_t n, const double size_host[3],
                   const double *origin_host, double distance, int flags, int32_t *bin_start, int32_t *sorted_id,
                   double *sorted_pos, int32_t *sorted_bin, int32_t *max_count, void *workspace,
-                  size_t workspace_bytes, int32_t *zero_table, void *stream);
+                  size_t workspace_bytes, int32_t *zero_table, const int32_t *global_id, void *stream);
 
 __device__ __forceinline__ int cell_bin_of(double x, double y, double z, const BinGeom &g) {
     return lin_bin(bin_coord_fast(x - g.origin[0], g.distance, g.inv_distance, g.dims[0]),

@@ -310,6 +310,10 @@ class SlabPipeline:
         self._sampled_local = local
 
 
+def _ptr_or_0(t):
+    return 0 if t is None else t.data_ptr()
+
+
 class NativeSlabOps:
     """slab.rank_step's select/pack/merge on the device (csrc/slab.cu): two C calls and two small host reads per
     step instead of a few dozen tensor ops."""
@@ -334,7 +338,12 @@ class NativeSlabOps:
     def outgoing(self, state, geom):
         eng, dev = self.eng, self.eng.device
         eng.use_current_stream()
-        n, stride, rec = state.n, state.stride, state.record_bytes()
+        pend = state.pending()
+        if pend is not None:          # last step's local arrays, owned count still on the device: no host sync
+            src, n, n_own_dev = pend
+        else:
+            src, n, n_own_dev = state.fields(), state.n, None
+        stride, rec = state.stride, state.record_bytes()
         ws = self._workspace(n)
         if self.send_cap == 0:
             self.send_cap = int(self.send_fraction * n) + 4096
@@ -345,8 +354,9 @@ class NativeSlabOps:
         out_r = torch.empty((cap, rec), dtype=torch.uint8, device=dev)
         counts = torch.empty(2, dtype=torch.int32, device=dev)
         _lib.check(self.lib.abm_slab_pack(
-            state.loc.data_ptr(), state.radii.data_ptr(), state.mot.data_ptr(), state.gid.data_ptr(),
-            state.bond_len.data_ptr(), state.bond_gid.data_ptr(), n, stride, geom.x_lo + geom.halo,
+            src["loc"].data_ptr(), src["radii"].data_ptr(), src["mot"].data_ptr(), src["gid"].data_ptr(),
+            src["bond_len"].data_ptr(), src["bond_gid"].data_ptr(), n, _ptr_or_0(n_own_dev), stride,
+            geom.x_lo + geom.halo,
             geom.x_hi - geom.halo, int(geom.has_left), int(geom.has_right), out_l.data_ptr(), cap,
             out_r.data_ptr(), cap, counts.data_ptr(), ws.data_ptr(), ws.numel(), eng.stream),
             "abm_slab_pack")

@@ -95,18 +95,48 @@ class SlabState:
     def __init__(self, loc, radii, mot, gid, stride=16):
         n = loc.shape[0]
         dev = loc.device
-        self.loc, self.radii, self.mot = loc.contiguous(), radii.contiguous(), mot.contiguous()
-        self.gid = gid.to(torch.int32).contiguous()
-        self.bond_len = torch.zeros(n, dtype=torch.int32, device=dev)
-        self.bond_gid = torch.full((n, stride), -1, dtype=torch.int32, device=dev)
+        self._d = dict(loc=loc.contiguous(), radii=radii.contiguous(), mot=mot.contiguous(),
+                       gid=gid.to(torch.int32).contiguous(),
+                       bond_len=torch.zeros(n, dtype=torch.int32, device=dev),
+                       bond_gid=torch.full((n, stride), -1, dtype=torch.int32, device=dev))
+        self._pending = None
+
+    # The owned cells of a finished step are the first n_own rows of the step's local arrays; when n_own is still
+    # on the device (LocalProblem with a lazy count) the slicing is deferred until somebody needs it, so that the
+    # next step's pack can be enqueued without waiting for the GPU.
+    def defer(self, full: dict, local: "LocalProblem"):
+        self._pending = (full, local)
+
+    def pending(self):
+        """(full arrays, rows, device owned-count) if the owned count has not been read yet, else None."""
+        if self._pending is None or isinstance(self._pending[1]._n_own, int):
+            return None
+        full, local = self._pending
+        return full, int(full["loc"].shape[0]), local._n_own
+
+    def _settle(self):
+        if self._pending is not None:
+            full, local = self._pending
+            n = local.n_own
+            self._d = {f: full[f][:n] for f in FIELDS}
+            self._pending = None
+
+    def _get(self, f):
+        self._settle()
+        return self._d[f]
+
+    def _set(self, f, v):
+        self._settle()
+        self._d[f] = v
 
     @property
     def n(self):
-        return int(self.loc.shape[0])
+        return int(self._get("loc").shape[0])
 
     @property
     def stride(self):
-        return int(self.bond_gid.shape[1])
+        d = self._pending[0] if self._pending is not None else self._d
+        return int(d["bond_gid"].shape[1])
 
     def record_bytes(self):
         return 24 + 8 + 24 + 4 + 4 + 4 * self.stride
@@ -115,8 +145,8 @@ class SlabState:
         return {f: getattr(self, f) for f in FIELDS}
 
     def set_fields(self, d):
-        for f in FIELDS:
-            setattr(self, f, d[f])
+        self._pending = None
+        self._d = {f: d[f] for f in FIELDS}
 
     def pack(self, idx) -> torch.Tensor:
         """One byte record per selected cell: loc | radius | motility | gid | bond_len | bond row."""
@@ -307,6 +337,10 @@ class LocalProblem:
         return self._n_own
 
 
+for _f in FIELDS:
+    setattr(SlabState, _f, property(lambda self, f=_f: self._get(f), lambda self, v, f=_f: self._set(f, v)))
+
+
 class TorchSlabOps:
     """Selecting / packing / merging with plain torch tensor ops: runs anywhere (the CPU + gloo tests use it) but
     costs a few dozen small kernels per step; on a GPU use pipeline.NativeSlabOps (csrc/slab.cu)."""
@@ -372,15 +406,18 @@ def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProb
 
     if field is not None and morphogen_first:
         begin = getattr(field_ops, "begin_side", None)
-        side = begin(local) if begin else None
-        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
-            field_ops.deposit(local, field)                   # owned + halo cells, where the step starts
+        side = begin(local) if begin else None                # snapshot of the positions, fork point
+        if side is not None:
+            blen, bgid = compute(local)                       # the mechanics are enqueued first: the GPU starts on
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):   # them while the host
+            field_ops.deposit(local, field)                   # feeds the second stream.  owned + halo cells deposit
             to_l, to_r = field.messages()
             from_l, from_r = yield Exchange("rows", to_l, to_r, field.gy, torch.float64, fixed_rows=field.halo_rows)
             field.absorb(from_l, from_r)
             field_ops.diffuse(field)
             field_ops.sample(local, field)
-        blen, bgid = compute(local)
+        if side is None:
+            blen, bgid = compute(local)
         if begin:
             field_ops.end_side()
         field = None                                          # done
@@ -393,9 +430,12 @@ def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProb
         field.absorb(from_l, from_r)
         field_ops.diffuse(field)                              # S_d substeps, no communication
         field_ops.sample(local, field)
-    n = local.n_own
-    state.set_fields(dict(loc=local.loc[:n], radii=local.radii[:n], mot=local.mot[:n], gid=local.gid[:n],
-                          bond_len=blen[:n], bond_gid=bgid[:n]))
+    full = dict(loc=local.loc, radii=local.radii, mot=local.mot, gid=local.gid, bond_len=blen, bond_gid=bgid)
+    if isinstance(local._n_own, int):
+        n = local.n_own
+        state.set_fields({f: full[f][:n] for f in FIELDS})
+    else:
+        state.defer(full, local)                              # owned count still on the device: slice when needed
     return local
 
 

@@ -51,6 +51,14 @@ else:
             a.record(); launch(); z.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(z) * 1e3)
         res["cold" if cold else "warm"] = float(np.median(ts))
+    # whole step enqueued eagerly (what the slab pipeline does), L2 flushed before each
+    ts = []
+    for _ in range(12):
+        flush.zero_()
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); pipe.step(); z.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(z) * 1e3)
+    res["eager_step_us"] = float(np.median(ts))
     # whole step as a CUDA-graph replay (no diffusion grid), L2 flushed before each
     if pipe.parity:
         pipe.step()

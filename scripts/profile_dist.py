@@ -35,6 +35,26 @@ for _ in range(3): step()
 torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
 for _ in range(10): step()
 torch.cuda.synchronize(); free = (time.perf_counter() - t0) / 10
+# host-side cost of each phase (no synchronisation: what the CPU spends enqueueing)
+host = collections.defaultdict(float)
+def hosted(name, fn):
+    def w(*a, **k):
+        t0 = time.perf_counter(); r = fn(*a, **k); host[name] += time.perf_counter() - t0; return r
+    return w
+saved = dict(outgoing=ops.outgoing, merge=ops.merge, exchange=fabric.exchange, compute=pipe.compute,
+             deposit=pipe.deposit, diffuse=pipe.diffuse, sample=pipe.sample)
+ops.outgoing = hosted("pack", ops.outgoing); ops.merge = hosted("merge(+count sync)", ops.merge)
+fabric.exchange = hosted("exchange", fabric.exchange); pipe.compute = hosted("compute", pipe.compute)
+pipe.deposit = hosted("deposit", pipe.deposit); pipe.diffuse = hosted("diffuse", pipe.diffuse)
+pipe.sample = hosted("sample", pipe.sample)
+dist.barrier(); t0 = time.perf_counter()
+for _ in range(10): step()
+torch.cuda.synchronize(); tot_h = (time.perf_counter() - t0) / 10
+if rank == 0:
+    print("host ms/step %.3f" % (tot_h * 1e3), {k: round(v / 10 * 1e3, 3) for k, v in host.items()},
+          "other(+n_own sync) %.3f" % ((tot_h - sum(host.values()) / 10) * 1e3))
+ops.outgoing, ops.merge, fabric.exchange, pipe.compute = saved["outgoing"], saved["merge"], saved["exchange"], saved["compute"]
+pipe.deposit, pipe.diffuse, pipe.sample = saved["deposit"], saved["diffuse"], saved["sample"]
 ops.outgoing = timed("pack", ops.outgoing); ops.merge = timed("merge", ops.merge)
 fabric.exchange = timed("exchange", fabric.exchange)
 pipe.compute = timed("compute", pipe.compute); pipe.deposit = timed("deposit", pipe.deposit)
