@@ -442,7 +442,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     fabric = slab.DistFabric(rank, world, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    ops = NativeSlabOps(pipe.eng, send_cap=int(0.12 * n) + 4096)      # the same on every rank
+    ops = NativeSlabOps(pipe.eng, send_cap=int(0.05 * n) + 4096)      # the same on every rank (2x the halo cells)
 
     def step():
         slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None, ops,

@@ -70,7 +70,7 @@ class ColonyEngine:
         self.max_radius = 0.0
         self.uniform_radius = 0.0   # common radius when all radii are equal (contact constants evaluated once)
         self.global_id = None   # int32 (n,) when bond rows are kept by global id (slab decomposition)
-        self._sort_ws = None
+        self._sort_wss = {}     # sort scratch per bin count (sorts of different lattices may run on different streams)
         self._sort_bufs = {}
         self._edge_ws = None
         self._bond_bufs = None
@@ -196,19 +196,24 @@ class ColonyEngine:
                 self._sort_bufs.clear()
             self._sort_bufs[nbins] = b
         need = self.lib.abm_bin_sort_workspace_bytes(n, nbins)
-        if self._sort_ws is None or self._sort_ws.numel() < need:
-            self._sort_ws = self._empty(int(1.1 * need) + 4096, torch.uint8)
+        ws = self._sort_wss.get(nbins)
+        if ws is None or ws.numel() < need:
+            if len(self._sort_wss) > 4:
+                self._sort_wss.clear()
+            ws = self._sort_wss[nbins] = self._empty(int(1.1 * need) + 4096, torch.uint8)
+        b["ws"] = ws
         return dims, nbins, b
 
-    def sort(self, distance, flags=0) -> SortState:
-        """Counting sort of the current locations into bins of edge `distance` (abm_bin_sort).
+    def sort(self, distance, flags=0, loc=None) -> SortState:
+        """Counting sort of the current locations (or `loc`) into bins of edge `distance` (abm_bin_sort).
         flags: _lib.SORT_STABLE | _lib.SORT_REFERENCE for the reference-shaped assign_bins() output."""
         n = self.n
         dims, nbins, b = self._sort_buffers(distance, flags)
-        _lib.check(self.lib.abm_bin_sort(_ptr(self.loc), _ptr(self.radii), n, self._extent_c, self._origin_c,
+        _lib.check(self.lib.abm_bin_sort(_ptr(self.loc if loc is None else loc), _ptr(self.radii), n,
+                                         self._extent_c, self._origin_c,
                                          float(distance), int(flags), _ptr(b["bin_start"]), _ptr(b["sorted_id"]),
                                          _ptr(b["sorted_pos"]), _ptr(b["sorted_bin"]), _ptr(b["max_count"]),
-                                         _ptr(self._sort_ws), self._sort_ws.numel(), self.stream), "abm_bin_sort")
+                                         _ptr(b["ws"]), b["ws"].numel(), self.stream), "abm_bin_sort")
         self.launches += (5 if flags & _lib.SORT_STABLE else 4) if n else 0
         return SortState(float(distance), dims, nbins, n, b["bin_start"], b["sorted_id"], b["sorted_pos"],
                          b["sorted_bin"], b["max_count"])
@@ -253,7 +258,7 @@ class ColonyEngine:
         g.entries = used
         return g
 
-    def enqueue_search(self, sort: SortState, distance, old, row_start, row_len, cols, cursor):
+    def enqueue_search(self, sort: SortState, distance, old, row_start, row_len, cols, cursor, loc=None):
         """One abm_neighbor_search launch into caller-provided buffers; no host sync (the caller checks
         cursor <= cols.numel() later)."""
         if distance > sort.distance * (1 + 1e-12):
@@ -261,7 +266,7 @@ class ColonyEngine:
         n = sort.n
         _lib.check(self.lib.abm_neighbor_search(
             _ptr(sort.bin_start), _ptr(sort.sorted_id), _ptr(sort.sorted_pos), _ptr(sort.sorted_bin), n,
-            _lib.i3(sort.dims), float(distance), _ptr(self.loc),
+            _lib.i3(sort.dims), float(distance), _ptr(self.loc if loc is None else loc),
             _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
             _ptr(row_start), _ptr(row_len), _ptr(cols), cols.numel(), _ptr(cursor), self.stream),
@@ -347,7 +352,7 @@ class ColonyEngine:
             _ptr(self.radii), _ptr(self.loc), _ptr(self.mot), n, self._extent_c, self._origin_c, self._size_c,
             float(distance), reach, len(dts), dts_c,
             _ptr(sb["bin_start"]), _ptr(sb["bin_start_b"]), _ptr(sb["sorted_id"]), _ptr(sb["sorted_pos"]),
-            _ptr(sb["sorted_bin"]), _ptr(sb["max_count"]), _ptr(self._sort_ws), self._sort_ws.numel(),
+            _ptr(sb["sorted_bin"]), _ptr(sb["max_count"]), _ptr(sb["ws"]), sb["ws"].numel(),
             _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
             _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),

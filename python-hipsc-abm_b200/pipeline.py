@@ -79,7 +79,7 @@ class HotPathStep:
         self.graphs = None
         self.launches_per_step = 0
         self._side = self._loc_snap = None
-        if cfg.grid is not None and cfg.overlap_morphogen:
+        if cfg.overlap_morphogen:
             self._side = torch.cuda.Stream(device=dev)
             self._loc_snap = torch.empty((max(n, 1), 3), dtype=torch.float64, device=dev)
         # start with an empty bond graph living in row buffer 0
@@ -93,21 +93,22 @@ class HotPathStep:
         eng, cfg = self.eng, self.cfg
         eng.use_current_stream()              # under torch.cuda.graph() this is the capture stream
         before = eng.launches
-        overlap = self.field is not None and cfg.overlap_morphogen
+        overlap = cfg.overlap_morphogen
         if overlap:
-            # fork: the morphogen stage works on a snapshot of the positions and runs beside search + mechanics
+            # fork: the neighbour search and the morphogen stage work on a snapshot of the positions and run on a
+            # second stream beside the mechanics (all three depend only on the positions the step starts with)
             main = torch.cuda.current_stream(eng.device)
-            self._loc_snap[:eng.n].copy_(eng.loc)
+            snap = self._loc_snap[:eng.n]
+            snap.copy_(eng.loc)
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 eng.use_current_stream()
-                self._morphogen(self._loc_snap)
+                self._search(snap)
+                if self.field is not None:
+                    self._morphogen(snap)
             eng.use_current_stream()
-        # neighbour graph (what the rule methods consume)
-        srt = eng.sort(cfg.search_radius)
-        self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self.nbr["row_start"],
-                                                 self.nbr["row_len"], self.nbr["cols"], self.nbr["cursor"])
-        torch.maximum(self.nbr["worst"], self.nbr["cursor"], out=self.nbr["worst"])   # sticky overflow record
+        else:
+            self._search(None)
         # mechanics: bonds alternate between row buffers 0 and 1, buffer 2 is the intermediate
         src = self.parity
         pair = [1 - src, 2]
@@ -121,6 +122,14 @@ class HotPathStep:
         elif self.field is not None:
             self._morphogen(None)
         self.launches_per_step = eng.launches - before
+
+    def _search(self, loc):
+        """Neighbour graph (what the rule methods consume) of the positions `loc` (None: the engine's)."""
+        eng, cfg = self.eng, self.cfg
+        srt = eng.sort(cfg.search_radius, loc=loc)
+        self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self.nbr["row_start"],
+                                                 self.nbr["row_len"], self.nbr["cols"], self.nbr["cursor"], loc=loc)
+        torch.maximum(self.nbr["worst"], self.nbr["cursor"], out=self.nbr["worst"])   # sticky overflow record
 
     def _morphogen(self, loc):
         """deposit -> diffuse -> sample on the engine's current stream (loc=None: the engine's positions)."""
@@ -204,6 +213,7 @@ class SlabPipeline:
         self._side = torch.cuda.Stream(device=device) if side_stream else None
         self._snap = None
         self._amounts = None
+        self._defer_search = False
 
     @property
     def sampled(self):
@@ -232,15 +242,27 @@ class SlabPipeline:
                              cols=torch.empty(int(1.1 * cap), dtype=torch.int32, device=dev),
                              cursor=torch.zeros(1, dtype=torch.int32, device=dev),
                              worst=torch.zeros(1, dtype=torch.int32, device=dev))
-        srt = eng.sort(cfg.search_radius)
-        self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self._nbr["row_start"],
-                                                 self._nbr["row_len"], self._nbr["cols"], self._nbr["cursor"])
-        torch.maximum(self._nbr["worst"], self._nbr["cursor"], out=self._nbr["worst"])
+        if not self._defer_search:
+            self._do_search(None)
         # mechanics with the bonds carried in from the previous step (fixed-stride rows of global ids)
         stride = int(local.bond_gid.shape[1])
         old = GraphTensors(n, None, stride, local.bond_len, local.bond_gid, True)
         bonds = eng.enqueue_mechanics(old, cfg.contact_radius, self.dts, stride, STOKES, zero_flag=False)
         return bonds.row_len, bonds.cols
+
+    def _do_search(self, loc):
+        eng, cfg = self.eng, self.cfg
+        srt = eng.sort(cfg.search_radius, loc=loc)
+        self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self._nbr["row_start"],
+                                                 self._nbr["row_len"], self._nbr["cols"], self._nbr["cursor"], loc=loc)
+        torch.maximum(self._nbr["worst"], self._nbr["cursor"], out=self._nbr["worst"])
+
+    def search(self, local):
+        """The step's neighbour search on the second stream (morphogen_first steps), on the snapshot."""
+        if self._defer_search:
+            self.eng.use_current_stream()
+            self._do_search(self._snap)
+            self._defer_search = False
 
     def check(self):
         """Host sync: raise if a fixed-capacity buffer overflowed in any step since the last check."""
@@ -263,6 +285,7 @@ class SlabPipeline:
             self._snap = torch.empty((int(1.1 * n) + 1024, 3), dtype=torch.float64, device=eng.device)
         self._snap[:n].copy_(local.loc)
         self._snap_n = n
+        self._defer_search = self._side is not None          # the search moves to the second stream as well
         if self._side is None:
             return None
         self._side.wait_stream(torch.cuda.current_stream(eng.device))

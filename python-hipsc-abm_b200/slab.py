@@ -410,7 +410,9 @@ def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProb
         if side is not None:
             blen, bgid = compute(local)                       # the mechanics are enqueued first: the GPU starts on
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):   # them while the host
-            field_ops.deposit(local, field)                   # feeds the second stream.  owned + halo cells deposit
+            if side is not None and hasattr(field_ops, "search"):                            # feeds the second
+                field_ops.search(local)                       # stream: the neighbour search (same snapshot), then
+            field_ops.deposit(local, field)                   # the morphogen stage.  owned + halo cells deposit
             to_l, to_r = field.messages()
             from_l, from_r = yield Exchange("rows", to_l, to_r, field.gy, torch.float64, fixed_rows=field.halo_rows)
             field.absorb(from_l, from_r)

@@ -17,7 +17,7 @@ side = wls[0]["size"][0]
 gsize = wls[0]["size"].copy(); gsize[0] = side * world
 halo = slab.required_halo(11, 10.3100107, slack=4.0) + spec["h"]
 geoms = [slab.SlabGeometry.uniform(gsize, world, r, halo) for r in range(world)]
-pipes = [SlabPipeline(g, cfg, dev) for g in geoms]
+pipes = [SlabPipeline(g, cfg, dev, uniform_radius=5.0, side_stream=False) for g in geoms]
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 states = []
 for r, (wl, g) in enumerate(zip(wls, geoms)):
@@ -32,6 +32,12 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
+if os.environ.get("ONLY_STEPS"):
+    for _ in range(int(os.environ["ONLY_STEPS"])):
+        step()
+    torch.cuda.synchronize()
+    print("n_local", [int(p.eng.n) for p in pipes])
+    sys.exit(0)
 t0 = time.perf_counter()
 for _ in range(5):
     step()
