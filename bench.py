@@ -444,6 +444,12 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
 
     ops = NativeSlabOps(pipe.eng, send_cap=int(0.05 * n) + 4096)      # the same on every rank (2x the halo cells)
 
+    # the step's main stream outranks the second stream (search + morphogen stage), whose kernels then fill what the
+    # mechanics leave idle instead of competing with them
+    main_stream = torch.cuda.Stream(device=dev, priority=-1)
+    main_stream.wait_stream(torch.cuda.current_stream(dev))
+    torch.cuda.set_stream(main_stream)
+
     def step():
         slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None, ops,
                        morphogen_first=first)

@@ -153,7 +153,8 @@ class HotPathStep:
         torch.cuda.synchronize(self.eng.device)
         self.graphs = []
         launches = self.eng.launches
-        stream = torch.cuda.Stream(device=self.eng.device)
+        # the mechanics stream outranks the second stream: search + morphogen kernels fill what the mechanics leave idle
+        stream = torch.cuda.Stream(device=self.eng.device, priority=-1)
         for _ in range(2):
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=stream):
