@@ -158,7 +158,7 @@ template <bool kUniform>
 __global__ void __launch_bounds__(kJkrThreads, kJkrMinBlocks)
 k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_id,
               const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
-              double reach2, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
+              double reach2, BandConst bandc, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
               double stokes, Friction fric, Box box, double dt, const int *__restrict__ gid_of,
               const int *__restrict__ slot_pid, NextSort next, int sort_rows) {
@@ -186,10 +186,13 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     org.y = __shfl_sync(kFullWarp, p.y, 0);
     org.z = __shfl_sync(kFullWarp, p.z, 0);
     const float pfx = (float)(p.x - org.x), pfy = (float)(p.y - org.y), pfz = (float)(p.z - org.z);
-    const float t_out = (float)reach2 + tile_band(pfx, pfy, pfz, sqrtf((float)reach2));
+    const float t_out = (float)reach2 + bandc.band(pfx, pfy, pfz);
     int nh = 0;                                                // parked partners (counts on past kMaxHits)
     bool slow = false;
     for (int dz = -1; dz <= 1; ++dz) {
+#if ABM_JKR_EXP & 8
+        break;                                                 // timing ablation: no walk (wrong results)
+#endif
         const int z = bz + dz;
         if (__all_sync(kFullWarp, !live || z < 0 || z >= st.dims[2])) continue;
         const LayerRuns R = stage_layer(live, bx, by, z, st, bin_start, spos, org, tile);
@@ -216,6 +219,10 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     }
     if (!live) return;                                         // no warp-wide operation below this line
     slow |= nh > kMaxHits;
+#if ABM_JKR_EXP & 4
+    nh = 0;                                                    // timing ablation: no contact loop (wrong results)
+    slow = false;
+#endif
 
 #if ABM_JKR_EXP & 1
     const double mx = mot[3 * (long long)i + 0], my = mot[3 * (long long)i + 1], mz = mot[3 * (long long)i + 2];
@@ -426,7 +433,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         loc[3 * (long long)i + 2] = nz;
     }
     if (next.counts) {                                        // hand-over to the next substep's sort, by slot
-        int b = cell_bin_of(nx, ny, nz, next.geom);
+        int b = cell_bin_of_loose(nx, ny, nz, next.geom);
         next.next_pos[s] = make_double4(nx, ny, nz, p.w);
         next.cell_bin[s] = b;
         next.prev_id[s] = i;
@@ -493,11 +500,9 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
     JkrConst c = make_jkr_const(poisson, youngs, adhesion_const, uniform_radius);
     GraphView old{old_row_start, (long long)old_row_stride, old_row_len, old_cols};
     Stencil stc;
+    stc.set(dims_host);
     Box box;
-    for (int k = 0; k < 3; ++k) {
-        stc.dims[k] = dims_host[k];
-        box.size[k] = size_host[k];
-    }
+    for (int k = 0; k < 3; ++k) box.size[k] = size_host[k];
     NextSort next;
     memset(&next, 0, sizeof(next));
     if (next_bin_counts) {
@@ -523,7 +528,7 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
     auto kernel = uniform_radius > 0 ? k_jkr_substep<true> : k_jkr_substep<false>;
     kernel<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
-        Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
+        Radius(distance), reach * reach, BandConst::make(reach * 1.0000001), old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
         locations, c, stokes, fric, box, move_dt, global_id, global_id ? slot_gid : sorted_id, next, sort_rows);
     ABM_CHECK_LAUNCH("k_jkr_substep");
     return 0;

@@ -230,7 +230,7 @@ ABM_EXPORT int abm_neighbor_search(const int32_t *bin_start, const int32_t *sort
     GraphView old{old_row_start, (long long)old_row_stride, old_row_len, old_cols};
     ABM_REQUIRE(!old.valid() || (locations && old_cols), "union needs locations and old_cols");
     Stencil stc;
-    for (int k = 0; k < 3; ++k) stc.dims[k] = dims_host[k];
+    stc.set(dims_host);
     k_search<<<ceil_div(n, kSearchThreads), kSearchThreads, 0, st>>>(
         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
         Radius(distance), locations, old, row_start, row_len, cols, (long long)cols_capacity, cursor);

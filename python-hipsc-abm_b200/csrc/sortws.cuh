@@ -68,4 +68,17 @@ __device__ __forceinline__ int cell_bin_of(double x, double y, double z, const B
                    bin_coord_fast(z - g.origin[2], g.distance, g.inv_distance, g.dims[2]), g.dims);
 }
 
+// Bin of a moved cell for the NEXT sort of the mechanics loop, without the exact-floor correction: the plain
+// floor((x - origin) * (1/d)) can be off by one bin only for a coordinate within ~1e-12 um of a bin boundary.  The
+// mechanics bins are `reach` = (largest bond distance) * (1 + 1e-9) wide, i.e. ~1e-8 um wider than any pair that has
+// to meet in adjacent bins, so every such pair still does -- the partition need not be the reference's, only
+// consistent within one sort.  (abm_bin_sort itself keeps the exact floor: there the bin edge may equal the search
+// radius and the reference-shaped outputs are defined by it.)
+__device__ __forceinline__ int cell_bin_of_loose(double x, double y, double z, const BinGeom &g) {
+    int bx = clampi(__double2int_rd((x - g.origin[0]) * g.inv_distance) + 1, 0, g.dims[0] - 1);
+    int by = clampi(__double2int_rd((y - g.origin[1]) * g.inv_distance) + 1, 0, g.dims[1] - 1);
+    int bz = clampi(__double2int_rd((z - g.origin[2]) * g.inv_distance) + 1, 0, g.dims[2] - 1);
+    return lin_bin(bx, by, bz, g.dims);
+}
+
 }  // namespace abm

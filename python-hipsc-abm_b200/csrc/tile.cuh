@@ -35,6 +35,25 @@ __device__ __forceinline__ float tile_band(float px, float py, float pz, float s
     return 2.0f * (3.5f * sqrt_threshold * e + 3.0f * e * e + t * 0x1p-22f) + 1e-5f;
 }
 
+// The same bound with the threshold-dependent factors evaluated once on the host: band = c0 + m (c1 + c2 m),
+// m = max |relative coordinate of the lane's own cell| (the + 2 sqrt(T) of tile_band is folded into the constants
+// with (m + k)^2 <= 2 m^2 + 2 k^2).
+struct BandConst {
+    float c0, c1, c2;
+    __host__ static BandConst make(double sqrt_threshold) {
+        const double k = 2.0 * sqrt_threshold, u = 0x1p-23, t = sqrt_threshold * sqrt_threshold;
+        BandConst b;
+        b.c1 = (float)(2.0 * 3.5 * sqrt_threshold * u * 1.0001);
+        b.c2 = (float)(2.0 * 3.0 * u * u * 2.0 * 1.0001);
+        b.c0 = (float)((2.0 * (3.5 * sqrt_threshold * u * k + 3.0 * u * u * 2.0 * k * k + t * 0x1p-22) + 1e-5) * 1.0001);
+        return b;
+    }
+    __device__ __forceinline__ float band(float px, float py, float pz) const {
+        float m = fmaxf(fmaxf(fabsf(px), fabsf(py)), fabsf(pz));
+        return fmaf(m, fmaf(m, c2, c1), c0);
+    }
+};
+
 // One z layer of a lane's stencil: per dy row, where the lane's run sits in the tile and in the sorted arrays.
 struct LayerRuns {
     int first[kTileRows];   // tile index of the lane's first candidate of row r
