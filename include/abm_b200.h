@@ -208,17 +208,18 @@ int abm_deposit_morphogens(const double *locations, const double *amounts, int64
  * A cell travels between ranks as one byte record:
  *   [0,24) position  [24,32) radius  [32,56) motility force  [56,60) global id  [60,64) bond_len
  *   [64,64+4*row_stride) bond row (global ids).
- * abm_slab_pack writes, in cell order, the records of the owned cells with x < x_send_left (to the left
+ * abm_slab_pack writes (in no particular order) the records of the owned cells with x < x_send_left (to the left
  * neighbour) and with x >= x_send_right (to the right one); counts (2) int32 receives the two record counts
  * (records beyond a capacity are dropped: the caller compares and retries with larger buffers).
  * n_own_device (may be NULL): device int32 -- only the first *n_own_device of the n_own rows are owned cells, the
  * rest (last step's halo cells) are skipped; lets a caller enqueue the pack before the owned count of the
  * finishing step has reached the host.
- * abm_slab_merge partitions the n_own owned cells followed by the n_received records into
+ * abm_slab_merge partitions the n_own owned cells followed by the received records (two segments, e.g. the
+ * messages of the left and of the right neighbour; either may be empty) into
  * [cells owned after the exchange | halo cells] -- owned iff x in [x_lo,x_hi) (open towards a missing
  * neighbour) -- keeping input order inside each part, and writes them to the out_* arrays (capacity
- * n_own + n_received); n_owned_out (1) int32 receives the size of the first part.
- * workspace: abm_slab_workspace_bytes(n) with n = n_own resp. n_own + n_received.  No host synchronisation. */
+ * n_own + n_received + n_received_b); n_owned_out (1) int32 receives the size of the first part.
+ * workspace (merge only): abm_slab_workspace_bytes(n_own + n_received + n_received_b).  No host synchronisation. */
 size_t abm_slab_workspace_bytes(int64_t n);
 int abm_slab_pack(const double *locations, const double *radii, const double *motility_forces,
                   const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t n_own,
@@ -227,7 +228,8 @@ int abm_slab_pack(const double *locations, const double *radii, const double *mo
                   int32_t *counts, void *workspace, size_t workspace_bytes, void *stream);
 int abm_slab_merge(const double *locations, const double *radii, const double *motility_forces,
                    const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t n_own,
-                   const uint8_t *received, int64_t n_received, int64_t row_stride, double x_lo, double x_hi,
+                   const uint8_t *received, int64_t n_received, const uint8_t *received_b, int64_t n_received_b,
+                   int64_t row_stride, double x_lo, double x_hi,
                    int has_left, int has_right, double *out_locations, double *out_radii, double *out_motility,
                    int32_t *out_global_id, int32_t *out_bond_len, int32_t *out_bond_rows, int32_t *n_owned_out,
                    void *workspace, size_t workspace_bytes, void *stream);

@@ -45,7 +45,8 @@ SIGNATURES = {
     "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P]),
     "abm_slab_workspace_bytes": (SZ, [I64]),
     "abm_slab_pack": (I32, [P, P, P, P, P, P, I64, P, I64, F64, F64, I32, I32, P, I64, P, I64, P, P, SZ, P]),
-    "abm_slab_merge": (I32, [P, P, P, P, P, P, I64, P, I64, I64, F64, F64, I32, I32, P, P, P, P, P, P, P, P, SZ, P]),
+    "abm_slab_merge": (I32, [P, P, P, P, P, P, I64, P, I64, P, I64, I64, F64, F64, I32, I32, P, P, P, P, P, P, P, P, SZ,
+                             P]),
     "abm_deposit_morphogens": (I32, [P, P, I64, P, L3, F64, I64, I64, P]),
 }
 

@@ -18,25 +18,6 @@ __device__ __forceinline__ bool owns(double x, double x_lo, double x_hi, int has
     return (!has_left || x >= x_lo) && (!has_right || x < x_hi);
 }
 
-// flags[i] = 1 if owned cell i goes to the left (side 0) / right (side 1) neighbour
-// n_own_dev (may be nullptr): only the first *n_own_dev of the n rows are owned cells (the rest are last step's
-// halo cells, which are not sent) -- lets the caller enqueue the pack before it knows the owned count itself
-__global__ void __launch_bounds__(256) k_slab_flags(const double *__restrict__ loc, int n,
-                                                    const int *__restrict__ n_own_dev, double x_send_left,
-                                                    double x_send_right, int has_left, int has_right,
-                                                    int *__restrict__ flag_l, int *__restrict__ flag_r) {
-    int i = blockIdx.x * 256 + threadIdx.x;
-    if (i > n) return;
-    int l = 0, r = 0;
-    if (i < n && (!n_own_dev || i < *n_own_dev)) {
-        double x = loc[3 * (long long)i];
-        l = has_left && x < x_send_left;
-        r = has_right && x >= x_send_right;
-    }
-    flag_l[i] = l;   // element n stays 0 so that the scan leaves the total there
-    flag_r[i] = r;
-}
-
 __device__ __forceinline__ void write_record(unsigned char *rec, const CellArrays &a, int i, int stride) {
     double *d = reinterpret_cast<double *>(rec);
     d[0] = a.loc[3 * (long long)i + 0];
@@ -69,39 +50,69 @@ __device__ __forceinline__ void read_record(const unsigned char *rec, const Cell
     for (int k = 0; k < stride; ++k) row[k] = w[2 + k];
 }
 
-// pos_* hold the exclusive scans of the flags: a flagged cell writes its record at that position
-__global__ void __launch_bounds__(256) k_slab_pack(CellArrays a, int n, int stride, int rec_bytes,
-                                                   const int *__restrict__ pos_l, const int *__restrict__ pos_r,
-                                                   unsigned char *__restrict__ out_l, unsigned char *__restrict__ out_r,
-                                                   long long cap_l, long long cap_r) {
+// One pass: a cell to be sent claims its record slot from the message's counter (one atomic per warp and side).
+// The order of the records inside a message is therefore unspecified -- nothing downstream depends on the local
+// order of the cells (rows are kept by global id, force sums are integer sums).
+// n_own_dev (may be nullptr): only the first *n_own_dev of the n rows are owned cells (the rest are last step's
+// halo cells, which are not sent) -- lets the caller enqueue the pack before it knows the owned count itself.
+__global__ void __launch_bounds__(256) k_slab_pack(CellArrays a, int n, const int *__restrict__ n_own_dev, int stride,
+                                                   int rec_bytes, double x_send_left, double x_send_right,
+                                                   int has_left, int has_right, unsigned char *__restrict__ out_l,
+                                                   unsigned char *__restrict__ out_r, long long cap_l, long long cap_r,
+                                                   int *__restrict__ counts) {
     int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    if (pos_l[i + 1] != pos_l[i] && pos_l[i] < cap_l) write_record(out_l + (long long)pos_l[i] * rec_bytes, a, i, stride);
-    if (pos_r[i + 1] != pos_r[i] && pos_r[i] < cap_r) write_record(out_r + (long long)pos_r[i] * rec_bytes, a, i, stride);
+    bool l = false, r = false;
+    if (i < n && (!n_own_dev || i < *n_own_dev)) {
+        double x = a.loc[3 * (long long)i];
+        l = has_left && x < x_send_left;
+        r = has_right && x >= x_send_right;
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const bool f = side ? r : l;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (m == 0) continue;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&counts[side], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (f) {
+            long long pos = base + __popc(m & ((1u << lane) - 1));
+            if (pos < (side ? cap_r : cap_l)) write_record((side ? out_r : out_l) + pos * rec_bytes, a, i, stride);
+        }
+    }
 }
 
+// The received records come as two segments (from the left and from the right neighbour): record j of the
+// concatenation lives in segment a for j < k_a, else in segment b.
+struct Received {
+    const unsigned char *a, *b;
+    int k_a, k_b;
+    __device__ __forceinline__ const unsigned char *record(int j, int rec_bytes) const {
+        return j < k_a ? a + (long long)j * rec_bytes : b + (long long)(j - k_a) * rec_bytes;
+    }
+};
+
 // keep[i] for the n_own owned cells followed by the k received records: 1 = owned after the exchange
-__global__ void __launch_bounds__(256) k_slab_keep(const double *__restrict__ loc, int n_own,
-                                                   const unsigned char *__restrict__ recv, int k, int rec_bytes,
-                                                   double x_lo, double x_hi, int has_left, int has_right,
-                                                   int *__restrict__ keep) {
+__global__ void __launch_bounds__(256) k_slab_keep(const double *__restrict__ loc, int n_own, Received recv,
+                                                   int rec_bytes, double x_lo, double x_hi, int has_left,
+                                                   int has_right, int *__restrict__ keep) {
     int i = blockIdx.x * 256 + threadIdx.x;
-    int total = n_own + k;
+    int total = n_own + recv.k_a + recv.k_b;
     if (i > total) return;
     int f = 0;
     if (i < n_own) f = owns(loc[3 * (long long)i], x_lo, x_hi, has_left, has_right);
     else if (i < total)
-        f = owns(*reinterpret_cast<const double *>(recv + (long long)(i - n_own) * rec_bytes), x_lo, x_hi, has_left,
+        f = owns(*reinterpret_cast<const double *>(recv.record(i - n_own, rec_bytes)), x_lo, x_hi, has_left,
                  has_right);
     keep[i] = f;
 }
 
 // stable two-way partition: owned-next cells first (in input order), then everything else (halo cells)
-__global__ void __launch_bounds__(256) k_slab_merge(CellArrays in, int n_own, const unsigned char *__restrict__ recv,
-                                                    int k, int rec_bytes, int stride, const int *__restrict__ pos,
-                                                    CellArrays out) {
+__global__ void __launch_bounds__(256) k_slab_merge(CellArrays in, int n_own, Received recv, int rec_bytes,
+                                                    int stride, const int *__restrict__ pos, CellArrays out) {
     int i = blockIdx.x * 256 + threadIdx.x;
-    int total = n_own + k;
+    int total = n_own + recv.k_a + recv.k_b;
     if (i >= total) return;
     int n_keep = pos[total];
     bool kept = pos[i + 1] != pos[i];
@@ -115,12 +126,20 @@ __global__ void __launch_bounds__(256) k_slab_merge(CellArrays in, int n_own, co
         out.mot[3 * (long long)dst + 1] = in.mot[3 * (long long)i + 1];
         out.mot[3 * (long long)dst + 2] = in.mot[3 * (long long)i + 2];
         out.gid[dst] = in.gid[i];
-        out.bond_len[dst] = in.bond_len[i];
+        const int len = in.bond_len[i];
+        out.bond_len[dst] = len;
         const int *src = in.bond_rows + (long long)i * stride;
         int *row = out.bond_rows + (long long)dst * stride;
-        for (int c = 0; c < stride; ++c) row[c] = src[c];
+        // only the live part of the row travels (entries beyond bond_len are never read), 16 bytes at a time when
+        // the rows are aligned
+        if ((stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(in.bond_rows) | reinterpret_cast<uintptr_t>(out.bond_rows)) & 15) == 0) {
+            for (int c = 0; c < len; c += 4)
+                *reinterpret_cast<int4 *>(row + c) = *reinterpret_cast<const int4 *>(src + c);
+        } else {
+            for (int c = 0; c < len; ++c) row[c] = src[c];
+        }
     } else {
-        read_record(recv + (long long)(i - n_own) * rec_bytes, out, dst, stride);
+        read_record(recv.record(i - n_own, rec_bytes), out, dst, stride);
     }
 }
 
@@ -143,44 +162,38 @@ ABM_EXPORT int abm_slab_pack(const double *locations, const double *radii, const
                              int64_t capacity_right, int32_t *counts, void *workspace, size_t workspace_bytes,
                              void *stream) {
     ABM_REQUIRE(n_own >= 0 && n_own < 0x7fffffff && row_stride > 0, "bad sizes");
-    ABM_REQUIRE(counts && workspace && workspace_bytes >= abm_slab_workspace_bytes(n_own), "workspace too small");
+    ABM_REQUIRE(counts, "null counts");
+    (void)workspace;
+    (void)workspace_bytes;
     cudaStream_t st = as_stream(stream);
     int rc = check_cuda(cudaMemsetAsync(counts, 0, 8, st), "memset counts");
     if (rc || n_own == 0) return rc;
     ABM_REQUIRE(locations && radii && motility_forces && global_id && bond_len && bond_rows, "null pointer");
-    size_t half = scan_ws_ints(n_own + 1);
-    int *flag_l = (int *)workspace, *flag_r = flag_l + half;
-    int *sums_l = flag_l + ((size_t)(n_own + 1) + 63) / 64 * 64, *sums_r = flag_r + ((size_t)(n_own + 1) + 63) / 64 * 64;
-    k_slab_flags<<<ceil_div(n_own + 1, 256), 256, 0, st>>>(locations, (int)n_own, n_own_device, x_send_left,
-                                                           x_send_right, has_left, has_right, flag_l, flag_r);
-    ABM_CHECK_LAUNCH("k_slab_flags");
-    rc = exclusive_scan_inplace(flag_l, n_own + 1, sums_l, nullptr, nullptr, st);
-    if (rc) return rc;
-    rc = exclusive_scan_inplace(flag_r, n_own + 1, sums_r, nullptr, nullptr, st);
-    if (rc) return rc;
-    rc = check_cuda(cudaMemcpyAsync(counts, flag_l + n_own, 4, cudaMemcpyDeviceToDevice, st), "count left");
-    if (rc) return rc;
-    rc = check_cuda(cudaMemcpyAsync(counts + 1, flag_r + n_own, 4, cudaMemcpyDeviceToDevice, st), "count right");
-    if (rc) return rc;
+    ABM_REQUIRE((!has_left || records_left || capacity_left == 0) && (!has_right || records_right || capacity_right == 0),
+                "null record buffer");
     CellArrays a{const_cast<double *>(locations), const_cast<double *>(radii), const_cast<double *>(motility_forces),
                  const_cast<int *>(global_id), const_cast<int *>(bond_len), const_cast<int *>(bond_rows)};
     int rec_bytes = 64 + 4 * (int)row_stride;
-    k_slab_pack<<<ceil_div(n_own, 256), 256, 0, st>>>(a, (int)n_own, (int)row_stride, rec_bytes, flag_l, flag_r,
-                                                      records_left, records_right, (long long)capacity_left,
-                                                      (long long)capacity_right);
+    k_slab_pack<<<ceil_div(n_own, 256), 256, 0, st>>>(a, (int)n_own, n_own_device, (int)row_stride, rec_bytes,
+                                                      x_send_left, x_send_right, has_left, has_right, records_left,
+                                                      records_right, (long long)capacity_left,
+                                                      (long long)capacity_right, counts);
     ABM_CHECK_LAUNCH("k_slab_pack");
     return 0;
 }
 
 ABM_EXPORT int abm_slab_merge(const double *locations, const double *radii, const double *motility_forces,
                               const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows,
-                              int64_t n_own, const uint8_t *received, int64_t n_received, int64_t row_stride,
+                              int64_t n_own, const uint8_t *received, int64_t n_received, const uint8_t *received_b,
+                              int64_t n_received_b, int64_t row_stride,
                               double x_lo, double x_hi, int has_left, int has_right, double *out_locations,
                               double *out_radii, double *out_motility, int32_t *out_global_id, int32_t *out_bond_len,
                               int32_t *out_bond_rows, int32_t *n_owned_out, void *workspace, size_t workspace_bytes,
                               void *stream) {
-    int64_t total = n_own + n_received;
-    ABM_REQUIRE(n_own >= 0 && n_received >= 0 && total < 0x7fffffff && row_stride > 0, "bad sizes");
+    int64_t total = n_own + n_received + n_received_b;
+    ABM_REQUIRE(n_own >= 0 && n_received >= 0 && n_received_b >= 0 && total < 0x7fffffff && row_stride > 0, "bad sizes");
+    ABM_REQUIRE((received || n_received == 0) && (received_b || n_received_b == 0), "null record segment");
+    Received recv{received, received_b, (int)n_received, (int)n_received_b};
     ABM_REQUIRE(n_owned_out && workspace && workspace_bytes >= abm_slab_workspace_bytes(total), "workspace too small");
     cudaStream_t st = as_stream(stream);
     int rc = check_cuda(cudaMemsetAsync(n_owned_out, 0, 4, st), "memset n_owned_out");
@@ -191,8 +204,8 @@ ABM_EXPORT int abm_slab_merge(const double *locations, const double *radii, cons
     int *keep = (int *)workspace;
     int *sums = keep + ((size_t)(total + 1) + 63) / 64 * 64;
     int rec_bytes = 64 + 4 * (int)row_stride;
-    k_slab_keep<<<ceil_div(total + 1, 256), 256, 0, st>>>(locations, (int)n_own, received, (int)n_received, rec_bytes,
-                                                          x_lo, x_hi, has_left, has_right, keep);
+    k_slab_keep<<<ceil_div(total + 1, 256), 256, 0, st>>>(locations, (int)n_own, recv, rec_bytes, x_lo, x_hi, has_left,
+                                                          has_right, keep);
     ABM_CHECK_LAUNCH("k_slab_keep");
     rc = exclusive_scan_inplace(keep, total + 1, sums, nullptr, nullptr, st);
     if (rc) return rc;
@@ -201,8 +214,7 @@ ABM_EXPORT int abm_slab_merge(const double *locations, const double *radii, cons
     CellArrays in{const_cast<double *>(locations), const_cast<double *>(radii), const_cast<double *>(motility_forces),
                   const_cast<int *>(global_id), const_cast<int *>(bond_len), const_cast<int *>(bond_rows)};
     CellArrays out{out_locations, out_radii, out_motility, out_global_id, out_bond_len, out_bond_rows};
-    k_slab_merge<<<ceil_div(total, 256), 256, 0, st>>>(in, (int)n_own, received, (int)n_received, rec_bytes,
-                                                       (int)row_stride, keep, out);
+    k_slab_merge<<<ceil_div(total, 256), 256, 0, st>>>(in, (int)n_own, recv, rec_bytes, (int)row_stride, keep, out);
     ABM_CHECK_LAUNCH("k_slab_merge");
     return 0;
 }

@@ -352,6 +352,8 @@ class NativeSlabOps:
         self.send_fraction = send_fraction
         self.worst = torch.zeros(2, dtype=torch.int32, device=engine.device)   # largest counts seen (overflow check)
         self.ws = None
+        self._out = None
+        self._pin = None
 
     def _workspace(self, n):
         need = int(self.lib.abm_slab_workspace_bytes(int(n)))
@@ -384,7 +386,7 @@ class NativeSlabOps:
             geom.x_hi - geom.halo, int(geom.has_left), int(geom.has_right), out_l.data_ptr(), cap,
             out_r.data_ptr(), cap, counts.data_ptr(), ws.data_ptr(), ws.numel(), eng.stream),
             "abm_slab_pack")
-        eng.launches += 6
+        eng.launches += 1
         torch.maximum(self.worst, counts, out=self.worst)
         return out_l, out_r, counts
 
@@ -395,37 +397,57 @@ class NativeSlabOps:
             raise _lib.AbmError(f"cell message capacity too small: needed {worst} rows, have {self.send_cap} "
                                 "(NativeSlabOps(send_cap=...))")
 
+    def _out_buffers(self, total, stride):
+        """Two alternating sets of output arrays (the merge is out of place: one set holds the step's inputs)."""
+        f64, i32, dev = torch.float64, torch.int32, self.eng.device
+        if self._out is None or self._out["cap"] < total or self._out["stride"] != stride:
+            cap = int(1.15 * total) + 8192
+            self._out = dict(cap=cap, stride=stride, turn=0, sets=[
+                dict(loc=torch.empty((cap, 3), dtype=f64, device=dev), radii=torch.empty(cap, dtype=f64, device=dev),
+                     mot=torch.empty((cap, 3), dtype=f64, device=dev), gid=torch.empty(cap, dtype=i32, device=dev),
+                     blen=torch.empty(cap, dtype=i32, device=dev),
+                     rows=torch.empty((cap, stride), dtype=i32, device=dev),
+                     n_owned=torch.empty(1, dtype=i32, device=dev)) for _ in range(2)])
+        self._out["turn"] ^= 1
+        return self._out["sets"][self._out["turn"]]
+
     def merge(self, state, geom, from_l, from_r, counts_in=None):
         from .slab import LocalProblem
-        eng, dev = self.eng, self.eng.device
-        n, stride, rec = state.n, state.stride, state.record_bytes()
-        if counts_in is not None:                 # the one host synchronisation of the exchange
-            n_l, n_r = (min(int(v), self.send_cap) for v in counts_in.tolist())
-            from_l = from_l[:n_l] if from_l is not None else None
-            from_r = from_r[:n_r] if from_r is not None else None
-        parts = [m for m in (from_l, from_r) if m is not None and m.shape[0]]
-        if len(parts) == 2:
-            recv = torch.cat(parts, dim=0)
-        elif parts:
-            recv = parts[0].contiguous()
+        eng = self.eng
+        stride = state.stride
+        if counts_in is not None:                 # the one host synchronisation of the exchange: the received counts
+            pend = state.pending()                # and (if still pending) last step's owned count in one round trip
+            if self._pin is None:
+                self._pin = torch.empty(3, dtype=torch.int32).pin_memory()
+            self._pin[0:2].copy_(counts_in, non_blocking=True)
+            if pend is not None:
+                self._pin[2:3].copy_(pend[2], non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            n_l, n_r, n_prev = (int(v) for v in self._pin.tolist())
+            n_l, n_r = min(n_l, self.send_cap), min(n_r, self.send_cap)
+            if pend is not None:
+                state._pending[1]._n_own = n_prev
         else:
-            recv = torch.empty((0, rec), dtype=torch.uint8, device=dev)
-        k = int(recv.shape[0])
-        total = n + k
+            n_l = int(from_l.shape[0]) if from_l is not None else 0
+            n_r = int(from_r.shape[0]) if from_r is not None else 0
+        n = state.n
+        if n_l and not from_l.is_contiguous():
+            from_l = from_l.contiguous()
+        if n_r and not from_r.is_contiguous():
+            from_r = from_r.contiguous()
+        total = n + n_l + n_r
         ws = self._workspace(total)
-        f64, i32 = torch.float64, torch.int32
-        loc = torch.empty((total, 3), dtype=f64, device=dev)
-        radii = torch.empty(total, dtype=f64, device=dev)
-        mot = torch.empty((total, 3), dtype=f64, device=dev)
-        gid = torch.empty(total, dtype=i32, device=dev)
-        blen = torch.empty(total, dtype=i32, device=dev)
-        rows = torch.empty((total, stride), dtype=i32, device=dev)
-        n_owned = torch.empty(1, dtype=i32, device=dev)
+        o = self._out_buffers(total, stride)
+        # the inputs must not live in the set that is written now (they do after a reallocation only)
+        assert state.loc.data_ptr() != o["loc"].data_ptr()
         _lib.check(self.lib.abm_slab_merge(
             state.loc.data_ptr(), state.radii.data_ptr(), state.mot.data_ptr(), state.gid.data_ptr(),
-            state.bond_len.data_ptr(), state.bond_gid.data_ptr(), n, recv.data_ptr(), k, stride, geom.x_lo, geom.x_hi,
-            int(geom.has_left), int(geom.has_right), loc.data_ptr(), radii.data_ptr(), mot.data_ptr(),
-            gid.data_ptr(), blen.data_ptr(), rows.data_ptr(), n_owned.data_ptr(), ws.data_ptr(), ws.numel(),
-            eng.stream), "abm_slab_merge")
+            state.bond_len.data_ptr(), state.bond_gid.data_ptr(), n,
+            from_l.data_ptr() if n_l else 0, n_l, from_r.data_ptr() if n_r else 0, n_r, stride, geom.x_lo, geom.x_hi,
+            int(geom.has_left), int(geom.has_right), o["loc"].data_ptr(), o["radii"].data_ptr(), o["mot"].data_ptr(),
+            o["gid"].data_ptr(), o["blen"].data_ptr(), o["rows"].data_ptr(), o["n_owned"].data_ptr(), ws.data_ptr(),
+            ws.numel(), eng.stream), "abm_slab_merge")
         eng.launches += 4
-        return LocalProblem(n_owned, loc, radii, mot, gid, blen, rows)      # owned count read when first needed
+        # owned count read when first needed
+        return LocalProblem(o["n_owned"], o["loc"][:total], o["radii"][:total], o["mot"][:total], o["gid"][:total],
+                            o["blen"][:total], o["rows"][:total])

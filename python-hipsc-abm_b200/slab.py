@@ -196,6 +196,7 @@ class DistFabric:
         self.dist, self.rank, self.world, self.device = dist, rank, world, device
         self.bytes_sent = 0
         self.exchanges = 0
+        self._recv = {}
 
     def _post(self, ops):
         for w in self.dist.batch_isend_irecv(ops) if ops else []:
@@ -210,9 +211,13 @@ class DistFabric:
         has_l, has_r = left >= 0, right < self.world
         if counts is not None:
             cap = int(fixed_rows)
-            from_left = torch.empty((cap if has_l else 0, width), dtype=dtype, device=dev)
-            from_right = torch.empty((cap if has_r else 0, width), dtype=dtype, device=dev)
-            counts_in = torch.zeros(2, dtype=counts.dtype, device=dev)
+            key = (cap, width, dtype)
+            if self._recv.get("key") != key:      # receive buffers are reused: the consumer (merge) is stream-ordered
+                self._recv = dict(key=key,        # before the next exchange
+                                  left=torch.empty((cap if has_l else 0, width), dtype=dtype, device=dev),
+                                  right=torch.empty((cap if has_r else 0, width), dtype=dtype, device=dev),
+                                  counts=torch.zeros(2, dtype=counts.dtype, device=dev))
+            from_left, from_right, counts_in = self._recv["left"], self._recv["right"], self._recv["counts"]
             ops = []
             if has_l:
                 ops += [dist.P2POp(dist.isend, to_left, left), dist.P2POp(dist.irecv, from_left, left),
