@@ -168,10 +168,10 @@ def cpu_sample_workload(name):
     return make_workload(name, seed=0, n_override=min(WORKLOADS[name]["n"], cap))
 
 
-def run_cpu(name, steps, warmup):
+def run_cpu(name, steps, warmup, threads=None):
     from oracle import oracle as orc
     wl = cpu_sample_workload(name)
-    threads = orc.max_threads()
+    threads = threads or orc.max_threads()
     step = oracle_step_fn(wl, threads)
     for _ in range(warmup):
         step()
@@ -315,16 +315,48 @@ def run_b200(args, rank, world, local_rank):
     eng.loc.copy_(loc_save)
     kbytes = substep_kernel_bytes(n, b10, ej)
     achieved = kbytes / (cold_us * 1e-6) / 1e9
-    traffic = None
+    traffic = l2_hit = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.workload, {}).get("k_jkr_substep")
-    roofline = {"bound": "hbm", "kernel": "k_jkr_substep", "achieved": round(achieved, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
-                "bytes_per_launch": kbytes, "launch_us_cold_l2": round(cold_us, 2),
+        prof = json.load(open(tpath))
+        traffic = prof.get(args.workload, {}).get("k_jkr_substep")
+        l2_hit = prof.get("l2_hit_pct", {}).get(args.workload, {}).get("k_jkr_substep")
+    nominal = 8000.0                                                     # B200 HBM3e nominal, SURVEY 8(d)
+    roofline = {"bound": "hbm", "kernel": "k_jkr_substep<uniform radius>", "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "peak_source": peak_src, "frac_of_nominal_8000": round(achieved / nominal, 4),
+                "l2_hit_pct_ncu": l2_hit, "bytes_per_launch": kbytes, "launch_us_cold_l2": round(cold_us, 2),
                 "launch_us_warm_l2": round(hot_us, 2), "launches_per_step": sm,
                 "step_algorithmic_bytes": bytes_step,
-                "step_frac": round(bytes_step / (total_s / args.steps) / 1e9 / peak, 4)}
+                "step_frac": round(bytes_step / (total_s / args.steps) / 1e9 / peak, 4),
+                "step_frac_of_nominal_8000": round(bytes_step / (total_s / args.steps) / 1e9 / nominal, 4)}
+
+    # ---- per-stage device times of one eager step (events around each stage, same stream, warm L2) -------------------
+    def timed_stage(fn, reps=5):
+        out = []
+        for _ in range(reps):
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            z.record()
+            torch.cuda.synchronize(dev)
+            out.append(a.elapsed_time(z) * 1e3)
+        return round(float(np.median(out)), 1)
+
+    eng.use_current_stream()
+    loc_keep = eng.loc.clone()
+    stage_bonds = pipe.current_bonds()
+
+    def stage_mechanics():
+        eng.enqueue_mechanics(stage_bonds, cfg.contact_radius, pipe.dts, cfg.bond_stride, zero_flag=False)
+    stages = {"search_r15_with_sort_us": timed_stage(lambda: pipe._search(None)),
+              "mechanics_11_substeps_us": timed_stage(stage_mechanics)}
+    eng.loc.copy_(loc_keep)
+    if wl["grid"]:
+        field_keep = pipe.field.clone()
+        stages["morphogen_deposit_diffuse_sample_us"] = timed_stage(lambda: pipe._morphogen(None))
+        pipe.field.copy_(field_keep)
+    stages["note"] = "each stage alone on one stream (eager launches); the graph replay overlaps search + morphogen with the mechanics"
 
     # ---- e2e: the reference-facing API with host numpy arrays ----------------------------------------------------------
     e2e = None
@@ -384,8 +416,10 @@ def run_b200(args, rank, world, local_rank):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, spp, threads, sample = run_cpu(args.workload, 2, 1)
+        v1, spp1, _, _ = run_cpu(args.workload, 1, 1, threads=1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-               "s_per_step": spp}
+               "s_per_step": spp, "single_thread": {"value": v1, "s_per_step": spp1, "cores": 1,
+                                                     "sample": "same sample, 1 step after 1 warm-up"}}
 
     if dist is not None:
         dist.barrier()
@@ -404,7 +438,8 @@ def run_b200(args, rank, world, local_rank):
                    wl["grid"] else "after the mechanics, same stream",
                    "timing": "CUDA events per step around a CUDA-graph replay, summed; max over ranks",
                    "parallelism": "single GPU" if world == 1 else f"{world} independent colonies (replicas)"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
+        "cpu_baseline": cpu,
     }
 
 
@@ -439,7 +474,9 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     if wl["grid"]:
         gx = int(np.ceil(gsize[0] / spec["h"])) + 1
         field = slab.FieldSlab(geom, (gx, wl["grid"][1]), spec["h"], spec["sd"] + 1, dev)
-    fabric = slab.DistFabric(rank, world, dev)
+    # the field rows travel on their own communicator: they are exchanged on the second stream and must not queue in
+    # front of the next step's cell exchange
+    fabric = slab.DistFabric(rank, world, dev, rows_group=dist.new_group(list(range(world))) if first else None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     ops = NativeSlabOps(pipe.eng, send_cap=int(0.05 * n) + 4096)      # the same on every rank (2x the halo cells)
@@ -465,10 +502,12 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     launches0, bytes0, ex0 = pipe.eng.launches, fabric.bytes_sent, fabric.exchanges
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in evs:
+    for k, (a, b) in enumerate(evs):
         flush.zero_()
         a.record()
         step()
+        if k == len(evs) - 1:
+            pipe.join_side()              # the last step's second-stream work belongs to the timed region
         b.record()
     barrier()
     clocks = sampler.stop()

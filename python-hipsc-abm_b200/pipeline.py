@@ -196,11 +196,16 @@ class SlabPipeline:
     the rank's owned + halo cells, binned over the slab's own box.  Use with slab.slab_step / loopback_step:
     `compute` is the mechanics callback, and the object itself is the `field_ops` for the morphogen slab."""
 
-    def __init__(self, geom, cfg: StepConfig, device, max_radius=5.0, uniform_radius=0.0, side_stream=True):
+    def __init__(self, geom, cfg: StepConfig, device, max_radius=5.0, uniform_radius=0.0, side_stream=True,
+                 trailing=True):
         """uniform_radius: the common radius if ALL cells of the colony have the same one (selects the kernel
-        variant with the contact constants folded in), else 0.  side_stream: run the morphogen stage of a
-        morphogen_first step on a second stream (off for several slabs emulated on one GPU, whose loopback
-        exchange does not synchronise streams)."""
+        variant with the contact constants folded in), else 0.  side_stream: run the neighbour search and the
+        morphogen stage of a morphogen_first step on a second stream (off for several slabs emulated on one GPU,
+        whose loopback exchange does not synchronise streams).  trailing: the second stream starts its work of a
+        step when that step's mechanics have finished, so that it fills the next step's exchange window (pack,
+        transfer, host round trip, merge -- when the main stream has little to run) instead of competing with the
+        mechanics for the SMs; results of a step (sampled, neighbor_graph, the field) are complete after
+        join_side()."""
         self.geom, self.cfg = geom, cfg
         self.eng = ColonyEngine(geom.size, device)
         self.eng.set_bin_lattice(*geom.local_box())
@@ -212,7 +217,11 @@ class SlabPipeline:
         self.neighbor_graph = None
         self._sampled_all = self._sampled_local = None
         self._side = torch.cuda.Stream(device=device) if side_stream else None
+        self.trailing = bool(trailing)
         self._snap = None
+        self._snaps = [None, None]          # two position snapshots: the second stream may still read the older one
+        self._side_done = [None, None]      # event after the second stream's work of the step that used snapshot k
+        self._turn = 0
         self._amounts = None
         self._defer_search = False
 
@@ -221,7 +230,13 @@ class SlabPipeline:
         """Concentrations sampled by the OWNED cells in the last step (reads the owned count if still pending)."""
         if self._sampled_all is None:
             return None
+        self.join_side()
         return self._sampled_all[:self._sampled_local.n_own]
+
+    def join_side(self):
+        """Make the current stream wait for everything enqueued on the second stream."""
+        if self._side is not None:
+            torch.cuda.current_stream(self.eng.device).wait_stream(self._side)
 
     def compute(self, local):
         """Mechanics of one step on the rank's owned + halo cells (slab.LocalProblem): positions are advanced
@@ -268,6 +283,7 @@ class SlabPipeline:
     def check(self):
         """Host sync: raise if a fixed-capacity buffer overflowed in any step since the last check."""
         eng = self.eng
+        self.join_side()
         if self._nbr is not None:
             used = eng.read_i32(self._nbr["worst"])
             if used > self._nbr["cols"].numel():
@@ -278,24 +294,46 @@ class SlabPipeline:
                 raise _lib.AbmError(f"bond rows too narrow: needed {worst}, have {eng._bond_bufs['stride']}")
 
     # ---- field_ops protocol of slab.rank_step ---------------------------------------------------------------------
+    def step_begin(self):
+        """Called at the start of a step (rank_step): the buffers this step overwrites (merge outputs, snapshot)
+        were last read by the second stream's work of two steps ago -- long finished, but make it formal."""
+        ev = self._side_done[self._turn ^ 1]
+        if ev is not None:
+            torch.cuda.current_stream(self.eng.device).wait_event(ev)
+
     def begin_side(self, local):
         """morphogen_first: snapshot the positions (the mechanics will move them) and fork the second stream."""
         eng = self.eng
         n = int(local.loc.shape[0])
-        if self._snap is None or self._snap.shape[0] < n:
-            self._snap = torch.empty((int(1.1 * n) + 1024, 3), dtype=torch.float64, device=eng.device)
+        main = torch.cuda.current_stream(eng.device)
+        self._turn ^= 1
+        if self._side_done[self._turn] is not None:          # the second stream's work of two steps ago: it read this
+            main.wait_event(self._side_done[self._turn])      # snapshot and that step's cell arrays (long finished)
+        if self._snaps[self._turn] is None or self._snaps[self._turn].shape[0] < n:
+            self._snaps[self._turn] = torch.empty((int(1.1 * n) + 1024, 3), dtype=torch.float64, device=eng.device)
+        self._snap = self._snaps[self._turn]
         self._snap[:n].copy_(local.loc)
         self._snap_n = n
         self._defer_search = self._side is not None          # the search moves to the second stream as well
         if self._side is None:
             return None
-        self._side.wait_stream(torch.cuda.current_stream(eng.device))
+        if not self.trailing:
+            self._side.wait_stream(main)
         return self._side
+
+    def after_compute(self):
+        """Called when the step's mechanics have been enqueued on the main stream (rank_step)."""
+        if self._side is not None and self.trailing:
+            self._side.wait_stream(torch.cuda.current_stream(self.eng.device))
 
     def end_side(self):
         self._snap_n = None
         if self._side is not None:
-            torch.cuda.current_stream(self.eng.device).wait_stream(self._side)
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            self._side_done[self._turn] = ev
+            if not self.trailing:
+                torch.cuda.current_stream(self.eng.device).wait_stream(self._side)
         self.eng.use_current_stream()
 
     def _positions(self, local):

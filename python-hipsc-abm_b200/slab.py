@@ -191,9 +191,12 @@ class DistFabric:
     """Neighbour exchange over torch.distributed (NCCL on GPUs, gloo on CPU): the row counts first, then one
     packed message per neighbour and direction, all transfers of a phase posted together."""
 
-    def __init__(self, rank, world, device):
+    def __init__(self, rank, world, device, rows_group=None):
+        """rows_group: optional second process group (its own communicator and stream) for the fixed-size field
+        row exchange, so that it never queues in front of -- or behind -- the cell exchange of the main stream."""
         import torch.distributed as dist
         self.dist, self.rank, self.world, self.device = dist, rank, world, device
+        self.rows_group = rows_group
         self.bytes_sent = 0
         self.exchanges = 0
         self._recv = {}
@@ -201,6 +204,11 @@ class DistFabric:
     def _post(self, ops):
         for w in self.dist.batch_isend_irecv(ops) if ops else []:
             w.wait()
+
+    def _p2p(self, fn, tensor, peer, group=None):
+        if group is None:
+            return self.dist.P2POp(fn, tensor, peer)
+        return self.dist.P2POp(fn, tensor, peer, group=group)
 
     def exchange(self, to_left, to_right, width, dtype=torch.float64, fixed_rows=None, counts=None):
         """Send `to_left` / `to_right` (2-D, `width` columns) to the x-neighbours, return what they sent.
@@ -245,15 +253,16 @@ class DistFabric:
             n_l, n_r = (fixed_rows if has_l else 0), (fixed_rows if has_r else 0)
         from_left = torch.empty((n_l, width), dtype=dtype, device=dev)
         from_right = torch.empty((n_r, width), dtype=dtype, device=dev)
+        grp = self.rows_group if fixed_rows is not None else None
         ops = []
         if has_l and to_left.shape[0]:
-            ops.append(dist.P2POp(dist.isend, to_left, left))
+            ops.append(self._p2p(dist.isend, to_left, left, grp))
         if has_l and n_l:
-            ops.append(dist.P2POp(dist.irecv, from_left, left))
+            ops.append(self._p2p(dist.irecv, from_left, left, grp))
         if has_r and to_right.shape[0]:
-            ops.append(dist.P2POp(dist.isend, to_right, right))
+            ops.append(self._p2p(dist.isend, to_right, right, grp))
         if has_r and n_r:
-            ops.append(dist.P2POp(dist.irecv, from_right, right))
+            ops.append(self._p2p(dist.irecv, from_right, right, grp))
         self._post(ops)
         self.bytes_sent += sum(t.numel() * t.element_size() for t, ok in ((to_left, has_l), (to_right, has_r)) if ok)
         self.exchanges += 1
@@ -400,6 +409,8 @@ def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProb
     independent of the mechanics: field_ops.begin_side(local) may return a second stream on which the stage
     (including its row exchange) runs beside them, field_ops.end_side() joins it."""
     ops = ops or TorchSlabOps()
+    if hasattr(field_ops, "step_begin"):
+        field_ops.step_begin()
     out = ops.outgoing(state, geom)
     if len(out) == 3:                                         # full-capacity buffers + device counts, no handshake
         reply = yield Exchange("cells", out[0], out[1], state.record_bytes(), torch.uint8,
@@ -414,13 +425,15 @@ def rank_step(state: SlabState, geom: SlabGeometry, compute: Callable[[LocalProb
         side = begin(local) if begin else None                # snapshot of the positions, fork point
         if side is not None:
             blen, bgid = compute(local)                       # the mechanics are enqueued first: the GPU starts on
+            if hasattr(field_ops, "after_compute"):
+                field_ops.after_compute()
         with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):   # them while the host
-            if side is not None and hasattr(field_ops, "search"):                            # feeds the second
-                field_ops.search(local)                       # stream: the neighbour search (same snapshot), then
-            field_ops.deposit(local, field)                   # the morphogen stage.  owned + halo cells deposit
+            field_ops.deposit(local, field)                   # feeds the second stream.  owned + halo cells deposit
             to_l, to_r = field.messages()
             from_l, from_r = yield Exchange("rows", to_l, to_r, field.gy, torch.float64, fixed_rows=field.halo_rows)
-            field.absorb(from_l, from_r)
+            if side is not None and hasattr(field_ops, "search"):
+                field_ops.search(local)                       # the neighbour search (same snapshot) while the rows
+            field.absorb(from_l, from_r)                      # travel
             field_ops.diffuse(field)
             field_ops.sample(local, field)
         if side is None:

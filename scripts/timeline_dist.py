@@ -16,13 +16,13 @@ cfg = StepConfig(grid=wl["grid"], spat_res=spec["h"], diffuse_dt=spec["diffuse_d
 gsize = wl["size"].copy(); gsize[0] *= world
 halo = slab.required_halo(11, 10.3100107, slack=4.0) + spec["h"]
 geom = slab.SlabGeometry.uniform(gsize, world, rank, halo)
-pipe = SlabPipeline(geom, cfg, dev, uniform_radius=5.0)
+pipe = SlabPipeline(geom, cfg, dev, uniform_radius=5.0, trailing=os.environ.get("TRAILING", "1") == "1")
 loc = wl["loc"].copy(); loc[:, 0] += geom.x_lo
 t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 state = slab.SlabState(t(loc), t(wl["radii"]), t(wl["mot"]), t(np.arange(n) + rank * n), 16)
 gx = int(np.ceil(gsize[0] / spec["h"])) + 1
 field = slab.FieldSlab(geom, (gx, wl["grid"][1]), spec["h"], spec["sd"] + 1, dev)
-fabric = slab.DistFabric(rank, world, dev); ops = NativeSlabOps(pipe.eng, send_cap=int(0.05 * n) + 4096)
+fabric = slab.DistFabric(rank, world, dev, rows_group=dist.new_group(list(range(world)))); ops = NativeSlabOps(pipe.eng, send_cap=int(0.05 * n) + 4096)
 main = torch.cuda.Stream(device=dev, priority=-1); torch.cuda.set_stream(main)
 marks = []
 def mark(name):
