@@ -479,7 +479,8 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     fabric = slab.DistFabric(rank, world, dev, rows_group=dist.new_group(list(range(world))) if first else None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    ops = NativeSlabOps(pipe.eng, send_cap=int(0.05 * n) + 4096)      # the same on every rank (2x the halo cells)
+    # message capacity, the same on every rank: 1.6x the cells expected within `halo` of an interface
+    ops = NativeSlabOps(pipe.eng, send_cap=int(1.6 * n * halo / side) + 4096)
 
     # the step's main stream outranks the second stream (search + morphogen stage), whose kernels then fill what the
     # mechanics leave idle instead of competing with them
