@@ -112,3 +112,118 @@ def test_diffusion_small_and_ragged_grids(shape, steps):
     for tma in ([False, True] if shape[1] % 2 == 0 else [False]):
         out = eng.diffuse(torch.from_numpy(field.copy()).cuda(), steps, dt, dt * 0.4, D, h * h, 2.0, 0.1, use_tma=tma)
         assert np.array_equal(out.cpu().numpy(), ref), f"tma={tma}"
+
+
+# ---- second-session kernels: warp tile, slot-order hand-over, multiply-high decode, slab plumbing ------------------
+def test_candidate_runs_longer_than_the_warp_tile():
+    # a dense strip: the stencil runs of a warp hold more than the 64 candidates the shared-memory tile takes, so
+    # those cells go through the slow path (exact walk from global memory).  The strip is crowded (cells overlap
+    # by several um), which makes the explicit integration amplify last-bit differences: pair sets must be
+    # identical, positions are compared after one step at 1e-9
+    rng = np.random.default_rng(3)
+    n = 700
+    size = [500.0, 200.0, 0.0]
+    loc = np.stack([rng.uniform(100.0, 400.0, n), rng.uniform(100.0, 112.0, n), np.zeros(n)], axis=1)
+    mot = rng.normal(0, 2e-9, (n, 3)) * [1, 1, 0]
+    sim = Cells(loc, 5.0, size)
+    ref = orc.OracleSim(loc, 5.0, size)
+    sim.motility_forces[:] = mot
+    ref.motility_forces[:] = mot
+    sim.get_neighbors("neighbor_graph", 15)
+    ref.get_neighbors("neighbor_graph", 15)
+    assert np.array_equal(sim.neighbor_graph.edge_array(), orc.canonical_edges(ref.neighbor_graph.edge_array()))
+    assert max(sim.neighbor_graph.num_neighbors(i) for i in range(n)) > 64
+    sim.apply_forces()
+    ref.apply_forces()
+    assert np.array_equal(sim.jkr_graph.edge_array(), ref.jkr_graph.edge_array())
+    assert np.abs(sim.locations - ref.locations).max() <= 1e-9 * np.abs(ref.locations).max()
+
+
+def test_sparse_colony_on_a_huge_lattice():
+    # 60000 um box: 5822^2 bins at the mechanics edge, bin ids beyond what the multiply-high decode covers
+    # (falls back to the division), almost all bins empty, warps straddling many bin rows
+    rng = np.random.default_rng(4)
+    n = 600
+    centres = rng.uniform(1000.0, 59000.0, (30, 2))
+    loc = np.zeros((n, 3))
+    loc[:, :2] = centres[rng.integers(0, 30, n)] + rng.normal(0, 14.0, (n, 2))
+    mot = rng.normal(0, 2e-9, (n, 3)) * [1, 1, 0]
+    same_as_oracle(loc, 5.0, [60000.0, 60000.0, 0.0], mot, steps=2)
+
+
+def test_mixed_radii_3d_in_fused_loop():
+    rng = np.random.default_rng(5)
+    n = 5000
+    size = np.array([170.0, 170.0, 170.0])
+    loc = rng.random((n, 3)) * size
+    radii = rng.uniform(5 / 2 ** 0.5, 5.0, n)
+    mot = rng.normal(0, 2e-9, (n, 3))
+    same_as_oracle(loc, radii, size, mot, steps=2)
+
+
+def test_mechanics_loop_equals_substep_by_substep():
+    # abm_mechanics_loop (cells handed from substep to sort in slot order, histogram sums accumulated by the kernel,
+    # loose binning, locations written once) must give the bits of the plain sequence: fresh sort from
+    # `locations` + one abm_jkr_substep, 11 times
+    from hipsc_abm_b200 import _lib
+    from hipsc_abm_b200.engine import GraphTensors
+    rng = np.random.default_rng(6)
+    for dim, n, size in ((2, 6000, [700.0, 700.0, 0.0]), (3, 6000, [180.0, 180.0, 180.0])):
+        size = np.array(size)
+        loc = rng.random((n, 3)) * size
+        mot = rng.normal(0, 2e-9, (n, 3)) * ([1, 1, 0] if dim == 2 else [1, 1, 1])
+        radii = np.full(n, 5.0)
+        dts = [180.0] * 10 + [0.0]
+        stride = 32
+        a = ColonyEngine(size)
+        a.upload(loc, radii, mot)
+        bonds_a, _ = a.mechanics(None, 10.0, dts, stride)
+
+        b = ColonyEngine(size)
+        b.upload(loc, radii, mot)
+        reach = b.jkr_reach(10.0)
+        rows = [torch.zeros((n, stride), dtype=torch.int32, device="cuda") for _ in range(2)]
+        lens = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(2)]
+        worst = torch.zeros(1, dtype=torch.int32, device="cuda")
+        old = None
+        for k, dt in enumerate(dts):
+            srt = b.sort(reach)
+            _lib.check(b.lib.abm_jkr_substep(
+                srt.bin_start.data_ptr(), srt.sorted_id.data_ptr(), srt.sorted_pos.data_ptr(),
+                srt.sorted_bin.data_ptr(), n, _lib.i3(srt.dims), 10.0, reach, 0, stride if old is not None else 0,
+                old[0].data_ptr() if old is not None else 0, old[1].data_ptr() if old is not None else 0,
+                lens[k & 1].data_ptr(), rows[k & 1].data_ptr(), stride, worst.data_ptr(), int(k == len(dts) - 1),
+                b.mot.data_ptr(), b.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0, _lib.d3(size), dt, 0,
+                b.uniform_radius, None, None, 0, 0, b.stream), "abm_jkr_substep")
+            old = (lens[k & 1], rows[k & 1])
+        assert int(worst.item()) <= stride
+        assert torch.equal(a.loc, b.loc), f"{dim}-D positions differ"
+        assert torch.equal(bonds_a.row_len[:n], old[0])
+        m = torch.arange(stride, device="cuda")[None, :] < old[0][:, None]
+        assert torch.equal(bonds_a.cols[:n][m], old[1][m])
+
+
+def test_slab_message_overflow_is_reported():
+    from hipsc_abm_b200 import _lib, slab
+    from hipsc_abm_b200.pipeline import NativeSlabOps
+    rng = np.random.default_rng(7)
+    n = 4000
+    size = np.array([800.0, 200.0, 0.0])
+    loc = rng.random((n, 3)) * size
+    dev = torch.device("cuda")
+    geom = slab.SlabGeometry.uniform(size, 2, 0, 150.0)
+    own = loc[:, 0] < geom.x_hi
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    state = slab.SlabState(t(loc[own]), t(np.full(own.sum(), 5.0)), t(np.zeros((own.sum(), 3))),
+                           t(np.arange(n)[own]), 16)
+    eng = ColonyEngine(size, dev)
+    ops = NativeSlabOps(eng, send_cap=8)                       # far fewer rows than cells near the interface
+    out_l, out_r, counts = ops.outgoing(state, geom)
+    assert int(counts[1].item()) == int((loc[own, 0] >= geom.x_hi - geom.halo).sum()) > 8
+    with pytest.raises(_lib.AbmError, match="capacity too small"):
+        ops.check()
+    ok = NativeSlabOps(eng, send_cap=4096)
+    out_l, out_r, counts = ok.outgoing(state, geom)
+    ok.check()
+    sent = slab.unpack(out_r[:int(counts[1].item())], 16)["gid"].cpu().numpy()
+    assert np.array_equal(np.sort(sent), np.arange(n)[own][loc[own, 0] >= geom.x_hi - geom.halo])

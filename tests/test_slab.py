@@ -228,3 +228,54 @@ def test_field_slabs_reproduce_single_domain(first):
     # (cells that migrated this step are sampled by their previous owner, so match through positions instead)
     assert all(o.sampled is not None and len(o.sampled) > 0 for o in ops)
     assert abs(sum(o.sampled.sum() for o in ops) - ref_sampled.sum()) <= 1e-9
+
+
+class PaddedOps(slab.TorchSlabOps):
+    """The protocol of pipeline.NativeSlabOps on the CPU: full-capacity messages with their valid row counts in a
+    tensor (no size handshake), the owned count of a merged step left in a tensor until somebody asks for it, and
+    the next pack fed from the not yet sliced local arrays."""
+    send_cap = 400
+
+    def outgoing(self, state, geom):
+        pend = state.pending()
+        if pend is not None:                                   # owned count still "on the device"
+            full, rows, n_own = pend
+            view = slab.SlabState.__new__(slab.SlabState)
+            view._pending, view._d = None, {f: full[f][:int(n_own.item())] for f in slab.FIELDS}
+            msgs = super().outgoing(view, geom)
+        else:
+            msgs = super().outgoing(state, geom)
+        rec = state.record_bytes()
+        out, counts = [], torch.zeros(2, dtype=torch.int32)
+        for k, m in enumerate(msgs):
+            buf = torch.full((self.send_cap, rec), 255, dtype=torch.uint8)     # garbage beyond the count
+            if m is not None:
+                assert m.shape[0] <= self.send_cap
+                buf[:m.shape[0]] = m
+                counts[k] = m.shape[0]
+            out.append(buf)
+        return out[0], out[1], counts
+
+    def merge(self, state, geom, from_l, from_r, counts_in=None):
+        n_l, n_r = (int(v) for v in counts_in.tolist())
+        local = super().merge(state, geom, from_l[:n_l] if from_l is not None else None,
+                              from_r[:n_r] if from_r is not None else None)
+        return slab.LocalProblem(torch.tensor([local.n_own]), local.loc, local.radii, local.mot, local.gid,
+                                 local.bond_len, local.bond_gid)
+
+
+def test_fixed_capacity_messages_and_deferred_owned_count():
+    world, steps = 3, 3
+    loc, radii, mot = make_cells()
+    halo = slab.required_halo(11, 10.3100107, slack=5.0)
+    ref_loc, ref_edges = single_domain(loc, radii, mot, steps)
+    geoms, states = split(loc, radii, mot, world, halo)
+    ops = [PaddedOps() for _ in geoms]
+    for _ in range(steps):
+        slab.loopback_step(states, geoms, oracle_compute, ops=ops)
+        assert all(s.pending() is not None for s in states)        # nothing forced the owned count yet
+    gid, got_loc, got_edges = collect(states)                      # reading the state settles it
+    assert all(s.pending() is None for s in states)
+    assert np.array_equal(gid, np.arange(len(loc)))
+    assert np.array_equal(got_edges, ref_edges)
+    assert np.abs(got_loc - ref_loc).max() <= 1e-9
