@@ -13,7 +13,8 @@ S_d diffusion substeps + sample.  Prints ONE JSON line (rank 0).
 
   value     whole-job throughput with everything resident in HBM (CUDA-graph replay, device-timed)
   e2e       same metric through the reference-facing Python API with HOST numpy arrays (H2D/D2H inside)
-  roofline  dominant kernel (k_jkr_substep): compulsory bytes per launch / event-timed launch duration
+  roofline  dominant kernel (k_jkr_substep): SURVEY 8(d) algorithmic bytes of the stages one launch fuses / event-timed
+            launch duration after an L2 flush (the smaller compulsory-byte figure of the fused kernel is reported too)
   cpu_baseline / --impl reference : the oracle port (oracle/abm_oracle.c, OpenMP) on the host cores
 """
 import argparse
@@ -130,9 +131,15 @@ def step_bytes(n, b15, b10, e15, e10, ej, g, sm, sd):
 
 def substep_kernel_bytes(n, b10, ej):
     """Compulsory traffic of ONE k_jkr_substep launch (DESIGN.md 'kernels'): read sorted {x,y,z,r} 4wN,
-    sorted_id+sorted_bin 8N, bin offsets 4B, motility 3wN; write locations 3wN, bond rows 2*4*E_j, row_len 4N.
-    (The stages it fuses would move 14wN + 4B + 16E + 25E_j under SURVEY 8d's per-stage formulas.)"""
+    sorted_id+sorted_bin 8N, bin offsets 4B, motility 3wN; write locations 3wN, bond rows 2*4*E_j, row_len 4N."""
     return 10 * W * n + 12 * n + 4 * b10 + 8 * ej
+
+
+def substep_algorithmic_bytes(n, b10, e10, ej):
+    """SURVEY 8(d)'s algorithmic bytes of the stages ONE k_jkr_substep launch replaces: search(r=10)
+    4wN+4B+8E, merge/dedupe 8(2E_j+E), force 9E_j+4wN, integrate 6wN (the sort's 7wN+4N+8B belongs to the sort
+    kernels)."""
+    return (4 * W * n + 4 * b10 + 8 * e10) + 8 * (2 * ej + e10) + (9 * ej + 4 * W * n) + 6 * W * n
 
 
 # ---- the CPU arm (oracle port) ----------------------------------------------------------------------------------
@@ -314,7 +321,9 @@ def run_b200(args, rank, world, local_rank):
     hot_us = time_launches(False)
     eng.loc.copy_(loc_save)
     kbytes = substep_kernel_bytes(n, b10, ej)
-    achieved = kbytes / (cold_us * 1e-6) / 1e9
+    abytes = substep_algorithmic_bytes(n, b10, ej, ej)
+    achieved = abytes / (cold_us * 1e-6) / 1e9
+    achieved_c = kbytes / (cold_us * 1e-6) / 1e9
     traffic = l2_hit = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -325,7 +334,11 @@ def run_b200(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "k_jkr_substep<uniform radius>", "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "frac_of_nominal_8000": round(achieved / nominal, 4),
-                "l2_hit_pct_ncu": l2_hit, "bytes_per_launch": kbytes, "launch_us_cold_l2": round(cold_us, 2),
+                "l2_hit_pct_ncu": l2_hit, "bytes_per_launch": abytes,
+                "bytes_model": "SURVEY 8(d) algorithmic bytes of the stages the launch fuses: search(r=10) + "
+                               "merge/dedupe + force + integrate",
+                "compulsory_bytes_per_launch": kbytes, "achieved_on_compulsory_bytes": round(achieved_c, 1),
+                "frac_on_compulsory_bytes": round(achieved_c / peak, 4), "launch_us_cold_l2": round(cold_us, 2),
                 "launch_us_warm_l2": round(hot_us, 2), "launches_per_step": sm,
                 "step_algorithmic_bytes": bytes_step,
                 "step_frac": round(bytes_step / (total_s / args.steps) / 1e9 / peak, 4),
