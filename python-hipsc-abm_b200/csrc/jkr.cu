@@ -9,7 +9,10 @@
 
 namespace abm {
 
-constexpr int kJkrThreads = 128;
+#ifndef ABM_JKR_THREADS
+#define ABM_JKR_THREADS 128
+#endif
+constexpr int kJkrThreads = ABM_JKR_THREADS;
 
 struct Box {
     double size[3];
@@ -90,7 +93,10 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 #ifndef ABM_JKR_EXP
 #define ABM_JKR_EXP 0
 #endif
-constexpr int kMaxHits = 16;
+#ifndef ABM_JKR_MAXHITS
+#define ABM_JKR_MAXHITS 16
+#endif
+constexpr int kMaxHits = ABM_JKR_MAXHITS;
 constexpr int kJkrMinBlocks = ABM_JKR_MINBLOCKS;
 constexpr double kForceUnit = 0x1p-76, kForceUnitInv = 0x1p76;   // fixed-point force accumulation (N)
 
@@ -578,8 +584,10 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
     for (int k = 0; k < n_substeps; ++k) {
         int32_t *table = (k & 1) ? bin_start_b : bin_start_a, *other = (k & 1) ? bin_start_a : bin_start_b;
         const bool prebin = k + 1 < n_substeps && n > 0;
+        // (the largest bin population is reported for the first sort of the loop only)
         int rc = bin_sort_impl(locations, radii, n, extent_host, origin_host, reach, k ? ABM_SORT_PREBINNED : 0, table,
-                               sorted_id, sorted_pos, sorted_bin, max_count, sort_workspace, sort_workspace_bytes,
+                               sorted_id, sorted_pos, sorted_bin, k ? nullptr : max_count, sort_workspace,
+                               sort_workspace_bytes,
                                prebin ? other : nullptr, global_id, stream);   // the idle table is cleared on the way
         if (rc) return rc;
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;

@@ -65,16 +65,15 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restr
                                                              int *__restrict__ max_out = nullptr) {
     __shared__ int smem[32];
     __shared__ int warp_tot[kScanThreads / 32];
-    // offset of this chunk = sum of the preceding block sums
-    int part = 0;
-    for (int b = threadIdx.x; b < (int)blockIdx.x; b += kScanThreads) part += block_sums[b];
-    int offset = block_reduce_sum(part, smem);
-
     // each thread owns kScanItems CONSECUTIVE elements, moved as two 16-byte vectors when the chunk is full
+    // (loaded first: their latency overlaps the reduction of the preceding block sums below)
     int64_t first = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;
     int v[kScanItems];
     int tsum = 0;
     const bool full = first + kScanItems <= n && ((reinterpret_cast<uintptr_t>(data + first) & 15) == 0);
+    // offset of this chunk = sum of the preceding block sums
+    int part = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += kScanThreads) part += block_sums[b];
     if (full) {
         int4 a = *reinterpret_cast<const int4 *>(data + first);
         int4 b = *reinterpret_cast<const int4 *>(data + first + 4);
@@ -87,6 +86,7 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restr
             v[k] = (i < n) ? data[i] : 0;
         }
     }
+    int offset = block_reduce_sum(part, smem);
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) tsum += v[k];
     int incl = warp_inclusive_scan(tsum);

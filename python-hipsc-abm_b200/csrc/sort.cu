@@ -151,6 +151,7 @@ ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_
                             const double *origin_host, double distance, int flags, int32_t *bin_start,
                             int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
                             void *workspace, size_t workspace_bytes, void *stream) {
+    ABM_REQUIRE(max_count, "null pointer");
     return abm::bin_sort_impl(locations, radii, n, size_host, origin_host, distance, flags, bin_start, sorted_id,
                               sorted_pos, sorted_bin, max_count, workspace, workspace_bytes, nullptr, nullptr, stream);
 }
@@ -164,7 +165,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
                        void *workspace, size_t workspace_bytes, int32_t *zero_table, const int32_t *global_id,
                        void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
-    ABM_REQUIRE(size_host && bin_start && max_count, "null pointer");
+    ABM_REQUIRE(size_host && bin_start, "null pointer");
     BinGeom g;
     int64_t nbins;
     ABM_REQUIRE(make_bin_geom(size_host, origin_host, distance, flags, g, nbins) == 0,
@@ -177,8 +178,10 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
         rc = check_cuda(cudaMemsetAsync(bin_start, 0, (size_t)(nbins + 1) * 4, st), "memset bin_start");
         if (rc) return rc;
     }
-    rc = check_cuda(cudaMemsetAsync(max_count, 0, 4, st), "memset max_count");
-    if (rc) return rc;
+    if (max_count) {                                           // nullptr: the caller does not want the statistic
+        rc = check_cuda(cudaMemsetAsync(max_count, 0, 4, st), "memset max_count");
+        if (rc) return rc;
+    }
     if (n == 0) {
         if (zero_table) return check_cuda(cudaMemsetAsync(zero_table, 0, (size_t)(nbins + 1) * 4, st), "memset table");
         return 0;
