@@ -23,6 +23,7 @@ L3 = C.POINTER(C.c_int64)     # host int64[3]
 SIGNATURES = {
     "abm_abi_version": (I32, []),
     "abm_compiled_arch": (I32, []),
+    "abm_set_option": (I32, [I32, I32]),
     "abm_last_error": (C.c_char_p, []),
     "abm_device_info": (I32, [C.POINTER(I32), C.POINTER(I32), C.POINTER(I32)]),
     "abm_bin_dims_host": (I32, [D3, F64, I32, I3]),
@@ -87,6 +88,7 @@ def check(rc: int, what: str) -> int:
 
 
 SORT_STABLE, SORT_REFERENCE, SORT_PREBINNED = 1, 2, 4
+OPTION_CHAINED_LAUNCH = 1
 
 
 def d3(values):

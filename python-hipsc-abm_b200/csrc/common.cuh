@@ -107,6 +107,44 @@ struct Radius {
     static __device__ __noinline__ bool tie(double s, double dist) { return __dsqrt_rn(s) <= dist; }
 };
 
+// ---- programmatic dependent launch -------------------------------------------------------------------
+// The kernels of the mechanics loop form a chain (scan -> placement -> fused substep -> scan ...), each consuming
+// what its predecessor wrote.  Launched with the programmatic-serialization attribute, a kernel's CTAs may become
+// resident while the predecessor's last wave drains: they run their prologue, then block in pdl_wait() until the
+// predecessor has completed and its writes are visible.  pdl_launch_dependents() (first statement of every chain
+// kernel) is what allows the successor to start being scheduled once every CTA of this grid has started.
+// Rule: no global-memory access before pdl_wait().
+#ifndef ABM_PDL
+#define ABM_PDL 1
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if ABM_PDL
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+#if ABM_PDL
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+extern int g_chained_launch;    // abm_set_option(ABM_OPTION_CHAINED_LAUNCH): lib.cu
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = (ABM_PDL && g_chained_launch) ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- warp helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

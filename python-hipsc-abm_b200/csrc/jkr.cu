@@ -171,8 +171,10 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     // column tid: first the parked partner slots, then (overwritten from the front) the ids of the new bond row
     __shared__ int column[kMaxHits][kJkrThreads];
     __shared__ float4 tiles[kJkrThreads / 32][kTileRows * kTileCap];
+    pdl_launch_dependents();
     const int tid = threadIdx.x;
     const int s = blockIdx.x * kJkrThreads + tid;
+    pdl_wait();
     if (s - (tid & 31) >= n) return;                           // the whole warp is past the last cell
     const bool live = s < n;
     float4 *tile = tiles[tid >> 5];
@@ -532,12 +534,13 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
         fric.uni_inv = 1.0 / f;
     }
     auto kernel = uniform_radius > 0 ? k_jkr_substep<true> : k_jkr_substep<false>;
-    kernel<<<ceil_div(n, kJkrThreads), kJkrThreads, 0, as_stream(stream)>>>(
-        bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
-        Radius(distance), reach * reach, BandConst::make(reach * 1.0000001), old, new_row_len, new_cols, (int)row_stride, max_len, motility_forces,
-        locations, c, stokes, fric, box, move_dt, global_id, global_id ? slot_gid : sorted_id, next, sort_rows);
-    ABM_CHECK_LAUNCH("k_jkr_substep");
-    return 0;
+    return check_cuda(launch_chained(kernel, ceil_div(n, kJkrThreads), kJkrThreads, as_stream(stream), bin_start,
+                                     sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
+                                     Radius(distance), reach * reach, BandConst::make(reach * 1.0000001), old,
+                                     new_row_len, new_cols, (int)row_stride, max_len, motility_forces, locations, c,
+                                     stokes, fric, box, move_dt, global_id, global_id ? slot_gid : sorted_id, next,
+                                     sort_rows),
+                      "k_jkr_substep");
 }
 
 ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,

@@ -65,6 +65,8 @@ static __global__ void __launch_bounds__(kScanThreads) k_scan_apply(int *__restr
                                                              int *__restrict__ max_out = nullptr) {
     __shared__ int smem[32];
     __shared__ int warp_tot[kScanThreads / 32];
+    pdl_launch_dependents();
+    pdl_wait();
     // each thread owns kScanItems CONSECUTIVE elements, moved as two 16-byte vectors when the chunk is full
     // (loaded first: their latency overlaps the reduction of the preceding block sums below)
     int64_t first = (int64_t)blockIdx.x * kScanChunk + (int64_t)threadIdx.x * kScanItems;

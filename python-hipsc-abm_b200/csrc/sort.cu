@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ 
                                                         double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
                                                         int *__restrict__ next_sums, int n_sums,
                                                         const int *__restrict__ gid_of, int *__restrict__ slot_gid) {
+    pdl_launch_dependents();
     int s = blockIdx.x * kThreads + threadIdx.x;
+    pdl_wait();
     // consumed by this sort's scan; the next hand-over adds to it
     for (int k = s; k < n_sums; k += gridDim.x * kThreads) next_sums[k] = 0;
     if (s >= n) return;
@@ -199,9 +201,10 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
     const int nb = scan_blocks(nbins + 1);
     if (prebinned) {
         // the mechanics kernel that binned the cells also summed the histogram per scan chunk: one scan launch
-        k_scan_apply<<<nb, kScanThreads, 0, st>>>(bin_start, nbins + 1, w.next_sums, nullptr, w.cursor, zero_table,
-                                                  max_count);
-        ABM_CHECK_LAUNCH("k_scan_apply");
+        rc = check_cuda(launch_chained(k_scan_apply, nb, kScanThreads, st, bin_start, nbins + 1,
+                                       (const int *)w.next_sums, (int *)nullptr, w.cursor, zero_table, max_count),
+                        "k_scan_apply");
+        if (rc) return rc;
     } else {
         k_scan_reduce<<<nb, kScanThreads, 0, st>>>(bin_start, nbins + 1, w.block_sums, max_count);
         ABM_CHECK_LAUNCH("k_scan_reduce");
@@ -211,9 +214,11 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
     }
     double4 *sp = reinterpret_cast<double4 *>(sorted_pos);
     if (prebinned) {
-        k_rescatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.tmp_id, w.next_pos, w.cursor, (int)n, sorted_id, sp,
-                                                 sorted_bin, w.next_sums, nb, global_id, w.slot_gid);
-        ABM_CHECK_LAUNCH("k_rescatter");
+        rc = check_cuda(launch_chained(k_rescatter, blocks, kThreads, st, (const int *)w.cell_bin,
+                                       (const int *)w.tmp_id, (const double4 *)w.next_pos, w.cursor, (int)n, sorted_id,
+                                       sp, sorted_bin, w.next_sums, nb, global_id, w.slot_gid),
+                        "k_rescatter");
+        if (rc) return rc;
     } else if (flags & ABM_SORT_STABLE) {
         rc = check_cuda(cudaMemsetAsync(w.next_sums, 0, (size_t)nb * 4, st), "memset next_sums");
         if (rc) return rc;

@@ -151,6 +151,8 @@ class HotPathStep:
         """Capture the two alternating step variants (bond rows in buffer 0 -> 1 and 1 -> 0)."""
         assert self.parity == 0, "capture() must start from an even step"
         torch.cuda.synchronize(self.eng.device)
+        # programmatic dependent launches pay off for eager launches but cost inside a graph (include/abm_b200.h)
+        chained = self.eng.lib.abm_set_option(_lib.OPTION_CHAINED_LAUNCH, 0)
         self.graphs = []
         launches = self.eng.launches
         # the mechanics stream outranks the second stream: search + morphogen kernels fill what the mechanics leave idle
@@ -160,6 +162,7 @@ class HotPathStep:
             with torch.cuda.graph(g, stream=stream):
                 self.enqueue()
             self.graphs.append(g)
+        self.eng.lib.abm_set_option(_lib.OPTION_CHAINED_LAUNCH, chained)
         # capturing enqueues nothing on the device: undo the launch accounting, and the state did not advance
         self.eng.use_current_stream()         # leave the capture stream
         self.eng.launches = launches
@@ -208,6 +211,7 @@ class SlabPipeline:
         join_side()."""
         self.geom, self.cfg = geom, cfg
         self.eng = ColonyEngine(geom.size, device)
+        self.eng.lib.abm_set_option(_lib.OPTION_CHAINED_LAUNCH, 1)     # eager launches: chain the mechanics kernels
         self.eng.set_bin_lattice(*geom.local_box())
         self.dts = cfg.substep_dts()
         self.max_radius = float(max_radius)
