@@ -90,8 +90,17 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 #ifndef ABM_JKR_MINBLOCKS
 #define ABM_JKR_MINBLOCKS 7      // register cap: 7 -> 72/thread (measured best of 5..8 at 500k cells)
 #endif
+// Build-time experiment switches (scripts/ab_substep.py builds variant libraries with -DABM_JKR_EXP=<bits>; the
+// shipped library uses 0).  Measured outcomes are in profiles/r01b_kernels_c3.md.
+//   1: load the motility force before the contact loop instead of at the end      (slower: register pressure)
+//   2: start fetching the previous bond row at the first shell partner             (slower: register pressure)
+//   4: TIMING ABLATION, WRONG RESULTS: skip the contact loop                        (attributes 23 of 56 us)
+//   8: TIMING ABLATION, WRONG RESULTS: skip the candidate walk                      (attributes  9 of 56 us)
 #ifndef ABM_JKR_EXP
 #define ABM_JKR_EXP 0
+#endif
+#if (ABM_JKR_EXP & 12) && !defined(ABM_ALLOW_WRONG_RESULTS)
+#error "ABM_JKR_EXP bits 4 and 8 are timing ablations that produce wrong results: add -DABM_ALLOW_WRONG_RESULTS"
 #endif
 #ifndef ABM_JKR_MAXHITS
 #define ABM_JKR_MAXHITS 16

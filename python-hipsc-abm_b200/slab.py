@@ -46,6 +46,23 @@ class SlabGeometry:
         size = np.asarray(size, dtype=np.float64)
         return SlabGeometry(size, world, rank, np.linspace(0.0, size[0], world + 1), float(halo))
 
+    @staticmethod
+    def balanced(size, world, rank, halo, x_all):
+        """Equal-count slabs: the interfaces are the k/world quantiles of the cells' x coordinates (x_all: 1-D
+        array-like of ALL cells' x, or of a representative sample; every rank must pass the same values, e.g.
+        after one all-gather at set-up).  A slab is never made thinner than the halo (its halo cells must all
+        come from its direct neighbours)."""
+        size = np.asarray(size, dtype=np.float64)
+        x = np.sort(np.asarray(x_all, dtype=np.float64).ravel())
+        inner = np.quantile(x, np.arange(1, world) / world) if world > 1 and x.size else np.zeros(0)
+        bounds = np.concatenate([[0.0], inner, [size[0]]])
+        width = float(halo) * (1.0 + 1e-9)
+        for k in range(1, world):                                   # enforce the minimum width, left to right
+            bounds[k] = min(max(bounds[k], bounds[k - 1] + width), size[0] - width * (world - k))
+        if np.any(np.diff(bounds) < float(halo)):
+            raise ValueError("the box is too short for this many slabs at least one halo wide")
+        return SlabGeometry(size, world, rank, bounds, float(halo))
+
     @property
     def x_lo(self):
         return float(self.bounds[self.rank])

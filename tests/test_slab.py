@@ -279,3 +279,47 @@ def test_fixed_capacity_messages_and_deferred_owned_count():
     assert np.array_equal(gid, np.arange(len(loc)))
     assert np.array_equal(got_edges, ref_edges)
     assert np.abs(got_loc - ref_loc).max() <= 1e-9
+
+
+def test_balanced_slabs_follow_the_cell_density():
+    rng = np.random.default_rng(11)
+    size = np.array([1200.0, 300.0, 0.0])
+    # three clusters of very different populations along x
+    x = np.concatenate([rng.normal(250, 110, 3000), rng.normal(600, 60, 600), rng.normal(1000, 40, 1400)]).clip(0, 1200)
+    halo = 40.0
+    geoms = [slab.SlabGeometry.balanced(size, 4, r, halo, x) for r in range(4)]
+    b = geoms[0].bounds
+    assert all(np.array_equal(g.bounds, b) for g in geoms) and b[0] == 0.0 and b[-1] == 1200.0
+    assert np.all(np.diff(b) >= halo)
+    counts = np.histogram(x, bins=b)[0]
+    uniform = np.histogram(x, bins=np.linspace(0, 1200, 5))[0]
+    assert counts.max() - counts.min() < 0.35 * len(x) / 4 < uniform.max() - uniform.min()
+    # every cell has exactly one owner under the position predicate
+    xt = torch.from_numpy(x)
+    assert int(sum(g.inside(xt).sum() for g in geoms)) == len(x)
+    with pytest.raises(ValueError):
+        slab.SlabGeometry.balanced(size, 40, 0, halo, x)
+
+
+def test_balanced_slabs_reproduce_single_domain():
+    world, steps = 3, 2
+    loc, radii, mot = make_cells()
+    loc = loc.copy()
+    loc[:, 0] = SIZE[0] * (loc[:, 0] / SIZE[0]) ** 1.6            # denser towards x = 0
+    halo = slab.required_halo(11, 10.3100107, slack=5.0)
+    ref_loc, ref_edges = single_domain(loc, radii, mot, steps)
+    geoms = [slab.SlabGeometry.balanced(SIZE, world, r, halo, loc[:, 0]) for r in range(world)]
+    gid = np.arange(len(loc))
+    states = []
+    for g in geoms:
+        m = g.inside(torch.from_numpy(loc[:, 0])).numpy()
+        states.append(slab.SlabState(torch.from_numpy(loc[m].copy()), torch.from_numpy(radii[m].copy()),
+                                     torch.from_numpy(mot[m].copy()), torch.from_numpy(gid[m].copy()), STRIDE))
+    uni = np.histogram(loc[:, 0], bins=np.linspace(0, SIZE[0], world + 1))[0]
+    assert max(s.n for s in states) - min(s.n for s in states) < uni.max() - uni.min()   # as far as the halo allows
+    for _ in range(steps):
+        slab.loopback_step(states, geoms, oracle_compute)
+    got_gid, got_loc, got_edges = collect(states)
+    assert np.array_equal(got_gid, gid)
+    assert np.array_equal(got_edges, ref_edges)
+    assert np.abs(got_loc - ref_loc).max() <= 1e-9
