@@ -63,9 +63,10 @@ __device__ __forceinline__ int walk_old_row(int i, double4 p, const GraphView &o
     return cnt;
 }
 
-// Candidates are filtered in fp32 out of the warp's shared-memory tile (tile.cuh); what passes is parked in a
-// per-thread column of shared memory and confirmed with the exact fp64 predicate.  A cell with more than kRowCap
-// partners, or whose candidate run does not fit the tile, falls back to the exact walk from global memory.
+// Candidates are classified in fp32 out of the warp's shared-memory tile (tile.cuh), which also carries their ids;
+// only a candidate inside the fp32 error band of the radius is confirmed with the exact fp64 predicate.  Partner
+// ids are collected in a per-thread column of shared memory.  A cell with more than kRowCap partners, or whose
+// candidate run does not fit the tile, falls back to the exact walk from global memory.
 __global__ void __launch_bounds__(kSearchThreads)
 k_search(const int *__restrict__ bin_start, const int *__restrict__ sorted_id, const double4 *__restrict__ spos,
          const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad, const double *__restrict__ loc,
@@ -73,11 +74,13 @@ k_search(const int *__restrict__ bin_start, const int *__restrict__ sorted_id, c
          long long capacity, int *__restrict__ cursor) {
     __shared__ int column[kRowCap][kSearchThreads];
     __shared__ float4 tiles[kSearchThreads / 32][kTileRows * kTileCap];
+    __shared__ int tile_ids[kSearchThreads / 32][kTileRows * kTileCap];
     const int tid = threadIdx.x;
     const int s = blockIdx.x * kSearchThreads + tid;
     if (s - (tid & 31) >= n) return;                           // the whole warp is past the last cell
     const bool active = s < n;
     float4 *tile = tiles[tid >> 5];
+    int *tile_id = tile_ids[tid >> 5];
     int i = 0, bx = 0, by = 0, bz = 0;
     double4 p = make_double4(0, 0, 0, 0);
     if (active) {
@@ -85,19 +88,21 @@ k_search(const int *__restrict__ bin_start, const int *__restrict__ sorted_id, c
         p = spos[s];
         st.decode(sorted_bin[s], bx, by, bz);
     }
-    // phase 1: fp32 filter over the staged stencil
+    // fp32 classification over the staged stencil: below the error band a candidate is a neighbour, above it it
+    // is not, inside it (a few per million) the exact fp64 predicate decides.  The column holds partner ids.
     TileOrigin org;
     org.x = __shfl_sync(kFullWarp, p.x, 0);
     org.y = __shfl_sync(kFullWarp, p.y, 0);
     org.z = __shfl_sync(kFullWarp, p.z, 0);
     const float pfx = (float)(p.x - org.x), pfy = (float)(p.y - org.y), pfz = (float)(p.z - org.z);
-    const float t_out = (float)rad.hi + tile_band(pfx, pfy, pfz, (float)rad.d);
-    int nh = 0;
+    const float band = tile_band(pfx, pfy, pfz, (float)rad.d);
+    const float t_in = (float)rad.lo - band, t_out = (float)rad.hi + band;
+    int cnt = 0;
     bool slow = false;
     for (int dz = -1; dz <= 1; ++dz) {
         const int z = bz + dz;
         if (__all_sync(kFullWarp, !active || z < 0 || z >= st.dims[2])) continue;
-        const LayerRuns R = stage_layer(active, bx, by, z, st, bin_start, spos, org, tile);
+        const LayerRuns R = stage_layer(active, bx, by, z, st, bin_start, spos, org, tile, sorted_id, tile_id);
 #pragma unroll
         for (int r = 0; r < kTileRows; ++r) {
             if (!((R.staged >> r) & 1u)) {                     // warp-uniform
@@ -105,45 +110,41 @@ k_search(const int *__restrict__ bin_start, const int *__restrict__ sorted_id, c
                 continue;
             }
             const float4 *run = tile + R.first[r];
+            const int *run_id = tile_id + R.first[r];
             const int nr = R.n[r];
             for (int u = 0; u < nr; ++u) {
                 const float4 q = run[u];
                 const float dx = pfx - q.x, dy = pfy - q.y, dzf = pfz - q.z;
                 const float s2f = fmaf(dzf, dzf, fmaf(dy, dy, dx * dx));
+                if (s2f > t_out) continue;
                 const int t = __float_as_int(q.w);
-                if (s2f <= t_out && t != s) {
-                    if (nh < kRowCap) column[nh][tid] = t;
-                    ++nh;
+                if (t == s) continue;
+                if (s2f >= t_in) {                             // inside the band: exact predicate
+                    const double4 e = spos[t];
+                    if (!rad.within(sumsq_nofma(e.x - p.x, e.y - p.y, e.z - p.z))) continue;
                 }
+                if (cnt < kRowCap) column[cnt][tid] = run_id[u];
+                ++cnt;
             }
         }
         __syncwarp();                                         // the tile is overwritten by the next layer
     }
-    // phase 2: exact predicate on what passed; the column then holds partner ids
-    int cnt = 0;
-    slow |= nh > kRowCap;
-    if (active && !slow) {
-        for (int k = 0; k < nh; ++k) {
-            const int t = column[k][tid];
-            const double4 q = spos[t];
-            const double s2 = sumsq_nofma(q.x - p.x, q.y - p.y, q.z - p.z);
-            if (rad.within(s2)) column[cnt++][tid] = sorted_id[t];   // cnt <= k
-        }
-        if (old.valid()) {                                    // union with the old graph (clear=False)
-            const long long os = old.start(i);
-            const int olen = old.row_len[i];
-            for (int k = 0; k < olen; ++k) {
-                const int j = old.cols[os + k];
-                const double s2 = sumsq_nofma(loc[3 * (long long)j + 0] - p.x, loc[3 * (long long)j + 1] - p.y,
-                                              loc[3 * (long long)j + 2] - p.z);
-                if (!rad.within(s2)) {
-                    if (cnt < kRowCap) column[cnt][tid] = j;
-                    ++cnt;
-                }
+    slow |= cnt > kRowCap;
+    if (active && !slow && old.valid()) {                     // union with the old graph (clear=False)
+        const long long os = old.start(i);
+        const int olen = old.row_len[i];
+        for (int k = 0; k < olen; ++k) {
+            const int j = old.cols[os + k];
+            const double s2 = sumsq_nofma(loc[3 * (long long)j + 0] - p.x, loc[3 * (long long)j + 1] - p.y,
+                                          loc[3 * (long long)j + 2] - p.z);
+            if (!rad.within(s2)) {
+                if (cnt < kRowCap) column[cnt][tid] = j;
+                ++cnt;
             }
-            slow |= cnt > kRowCap;
         }
+        slow |= cnt > kRowCap;
     }
+    if (!active) cnt = 0;
     if (active && slow) {                                     // count only; the row is written straight to cols below
         cnt = walk_stencil<false>(s, bx, by, bz, st, bin_start, sorted_id, spos, p, rad, nullptr, 0, nullptr, 0);
         if (old.valid()) cnt = walk_old_row<false>(i, p, old, loc, rad, nullptr, 0, nullptr, cnt);

@@ -64,10 +64,12 @@ struct LayerRuns {
 
 // Stage the runs of one z layer.  Every lane of the warp must call it (lanes without a cell pass live=false).
 // tile: kTileRows*kTileCap float4 of this warp; entry = {x-ox, y-oy, z-oz, slot as int bits}.
+// ids / tile_id (optional): also stage sorted_id of every candidate (tile_id: kTileRows*kTileCap ints of the warp).
 __device__ __forceinline__ LayerRuns stage_layer(bool live, int bx, int by, int z, const Stencil &st,
                                                  const int *__restrict__ bin_start,
                                                  const double4 *__restrict__ spos, const TileOrigin &o,
-                                                 float4 *tile) {
+                                                 float4 *tile, const int *__restrict__ ids = nullptr,
+                                                 int *tile_id = nullptr) {
     LayerRuns R;
     const int lane = threadIdx.x & 31;
     const bool zok = live && z >= 0 && z < st.dims[2];
@@ -103,6 +105,7 @@ __device__ __forceinline__ LayerRuns stage_layer(bool live, int bx, int by, int 
                     double4 q = spos[t];
                     tile[r * kTileCap + c] = make_float4((float)(q.x - o.x), (float)(q.y - o.y), (float)(q.z - o.z),
                                                          __int_as_float(t));
+                    if (ids) tile_id[r * kTileCap + c] = ids[t];
                 }
             }
         }
