@@ -207,11 +207,12 @@ int abm_sample_concentrations(const double *locations, int64_t n, const double *
                               double *sampled, void *stream);
 
 /* Replaces per-cell adjust_morphogens (cell_methods.py:485-521) for all cells: amounts[i] is shared
- * equally by the in-bounds corner points closer than spat_res (fp64 atomic adds).  Shares that fall on rows
+ * equally by the in-bounds corner points closer than spat_res (fp64 atomic adds); amounts == NULL: every cell
+ * deposits uniform_amount.  Shares that fall on rows
  * outside [row_lo,row_hi) belong to another slab and are skipped (the share size still counts them).  */
-int abm_deposit_morphogens(const double *locations, const double *amounts, int64_t n, double *field,
-                           const int64_t gsize_host[3], double spat_res, int64_t row_lo, int64_t row_hi,
-                           void *stream);
+int abm_deposit_morphogens(const double *locations, const double *amounts, double uniform_amount, int64_t n,
+                           double *field, const int64_t gsize_host[3], double spat_res, int64_t row_lo,
+                           int64_t row_hi, void *stream);
 
 /* ---- slab decomposition plumbing (no reference counterpart; see hipsc_abm_b200/slab.py) -------------------
  * A cell travels between ranks as one byte record:

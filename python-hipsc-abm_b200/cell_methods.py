@@ -75,7 +75,7 @@ class B200CellMethods:
         plane = eng.to_device(np.ascontiguousarray(field[:, :, 0], dtype=np.float64), "field")
         out = eng.diffuse(plane, steps, self.diffuse_dt, last_dt, self.diffuse_const, self.spat_res2,
                           self.max_concentration, self.degradation)
-        field[:, :, 0] = eng.host(out)
+        eng.host_into(out, field[:, :, 0])
 
     # ---- a12/a13 ---------------------------------------------------------------------------------------------
     def get_concentration(self, gradient_name, index):
@@ -101,9 +101,12 @@ class B200CellMethods:
             f = eng.to_device(np.ascontiguousarray(field, dtype=np.float64), "field")
             sampled = eng.host(eng.sample(f, self.spat_res)) if sample else None
             if amounts is not None:
-                a = np.ascontiguousarray(np.broadcast_to(np.asarray(amounts, dtype=np.float64), (eng.n,)))
-                eng.deposit(f, eng.to_device(a, "amounts"), self.spat_res)
-                field[...] = eng.host(f)
+                if np.ndim(amounts) == 0:                     # one amount for every cell: no array travels
+                    eng.deposit(f, float(amounts), self.spat_res)
+                else:
+                    a = np.ascontiguousarray(np.broadcast_to(np.asarray(amounts, dtype=np.float64), (eng.n,)))
+                    eng.deposit(f, eng.to_device(a, "amounts"), self.spat_res)
+                eng.host_into(f.view(field.shape), field)
         finally:
             eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng.max_radius = saved
         return sampled

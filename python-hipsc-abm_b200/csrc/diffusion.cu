@@ -168,8 +168,9 @@ __global__ void k_sample(const double *__restrict__ loc, int n, const double *__
     out[i] = field[((r - row_lo) * g1 + idx[1]) * g2 + idx[2]];
 }
 
-__global__ void k_deposit(const double *__restrict__ loc, const double *__restrict__ amounts, int n,
-                          double *__restrict__ field, long long g0, long long g1, long long g2, double h,
+// amounts == nullptr: every cell deposits uniform_amount
+__global__ void k_deposit(const double *__restrict__ loc, const double *__restrict__ amounts, double uniform_amount,
+                          int n, double *__restrict__ field, long long g0, long long g1, long long g2, double h,
                           long long row_lo, long long row_hi) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -190,7 +191,7 @@ __global__ void k_deposit(const double *__restrict__ loc, const double *__restri
         }
     }
     if (total == 0) return;
-    double share = __ddiv_rn(amounts[i], (double)total);
+    double share = __ddiv_rn(amounts ? amounts[i] : uniform_amount, (double)total);
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         if (!near[p]) continue;
@@ -320,15 +321,16 @@ ABM_EXPORT int abm_sample_concentrations(const double *locations, int64_t n, con
     return 0;
 }
 
-ABM_EXPORT int abm_deposit_morphogens(const double *locations, const double *amounts, int64_t n, double *field,
-                                      const int64_t gsize_host[3], double spat_res, int64_t row_lo, int64_t row_hi,
-                                      void *stream) {
+ABM_EXPORT int abm_deposit_morphogens(const double *locations, const double *amounts, double uniform_amount,
+                                      int64_t n, double *field, const int64_t gsize_host[3], double spat_res,
+                                      int64_t row_lo, int64_t row_hi, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
-    ABM_REQUIRE(locations && amounts && field && gsize_host, "null pointer");
+    ABM_REQUIRE(locations && field && gsize_host, "null pointer");
     ABM_REQUIRE(spat_res > 0 && gsize_host[0] > 0 && gsize_host[1] > 0 && gsize_host[2] > 0, "bad grid");
     ABM_REQUIRE(row_lo >= 0 && row_hi <= gsize_host[0] && row_lo < row_hi, "bad row window");
-    k_deposit<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(locations, amounts, (int)n, field, gsize_host[0],
+    k_deposit<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(locations, amounts, uniform_amount, (int)n, field,
+                                                               gsize_host[0],
                                                                gsize_host[1], gsize_host[2], spat_res, row_lo,
                                                                row_hi);
     ABM_CHECK_LAUNCH("k_deposit");

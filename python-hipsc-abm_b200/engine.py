@@ -27,6 +27,82 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+class PinnedArrays:
+    """Page-locks long-lived numpy arrays of the caller IN PLACE (cudaHostRegister), so that the copies between
+    them and the device are plain DMA transfers instead of going through a pinned staging buffer and a host memcpy.
+
+    The reference keeps its agent arrays and morphogen fields as attributes that are edited in place step after
+    step (`self.motility_forces[:, :] = 0`, `self.fgf4_values[:, :, 0] = ...`): an array that shows up at the same
+    address with the same size twice in a row is taken to be such an array and registered.  Arrays that the rule
+    methods replace every step (np.concatenate / np.delete on division and death) never reach the second sighting
+    and keep using the staging path.  A registration is dropped when the owning numpy object dies (weakref) or
+    when another array turns up at an overlapping address."""
+    MIN_BYTES = 1 << 20
+
+    def __init__(self):
+        self.sightings = {}     # (ptr, nbytes) -> count
+        self.registered = {}    # ptr -> (nbytes, finalizer)
+        self.refused = set()
+        self.bytes = 0
+
+    @staticmethod
+    def _owner(a: np.ndarray):
+        while isinstance(a.base, np.ndarray):
+            a = a.base
+        return a if a.base is None else None            # memory owned by something we cannot watch: leave alone
+
+    def _unregister(self, ptr):
+        entry = self.registered.pop(ptr, None)
+        if entry is not None:
+            entry[1].detach()
+            torch.cuda.cudart().cudaHostUnregister(ptr)
+            self.bytes -= entry[0]
+
+    def is_registered(self, a: np.ndarray) -> bool:
+        e = self.registered.get(a.ctypes.data)
+        return e is not None and e[0] == a.nbytes
+
+    def consider(self, a: np.ndarray) -> bool:
+        """True if `a` is (now) page-locked in place."""
+        if a.nbytes < self.MIN_BYTES or not a.flags.c_contiguous or not a.flags.writeable:
+            return False
+        ptr, key = a.ctypes.data, (a.ctypes.data, a.nbytes)
+        if self.is_registered(a):
+            return True
+        if key in self.refused:
+            return False
+        seen = self.sightings.get(key, 0) + 1
+        if len(self.sightings) > 256:
+            self.sightings.clear()
+        self.sightings[key] = seen
+        if seen < 2:
+            return False
+        owner = self._owner(a)
+        if owner is None:
+            self.refused.add(key)
+            return False
+        for p, (nb, _) in list(self.registered.items()):      # a stale registration at an overlapping address
+            if p < ptr + a.nbytes and ptr < p + nb:
+                self._unregister(p)
+        import weakref
+        err = torch.cuda.cudart().cudaHostRegister(ptr, a.nbytes, 0)
+        if int(err) != 0:
+            self.refused.add(key)
+            return False
+        self.registered[ptr] = (a.nbytes, weakref.finalize(owner, self._owner_died, ptr))
+        self.bytes += a.nbytes
+        return True
+
+    def _owner_died(self, ptr):
+        entry = self.registered.pop(ptr, None)
+        if entry is not None:
+            try:
+                torch.cuda.cudart().cudaHostUnregister(ptr)
+            except Exception:
+                pass
+            self.bytes -= entry[0]
+
+
 @dataclass
 class SortState:
     """Result of one counting sort (abm_bin_sort)."""
@@ -82,6 +158,7 @@ class ColonyEngine:
         self.d2h_bytes = 0
         self._pinned = {}
         self._handed_out = weakref.WeakValueDictionary()   # data pointer -> pinned tensor backing a numpy array
+        self.pin_in_place = PinnedArrays()                 # long-lived caller arrays, page-locked where they are
 
     # ------------------------------------------------------------------------------------------------
     def use_current_stream(self):
@@ -108,6 +185,8 @@ class ColonyEngine:
         if backing is not None and backing.numel() * backing.element_size() == a.nbytes and \
                 backing.dtype == torch.from_numpy(a[:0].copy()).dtype:
             return backing.view(a.shape).to(self.device, non_blocking=True)
+        if self.pin_in_place.consider(a):
+            return torch.from_numpy(a).to(self.device, non_blocking=True)      # DMA straight out of the caller's array
         t = torch.from_numpy(a) if a.flags.writeable else torch.from_numpy(a.copy())
         if name is None:
             return t.to(self.device)
@@ -138,12 +217,27 @@ class ColonyEngine:
         self._handed_out[arr.ctypes.data] = dst
         return arr
 
+    def host_into(self, t: torch.Tensor, dst: np.ndarray):
+        """device -> an existing numpy array of the caller (counted).  Straight DMA if the array is page-locked in
+        place, else through a pinned buffer and one host copy."""
+        if dst.shape != tuple(t.shape):
+            raise ValueError("host_into: shape mismatch")
+        if dst.flags.c_contiguous and dst.dtype == np.dtype(str(t.dtype).replace("torch.", "")) and \
+                self.pin_in_place.consider(dst):
+            self.d2h_bytes += t.numel() * t.element_size()
+            torch.from_numpy(dst).copy_(t, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            dst[...] = self.host(t)
+
     def upload(self, locations, radii, motility=None, jkr=None):
         """Host -> device copy of the agent arrays the path reads (reference dtypes: float64)."""
         self.use_current_stream()
         loc = np.ascontiguousarray(locations, dtype=np.float64)
         n = loc.shape[0]
-        rad = np.ascontiguousarray(np.broadcast_to(np.asarray(radii, dtype=np.float64), (n,)))
+        rad = np.asarray(radii, dtype=np.float64)
+        if rad.shape != (n,) or not rad.flags.c_contiguous:      # a scalar or a strided view: materialise it
+            rad = np.ascontiguousarray(np.broadcast_to(rad, (n,)))
         self.n = n
         self.loc = self.to_device(loc, "loc")
         self.radii = self.to_device(rad, "radii")
@@ -411,15 +505,17 @@ class ColonyEngine:
         self.launches += 1 if n else 0
         return out[:n]
 
-    def deposit(self, field: torch.Tensor, amounts: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None,
-                n=None):
+    def deposit(self, field: torch.Tensor, amounts, spat_res, rows=None, grid_rows=None, loc=None, n=None):
+        """adjust_morphogens for every cell; amounts: a device tensor (one per cell) or a python float (all cells)."""
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
         lo, hi = (0, gs[0]) if rows is None else rows
         if grid_rows is not None:
             gs[0] = int(grid_rows)
         n = self.n if n is None else int(n)
-        _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc if loc is None else loc), _ptr(amounts), n,
-                                                   _ptr(field), _lib.l3(gs),
+        scalar = not isinstance(amounts, torch.Tensor)
+        _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc if loc is None else loc),
+                                                   0 if scalar else _ptr(amounts), float(amounts) if scalar else 0.0,
+                                                   n, _ptr(field), _lib.l3(gs),
                                                    float(spat_res), int(lo), int(hi), self.stream),
                    "abm_deposit_morphogens")
         self.launches += 1 if n else 0
