@@ -46,13 +46,24 @@ class B200CellMethods:
                  getattr(type(self).get_neighbors, "__wrapped__", None) is
                  getattr(B200Simulation.get_neighbors, "__wrapped__", None))
         if fused:
+            import torch
             eng = self.b200_upload(with_forces="motility")
+            uploaded = torch.cuda.Event()
+            uploaded.record(torch.cuda.current_stream(eng.device))
             graph = self.jkr_graph
             old = graph.device_tensors(eng)
-            bonds, graph.row_stride_hint = eng.mechanics(old, distance, dts, graph.row_stride_hint, STOKES)
+
+            def reset_forces():
+                # the reference leaves both force arrays zeroed (cell_methods.py:436,439); do it while the device
+                # runs the loop -- jkr_forces is not read by the fused loop, motility_forces once its upload is done
+                self.jkr_forces[:, :] = 0
+                uploaded.synchronize()
+                self.motility_forces[:, :] = 0
+            bonds, graph.row_stride_hint = eng.mechanics(old, distance, dts, graph.row_stride_hint, STOKES,
+                                                         meanwhile=reset_forces)
             graph.set_device(bonds, eng)
             self.locations = eng.locations_host()
-            self.jkr_forces[:, :] = 0
+            return
         else:
             for step in range(total_steps):
                 self.get_neighbors("jkr_graph", distance, clear=False)
@@ -94,7 +105,7 @@ class B200CellMethods:
         eng = self.b200_engine()
         field = self.__dict__[gradient_name]
         locations = np.ascontiguousarray(self.locations[cells], dtype=np.float64)
-        saved = (eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng.max_radius)
+        saved = (eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng._max_radius)
         eng.n = len(locations)
         eng.loc = eng.to_device(locations, "loc")
         try:
@@ -108,5 +119,5 @@ class B200CellMethods:
                     eng.deposit(f, eng.to_device(a, "amounts"), self.spat_res)
                 eng.host_into(f.view(field.shape), field)
         finally:
-            eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng.max_radius = saved
+            eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng._max_radius = saved
         return sampled

@@ -143,8 +143,8 @@ class ColonyEngine:
         self.set_bin_lattice(None, None)
         self.n = 0
         self.loc = self.radii = self.mot = self.jkr = None
-        self.max_radius = 0.0
-        self.uniform_radius = 0.0   # common radius when all radii are equal (contact constants evaluated once)
+        self._max_radius = 0.0      # None: not evaluated yet for the current radii (done on the device when needed)
+        self._uniform_radius = 0.0  # common radius when all radii are equal (contact constants evaluated once)
         self.global_id = None   # int32 (n,) when bond rows are kept by global id (slab decomposition)
         self._sort_wss = {}     # sort scratch per bin count (sorts of different lattices may run on different streams)
         self._sort_bufs = {}
@@ -241,8 +241,7 @@ class ColonyEngine:
         self.n = n
         self.loc = self.to_device(loc, "loc")
         self.radii = self.to_device(rad, "radii")
-        self.max_radius = float(rad.max()) if n else 0.0
-        self.uniform_radius = self.max_radius if n and float(rad.min()) == self.max_radius else 0.0
+        self._max_radius = self._uniform_radius = None if n else 0.0    # only the mechanics need them: lazily
         self.mot = (self.to_device(np.asarray(motility, dtype=np.float64), "mot")
                     if motility is not None else self._zeros((n, 3), torch.float64))
         self.jkr = (self.to_device(np.asarray(jkr, dtype=np.float64), "jkr")
@@ -255,8 +254,33 @@ class ColonyEngine:
         self.loc, self.radii = loc, radii
         self.mot = mot if mot is not None else self._zeros((self.n, 3), torch.float64)
         self.jkr = jkr if jkr is not None else self._zeros((self.n, 3), torch.float64)
-        self.max_radius = float(max_radius) if max_radius is not None else float(radii.max().item())
-        self.uniform_radius = float(uniform_radius)
+        self._max_radius = float(max_radius) if max_radius is not None else float(radii.max().item())
+        self._uniform_radius = float(uniform_radius)
+
+    def _radius_stats(self):
+        lo, hi = (float(v) for v in torch.aminmax(self.radii[:self.n]))       # one small kernel + one read-back
+        self._max_radius = hi
+        self._uniform_radius = hi if lo == hi else 0.0
+
+    @property
+    def max_radius(self) -> float:
+        if self._max_radius is None:
+            self._radius_stats()
+        return self._max_radius
+
+    @max_radius.setter
+    def max_radius(self, v):
+        self._max_radius = v
+
+    @property
+    def uniform_radius(self) -> float:
+        if self._uniform_radius is None:
+            self._radius_stats()
+        return self._uniform_radius
+
+    @uniform_radius.setter
+    def uniform_radius(self, v):
+        self._uniform_radius = v
 
     def locations_host(self) -> np.ndarray:
         return self.host(self.loc)
@@ -457,14 +481,20 @@ class ColonyEngine:
         last = pair[(len(dts) - 1) & 1]
         return GraphTensors(n, None, stride, b["len"][last], b["cols"][last], True)
 
-    def mechanics(self, old: Optional[GraphTensors], distance, dts, stride=16, stokes=STOKES):
+    def mechanics(self, old: Optional[GraphTensors], distance, dts, stride=16, stokes=STOKES, meanwhile=None):
         """The whole substep loop of CellMethods.apply_forces on the device, with the reference's
-        grow-and-retry on row overflow.  Returns (bond graph, stride used)."""
+        grow-and-retry on row overflow.  Returns (bond graph, stride used).  meanwhile: host work to do once while
+        the device runs the loop (called after the launches are enqueued, before the first wait)."""
         if self.n == 0 or len(dts) == 0:
+            if meanwhile is not None:
+                meanwhile()
             return old, stride
         start = self.loc.clone()
         while True:
             g = self.enqueue_mechanics(old, distance, dts, stride, stokes)
+            if meanwhile is not None:
+                meanwhile()
+                meanwhile = None
             worst = self.read_i32(self._bond_bufs["max_len"])
             if worst <= stride:
                 return g, stride

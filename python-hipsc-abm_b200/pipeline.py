@@ -56,6 +56,7 @@ class HotPathStep:
     def __init__(self, engine: ColonyEngine, cfg: StepConfig):
         self.eng = engine
         self.cfg = cfg
+        _ = engine.max_radius, engine.uniform_radius      # evaluated now (device read-back), not inside a capture
         n = engine.n
         dev = engine.device
         self.dts = cfg.substep_dts()
