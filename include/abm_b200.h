@@ -59,7 +59,7 @@ int abm_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * Unless ABM_SORT_REFERENCE is set, a flat world (size[2] == 0) gets one z layer instead of three (the other
  * two are always empty; candidates are a superset and the predicate is exact, so results are unchanged).
  * Unless ABM_SORT_STABLE is set, the order of the cells INSIDE a bin is unspecified (every consumer in this
- * library orders rows and force sums by cell id, so results do not depend on it).                    */
+ * library orders rows by cell id and sums forces in fixed point, so results do not depend on it).    */
 int abm_bin_dims_host(const double size_host[3], double distance, int flags, int32_t dims_host[3]);
 
 /* bytes of scratch abm_bin_sort needs for n cells and nbins bins */
@@ -67,11 +67,13 @@ size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins);
 
 /* Outputs:
  *   bin_start  (nbins+1) int32  exclusive prefix of per-bin counts, bin_start[nbins] = n
- *   sorted_id  (n)       int32  sorted slot -> cell id; ascending id inside a bin (the reference's
- *                               serial fill order, backend.py:36-48)
+ *   sorted_id  (n)       int32  sorted slot -> cell id; with ABM_SORT_STABLE ascending id inside a bin (the
+ *                               reference's serial fill order, backend.py:36-48)
  *   sorted_pos (n,4)     f64    {x,y,z,radius} of the cell in that slot (32-byte rows)
  *   sorted_bin (n)       int32  linear bin of the slot
  *   max_count  (1)       int32  largest bin population (what drives the reference's max_agents)
+ * With ABM_SORT_PREBINNED `locations` and `radii` are not read (may be NULL): the cells come from the workspace,
+ * where the preceding abm_jkr_substep left them in the previous sort's slot order.
  * origin_host (may be NULL = 0,0,0) shifts the bin lattice only: bin = floor_divide(x-origin,distance)+1 over
  * an extent of size_host.  A slab-decomposed colony bins its slab (+halo) this way while positions, the
  * distance predicate and the [0,size] clamp stay in global coordinates.                              */
