@@ -1,6 +1,6 @@
 """Slab decomposition with the real kernels: several slabs emulated on one GPU (loopback exchange) must
-reproduce the single-domain device run -- bonds identical by global id, positions and morphogen field within
-fp64 round-off (the local indexing changes summation order)."""
+reproduce the single-domain device run -- bonds identical by global id, positions bit-identical (integer force
+sums), morphogen field within fp64 round-off (its deposits are fp64 atomics)."""
 import numpy as np
 import pytest
 import torch
@@ -78,7 +78,9 @@ def test_emulated_slabs_match_single_domain(world, dim, native, first):
     edges = orc.canonical_edges(np.concatenate(
         [bonds_as_gid_edges(s.gid, s.bond_len, s.bond_gid) for s in states]))
     assert np.array_equal(edges, ref_edges)
-    assert np.abs(got_loc - ref_loc).max() <= 1e-9
+    # fixed-point force sums: the trajectory does not depend on the local order of the cells, so the slabs give the
+    # single-domain positions bit for bit
+    assert np.array_equal(got_loc, ref_loc)
     if grid:
         got = torch.cat([f.owned() for f in fields]).cpu().numpy()
         assert got.shape == grid
