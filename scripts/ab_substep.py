@@ -4,12 +4,15 @@
 import importlib.util, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-VARIANTS = {
+VARIANTS = {                      # -D switches of csrc/jkr.cu (see the comment at ABM_JKR_EXP there)
     "base": [],
-    "exp1": ["ABM_JKR_EXP=1"], "exp8": ["ABM_JKR_EXP=8"], "exp16": ["ABM_JKR_EXP=16"], "exp24": ["ABM_JKR_EXP=24"],
-    "exp9": ["ABM_JKR_EXP=9"],
-
-
+    "regs64": ["ABM_JKR_MINBLOCKS=8"], "regs80": ["ABM_JKR_MINBLOCKS=6"], "regs96": ["ABM_JKR_MINBLOCKS=5"],
+    "cta64": ["ABM_JKR_THREADS=64", "ABM_JKR_MINBLOCKS=14"], "cta256": ["ABM_JKR_THREADS=256", "ABM_JKR_MINBLOCKS=3"],
+    "hits12": ["ABM_JKR_MAXHITS=12"],
+    "early_motility": ["ABM_JKR_EXP=1"], "early_old_row": ["ABM_JKR_EXP=2"],
+    "no_contact_loop": ["ABM_JKR_EXP=4", "ABM_ALLOW_WRONG_RESULTS"],            # timing ablations
+    "no_walk_no_contact": ["ABM_JKR_EXP=12", "ABM_ALLOW_WRONG_RESULTS"],
+    "no_pdl": ["ABM_PDL=0"],
 }
 if sys.argv[1] == "build":
     spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "python-hipsc-abm_b200", "build.py"))
