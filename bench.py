@@ -240,6 +240,11 @@ def run_b200(args, rank, world, local_rank):
     pipe.capture()
     sampler = ClockSampler(local_rank)
     sampler.start()                       # sampled from the warm-up replays to the end of the timed steps
+    t_wait = time.time()                  # nvidia-smi takes a while to print its first row: keep the GPU under load
+    while not sampler.rows and sampler.proc is not None and time.time() - t_wait < 3.0:
+        pipe.replay()
+        pipe.replay()
+        torch.cuda.synchronize(dev)
     for _ in range(max(args.warmup, 3) + 40):           # 40 extra replays: a few 20 ms clock samples under load
         pipe.replay()
     pipe.check()

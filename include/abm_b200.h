@@ -33,6 +33,9 @@ extern "C" {
 /* flags of abm_bin_dims_host / abm_bin_sort */
 #define ABM_SORT_STABLE 1     /* ascending cell id inside a bin (the reference's fill order) */
 #define ABM_SORT_REFERENCE 2  /* keep the reference's 3 z-layers in a flat (size_z == 0) world */
+#define ABM_LOOP_CARRY_OUT 1   /* abm_mechanics_loop: the last substep also hands its cells to the NEXT call's first sort */
+#define ABM_LOOP_CARRY_IN 2    /* abm_mechanics_loop: the previous call did so (same n, lattice, workspace; its idle
+                                  offset table is passed as bin_start_a): the first sort needs no histogram pass */
 #define ABM_SORT_PREBINNED 4  /* histogram + per-cell bin already written by abm_jkr_substep */
 
 /* ---- library ----------------------------------------------------------------------------------- */
@@ -186,7 +189,7 @@ int abm_mechanics_loop(const double *radii, double *locations, const double *mot
                        const int32_t *old_row_start, int64_t old_row_stride, const int32_t *old_row_len,
                        const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
                        int64_t row_stride, int32_t *max_len, const int32_t *global_id, double uniform_radius,
-                       double poisson, double youngs, double adhesion_const, double stokes, void *stream);
+                       double poisson, double youngs, double adhesion_const, double stokes, int flags, void *stream);
 
 /* ---- morphogen diffusion ---------------------------------------------------------------------------
  * Replaces CellMethods.update_diffusion + update_diffusion_jit (cell_methods.py:441-468,

@@ -41,7 +41,7 @@ SIGNATURES = {
                               F64, F64, F64, F64, D3, F64, P, F64, D3, D3, P, P, P]),
     "abm_mechanics_loop": (I32, [P, P, P, I64, D3, D3, D3, F64, F64, I32, C.POINTER(C.c_double),
                                  P, P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, P,
-                                 F64, F64, F64, F64, F64, P]),
+                                 F64, F64, F64, F64, F64, I32, P]),
     "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),
     "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P]),
     "abm_slab_workspace_bytes": (SZ, [I64]),
@@ -89,6 +89,7 @@ def check(rc: int, what: str) -> int:
 
 SORT_STABLE, SORT_REFERENCE, SORT_PREBINNED = 1, 2, 4
 OPTION_CHAINED_LAUNCH = 1
+LOOP_CARRY_OUT, LOOP_CARRY_IN = 1, 2
 
 
 def d3(values):

@@ -583,8 +583,10 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                                   const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a,
                                   int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
                                   int32_t *max_len, const int32_t *global_id, double uniform_radius, double poisson,
-                                  double youngs, double adhesion_const, double stokes, void *stream) {
+                                  double youngs, double adhesion_const, double stokes, int flags, void *stream) {
     ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
+    const bool carry_in = (flags & ABM_LOOP_CARRY_IN) && n > 0 && n_substeps > 0;
+    const bool carry_out = (flags & ABM_LOOP_CARRY_OUT) && n > 0;
     ABM_REQUIRE(extent_host && size_host && bin_start_a && bin_start_b && bin_start_a != bin_start_b,
                 "need two distinct offset tables");
     BinGeom g;
@@ -595,9 +597,11 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
     int64_t cur_stride = old_row_stride;
     for (int k = 0; k < n_substeps; ++k) {
         int32_t *table = (k & 1) ? bin_start_b : bin_start_a, *other = (k & 1) ? bin_start_a : bin_start_b;
-        const bool prebin = k + 1 < n_substeps && n > 0;
+        const bool last = k + 1 == n_substeps;
+        const bool prebin = n > 0 && (!last || carry_out);        // hand the moved cells to the next sort
         // (the largest bin population is reported for the first sort of the loop only)
-        int rc = bin_sort_impl(locations, radii, n, extent_host, origin_host, reach, k ? ABM_SORT_PREBINNED : 0, table,
+        int rc = bin_sort_impl(locations, radii, n, extent_host, origin_host, reach,
+                               (k || carry_in) ? ABM_SORT_PREBINNED : 0, table,
                                sorted_id, sorted_pos, sorted_bin, k ? nullptr : max_count, sort_workspace,
                                sort_workspace_bytes,
                                prebin ? other : nullptr, global_id, stream);   // the idle table is cleared on the way
@@ -606,7 +610,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
         const int32_t *slot_gid = (global_id && n > 0) ? sort_ws_carve(sort_workspace, n, nbins).slot_gid : nullptr;
         rc = jkr_substep_impl(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
                               cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, k == n_substeps - 1,
-                              motility_forces, prebin ? nullptr : locations, poisson, youngs, adhesion_const, stokes,
+                              motility_forces, last ? locations : nullptr, poisson, youngs, adhesion_const, stokes,
                               size_host, dts_host[k], global_id, slot_gid, uniform_radius,
                               prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
                               prebin ? sort_workspace : nullptr, stream);

@@ -147,6 +147,7 @@ class ColonyEngine:
         self._uniform_radius = 0.0  # common radius when all radii are equal (contact constants evaluated once)
         self.global_id = None   # int32 (n,) when bond rows are kept by global id (slab decomposition)
         self._sort_wss = {}     # sort scratch per bin count (sorts of different lattices may run on different streams)
+        self._carry = None      # (nbins, n, pointers..., table index) when the last mechanics loop handed its cells over
         self._sort_bufs = {}
         self._edge_ws = None
         self._bond_bufs = None
@@ -239,6 +240,7 @@ class ColonyEngine:
         if rad.shape != (n,) or not rad.flags.c_contiguous:      # a scalar or a strided view: materialise it
             rad = np.ascontiguousarray(np.broadcast_to(rad, (n,)))
         self.n = n
+        self._carry = None
         self.loc = self.to_device(loc, "loc")
         self.radii = self.to_device(rad, "radii")
         self._max_radius = self._uniform_radius = None if n else 0.0    # only the mechanics need them: lazily
@@ -250,6 +252,7 @@ class ColonyEngine:
     def set_device_state(self, loc, radii, mot=None, jkr=None, max_radius=None, uniform_radius=0.0):
         """Adopt tensors that already live on the device (no copies)."""
         self.use_current_stream()
+        self._carry = None
         self.n = int(loc.shape[0])
         self.loc, self.radii = loc, radii
         self.mot = mot if mot is not None else self._zeros((self.n, 3), torch.float64)
@@ -327,6 +330,8 @@ class ColonyEngine:
         flags: _lib.SORT_STABLE | _lib.SORT_REFERENCE for the reference-shaped assign_bins() output."""
         n = self.n
         dims, nbins, b = self._sort_buffers(distance, flags)
+        if self._carry is not None and self._carry[0] == nbins:
+            self._carry = None                               # this sort reuses the workspace the hand-over lives in
         _lib.check(self.lib.abm_bin_sort(_ptr(self.loc if loc is None else loc), _ptr(self.radii), n,
                                          self._extent_c, self._origin_c,
                                          float(distance), int(flags), _ptr(b["bin_start"]), _ptr(b["sorted_id"]),
@@ -422,6 +427,7 @@ class ColonyEngine:
         self.launches += 1 if g.n else 0
 
     def integrate(self, move_dt, zero_jkr=True, stokes=STOKES):
+        self._carry = None
         _lib.check(self.lib.abm_apply_forces(_ptr(self.jkr), _ptr(self.mot), _ptr(self.loc), _ptr(self.radii),
                                              self.n, float(stokes), self._size_c, float(move_dt),
                                              _ptr(self.jkr) if zero_jkr else 0, self.stream), "abm_apply_forces")
@@ -450,9 +456,13 @@ class ColonyEngine:
         return b
 
     def enqueue_mechanics(self, old: Optional[GraphTensors], distance, dts, stride, stokes=STOKES, pair=None,
-                          zero_flag=True):
+                          zero_flag=True, carry=False):
         """Enqueue len(dts) fused substeps (sort + abm_jkr_substep each).  No host sync.  Returns the
-        fixed-stride graph holding the final bonds; overflow is reported through bufs['max_len']."""
+        fixed-stride graph holding the final bonds; overflow is reported through bufs['max_len'].
+        carry: the caller runs such loops back to back on device-resident cells (pipeline.HotPathStep): the last
+        substep then hands its cells to the next call's first sort, which skips its histogram pass.  The hand-over
+        is dropped whenever the cells or the sort workspace are touched in between (upload, set_device_state,
+        integrate, a stand-alone sort on the same lattice, a loop without `carry`)."""
         n = self.n
         b = self._bond_buffers(n, stride)
         if zero_flag:
@@ -466,18 +476,31 @@ class ColonyEngine:
             pair = [i for i in range(3) if i not in held][:2]
         dims, nbins, sb = self._sort_buffers(reach)
         dts_c = (C.c_double * len(dts))(*[float(d) for d in dts])
+        tables = [sb["bin_start"], sb["bin_start_b"]]
+        flags, first = 0, 0
+        # everything the hand-over depends on: lattice, cells, radii (they travel with the positions), the buffers
+        key = (nbins, n, self.loc.data_ptr(), self.radii.data_ptr(), reach, sb["ws"].data_ptr(),
+               sb["bin_start"].data_ptr(), sb["bin_start_b"].data_ptr())
+        if carry and n:
+            flags |= _lib.LOOP_CARRY_OUT
+            if self._carry is not None and self._carry[:-1] == key:
+                flags |= _lib.LOOP_CARRY_IN
+                first = self._carry[-1]                      # the table the previous call left the histogram in
         _lib.check(self.lib.abm_mechanics_loop(
             _ptr(self.radii), _ptr(self.loc), _ptr(self.mot), n, self._extent_c, self._origin_c, self._size_c,
             float(distance), reach, len(dts), dts_c,
-            _ptr(sb["bin_start"]), _ptr(sb["bin_start_b"]), _ptr(sb["sorted_id"]), _ptr(sb["sorted_pos"]),
+            _ptr(tables[first]), _ptr(tables[1 - first]), _ptr(sb["sorted_id"]), _ptr(sb["sorted_pos"]),
             _ptr(sb["sorted_bin"]), _ptr(sb["max_count"]), _ptr(sb["ws"]), sb["ws"].numel(),
             _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
             _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),
             stride, _ptr(b["max_len"]), _ptr(self.global_id), float(self.uniform_radius), JKR_POISSON, JKR_YOUNGS,
-            JKR_ADHESION, float(stokes), self.stream), "abm_mechanics_loop")
-        # first substep: histogram, scan x2, scatter, substep; every later one: scan, rescatter, substep
-        self.launches += (3 * len(dts) + 2) if n else 0
+            JKR_ADHESION, float(stokes), flags, self.stream), "abm_mechanics_loop")
+        # the last substep k = K-1 sorted with table (first + K-1) % 2 and left the next histogram in the other one
+        self._carry = key + ((first + len(dts)) % 2,) if flags & _lib.LOOP_CARRY_OUT else None
+        # first substep: histogram, scan x2, scatter, substep (scan, rescatter, substep when the cells were handed
+        # over by the previous call); every later one: scan, rescatter, substep
+        self.launches += (3 * len(dts) + (0 if flags & _lib.LOOP_CARRY_IN else 2)) if n else 0
         last = pair[(len(dts) - 1) & 1]
         return GraphTensors(n, None, stride, b["len"][last], b["cols"][last], True)
 

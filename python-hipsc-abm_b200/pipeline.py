@@ -114,7 +114,7 @@ class HotPathStep:
         src = self.parity
         pair = [1 - src, 2]
         self.bonds = eng.enqueue_mechanics(self.bonds, cfg.contact_radius, self.dts, cfg.bond_stride, STOKES,
-                                           pair=pair, zero_flag=False)
+                                           pair=pair, zero_flag=False, carry=True)
         self.parity = 1 - src if len(self.dts) % 2 else src
         if len(self.dts) % 2 == 0:
             raise ValueError("even substep counts are not wired in HotPathStep")
@@ -158,11 +158,18 @@ class HotPathStep:
         launches = self.eng.launches
         # the mechanics stream outranks the second stream: search + morphogen kernels fill what the mechanics leave idle
         stream = torch.cuda.Stream(device=self.eng.device, priority=-1)
+        # a captured step may start from the cells its predecessor handed over (engine.enqueue_mechanics `carry`):
+        # remember which hand-over each graph expects and leaves, so that replay() can refuse a broken chain
+        self._carry_before, self._carry_after, self._launches = [], [], []
         for _ in range(2):
             g = torch.cuda.CUDAGraph()
+            self._carry_before.append(self.eng._carry)
             with torch.cuda.graph(g, stream=stream):
                 self.enqueue()
             self.graphs.append(g)
+            self._carry_after.append(self.eng._carry)
+            self._launches.append(self.launches_per_step)
+        self.eng._carry = self._carry_before[0]
         self.eng.lib.abm_set_option(_lib.OPTION_CHAINED_LAUNCH, chained)
         # capturing enqueues nothing on the device: undo the launch accounting, and the state did not advance
         self.eng.use_current_stream()         # leave the capture stream
@@ -173,8 +180,13 @@ class HotPathStep:
         self._replays = 0
 
     def replay(self):
-        self.graphs[self._replays & 1].replay()
+        k = self._replays & 1
+        if self._carry_before[k] is not None and self.eng._carry != self._carry_before[k]:
+            raise _lib.AbmError("the cells or the sort workspace changed since the previous step: capture() again")
+        self.graphs[k].replay()
+        self.eng._carry = self._carry_after[k]
         self._replays += 1
+        self.launches_per_step = self._launches[k]
         self.eng.launches += self.launches_per_step
 
     # ---- capacity check ------------------------------------------------------------------------------------------

@@ -72,3 +72,48 @@ def test_hot_path_step_matches_oracle(first, graph):
     assert np.array_equal(eng.edge_list(pipe.neighbor_graph), ref_edges15)
     assert np.abs(pipe.field.cpu().numpy() - ref_field).max() <= 1e-12        # deposits: fp64 atomics, other order
     assert np.abs(pipe.sampled.cpu().numpy() - ref_sampled).max() <= 1e-12
+
+
+def _colony(n=4000, seed=5):
+    rng = np.random.default_rng(seed)
+    size = np.array([600.0, 600.0, 0.0])
+    loc = rng.random((n, 3)) * size
+    mot = rng.normal(0, 1.5e-9, (n, 3)) * [1, 1, 0]
+    return size, loc, np.full(n, 5.0), mot
+
+
+def test_handed_over_cells_equal_a_fresh_sort():
+    """Back-to-back device-resident steps hand the moved cells to the next step's first sort (ABM_LOOP_CARRY_*): the
+    positions and bonds are bit-identical to steps that re-bin `locations` from scratch."""
+    size, loc, radii, mot = _colony()
+    results = []
+    for carry in (True, False):
+        eng = ColonyEngine(size)
+        eng.upload(loc, radii, mot)
+        pipe = HotPathStep(eng, StepConfig(bond_stride=32, search_cols_per_cell=40.0))
+        for k in range(5):
+            if not carry:
+                eng._carry = None                       # forget the hand-over: the next loop starts with a histogram
+            pipe.step()
+            assert (eng._carry is not None)
+        torch.cuda.synchronize()
+        pipe.check()
+        results.append((eng.locations_host(), eng.edge_list(pipe.current_bonds()), eng.launches))
+    assert results[0][2] == results[1][2] - 2 * 4          # steps 2..5 skip the histogram and one scan pass
+    assert np.array_equal(results[0][0], results[1][0])
+    assert np.array_equal(results[0][1], results[1][1])
+
+
+def test_replay_refuses_a_broken_hand_over():
+    size, loc, radii, mot = _colony(n=1500)
+    eng = ColonyEngine(size)
+    eng.upload(loc, radii, mot)
+    pipe = HotPathStep(eng, StepConfig(bond_stride=32, search_cols_per_cell=40.0))
+    pipe.step()
+    pipe.step()
+    pipe.capture()
+    pipe.replay()
+    eng.integrate(0.0)                                 # anything that may move the cells drops the hand-over
+    from hipsc_abm_b200._lib import AbmError
+    with pytest.raises(AbmError):
+        pipe.replay()
