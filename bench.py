@@ -239,7 +239,8 @@ def run_b200(args, rank, world, local_rank):
         pipe.step()
     pipe.capture()
     sampler = ClockSampler(local_rank)
-    sampler.start()                       # sampled from the warm-up replays to the end of the timed steps
+    if not args.no_clocks:
+        sampler.start()                   # sampled from the warm-up replays to the end of the timed steps
     t_wait = time.time()                  # nvidia-smi takes a while to print its first row: keep the GPU under load
     while not sampler.rows and sampler.proc is not None and time.time() - t_wait < 3.0:
         pipe.replay()
@@ -614,6 +615,8 @@ def main():
                     help="c3 = BASELINE configs[2], the 500k-cell headline colony quoted at 1 and 8 B200 (default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-clocks", action="store_true",
+                    help="no nvidia-smi sampling (profiler runs: keeps the launch sequence deterministic)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="run deposit/diffusion/sample after the mechanics on one stream instead of beside them")
     ap.add_argument("--bond-stride", type=int, default=0, help="fixed width of the JKR bond rows (0 = 16 / 32)")
