@@ -59,10 +59,10 @@ class B200CellMethods:
                 self.jkr_forces[:, :] = 0
                 uploaded.synchronize()
                 self.motility_forces[:, :] = 0
-            bonds, graph.row_stride_hint = eng.mechanics(old, distance, dts, graph.row_stride_hint, STOKES,
-                                                         meanwhile=reset_forces)
+            bonds, graph.row_stride_hint, moved = eng.mechanics(old, distance, dts, graph.row_stride_hint, STOKES,
+                                                                meanwhile=reset_forces, fetch_locations=True)
             graph.set_device(bonds, eng)
-            self.locations = eng.locations_host()
+            self.locations = moved
             return
         else:
             for step in range(total_steps):
