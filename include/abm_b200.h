@@ -50,6 +50,10 @@ const char *abm_last_error(void);   /* thread-local text of the last non-zero re
  *   about -4 % per step for eager stream launches, but +3..15 % inside a captured CUDA graph -- switch it on for
  *   eager pipelines only.                                                                              */
 #define ABM_OPTION_CHAINED_LAUNCH 1
+/* ABM_OPTION_DIFFUSION_FUSE (default 5, range 1..5): diffusion substeps advanced per kernel launch by
+ *   abm_diffusion (temporal blocking in shared memory; results are bit-identical for every value).  1 = one
+ *   launch per substep.                                                                                */
+#define ABM_OPTION_DIFFUSION_FUSE 2
 int abm_set_option(int option, int value);
 /* fills sm_count / cc_major / cc_minor of the current device; <0 if there is no CUDA device */
 int abm_device_info(int *sm_count, int *cc_major, int *cc_minor);
@@ -199,10 +203,14 @@ int abm_mechanics_loop(const double *radii, double *locations, const double *mot
  * bit-identical.  scratch: gx*gy doubles.  use_tma: 1 = TMA-staged tiles (needs gy even and
  * 16-byte aligned pointers, returns -1 otherwise), 0 = plain staged loads.  Substeps ping-pong between
  * field and scratch: if result_in_scratch_host is NULL the result is copied back into `field` when
- * `steps` is odd; otherwise no copy is made and *result_in_scratch_host says where the result is.   */
+ * `steps` is odd; otherwise no copy is made and *result_in_scratch_host says where the result is.
+ * Up to ABM_OPTION_DIFFUSION_FUSE substeps run per launch (k_diffuse_fused); chains of one use k_diffuse.   */
 int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t gy, int64_t steps, double diffuse_dt,
                   double last_dt, double diffuse_const, double spat_res2, double max_concentration,
                   double degradation, int use_tma, int *result_in_scratch_host, void *stream);
+/* number of kernel launches abm_diffusion enqueues for `steps` substeps under the current ABM_OPTION_DIFFUSION_FUSE
+ * (it has the parity of `steps`, so the result lands where the substep-by-substep ping-pong would leave it) */
+int64_t abm_diffusion_launches(int64_t steps);
 
 /* Replaces per-cell get_concentration (cell_methods.py:470-483) for all cells: nearest grid point
  * idx = ceil(floor(2x/h)/2) on the (gx,gy,gz) grid.  `field` holds the global rows [row_lo,row_hi) of that grid,

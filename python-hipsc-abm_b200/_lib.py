@@ -43,6 +43,7 @@ SIGNATURES = {
                                  P, P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, P,
                                  F64, F64, F64, F64, F64, I32, P]),
     "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),
+    "abm_diffusion_launches": (I64, [I64]),
     "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P]),
     "abm_slab_workspace_bytes": (SZ, [I64]),
     "abm_slab_pack": (I32, [P, P, P, P, P, P, I64, P, I64, F64, F64, I32, I32, P, I64, P, I64, P, P, SZ, P]),
@@ -75,6 +76,9 @@ def load():
         fn.argtypes = args
     if lib.abm_abi_version() != 1:
         raise AbmError("libabm_b200.so ABI version mismatch")
+    fuse = os.environ.get("ABM_B200_DIFFUSION_FUSE")        # A/B switch: diffusion substeps per launch (1..5)
+    if fuse:
+        lib.abm_set_option(2, int(fuse))
     _lib = lib
     return lib
 
@@ -89,6 +93,7 @@ def check(rc: int, what: str) -> int:
 
 SORT_STABLE, SORT_REFERENCE, SORT_PREBINNED = 1, 2, 4
 OPTION_CHAINED_LAUNCH = 1
+OPTION_DIFFUSION_FUSE = 2
 LOOP_CARRY_OUT, LOOP_CARRY_IN = 1, 2
 
 

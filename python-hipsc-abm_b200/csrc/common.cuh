@@ -128,6 +128,7 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+extern int g_diffusion_fuse;     // abm_set_option(ABM_OPTION_DIFFUSION_FUSE): diffusion.cu
 extern int g_chained_launch;    // abm_set_option(ABM_OPTION_CHAINED_LAUNCH): lib.cu
 
 template <typename... KArgs, typename... Args>

@@ -2,6 +2,12 @@
 // per-cell sample / deposit coupling.  Replaces CellMethods.update_diffusion + update_diffusion_jit,
 // get_concentration and adjust_morphogens (reference cell_methods.py:441-521, cell_backend.py:175-204).
 //
+// Two kernels.  k_diffuse_fused<N> advances N = 2..5 substeps per launch (temporal blocking): a CTA stages the
+// (kTileI+2N) x (kTileJ+2N) neighbourhood of its output tile in shared memory (one TMA box, or plain loads), runs
+// the substeps there on a region that shrinks by one ring per substep, and writes the tile once -- 2wG bytes of
+// field traffic and one launch per N substeps, for ~1.4x the arithmetic.  Every point still sees exactly the
+// reference's operations in the reference's order, so the result is bit-identical to substep-by-substep launches.
+// k_diffuse does a single substep (chains of length 1, and ABM_OPTION_DIFFUSION_FUSE = 1):
 // One launch = one substep.  Persistent CTAs walk (kTileI x kTileJ) output tiles; the (kTileI+2) x
 // (kTileJ+4) input box of each tile is staged in shared memory through a kStages-deep ring, filled either
 // by TMA (cp.async.bulk.tensor.2d + mbarrier complete_tx, one elected thread) or by plain cooperative loads.
@@ -147,6 +153,102 @@ k_diffuse(const __grid_constant__ CUtensorMap src_map, const double *__restrict_
     }
 }
 
+// ---- temporal blocking: N substeps per launch -------------------------------------------------------------------
+constexpr int kMaxFuse = 5;
+
+struct FuseParams {
+    long long gx, gy;
+    int tiles_j;
+    double a[kMaxFuse], b[kMaxFuse];   // per substep of this launch (the chain's last substep has its own dt)
+    double cmax, keep;
+    int clamp_in, degrade_out;         // this launch starts / ends the chain
+};
+
+template <int N>
+struct FuseGeom {
+    static constexpr int kHaloI = N;
+    static constexpr int kHaloJ = (N + 1) & ~1;          // even: the TMA box must start on a 16-byte boundary
+    static constexpr int kColSkip = kHaloJ - N;           // staged but unused columns on each side (0 or 1)
+    static constexpr int kBoxI = kTileI + 2 * kHaloI;
+    static constexpr int kBoxJ = kTileJ + 2 * kHaloJ;
+    static constexpr int kBufBytes = ((kBoxI * kBoxJ * 8 + 127) / 128) * 128;
+    static constexpr size_t kSmem = 2 * (size_t)kBufBytes + 128 /*alignment slack*/ + 8;
+};
+
+template <int N, bool kTma>
+__global__ void __launch_bounds__(kDiffThreads)
+k_diffuse_fused(const __grid_constant__ CUtensorMap src_map, const double *__restrict__ src, double *__restrict__ dst,
+                FuseParams P) {
+    using G = FuseGeom<N>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *base = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~uintptr_t(127));
+    double *cur = (double *)base, *nxt = (double *)(base + G::kBufBytes);
+    uint64_t *bar = (uint64_t *)(base + 2 * (size_t)G::kBufBytes);
+    const int tid = threadIdx.x;
+    const int ti = blockIdx.x / P.tiles_j, tj = blockIdx.x % P.tiles_j;
+    // global coordinates of the box element (0,0)
+    const long long i0 = (long long)ti * kTileI - G::kHaloI, j0 = (long long)tj * kTileJ - G::kHaloJ;
+
+    if (kTma) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar, G::kBoxI * G::kBoxJ * 8);
+            tma_load_2d(cur, &src_map, bar, (int)j0, (int)i0);       // outside the field: zero fill (never read)
+        }
+        mbar_wait(bar, 0);
+    } else {
+        for (int e = tid; e < G::kBoxI * G::kBoxJ; e += kDiffThreads) {
+            const int li = e / G::kBoxJ, lj = e % G::kBoxJ;
+            const long long gi = i0 + li, gj = j0 + lj;
+            double v = 0.0;
+            if (gi >= 0 && gi < P.gx && gj >= 0 && gj < P.gy) v = src[gi * P.gy + gj];
+            cur[e] = v;
+        }
+        __syncthreads();
+    }
+    if (P.clamp_in) {                                      // reference cell_methods.py:454-455, once per chain
+        for (int e = tid; e < G::kBoxI * G::kBoxJ; e += kDiffThreads) cur[e] = fmin(fmax(cur[e], 0.0), P.cmax);
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int s = 1; s <= N; ++s) {
+        // substep s is evaluated on the tile grown by N-s rings; its inputs (substep s-1 on N-s+1 rings) are in `cur`
+        const int rows = G::kBoxI - 2 * s, cols = kTileJ + 2 * (N - s);
+        const int l0 = s, c0 = G::kColSkip + s;
+        const double a = P.a[s - 1], b = P.b[s - 1];
+        for (int e = tid; e < rows * cols; e += kDiffThreads) {
+            const int r = e / cols;
+            const int li = l0 + r, lj = c0 + (e - r * cols);
+            const long long gi = i0 + li, gj = j0 + lj;
+            if (gi < 0 || gi >= P.gx || gj < 0 || gj >= P.gy) continue;
+            const int iu = (gi == 0) ? 0 : -1, id = (gi == P.gx - 1) ? 0 : 1;     // reflecting wall: the point itself
+            const int jl = (gj == 0) ? 0 : -1, jr = (gj == P.gy - 1) ? 0 : 1;
+            const double *c = cur + li * G::kBoxJ + lj;
+            const double vc = c[0], vd = c[id * G::kBoxJ], vu = c[iu * G::kBoxJ], vr = c[jr], vl = c[jl];
+            // reference order: temp = a*(((down+up)+right)+left); new = center*b + temp   (no FMA)
+            const double t = __dmul_rn(a, __dadd_rn(__dadd_rn(__dadd_rn(vd, vu), vr), vl));
+            double v = __dadd_rn(__dmul_rn(vc, b), t);
+            if (s == N) {
+                if (P.degrade_out) v = __dmul_rn(v, P.keep);
+                dst[gi * P.gy + gj] = v;
+            } else {
+                nxt[li * G::kBoxJ + lj] = v;
+            }
+        }
+        if (s < N) {
+            __syncthreads();
+            double *tmp = cur;
+            cur = nxt;
+            nxt = tmp;
+        }
+    }
+}
+
 // `field` holds global rows [row_lo,row_hi) of a (g0,g1,g2) grid (a slab of it, or all of it); indices are computed
 // on the global grid exactly as the reference does and then shifted.
 __global__ void k_sample(const double *__restrict__ loc, int n, const double *__restrict__ field, long long g0,
@@ -207,7 +309,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_field_map(CUtensorMap *map, const double *ptr, long long gx, long long gy) {
+static int make_field_map(CUtensorMap *map, const double *ptr, long long gx, long long gy, int box_j = kBoxJ,
+                          int box_i = kBoxI) {
     static EncodeTiledFn encode = nullptr;
     if (!encode) {
         void *fn = nullptr;
@@ -223,7 +326,7 @@ static int make_field_map(CUtensorMap *map, const double *ptr, long long gx, lon
     }
     cuuint64_t gdim[2] = {(cuuint64_t)gy, (cuuint64_t)gx};
     cuuint64_t gstride[1] = {(cuuint64_t)gy * 8};
-    cuuint32_t box[2] = {(cuuint32_t)kBoxJ, (cuuint32_t)kBoxI};
+    cuuint32_t box[2] = {(cuuint32_t)box_j, (cuuint32_t)box_i};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void *)ptr, gdim, gstride, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -232,6 +335,35 @@ static int make_field_map(CUtensorMap *map, const double *ptr, long long gx, lon
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (gx=%lld gy=%lld)", (int)r, gx, gy);
         return -1;
     }
+    return 0;
+}
+
+int g_diffusion_fuse = kMaxFuse;     // abm_set_option(ABM_OPTION_DIFFUSION_FUSE): substeps per launch, 1..kMaxFuse
+
+template <int N>
+static int launch_fused(const double *from, double *to, long long gx, long long gy, int use_tma, const FuseParams &P,
+                        int ntiles, cudaStream_t st) {
+    using G = FuseGeom<N>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[use_tma ? 1 : 0]) {
+        cudaError_t e = use_tma ? cudaFuncSetAttribute(k_diffuse_fused<N, true>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem)
+                                : cudaFuncSetAttribute(k_diffuse_fused<N, false>,
+                                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem);
+        int rc = check_cuda(e, "cudaFuncSetAttribute(k_diffuse_fused)");
+        if (rc) return rc;
+        attr_set[use_tma ? 1 : 0] = true;
+    }
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (use_tma) {
+        int rc = make_field_map(&map, from, gx, gy, G::kBoxJ, G::kBoxI);
+        if (rc) return rc;
+        k_diffuse_fused<N, true><<<ntiles, kDiffThreads, G::kSmem, st>>>(map, from, to, P);
+    } else {
+        k_diffuse_fused<N, false><<<ntiles, kDiffThreads, G::kSmem, st>>>(map, from, to, P);
+    }
+    ABM_CHECK_LAUNCH("k_diffuse_fused");
     return 0;
 }
 
@@ -282,18 +414,49 @@ ABM_EXPORT int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t
     int ntiles = P.tiles_i * P.tiles_j;
     int grid = ntiles < 2 * sm_count ? ntiles : 2 * sm_count;   // two resident CTAs per SM (106 KB each)
     double *bufs[2] = {field, scratch};
-    for (int64_t k = 0; k < steps; ++k) {
-        double dt = (k == steps - 1) ? last_dt : diffuse_dt;
-        P.a = dt * diffuse_const / spat_res2;
-        P.b = 1 - 4 * P.a;
-        P.clamp_in = (k == 0);
-        P.degrade_out = (k == steps - 1);
-        int from = (int)(k & 1), to = from ^ 1;
-        if (use_tma)
-            k_diffuse<true><<<grid, kDiffThreads, kDiffSmem, st>>>(maps[from], bufs[from], bufs[to], P);
-        else
-            k_diffuse<false><<<grid, kDiffThreads, kDiffSmem, st>>>(maps[from], bufs[from], bufs[to], P);
-        ABM_CHECK_LAUNCH("k_diffuse");
+    // Chains of up to g_diffusion_fuse substeps per launch.  The number of launches keeps the parity of `steps`, so
+    // the result lands in the buffer the substep-by-substep chain would leave it in.
+    const int64_t launches = abm_diffusion_launches(steps);
+    const int64_t per = steps / launches, longer = steps % launches;    // the first `longer` launches take per+1
+    int64_t k = 0;
+    for (int64_t l = 0; l < launches; ++l) {
+        const int len = (int)(per + (l < longer ? 1 : 0));
+        const int from = (int)(l & 1), to = from ^ 1;
+        if (len == 1) {
+            double dt = (k == steps - 1) ? last_dt : diffuse_dt;
+            P.a = dt * diffuse_const / spat_res2;
+            P.b = 1 - 4 * P.a;
+            P.clamp_in = (k == 0);
+            P.degrade_out = (k == steps - 1);
+            if (use_tma)
+                k_diffuse<true><<<grid, kDiffThreads, kDiffSmem, st>>>(maps[from], bufs[from], bufs[to], P);
+            else
+                k_diffuse<false><<<grid, kDiffThreads, kDiffSmem, st>>>(maps[from], bufs[from], bufs[to], P);
+            ABM_CHECK_LAUNCH("k_diffuse");
+        } else {
+            FuseParams F;
+            F.gx = gx;
+            F.gy = gy;
+            F.tiles_j = P.tiles_j;
+            F.cmax = P.cmax;
+            F.keep = P.keep;
+            for (int s = 0; s < kMaxFuse; ++s) {
+                double dt = (k + s == steps - 1) ? last_dt : diffuse_dt;
+                F.a[s] = dt * diffuse_const / spat_res2;
+                F.b[s] = 1 - 4 * F.a[s];
+            }
+            F.clamp_in = (k == 0);
+            F.degrade_out = (k + len == steps);
+            int rc = 0;
+            switch (len) {
+                case 2: rc = launch_fused<2>(bufs[from], bufs[to], gx, gy, use_tma, F, ntiles, st); break;
+                case 3: rc = launch_fused<3>(bufs[from], bufs[to], gx, gy, use_tma, F, ntiles, st); break;
+                case 4: rc = launch_fused<4>(bufs[from], bufs[to], gx, gy, use_tma, F, ntiles, st); break;
+                default: rc = launch_fused<5>(bufs[from], bufs[to], gx, gy, use_tma, F, ntiles, st); break;
+            }
+            if (rc) return rc;
+        }
+        k += len;
     }
     int in_scratch = (int)(steps & 1);
     if (result_in_scratch_host) {
@@ -304,6 +467,14 @@ ABM_EXPORT int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t
         if (rc) return rc;
     }
     return 0;
+}
+
+ABM_EXPORT int64_t abm_diffusion_launches(int64_t steps) {
+    if (steps < 1) return 0;
+    const int64_t fuse = g_diffusion_fuse;
+    int64_t launches = (steps + fuse - 1) / fuse;
+    if ((launches ^ steps) & 1) ++launches;
+    return launches;
 }
 
 ABM_EXPORT int abm_sample_concentrations(const double *locations, int64_t n, const double *field,

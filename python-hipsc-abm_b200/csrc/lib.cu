@@ -54,6 +54,11 @@ ABM_EXPORT int abm_set_option(int option, int value) {
         abm::g_chained_launch = value ? 1 : 0;
         return old;
     }
+    if (option == ABM_OPTION_DIFFUSION_FUSE) {
+        int old = abm::g_diffusion_fuse;
+        abm::g_diffusion_fuse = value < 1 ? 1 : (value > 5 ? 5 : value);
+        return old;
+    }
     abm::set_error("abm_set_option: unknown option %d", option);
     return -1;
 }

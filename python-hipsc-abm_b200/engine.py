@@ -554,7 +554,7 @@ class ColonyEngine:
                                           float(last_dt), float(diffuse_const), float(spat_res2),
                                           float(max_concentration), float(degradation), 1 if use_tma else 0,
                                           C.byref(where), self.stream), "abm_diffusion")
-        self.launches += int(steps)
+        self.launches += int(self.lib.abm_diffusion_launches(int(steps)))
         return scratch if where.value else field
 
     def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None, n=None) -> torch.Tensor:

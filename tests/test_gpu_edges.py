@@ -101,7 +101,7 @@ def test_mixed_radii_in_fused_loop():
 
 
 @pytest.mark.parametrize("shape", [(1, 1), (1, 7), (5, 1), (2, 2), (33, 129), (32, 128), (31, 260)])
-@pytest.mark.parametrize("steps", [1, 4])
+@pytest.mark.parametrize("steps", [1, 2, 4, 5, 7, 8, 9])
 def test_diffusion_small_and_ragged_grids(shape, steps):
     rng = np.random.default_rng(shape[0] * 100 + shape[1])
     field = rng.random(shape) * 3 - 0.5
@@ -112,6 +112,39 @@ def test_diffusion_small_and_ragged_grids(shape, steps):
     for tma in ([False, True] if shape[1] % 2 == 0 else [False]):
         out = eng.diffuse(torch.from_numpy(field.copy()).cuda(), steps, dt, dt * 0.4, D, h * h, 2.0, 0.1, use_tma=tma)
         assert np.array_equal(out.cpu().numpy(), ref), f"tma={tma}"
+
+
+@pytest.mark.parametrize("steps", [2, 3, 6, 10, 11])
+def test_fused_diffusion_substeps_equal_one_launch_per_substep(steps):
+    """abm_diffusion advances up to five substeps per launch in shared memory (k_diffuse_fused): the field is
+    bit-identical to the substep-by-substep chain (ABM_OPTION_DIFFUSION_FUSE = 1), lands in the same buffer, and
+    takes the announced number of launches."""
+    from hipsc_abm_b200 import _lib
+    rng = np.random.default_rng(steps)
+    field = rng.random((203, 390)) * 3 - 0.5               # ragged in both directions, negative and >max values
+    h, D = 7.0, 50.0
+    dt = 0.23 * h * h / D
+    eng = ColonyEngine([1, 1, 0])
+    out = {}
+    for fuse in (1, 5, 3):
+        old = eng.lib.abm_set_option(_lib.OPTION_DIFFUSION_FUSE, fuse)
+        try:
+            assert eng.lib.abm_diffusion_launches(steps) % 2 == steps % 2
+            if fuse == 1:
+                assert eng.lib.abm_diffusion_launches(steps) == steps
+            else:
+                assert eng.lib.abm_diffusion_launches(steps) <= (steps + fuse - 1) // fuse + 1
+            for tma in (False, True):
+                src = torch.from_numpy(field.copy()).cuda()
+                scratch = torch.full_like(src, float("nan"))
+                res = eng.diffuse(src, steps, dt, dt * 0.4, D, h * h, 2.0, 0.1, use_tma=tma, scratch=scratch)
+                assert (res.data_ptr() == scratch.data_ptr()) == bool(steps % 2)
+                out[fuse, tma] = res.cpu().numpy()
+        finally:
+            eng.lib.abm_set_option(_lib.OPTION_DIFFUSION_FUSE, old)
+    ref = orc.diffuse_field(field, steps, dt, dt * 0.4, D, h * h, 2.0, 0.1)
+    for key, got in out.items():
+        assert np.array_equal(got, ref), key
 
 
 # ---- second-session kernels: warp tile, slot-order hand-over, multiply-high decode, slab plumbing ------------------
