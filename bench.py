@@ -241,10 +241,11 @@ def run_b200(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
     if not args.no_clocks:
         sampler.start()                   # sampled from the warm-up replays to the end of the timed steps
-    t_wait = time.time()                  # nvidia-smi takes a while to print its first row: keep the GPU under load
+    # nvidia-smi takes a while to print its first row.  Keep the GPU busy meanwhile, but not with steps of the colony:
+    # the motility forces are constant, so seconds of extra steps would pile the cells up against the walls
+    t_wait = time.time()
     while not sampler.rows and sampler.proc is not None and time.time() - t_wait < 3.0:
-        pipe.replay()
-        pipe.replay()
+        flush.zero_()
         torch.cuda.synchronize(dev)
     for _ in range(max(args.warmup, 3) + 40):           # 40 extra replays: a few 20 ms clock samples under load
         pipe.replay()
