@@ -21,8 +21,17 @@
 
 namespace abm {
 
-constexpr int kTileI = 32;                 // rows (slow axis, stride gy)
-constexpr int kTileJ = 128;                // columns (contiguous axis)
+// Build-time tile shape (scripts/ab_substep.py builds variants): kTileJ must be a power of two <= 256 that divides
+// kDiffThreads or is a multiple of it; the shipped library uses 32 x 128.
+#ifndef ABM_DIFF_TILE_I
+#define ABM_DIFF_TILE_I 32
+#endif
+#ifndef ABM_DIFF_TILE_J
+#define ABM_DIFF_TILE_J 128
+#endif
+constexpr int kTileI = ABM_DIFF_TILE_I;    // rows (slow axis, stride gy)
+constexpr int kTileJ = ABM_DIFF_TILE_J;    // columns (contiguous axis)
+static_assert((kTileJ & (kTileJ - 1)) == 0 && kTileJ >= 32 && kTileJ <= 256 && kTileI >= 1 && kTileI <= 200, "tile shape");
 constexpr int kHaloJ = 2;                  // TMA needs the box to START on a 16-byte boundary in global memory:
                                            // with 8-byte elements the inner start coordinate must be even, so the
                                            // column halo is 2 wide on each side although the stencil needs 1

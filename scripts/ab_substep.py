@@ -13,6 +13,9 @@ VARIANTS = {                      # -D switches of csrc/jkr.cu (see the comment 
     "no_contact_loop": ["ABM_JKR_EXP=4", "ABM_ALLOW_WRONG_RESULTS"],            # timing ablations
     "no_walk_no_contact": ["ABM_JKR_EXP=12", "ABM_ALLOW_WRONG_RESULTS"],
     "no_pdl": ["ABM_PDL=0"],
+    # tile of the diffusion kernels (csrc/diffusion.cu); timed by the "diffuse_10_us" entry below
+    "diff_16x128": ["ABM_DIFF_TILE_I=16"], "diff_32x64": ["ABM_DIFF_TILE_J=64"],
+    "diff_16x64": ["ABM_DIFF_TILE_I=16", "ABM_DIFF_TILE_J=64"], "diff_64x128": ["ABM_DIFF_TILE_I=64"],
 }
 if sys.argv[1] == "build":
     spec = importlib.util.spec_from_file_location("b", os.path.join(ROOT, "python-hipsc-abm_b200", "build.py"))
@@ -76,4 +79,17 @@ else:
         ts.append(a.elapsed_time(z) * 1e3)
     res["step_us"] = float(np.median(ts))
     pipe.check()
+    # ten diffusion substeps alone on the workload's grid (two fused launches by default), L2 flushed before each
+    if wl["grid"]:
+        field = torch.rand(wl["grid"], dtype=torch.float64, device="cuda")
+        scratch = torch.empty_like(field)
+        ts = []
+        for _ in range(20):
+            flush.zero_()
+            a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.diffuse(field, 10, spec["diffuse_dt"], spec["diffuse_dt"], 50.0, spec["h"] ** 2, 2.0, 0.1, scratch=scratch)
+            z.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(z) * 1e3)
+        res["diffuse_10_us"] = float(np.median(ts))
     print(os.path.basename(os.environ.get("ABM_B200_LIB", "default")), name, {k: round(v, 1) for k, v in res.items()})
