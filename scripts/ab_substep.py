@@ -1,6 +1,9 @@
 """A/B timing of k_jkr_substep variants: builds variant libraries (local, needs nvcc) or times one (GPU box).
   build:  python scripts/ab_substep.py build
-  time:   ABM_B200_LIB=<so> python scripts/ab_substep.py time <workload>"""
+  time:   ABM_B200_LIB=<so> python scripts/ab_substep.py time <workload>
+  run:    python scripts/ab_substep.py run <workload> [variant ...]      (GPU box, ONE gpurun call: for every variant
+          library in build_ab/ -- or the named ones -- the GPU parity tests, then the timing; variants whose name
+          starts with "no_" are timing ablations with wrong results and skip the tests)"""
 import importlib.util, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -23,6 +26,21 @@ if sys.argv[1] == "build":
     os.makedirs(os.path.join(ROOT, "build_ab"), exist_ok=True)
     for name, defs in VARIANTS.items():
         print(name, b.build(defines=defs, out=os.path.join(ROOT, "build_ab", f"libabm_{name}.so")))
+elif sys.argv[1] == "run":
+    import glob, subprocess
+    names = sys.argv[3:] or sorted(os.path.basename(f)[len("libabm_"):-3] for f in glob.glob(os.path.join(ROOT, "build_ab", "libabm_*.so")))
+    for name in ["default"] + names:
+        env = dict(os.environ)
+        if name != "default":
+            env["ABM_B200_LIB"] = os.path.join(ROOT, "build_ab", f"libabm_{name}.so")
+        if not name.startswith("no_"):
+            t = subprocess.run([sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-x", "-q"], cwd=ROOT, env=env,
+                               capture_output=True, text=True)
+            print(name, "tests:", (t.stdout.strip().splitlines() or ["?"])[-1], flush=True)
+            if t.returncode != 0:
+                print(t.stdout[-1500:])
+                continue
+        subprocess.run([sys.executable, os.path.abspath(__file__), "time", sys.argv[2]], cwd=ROOT, env=env)
 else:
     import numpy as np, torch, bench
     from hipsc_abm_b200 import _lib as _l
