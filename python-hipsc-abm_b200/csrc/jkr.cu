@@ -96,6 +96,9 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 //   2: start fetching the previous bond row at the first shell partner             (slower: register pressure)
 //   4: TIMING ABLATION, WRONG RESULTS: skip the contact loop                        (attributes 23 of 56 us)
 //   8: TIMING ABLATION, WRONG RESULTS: skip the candidate walk                      (attributes  9 of 56 us)
+//  16: bond rows keyed by sorted slot between the substeps of abm_mechanics_loop (written coalesced; the previous
+//      row is found through the prev_slot index the placement kernel records); the first substep still reads and
+//      the last one still writes rows keyed by cell id                               (written blind: not yet measured)
 #ifndef ABM_JKR_EXP
 #define ABM_JKR_EXP 0
 #endif
@@ -176,7 +179,8 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               double reach2, BandConst bandc, GraphView old, int *__restrict__ new_len, int *__restrict__ new_cols, int stride,
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
               double stokes, Friction fric, Box box, double dt, const int *__restrict__ gid_of,
-              const int *__restrict__ slot_pid, NextSort next, int sort_rows) {
+              const int *__restrict__ slot_pid, NextSort next, int sort_rows, const int *__restrict__ prev_slot,
+              int row_keys) {
     // column tid: first the parked partner slots, then (overwritten from the front) the ids of the new bond row
     __shared__ int column[kMaxHits][kJkrThreads];
     __shared__ float4 tiles[kJkrThreads / 32][kTileRows * kTileCap];
@@ -244,7 +248,13 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
 #if ABM_JKR_EXP & 1
     const double mx = mot[3 * (long long)i + 0], my = mot[3 * (long long)i + 1], mz = mot[3 * (long long)i + 2];
 #endif
-    int *row = new_cols + (long long)i * stride;
+#if ABM_JKR_EXP & 16
+    const int oi = (row_keys & 1) ? prev_slot[s] : i;          // key of this cell's previous bond row
+    const int ni = (row_keys & 2) ? s : i;                     // key of the row it writes
+#else
+    const int oi = i, ni = i;
+#endif
+    int *row = new_cols + (long long)ni * stride;
     long long fxi = 0, fyi = 0, fzi = 0;
     BondEval ev;
     if (!kUniform) ev.preset(c, p.w);
@@ -287,15 +297,15 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     };
     // membership of j in this cell's previous bond row, straight from global memory (slow path only)
     auto was_bonded_slow = [&](int j) {
-        long long os = old.start(i);
-        int olen = old.row_len[i];
+        long long os = old.start(oi);
+        int olen = old.row_len[oi];
         bool found = false;
         for (int k = 0; k < olen; ++k) found |= (old.cols[os + k] == j);
         return found;
     };
 
     int nsh = 0, sh0 = 0, sh1 = 0, shj0 = 0, shj1 = 0;         // hysteresis-shell partners, looked up in phase 3
-    const long long os = old.valid() ? old.start(i) : 0;
+    const long long os = old.valid() ? old.start(oi) : 0;
     // fixed-stride rows of >= 8 entries (stride % 4 == 0): the first 8 ids come as two unconditional 16-byte loads
     const bool wide = old.valid() && !old.row_start && (old.stride & 3) == 0 && old.stride >= 8;
     int olen = 0;
@@ -327,7 +337,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                     sh0 = t;
                     shj0 = j;
 #if ABM_JKR_EXP & 2
-                    olen = old.row_len[i];                    // the previous row starts its way here now
+                    olen = old.row_len[oi];                   // the previous row starts its way here now
                     if (wide) {
                         oa = *reinterpret_cast<const int4 *>(old.cols + os);
                         ob = *reinterpret_cast<const int4 *>(old.cols + os + 4);
@@ -345,7 +355,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         // ---- phase 3: hysteresis -- shell partners that are in the previous row --------------------------------
         if (nsh > 0) {
 #if !(ABM_JKR_EXP & 2)
-            olen = old.row_len[i];
+            olen = old.row_len[oi];
             if (wide) {
                 oa = *reinterpret_cast<const int4 *>(old.cols + os);
                 ob = *reinterpret_cast<const int4 *>(old.cols + os + 4);
@@ -430,7 +440,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         }
         if (sort_rows && direct > 0) insertion_sort(row, kept);
     }
-    new_len[i] = kept;
+    new_len[ni] = kept;
     if (total > stride) atomicMax(max_len, total);            // overflow report (rare): the host doubles the stride
     // integration (reference cell_backend.py:155-170); positions are read from the sorted snapshot only
     double friction = fric.uni, inv_f = fric.uni_inv;
@@ -504,9 +514,11 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                             double adhesion_const, double stokes, const double size_host[3], double move_dt,
                             const int32_t *global_id, const int32_t *slot_gid, double uniform_radius,
                             const double *next_extent_host, const double *next_origin_host,
-                            int32_t *next_bin_counts, void *next_sort_workspace, void *stream) {
+                            int32_t *next_bin_counts, void *next_sort_workspace, void *stream,
+                            const int32_t *prev_slot = nullptr, int row_keys = 0) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
+    ABM_REQUIRE(!(row_keys & 1) || prev_slot, "rows keyed by the previous slot need the prev_slot index");
     ABM_REQUIRE(bin_start && sorted_id && sorted_pos && sorted_bin && dims_host && new_row_len && new_cols &&
                     max_len && motility_forces && size_host,
                 "null pointer");
@@ -548,7 +560,7 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                                      Radius(distance), reach * reach, BandConst::make(reach * 1.0000001), old,
                                      new_row_len, new_cols, (int)row_stride, max_len, motility_forces, locations, c,
                                      stokes, fric, box, move_dt, global_id, global_id ? slot_gid : sorted_id, next,
-                                     sort_rows),
+                                     sort_rows, prev_slot, row_keys),
                       "k_jkr_substep");
 }
 
@@ -608,12 +620,20 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
         if (rc) return rc;
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
         const int32_t *slot_gid = (global_id && n > 0) ? sort_ws_carve(sort_workspace, n, nbins).slot_gid : nullptr;
+        const int32_t *prev_slot = nullptr;
+        int row_keys = 0;
+#if ABM_JKR_EXP & 16
+        if (n > 0) {
+            prev_slot = sort_ws_carve(sort_workspace, n, nbins).prev_slot;
+            row_keys = (k > 0 ? 1 : 0) | (last ? 0 : 2);          // first reads / last writes rows keyed by cell id
+        }
+#endif
         rc = jkr_substep_impl(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
                               cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, k == n_substeps - 1,
                               motility_forces, last ? locations : nullptr, poisson, youngs, adhesion_const, stokes,
                               size_host, dts_host[k], global_id, slot_gid, uniform_radius,
                               prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
-                              prebin ? sort_workspace : nullptr, stream);
+                              prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys);
         if (rc) return rc;
         cur_start = nullptr;
         cur_stride = row_stride;

@@ -14,6 +14,10 @@
 // the bin of every cell, written by the fused mechanics kernel of the previous substep.
 #include "sortws.cuh"
 
+#ifndef ABM_JKR_EXP
+#define ABM_JKR_EXP 0      // build-time experiment switches of csrc/jkr.cu (bit 16 needs the sort's help)
+#endif
+
 namespace abm {
 
 constexpr int kThreads = 256;
@@ -58,7 +62,8 @@ __global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ 
                                                         int n, int *__restrict__ sorted_id,
                                                         double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
                                                         int *__restrict__ next_sums, int n_sums,
-                                                        const int *__restrict__ gid_of, int *__restrict__ slot_gid) {
+                                                        const int *__restrict__ gid_of, int *__restrict__ slot_gid,
+                                                        int *__restrict__ prev_slot) {
     pdl_launch_dependents();
     int s = blockIdx.x * kThreads + threadIdx.x;
     pdl_wait();
@@ -72,6 +77,7 @@ __global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ 
     sorted_id[dest] = id;
     sorted_bin[dest] = b;
     if (gid_of) slot_gid[dest] = gid_of[id];
+    if (prev_slot) prev_slot[dest] = s;
 }
 
 __global__ void __launch_bounds__(kThreads) k_place(const int *__restrict__ cell_bin, int *__restrict__ cursor, int n,
@@ -216,7 +222,8 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
     if (prebinned) {
         rc = check_cuda(launch_chained(k_rescatter, blocks, kThreads, st, (const int *)w.cell_bin,
                                        (const int *)w.tmp_id, (const double4 *)w.next_pos, w.cursor, (int)n, sorted_id,
-                                       sp, sorted_bin, w.next_sums, nb, global_id, w.slot_gid),
+                                       sp, sorted_bin, w.next_sums, nb, global_id, w.slot_gid,
+                                       (ABM_JKR_EXP & 16) ? w.prev_slot : (int *)nullptr),
                         "k_rescatter");
         if (rc) return rc;
     } else if (flags & ABM_SORT_STABLE) {

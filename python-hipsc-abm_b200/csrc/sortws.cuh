@@ -14,13 +14,15 @@ struct SortWs {
                       // (the placement kernel of every sort leaves them zeroed for the next one)
     double4 *next_pos;// n   : ABM_SORT_PREBINNED: moved {x,y,z,r} of the cell in previous slot s
     int *slot_gid;    // n   : global id of the cell in slot s (mechanics loop of a slab-decomposed colony)
+    int *prev_slot;   // n   : ABM_SORT_PREBINNED: the slot the cell in slot s had in the previous sort (experiment
+                      //       ABM_JKR_EXP & 16: bond rows keyed by slot between the substeps of a loop)
 };
 
 inline size_t sort_align(size_t v) { return (v + 255) & ~size_t(255); }
 
 inline size_t sort_ws_bytes(int64_t n, int64_t nbins) {
     return 2 * sort_align((size_t)n * 4) + sort_align((size_t)(nbins + 1) * 4) +
-           2 * sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4) + sort_align((size_t)n * 32) + sort_align((size_t)n * 4) + 512;
+           2 * sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4) + sort_align((size_t)n * 32) + 2 * sort_align((size_t)n * 4) + 512;
 }
 
 inline SortWs sort_ws_carve(void *ws, int64_t n, int64_t nbins) {
@@ -33,7 +35,8 @@ inline SortWs sort_ws_carve(void *ws, int64_t n, int64_t nbins) {
     w.next_sums = (int *)p;  p += sort_align((size_t)scan_blocks(nbins + 1) * 4 + 4);
     p = (char *)(((uintptr_t)p + 255) & ~uintptr_t(255));    // the caller's buffer need not be aligned
     w.next_pos = (double4 *)p; p += sort_align((size_t)n * 32);
-    w.slot_gid = (int *)p;
+    w.slot_gid = (int *)p;   p += sort_align((size_t)n * 4);
+    w.prev_slot = (int *)p;
     return w;
 }
 
