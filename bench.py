@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "cell-updates/sec (neighbor+force+diffusion step)"
+MOTILITY_NOTE = ("2 nN per cell in a fixed random direction, sign alternating from step to step (the colony stays "
+                 "statistically stationary for any number of steps)")
 UNIT = "cell-updates/s"
 
 WORKLOADS = {
@@ -66,6 +68,11 @@ def make_workload(name, seed=0, n_override=None):
         phi = rng.random(n) * 2 * np.pi
         mot[:, 0], mot[:, 1], mot[:, 2] = np.cos(phi) * np.cos(theta), np.cos(phi) * np.sin(theta), np.sin(phi)
     mot *= 2e-9                                     # motility force, reference cell_methods.py:252
+    # The reference draws a new direction for (most) cells every step.  The bench keeps ONE direction per cell and
+    # alternates its sign from step to step (every arm: B200, slabs, end-to-end API, CPU): with a constant force
+    # the cells travel 3.8 um per step, pile up against the walls and each other, and after ~190 steps a cell has
+    # more than 16 bonds (checked with the oracle); with the alternating sign bonds and neighbours per cell settle
+    # (3.9 and 5.7 on average, at most 6 and 9) and stay there.
     grid = None
     if spec["h"]:
         g = int(np.ceil(side / spec["h"])) + 1      # gradient_size, reference cell_simulation.py:67
@@ -156,9 +163,12 @@ def oracle_step_fn(wl, threads):
         sim.max_concentration, sim.degradation = 2.0, 0.1
         sim.fgf4_values = np.zeros(wl["grid"] + (1,))
 
+    count = [0]
+
     def step():
         sim.get_neighbors("neighbor_graph", 15)
-        sim.motility_forces[:] = wl["mot"]
+        sim.motility_forces[:] = wl["mot"] if count[0] % 2 == 0 else -wl["mot"]
+        count[0] += 1
         sim.apply_forces()
         if wl["grid"]:
             orc.adjust_morphogens(sim.locations, 1.0, sim.fgf4_values, sim.spat_res)
@@ -228,7 +238,9 @@ def run_b200(args, rank, world, local_rank):
         return line
     eng = ColonyEngine(wl["size"], dev)
     eng.upload(wl["loc"], wl["radii"], wl["mot"])
-    pipe = HotPathStep(eng, cfg)
+    # the motility forces alternate in sign from step to step (see make_workload): the colony then stays statistically
+    # stationary, so the timed steps do the same work whatever --steps / --warmup say
+    pipe = HotPathStep(eng, cfg, motility_by_parity=(eng.mot, -eng.mot))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     # warm-up (eager), then capture and a couple of replays
@@ -400,14 +412,18 @@ def run_b200(args, rank, world, local_rank):
             sim.max_concentration, sim.degradation = 2.0, 0.1
             sim.fgf4_values = np.zeros(wl["grid"] + (1,))
 
+        mot_by_parity = (wl["mot"], -wl["mot"])
+        api_count = [0]
+
         def api_step():
             sim.get_neighbors("neighbor_graph", 15)          # (returns with the device idle: record_time synchronises)
             # stands in for cell_motility, a rule method outside the path (rule methods are not timed):
             # apply_forces leaves motility_forces zeroed, so the step's input has to be written again -- host-only
             # work between two public calls, clocked and subtracted
             t = time.perf_counter()
-            sim.motility_forces[:] = wl["mot"]
+            sim.motility_forces[:] = mot_by_parity[api_count[0] % 2]
             fill = time.perf_counter() - t
+            api_count[0] += 1
             sim.apply_forces()
             if wl["grid"]:
                 # S_d substeps exactly: step_dt = (S_d-1)*dt + dt (divmod gives S_d-1 full substeps + remainder)
@@ -461,6 +477,7 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": f"{args.workload}: {spec['desc']}", "cells_per_gpu": n, "dim": spec["dim"],
                    "mechanics_substeps": sm, "diffusion_substeps": spec["sd"], "grid": wl["grid"],
                    "edges_r15": e15, "jkr_bonds": ej, "l2": "flushed between timed steps (256 MiB memset)",
+                   "motility": MOTILITY_NOTE,
                    "morphogen_stage": ("reference order (before the mechanics, on the step's starting positions), "
                                        "on a second stream beside search + mechanics") if cfg.overlap_morphogen and
                    wl["grid"] else "after the mechanics, same stream",
@@ -519,6 +536,11 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     def step():
         slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None, ops,
                        morphogen_first=first)
+        # alternating motility sign (make_workload); the forces migrate with the cells.  While the owned count of
+        # the step is still on the device the state is the step's whole local arrays (owned + halo rows): negate
+        # those -- touching state.mot would wait for the count
+        pend = state.pending()
+        (pend[0]["mot"] if pend is not None else state.mot).neg_()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -586,7 +608,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
                                        "stream beside search + mechanics") if first else "after the mechanics",
                    "exchanges_per_step": (fabric.exchanges - ex0) / max(args.steps + e_steps, 1),
                    "bytes_sent_per_step_rank0": (fabric.bytes_sent - bytes0) // max(args.steps + e_steps, 1),
-                   "l2": "flushed between timed steps (256 MiB memset)",
+                   "l2": "flushed between timed steps (256 MiB memset)", "motility": MOTILITY_NOTE,
                    "timing": "CUDA events per step, summed; max over ranks",
                    "parallelism": f"slab{world}: 1-D slab decomposition along x; per step one cell-halo exchange "
                                   "(migration rides on it; fixed-capacity messages, no size handshake) and one "

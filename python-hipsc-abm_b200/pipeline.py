@@ -53,9 +53,20 @@ class StepConfig:
 
 
 class HotPathStep:
-    def __init__(self, engine: ColonyEngine, cfg: StepConfig):
+    def __init__(self, engine: ColonyEngine, cfg: StepConfig, motility_by_parity=None):
+        """motility_by_parity: optional pair of (n,3) float64 device tensors; even steps (counted from the creation
+        of this object) then use the first as the motility forces, odd steps the second, instead of engine.mot.
+        The reference draws new motility forces every step (cell_methods.py:236-340); a synthetic colony that kept
+        one set for hundreds of steps would pile its cells up against the walls, whereas forces that alternate in
+        sign keep it statistically stationary (bench.py)."""
         self.eng = engine
         self.cfg = cfg
+        self.motility_by_parity = None
+        if motility_by_parity is not None:
+            a, b = motility_by_parity
+            if tuple(a.shape) != (engine.n, 3) or tuple(b.shape) != (engine.n, 3):
+                raise ValueError("motility_by_parity: two (n,3) tensors expected")
+            self.motility_by_parity = (a, b)
         _ = engine.max_radius, engine.uniform_radius      # evaluated now (device read-back), not inside a capture
         n = engine.n
         dev = engine.device
@@ -112,6 +123,8 @@ class HotPathStep:
             self._search(None)
         # mechanics: bonds alternate between row buffers 0 and 1, buffer 2 is the intermediate
         src = self.parity
+        if self.motility_by_parity is not None:
+            eng.mot = self.motility_by_parity[src]
         pair = [1 - src, 2]
         self.bonds = eng.enqueue_mechanics(self.bonds, cfg.contact_radius, self.dts, cfg.bond_stride, STOKES,
                                            pair=pair, zero_flag=False, carry=True)
