@@ -536,11 +536,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     def step():
         slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None, ops,
                        morphogen_first=first)
-        # alternating motility sign (make_workload); the forces migrate with the cells.  While the owned count of
-        # the step is still on the device the state is the step's whole local arrays (owned + halo rows): negate
-        # those -- touching state.mot would wait for the count
-        pend = state.pending()
-        (pend[0]["mot"] if pend is not None else state.mot).neg_()
+        state.negate_motility()           # alternating motility sign (make_workload); no wait for the owned count
 
     for _ in range(max(args.warmup, 3)):
         step()

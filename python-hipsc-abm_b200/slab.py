@@ -131,6 +131,14 @@ class SlabState:
         full, local = self._pending
         return full, int(full["loc"].shape[0]), local._n_own
 
+    def negate_motility(self):
+        """Flip the sign of the owned cells' motility forces in place (bench.py's stationary synthetic colony).
+        While the owned count is still on the device the state IS the finished step's local arrays (owned rows
+        first, halo rows behind them, which the next pack ignores): those are negated as a whole, so that nothing
+        waits for the count."""
+        pend = self.pending()
+        (pend[0]["mot"] if pend is not None else self._get("mot")).neg_()
+
     def _settle(self):
         if self._pending is not None:
             full, local = self._pending

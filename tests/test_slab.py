@@ -281,6 +281,33 @@ def test_fixed_capacity_messages_and_deferred_owned_count():
     assert np.abs(got_loc - ref_loc).max() <= 1e-9
 
 
+def test_alternating_motility_sign_on_a_deferred_state():
+    """bench.py flips the sign of the motility forces after every step (stationary synthetic colony) through
+    SlabState.negate_motility(), which must not force the deferred owned count and must follow migrating cells."""
+    world, steps = 3, 4
+    loc, radii, mot = make_cells()
+    halo = slab.required_halo(11, 10.3100107, slack=5.0)
+    sim = orc.OracleSim(loc, radii, SIZE)
+    for k in range(steps):
+        sim.motility_forces = mot.copy() if k % 2 == 0 else -mot
+        sim.apply_forces()
+    geoms, states = split(loc, radii, mot, world, halo)
+    ops = [PaddedOps() for _ in geoms]
+    for _ in range(steps):
+        slab.loopback_step(states, geoms, oracle_compute, ops=ops)
+        for s in states:
+            s.negate_motility()
+        assert all(s.pending() is not None for s in states)        # the flip did not read the owned count
+    gid, got_loc, got_edges = collect(states)
+    assert np.array_equal(gid, np.arange(len(loc)))
+    assert np.array_equal(got_edges, sim.jkr_graph.edge_array())
+    assert np.abs(got_loc - sim.locations).max() <= 1e-9
+    # settled state: the flip works on the owned rows themselves
+    before = states[0].mot.clone()
+    states[0].negate_motility()
+    assert torch.equal(states[0].mot, -before)
+
+
 def test_balanced_slabs_follow_the_cell_density():
     rng = np.random.default_rng(11)
     size = np.array([1200.0, 300.0, 0.0])
