@@ -571,15 +571,20 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     # e2e: the same step with the host in the loop -- the rule methods' inputs (motility forces of the owned
     # cells) are uploaded from pinned memory and the positions + sampled concentrations downloaded, every step
     e_steps = max(3, min(args.steps, 10))
-    pin_mot = torch.empty((state.n + 4096, 3), dtype=torch.float64).pin_memory()
+    pin_mot = torch.zeros((state.n + 4096, 3), dtype=torch.float64).pin_memory()
+    pin_mot[:state.n].copy_(state.mot)                    # realistic values (rows beyond the current count: no force)
     h2d = d2h = 0
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e_steps):
+    for it in range(e_steps):
         k = state.n
         if k > pin_mot.shape[0]:
-            pin_mot = torch.empty((k + 4096, 3), dtype=torch.float64).pin_memory()
+            grown = torch.zeros((k + 4096, 3), dtype=torch.float64).pin_memory()
+            grown[:pin_mot.shape[0]].copy_(pin_mot)
+            pin_mot = grown
         state.mot = pin_mot[:k].to(dev, non_blocking=True)
+        if it % 2:
+            state.mot.neg_()                              # the alternating sign of make_workload
         step()
         out_loc = state.loc.cpu()
         out_c = pipe.sampled.cpu() if pipe.sampled is not None else None
