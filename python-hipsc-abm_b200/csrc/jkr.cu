@@ -99,6 +99,8 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 //  16: bond rows keyed by sorted slot between the substeps of abm_mechanics_loop (written coalesced; the previous
 //      row is found through the prev_slot index the placement kernel records); the first substep still reads and
 //      the last one still writes rows keyed by cell id                               (written blind: not yet measured)
+//  32: contact model with a Horner-form force polynomial and an rsqrt without special-case handling (s2 is a normal
+//      number; forces move by ~1e-16 relative, inside the 1e-12 gate)                (written blind: not yet measured)
 #ifndef ABM_JKR_EXP
 #define ABM_JKR_EXP 0
 #endif
@@ -141,6 +143,17 @@ struct BondEval {
         }
     }
 };
+
+// 1/sqrt(x) for a normal, positive x (squared centre distances: 1 .. ~110 um^2): single-precision seed and two Newton
+// steps y += y*(0.5 - (x/2)*y*y), no handling of zeros, infinities or subnormals (x == 0 yields NaN, which the callers
+// never use).  Experiment ABM_JKR_EXP & 32.
+__device__ __forceinline__ double rsqrt_normal(double x) {
+    double y = (double)rsqrtf((float)x);
+    const double h = 0.5 * x;
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    y = fma(y, fma(-h * y, y, 0.5), y);
+    return y;
+}
 
 struct NextSort {          // hand-over of the moved cells to the following substep's sort (counts == nullptr: off),
     BinGeom geom;          // in THIS sort's slot order: the next permutation is then nearly the identity
@@ -276,11 +289,19 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         const double rsum = kUniform ? c.uni_r + c.uni_r : ev.rsum;
         const double inv_scale = kUniform ? c.uni_inv_scale : ev.inv_scale;
         const double force_scale = kUniform ? c.uni_force_scale : ev.force_scale;
+#if ABM_JKR_EXP & 32
+        double inv_mag = rsqrt_normal(s2);                  // NaN for coincident cells, not used below
+#else
         double inv_mag = rsqrt(s2);                         // +inf for coincident cells, handled below
+#endif
         double mag = s2 > 0.0 ? s2 * inv_mag : 0.0;
         double d = (rsum - mag) * inv_scale;
         if (d > -0.360562) {
+#if ABM_JKR_EXP & 32
+            double f = fma(fma(fma(-0.0204, d, 0.4942), d, 1.0801), d, -1.324);
+#else
             double f = (-0.0204 * (d * d * d)) + (0.4942 * (d * d)) + (1.0801 * d) - 1.324;
+#endif
             if (s2 > 0.0) {
                 double w = f * force_scale * inv_mag * kForceUnitInv;
                 fxi += __double2ll_rn(w * vx);

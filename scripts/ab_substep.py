@@ -16,6 +16,8 @@ VARIANTS = {                      # -D switches of csrc/jkr.cu (see the comment 
     "no_contact_loop": ["ABM_JKR_EXP=4", "ABM_ALLOW_WRONG_RESULTS"],            # timing ablations
     "no_walk_no_contact": ["ABM_JKR_EXP=12", "ABM_ALLOW_WRONG_RESULTS"],
     "no_pdl": ["ABM_PDL=0"],
+    "trim_math": ["ABM_JKR_EXP=32"],       # Horner polynomial + rsqrt without special cases (written without a GPU)
+    "slot_rows_trim_math": ["ABM_JKR_EXP=48"],
     "slot_rows": ["ABM_JKR_EXP=16"],       # bond rows keyed by slot between substeps (written without a GPU: run the tests)
     # tile of the diffusion kernels (csrc/diffusion.cu); timed by the "diffuse_10_us" entry below
     "diff_16x128": ["ABM_DIFF_TILE_I=16"], "diff_32x64": ["ABM_DIFF_TILE_J=64"],
