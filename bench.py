@@ -179,16 +179,52 @@ def oracle_step_fn(wl, threads):
     return step
 
 
-def cpu_sample_workload(name):
-    """Bounded sample of the workload for the CPU legs: the same density/geometry, at most 100k cells."""
-    cap = 100_000
-    return make_workload(name, seed=0, n_override=min(WORKLOADS[name]["n"], cap))
+def host_cores():
+    """Host threads the CPU arm uses: the cores this process may run on.  Set explicitly on the OpenMP runtime --
+    torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which would silently make the reference arm a
+    single-threaded one at N > 1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
-def run_cpu(name, steps, warmup, threads=None):
+# cell-steps one CPU leg may cost (16 cores run ~0.15 M cell-steps/s in 2-D, ~0.06 M in 3-D): the full 500,000-cell
+# colony of c3 fits `--steps 20 --warmup 5` (about 85 s); only c4's 4 M cells are sampled
+CPU_BUDGET_CELL_STEPS = {2: 14_000_000, 3: 5_000_000}
+
+
+def cpu_sample_cells(name, total_steps):
+    spec = WORKLOADS[name]
+    return int(min(spec["n"], max(100_000, CPU_BUDGET_CELL_STEPS[spec["dim"]] // max(total_steps, 1))))
+
+
+def workload_label(name, cells=None, world=1, cpu_arm=False):
+    """config.workload.  The CPU arm runs the stated colony whenever it fits its time budget; when it has to run a
+    smaller sample of it (c4, or the N-GPU colony at N > 1), the label says so -- the two arms' configs then differ,
+    as they should."""
+    spec = WORKLOADS[name]
+    label = f"{name}: {spec['desc']}" if world == 1 else f"{name} x {world}: {spec['desc']} per GPU, one colony"
+    if cpu_arm and (cells != spec["n"] or world > 1):
+        label += f" -- CPU arm on a {cells}-cell sample of it (same density, geometry per cell and step recipe)"
+    return label
+
+
+def common_config(name, wl, sm, world=1, cpu_arm=False):
+    """The part of `config` that defines the workload: identical, key for key, in the B200 line and in the
+    `--impl reference` line whenever both run the same colony."""
+    spec = WORKLOADS[name]
+    return {"workload": workload_label(name, wl["n"], world, cpu_arm), "cells_per_gpu": wl["n"], "dim": spec["dim"],
+            "mechanics_substeps": sm, "diffusion_substeps": spec["sd"],
+            "grid": list(wl["grid"]) if wl["grid"] else None, "motility": MOTILITY_NOTE,
+            "l2": "B200 arm: flushed between timed steps (256 MiB memset); CPU arm: not applicable"}
+
+
+def run_cpu(name, steps, warmup, threads=None, cells=None):
     from oracle import oracle as orc
-    wl = cpu_sample_workload(name)
-    threads = threads or orc.max_threads()
+    cells = cells or cpu_sample_cells(name, steps + warmup)
+    wl = make_workload(name, seed=0, n_override=cells)
+    threads = threads or host_cores()
     step = oracle_step_fn(wl, threads)
     for _ in range(warmup):
         step()
@@ -196,9 +232,78 @@ def run_cpu(name, steps, warmup, threads=None):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    sample = (f"{wl['n']} cells of workload {name} (same density and step recipe), {steps} steps after "
-              f"{warmup} warm-up, oracle/abm_oracle.c with OpenMP")
-    return wl["n"] * steps / dt, dt / steps, threads, sample
+    full = cells == WORKLOADS[name]["n"]
+    sample = ((f"the whole workload {name} ({cells} cells)" if full else
+               f"{cells} cells of workload {name} (same density and step recipe)") +
+              f", {steps} steps after {warmup} warm-up, oracle/abm_oracle.c with OpenMP on {threads} threads")
+    return wl["n"] * steps / dt, dt / steps, threads, sample, wl
+
+
+def parity_check(name, dev, steps=5, cells=100_000):
+    """The colony bench.py times is not compared with anything while it is timed; this runs the same step recipe on
+    a `cells`-cell sample of the workload through BOTH arms (the B200 path through the reference-facing API, the CPU
+    oracle with its serial force pass) for a few steps and reports how far they are apart."""
+    from oracle import oracle as orc
+    from hipsc_abm_b200.cell_methods import B200CellMethods
+    from hipsc_abm_b200.simulation import ColonySimulation
+    wl = make_workload(name, seed=7, n_override=min(cells, WORKLOADS[name]["n"]))
+    spec, n = wl["spec"], wl["n"]
+
+    class Cells(B200CellMethods, ColonySimulation):
+        pass
+    sim = Cells(wl["size"], dev)
+    sim.add_agents(n)
+    sim.agent_array("locations", override=wl["loc"].copy())
+    sim.agent_array("radii", override=wl["radii"].copy())
+    sim.agent_array("motility_forces", vector=3)
+    sim.agent_array("jkr_forces", vector=3)
+    sim.agent_graph("neighbor_graph")
+    sim.agent_graph("jkr_graph")
+    sim.max_radius, sim.step_dt, sim.move_dt = 5.0, 1800, 180
+    orc.set_threads(host_cores())
+    ref = orc.OracleSim(wl["loc"], wl["radii"], wl["size"])
+    ref.multithread = False                       # serial force pass: the reference's parallel one races (SURVEY 0.6)
+    if wl["grid"]:
+        h = spec["h"]
+        for o in (sim, ref):
+            o.spat_res, o.spat_res2, o.diffuse_const, o.diffuse_dt = h, h * h, 50.0, spec["diffuse_dt"]
+            o.max_concentration, o.degradation = 2.0, 0.1
+            o.fgf4_values = np.zeros(wl["grid"] + (1,))
+    out = {"cells": n, "steps": steps, "neighbor_edges_equal": True, "jkr_bonds_equal": True, "max_abs_dx_um": 0.0,
+           "max_abs_dfield": 0.0 if wl["grid"] else None, "max_abs_dsample": 0.0 if wl["grid"] else None}
+    for k in range(steps):
+        mot = wl["mot"] if k % 2 == 0 else -wl["mot"]
+        sim.get_neighbors("neighbor_graph", 15)
+        ref.get_neighbors("neighbor_graph", 15)
+        out["neighbor_edges_equal"] &= bool(np.array_equal(sim.neighbor_graph.edge_array(),
+                                                           orc.canonical_edges(ref.neighbor_graph.edge_array())))
+        sim.motility_forces[:] = mot
+        ref.motility_forces[:] = mot
+        sim.apply_forces()
+        ref.apply_forces()
+        out["jkr_bonds_equal"] &= bool(np.array_equal(sim.jkr_graph.edge_array(), ref.jkr_graph.edge_array()))
+        out["max_abs_dx_um"] = max(out["max_abs_dx_um"], float(np.abs(sim.locations - ref.locations).max()))
+        if wl["grid"]:
+            keep = sim.step_dt
+            sim.step_dt = spec["diffuse_dt"] * (spec["sd"] - 1) + 0.5 * spec["diffuse_dt"]
+            sim.update_concentrations("fgf4_values", 1.0, sample=False)
+            sim.update_diffusion("fgf4_values")
+            got = sim.update_concentrations("fgf4_values", None)
+            sim.step_dt = keep
+            orc.adjust_morphogens(ref.locations, 1.0, ref.fgf4_values, ref.spat_res)
+            keep = ref.step_dt
+            ref.step_dt = spec["diffuse_dt"] * (spec["sd"] - 1) + 0.5 * spec["diffuse_dt"]
+            ref.update_diffusion("fgf4_values")
+            ref.step_dt = keep
+            want = orc.get_concentrations(ref.locations, ref.fgf4_values, ref.spat_res)
+            out["max_abs_dfield"] = max(out["max_abs_dfield"], float(np.abs(sim.fgf4_values - ref.fgf4_values).max()))
+            out["max_abs_dsample"] = max(out["max_abs_dsample"], float(np.abs(np.asarray(got) - want).max()))
+    scale = float(np.abs(ref.locations).max())
+    out["max_rel_dx"] = out["max_abs_dx_um"] / scale
+    out["gates"] = "edges identical; positions 1e-12 relative (fp64 mode); field 1e-6"
+    out["ok"] = bool(out["neighbor_edges_equal"] and out["jkr_bonds_equal"] and out["max_rel_dx"] <= 1e-12 and
+                     (out["max_abs_dfield"] is None or out["max_abs_dfield"] <= 1e-6))
+    return out
 
 
 # ---- the B200 arm -------------------------------------------------------------------------------------------------
@@ -417,9 +522,9 @@ def run_b200(args, rank, world, local_rank):
 
         def api_step():
             sim.get_neighbors("neighbor_graph", 15)          # (returns with the device idle: record_time synchronises)
-            # stands in for cell_motility, a rule method outside the path (rule methods are not timed):
-            # apply_forces leaves motility_forces zeroed, so the step's input has to be written again -- host-only
-            # work between two public calls, clocked and subtracted
+            # stands in for cell_motility (a rule method outside the path): apply_forces leaves motility_forces
+            # zeroed, so the step's input has to be written again.  Host-only work between two public calls; it is
+            # INSIDE the e2e clock (and reported separately as input_fill_ms_per_step)
             t = time.perf_counter()
             sim.motility_forces[:] = mot_by_parity[api_count[0] % 2]
             fill = time.perf_counter() - t
@@ -445,7 +550,7 @@ def run_b200(args, rank, world, local_rank):
         for _ in range(e_steps):
             fill_s += api_step()
         torch.cuda.synchronize(dev)
-        e_s = time.perf_counter() - t0 - fill_s
+        e_s = time.perf_counter() - t0
         if dist is not None:
             t = torch.tensor([e_s], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -454,16 +559,18 @@ def run_b200(args, rank, world, local_rank):
                "h2d_bytes_per_step": (eng2.h2d_bytes - h2d0) // e_steps,
                "d2h_bytes_per_step": (eng2.d2h_bytes - d2h0) // e_steps, "steps": e_steps,
                "ms_per_step": e_s / e_steps * 1e3,
-               "input_fill_ms_per_step_not_timed": fill_s / e_steps * 1e3,
+               "input_fill_ms_per_step": fill_s / e_steps * 1e3,
+               "input_fill": "host write of the step's motility forces (stand-in for cell_motility), inside the clock",
                "api": "Simulation.get_neighbors + CellMethods.apply_forces + update_diffusion/update_concentrations"}
 
-    cpu = None
+    cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, spp, threads, sample = run_cpu(args.workload, 2, 1)
-        v1, spp1, _, _ = run_cpu(args.workload, 1, 1, threads=1)
+        parity = parity_check(args.workload, dev)
+        v, spp, threads, sample, _ = run_cpu(args.workload, 2, 1)
+        v1, spp1, _, sample1, _ = run_cpu(args.workload, 1, 1, threads=1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                "s_per_step": spp, "single_thread": {"value": v1, "s_per_step": spp1, "cores": 1,
-                                                     "sample": "same sample, 1 step after 1 warm-up"}}
+                                                     "sample": sample1}}
 
     if dist is not None:
         dist.barrier()
@@ -474,15 +581,14 @@ def run_b200(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {spec['desc']}", "cells_per_gpu": n, "dim": spec["dim"],
-                   "mechanics_substeps": sm, "diffusion_substeps": spec["sd"], "grid": wl["grid"],
-                   "edges_r15": e15, "jkr_bonds": ej, "l2": "flushed between timed steps (256 MiB memset)",
-                   "motility": MOTILITY_NOTE,
+        "config": common_config(args.workload, wl, sm),
+        "method": {"edges_r15": e15, "jkr_bonds": ej,
                    "morphogen_stage": ("reference order (before the mechanics, on the step's starting positions), "
                                        "on a second stream beside search + mechanics") if cfg.overlap_morphogen and
                    wl["grid"] else "after the mechanics, same stream",
                    "timing": "CUDA events per step around a CUDA-graph replay, summed; max over ranks",
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent colonies (replicas)"},
+                   "parallelism": "single GPU"},
+        "parity_check": parity,
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "stages": stages,
         "cpu_baseline": cpu,
     }
@@ -602,14 +708,12 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.workload} x {world}: {spec['desc']} per GPU, one colony", "cells_per_gpu": n,
-                   "cells_total": int(cells.item()), "dim": spec["dim"], "mechanics_substeps": len(cfg.substep_dts()),
-                   "diffusion_substeps": spec["sd"], "halo_um": halo,
+        "config": common_config(args.workload, wl, len(cfg.substep_dts()), world),
+        "method": {"cells_total": int(cells.item()), "halo_um": halo,
                    "morphogen_stage": ("reference order (before the mechanics), with its row exchange on a second "
                                        "stream beside search + mechanics") if first else "after the mechanics",
                    "exchanges_per_step": (fabric.exchanges - ex0) / max(args.steps + e_steps, 1),
                    "bytes_sent_per_step_rank0": (fabric.bytes_sent - bytes0) // max(args.steps + e_steps, 1),
-                   "l2": "flushed between timed steps (256 MiB memset)", "motility": MOTILITY_NOTE,
                    "timing": "CUDA events per step, summed; max over ranks",
                    "parallelism": f"slab{world}: 1-D slab decomposition along x; per step one cell-halo exchange "
                                   "(migration rides on it; fixed-capacity messages, no size handshake) and one "
@@ -627,12 +731,12 @@ def run_reference(args, rank, world):
     itself cannot travel to the GPU box), all host threads, on the same workload recipe."""
     if rank != 0:
         return None
-    v, spp, threads, sample = run_cpu(args.workload, args.steps, args.warmup)
-    spec = WORKLOADS[args.workload]
+    v, spp, threads, sample, wl = run_cpu(args.workload, args.steps, args.warmup)
+    sm = int(1800 // 180) + 1
     return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": spp * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {spec['desc']}"},
+            "config": common_config(args.workload, wl, sm, world, cpu_arm=True),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

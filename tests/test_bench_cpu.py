@@ -66,3 +66,28 @@ def test_reference_arm_prints_the_contract_line():
     cb = line["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == line["value"] and cb["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_cpu_arm_runs_the_stated_colony_when_it_fits_the_budget():
+    # c3 at the driver's --steps 20 --warmup 5: the whole 500,000-cell colony; c4's 4 M cells are sampled and say so
+    assert bench.cpu_sample_cells("c3", 25) == 500_000
+    assert bench.cpu_sample_cells("c2", 25) == 50_000
+    n4 = bench.cpu_sample_cells("c4", 25)
+    assert 100_000 <= n4 < 4_000_000
+    assert "sample" not in bench.workload_label("c3", 500_000, cpu_arm=True)
+    assert f"{n4}-cell sample" in bench.workload_label("c4", n4, cpu_arm=True)
+    assert "sample" in bench.workload_label("c3", 500_000, world=8, cpu_arm=True)     # one GPU's share of the colony
+    # both arms print the same workload-defining config when they run the same colony
+    wl = bench.make_workload("c2")
+    assert bench.common_config("c2", wl, 11) == bench.common_config("c2", wl, 11, cpu_arm=True)
+
+
+def test_reference_arm_ignores_torchrun_thread_cap():
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, cwd=ROOT, timeout=600,
+                         env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["cores"] == bench.host_cores()
+    assert f"on {bench.host_cores()} threads" in line["cpu_baseline"]["sample"]
