@@ -11,9 +11,16 @@
  *   - The caller owns every buffer, including workspaces; the library allocates nothing persistent.
  *   - Every call is asynchronous on `stream` (a cudaStream_t passed as void*) and never synchronises,
  *     except the *_sync helpers that must hand a count back to the host.
- *   - Return value: 0 ok; >0 capacity overflow (the wrapper grows the buffer and calls again, mirroring
- *     the reference's grow-and-retry loops simulation.py:217-221, 277-281); <0 invalid argument (-1) or
- *     -(1000+cudaError_t).  Nothing throws across the ABI; abm_last_error() describes the last failure.
+ *   - Return value: 0 ok; <0 invalid argument (-1) or -(1000+cudaError_t).  Nothing throws across the ABI;
+ *     abm_last_error() describes the last failure.
+ *   - Capacity overflow is NOT a return code (a call never waits for the device, so it cannot know): a kernel
+ *     that runs out of room writes what fits, and records the size it needed in a device counter the caller
+ *     passed in (`cursor` of abm_neighbor_search, `max_len` of abm_jkr_substep / abm_mechanics_loop, `counts` of
+ *     abm_slab_pack).  The caller reads the counter when it next synchronises (abm_read_i32_sync), and if it
+ *     exceeds the capacity it grows the buffer and calls again -- the reference's grow-and-retry loops
+ *     (simulation.py:217-221, 277-281) with the check moved off the critical path.
+ *   - No process-wide mutable state: every option is an argument of the call it affects (flags below); the only
+ *     things the library caches are per-device kernel attributes and the per-thread text of the last error.
  *   - Cell ids, bin ids, row offsets are int32; positions/forces/fields are float64 exactly as the
  *     reference holds them (simulation.py:136-149 dtypes).
  *   - Positions are (N,3) row-major float64 ("AoS", the reference's `locations`), radii (N,) float64.
@@ -28,7 +35,7 @@
 extern "C" {
 #endif
 
-#define ABM_B200_ABI_VERSION 1
+#define ABM_B200_ABI_VERSION 2
 
 /* flags of abm_bin_dims_host / abm_bin_sort */
 #define ABM_SORT_STABLE 1     /* ascending cell id inside a bin (the reference's fill order) */
@@ -37,24 +44,17 @@ extern "C" {
 #define ABM_LOOP_CARRY_IN 2    /* abm_mechanics_loop: the previous call did so (same n, lattice, workspace; its idle
                                   offset table is passed as bin_start_a): the first sort needs no histogram pass */
 #define ABM_SORT_PREBINNED 4  /* histogram + per-cell bin already written by abm_jkr_substep */
+#define ABM_SORT_CHAINED 8    /* abm_bin_sort(ABM_SORT_PREBINNED): launch its kernels with programmatic stream
+                                 serialization (see ABM_LOOP_CHAINED) */
+#define ABM_LOOP_CHAINED 4    /* abm_mechanics_loop: launch the kernels of the loop with programmatic stream
+                                 serialization, so that a kernel's CTAs become resident while the last wave of its
+                                 predecessor drains (they wait for its completion before touching memory) */
 
 /* ---- library ----------------------------------------------------------------------------------- */
 int abm_abi_version(void);          /* == ABM_B200_ABI_VERSION */
 int abm_compiled_arch(void);        /* 100 : built for sm_100a only */
 const char *abm_last_error(void);   /* thread-local text of the last non-zero return */
 
-/* Process-wide launch options; returns the previous value (>= 0) or -1 for an unknown option.
- * ABM_OPTION_CHAINED_LAUNCH (default 0): launch the kernels of abm_mechanics_loop / abm_bin_sort(PREBINNED) /
- *   abm_jkr_substep with programmatic stream serialization, so that a kernel's CTAs become resident while the
- *   last wave of its predecessor drains (they wait for its completion before touching memory).  Measured on B200:
- *   about -4 % per step for eager stream launches, but +3..15 % inside a captured CUDA graph -- switch it on for
- *   eager pipelines only.                                                                              */
-#define ABM_OPTION_CHAINED_LAUNCH 1
-/* ABM_OPTION_DIFFUSION_FUSE (default 5, range 1..5): diffusion substeps advanced per kernel launch by
- *   abm_diffusion (temporal blocking in shared memory; results are bit-identical for every value).  1 = one
- *   launch per substep.                                                                                */
-#define ABM_OPTION_DIFFUSION_FUSE 2
-int abm_set_option(int option, int value);
 /* fills sm_count / cc_major / cc_minor of the current device; <0 if there is no CUDA device */
 int abm_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
@@ -204,13 +204,15 @@ int abm_mechanics_loop(const double *radii, double *locations, const double *mot
  * 16-byte aligned pointers, returns -1 otherwise), 0 = plain staged loads.  Substeps ping-pong between
  * field and scratch: if result_in_scratch_host is NULL the result is copied back into `field` when
  * `steps` is odd; otherwise no copy is made and *result_in_scratch_host says where the result is.
- * Up to ABM_OPTION_DIFFUSION_FUSE substeps run per launch (k_diffuse_fused); chains of one use k_diffuse.   */
+ * max_fused_substeps (1..5; 0 = 5): diffusion substeps advanced per kernel launch (temporal blocking in shared
+ * memory, k_diffuse_fused; results are bit-identical for every value); chains of one use k_diffuse.   */
 int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t gy, int64_t steps, double diffuse_dt,
                   double last_dt, double diffuse_const, double spat_res2, double max_concentration,
-                  double degradation, int use_tma, int *result_in_scratch_host, void *stream);
-/* number of kernel launches abm_diffusion enqueues for `steps` substeps under the current ABM_OPTION_DIFFUSION_FUSE
- * (it has the parity of `steps`, so the result lands where the substep-by-substep ping-pong would leave it) */
-int64_t abm_diffusion_launches(int64_t steps);
+                  double degradation, int use_tma, int max_fused_substeps, int *result_in_scratch_host,
+                  void *stream);
+/* number of kernel launches abm_diffusion enqueues for `steps` substeps with that max_fused_substeps (it has the
+ * parity of `steps`, so the result lands where the substep-by-substep ping-pong would leave it) */
+int64_t abm_diffusion_launches(int64_t steps, int max_fused_substeps);
 
 /* Replaces per-cell get_concentration (cell_methods.py:470-483) for all cells: nearest grid point
  * idx = ceil(floor(2x/h)/2) on the (gx,gy,gz) grid.  `field` holds the global rows [row_lo,row_hi) of that grid,

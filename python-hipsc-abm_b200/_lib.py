@@ -23,7 +23,6 @@ L3 = C.POINTER(C.c_int64)     # host int64[3]
 SIGNATURES = {
     "abm_abi_version": (I32, []),
     "abm_compiled_arch": (I32, []),
-    "abm_set_option": (I32, [I32, I32]),
     "abm_last_error": (C.c_char_p, []),
     "abm_device_info": (I32, [C.POINTER(I32), C.POINTER(I32), C.POINTER(I32)]),
     "abm_bin_dims_host": (I32, [D3, F64, I32, I3]),
@@ -42,8 +41,8 @@ SIGNATURES = {
     "abm_mechanics_loop": (I32, [P, P, P, I64, D3, D3, D3, F64, F64, I32, C.POINTER(C.c_double),
                                  P, P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, P,
                                  F64, F64, F64, F64, F64, I32, P]),
-    "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),
-    "abm_diffusion_launches": (I64, [I64]),
+    "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, I32, C.POINTER(I32), P]),
+    "abm_diffusion_launches": (I64, [I64, I32]),
     "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P]),
     "abm_slab_workspace_bytes": (SZ, [I64]),
     "abm_slab_pack": (I32, [P, P, P, P, P, P, I64, P, I64, F64, F64, I32, I32, P, I64, P, I64, P, P, SZ, P]),
@@ -51,6 +50,9 @@ SIGNATURES = {
                              P]),
     "abm_deposit_morphogens": (I32, [P, P, F64, I64, P, L3, F64, I64, I64, P]),
 }
+
+
+ABI_VERSION = 2
 
 
 class AbmError(RuntimeError):
@@ -74,11 +76,9 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.abm_abi_version() != 1:
-        raise AbmError("libabm_b200.so ABI version mismatch")
-    fuse = os.environ.get("ABM_B200_DIFFUSION_FUSE")        # A/B switch: diffusion substeps per launch (1..5)
-    if fuse:
-        lib.abm_set_option(2, int(fuse))
+    if lib.abm_abi_version() != ABI_VERSION:
+        raise AbmError(f"libabm_b200.so ABI version {lib.abm_abi_version()} != {ABI_VERSION}: rebuild it "
+                       "(python python-hipsc-abm_b200/build.py)")
     _lib = lib
     return lib
 
@@ -91,10 +91,8 @@ def check(rc: int, what: str) -> int:
     return rc
 
 
-SORT_STABLE, SORT_REFERENCE, SORT_PREBINNED = 1, 2, 4
-OPTION_CHAINED_LAUNCH = 1
-OPTION_DIFFUSION_FUSE = 2
-LOOP_CARRY_OUT, LOOP_CARRY_IN = 1, 2
+SORT_STABLE, SORT_REFERENCE, SORT_PREBINNED, SORT_CHAINED = 1, 2, 4, 8
+LOOP_CARRY_OUT, LOOP_CARRY_IN, LOOP_CHAINED = 1, 2, 4
 
 
 def d3(values):

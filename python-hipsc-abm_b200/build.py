@@ -10,6 +10,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabm_b200.so")
 SOURCES = ["lib.cu", "sort.cu", "search.cu", "jkr.cu", "diffusion.cu", "slab.cu"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
+         "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 
 
 def nvcc_path():
@@ -19,21 +21,37 @@ def nvcc_path():
     raise RuntimeError("nvcc not found: libabm_b200.so cannot be built")
 
 
+STAMP = LIB + ".sha256"          # hash of the sources + flags the in-tree library was built from
+
+
+def source_hash(defines=()):
+    """sha256 over every file of csrc/, the public header, this recipe's flags and the -D switches."""
+    import hashlib
+    h = hashlib.sha256()
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(ROOT, "include", "abm_b200.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as f:
+            h.update(f.read())
+    h.update(repr((FLAGS, sorted(defines))).encode())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    """True unless the in-tree library was built from exactly the sources that are in the tree now (a hash, not a
+    modification time: a checkout, a copy to another box or a touched file must not fool it)."""
+    if not (os.path.exists(LIB) and os.path.exists(STAMP)):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "abm_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False, defines=(), out=None):
     """defines/out: build a variant library with -D switches (kernel A/B experiments, scripts/ab_substep.py)."""
     if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), "-shared", "-o", out or LIB, "-O3", "-std=c++17", "-lineinfo",
-           "-gencode", "arch=compute_100a,code=sm_100a",
-           "-Xcompiler", "-fPIC,-fvisibility=hidden", "-I", os.path.join(ROOT, "include"), "-I", CSRC,
+    cmd = [nvcc_path(), "-shared", "-o", out or LIB] + FLAGS + [
+           "-I", os.path.join(ROOT, "include"), "-I", CSRC,
            "-Xptxas", "-v" if verbose else "-warn-spills"] + [os.path.join(CSRC, s) for s in SOURCES]
     # the image's CC wrapper lacks pieces nvcc's host pass wants; use the distro g++ explicitly
     cmd += ["-D" + d for d in defines]
@@ -44,6 +62,9 @@ def build(force=False, verbose=False, defines=(), out=None):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
+    if out is None:
+        with open(STAMP, "w") as f:
+            f.write(source_hash() + "\n")
     return out or LIB
 
 

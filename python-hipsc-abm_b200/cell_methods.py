@@ -18,8 +18,10 @@ class B200CellMethods:
         """reference cell_methods.py:342-384: JKR force of every bond of jkr_graph into self.jkr_forces;
         bonds with d <= -0.360562 are deleted from the graph."""
         graph = self.jkr_graph
-        if graph.ecount() == 0 and graph._dev is None:
+        if graph._dev is None and graph.ecount() == 0:       # (device copy first: ecount() would download it)
             return
+        if graph.n != self.number_agents:
+            raise ValueError(f"jkr_graph has {graph.n} vertices for {self.number_agents} agents")
         eng = self.b200_upload(with_forces=True)
         g = graph.device_tensors(eng)
         eng.jkr_forces(g)
@@ -51,6 +53,9 @@ class B200CellMethods:
             uploaded = torch.cuda.Event()
             uploaded.record(torch.cuda.current_stream(eng.device))
             graph = self.jkr_graph
+            if graph.n != self.number_agents:
+                # a graph left un-resized after division / death would be read out of bounds on the device
+                raise ValueError(f"jkr_graph has {graph.n} vertices for {self.number_agents} agents")
             old = graph.device_tensors(eng)
 
             def reset_forces():

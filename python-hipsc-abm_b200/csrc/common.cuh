@@ -128,11 +128,11 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
-extern int g_diffusion_fuse;     // abm_set_option(ABM_OPTION_DIFFUSION_FUSE): diffusion.cu
-extern int g_chained_launch;    // abm_set_option(ABM_OPTION_CHAINED_LAUNCH): lib.cu
-
+// chained: launch with the programmatic-serialization attribute (the caller's ABM_LOOP_CHAINED / ABM_SORT_CHAINED
+// flag; there is no process-wide switch)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+inline cudaError_t launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool chained,
+                                  Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)block);
@@ -140,10 +140,20 @@ inline cudaError_t launch_chained(void (*kernel)(KArgs...), int grid, int block,
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = (ABM_PDL && g_chained_launch) ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (ABM_PDL && chained) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---- per-device caches ------------------------------------------------------------------------------
+// Function attributes (opt-in dynamic shared memory) and the SM count belong to a DEVICE, not to the process: a
+// second engine on cuda:1 must not inherit what was set / read on cuda:0.  Slot of the current device, or -1.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
 }
 
 // ---- warp helpers ----------------------------------------------------------------------------------

@@ -7,7 +7,7 @@
 // the substeps there on a region that shrinks by one ring per substep, and writes the tile once -- 2wG bytes of
 // field traffic and one launch per N substeps, for ~1.4x the arithmetic.  Every point still sees exactly the
 // reference's operations in the reference's order, so the result is bit-identical to substep-by-substep launches.
-// k_diffuse does a single substep (chains of length 1, and ABM_OPTION_DIFFUSION_FUSE = 1):
+// k_diffuse does a single substep (chains of length 1, and max_fused_substeps = 1):
 // One launch = one substep.  Persistent CTAs walk (kTileI x kTileJ) output tiles; the (kTileI+2) x
 // (kTileJ+4) input box of each tile is staged in shared memory through a kStages-deep ring, filled either
 // by TMA (cp.async.bulk.tensor.2d + mbarrier complete_tx, one elected thread) or by plain cooperative loads.
@@ -347,21 +347,21 @@ static int make_field_map(CUtensorMap *map, const double *ptr, long long gx, lon
     return 0;
 }
 
-int g_diffusion_fuse = kMaxFuse;     // abm_set_option(ABM_OPTION_DIFFUSION_FUSE): substeps per launch, 1..kMaxFuse
 
 template <int N>
 static int launch_fused(const double *from, double *to, long long gx, long long gy, int use_tma, const FuseParams &P,
                         int ntiles, cudaStream_t st) {
     using G = FuseGeom<N>;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[use_tma ? 1 : 0]) {
+    static bool attr_set[kMaxDevices][2] = {};          // per device (a function attribute is per device)
+    const int slot = current_device_slot();
+    if (slot < 0 || !attr_set[slot][use_tma ? 1 : 0]) {
         cudaError_t e = use_tma ? cudaFuncSetAttribute(k_diffuse_fused<N, true>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem)
                                 : cudaFuncSetAttribute(k_diffuse_fused<N, false>,
                                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::kSmem);
         int rc = check_cuda(e, "cudaFuncSetAttribute(k_diffuse_fused)");
         if (rc) return rc;
-        attr_set[use_tma ? 1 : 0] = true;
+        if (slot >= 0) attr_set[slot][use_tma ? 1 : 0] = true;
     }
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
@@ -382,16 +382,19 @@ using namespace abm;
 
 ABM_EXPORT int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t gy, int64_t steps,
                              double diffuse_dt, double last_dt, double diffuse_const, double spat_res2,
-                             double max_concentration, double degradation, int use_tma,
+                             double max_concentration, double degradation, int use_tma, int max_fused_substeps,
                              int *result_in_scratch_host, void *stream) {
     ABM_REQUIRE(field && scratch && field != scratch, "field/scratch must be distinct non-null buffers");
     ABM_REQUIRE(gx >= 1 && gy >= 1 && gx * gy < (1ll << 40), "bad grid size");
     ABM_REQUIRE(steps >= 1, "steps must be >= 1 (the reference always runs int(step_dt // diffuse_dt) + 1)");
     cudaStream_t st = as_stream(stream);
-    static int sm_count = 0;
+    static int sm_counts[kMaxDevices] = {};             // per device
+    const int slot = current_device_slot();
+    int sm_count = slot >= 0 ? sm_counts[slot] : 0;
     if (!sm_count) {
         int rc = abm_device_info(&sm_count, nullptr, nullptr);
         if (rc) return rc;
+        if (slot >= 0) sm_counts[slot] = sm_count;
     }
     CUtensorMap maps[2];
     memset(maps, 0, sizeof(maps));
@@ -403,15 +406,15 @@ ABM_EXPORT int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t
         rc = make_field_map(&maps[1], scratch, gx, gy);
         if (rc) return rc;
     }
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[use_tma ? 1 : 0]) {
+    static bool attr_set[kMaxDevices][2] = {};
+    if (slot < 0 || !attr_set[slot][use_tma ? 1 : 0]) {
         cudaError_t e = use_tma ? cudaFuncSetAttribute(k_diffuse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                        (int)kDiffSmem)
                                 : cudaFuncSetAttribute(k_diffuse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                        (int)kDiffSmem);
         int rc = check_cuda(e, "cudaFuncSetAttribute(k_diffuse)");
         if (rc) return rc;
-        attr_set[use_tma ? 1 : 0] = true;
+        if (slot >= 0) attr_set[slot][use_tma ? 1 : 0] = true;
     }
     DiffParams P;
     P.gx = gx;
@@ -423,9 +426,9 @@ ABM_EXPORT int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t
     int ntiles = P.tiles_i * P.tiles_j;
     int grid = ntiles < 2 * sm_count ? ntiles : 2 * sm_count;   // two resident CTAs per SM (106 KB each)
     double *bufs[2] = {field, scratch};
-    // Chains of up to g_diffusion_fuse substeps per launch.  The number of launches keeps the parity of `steps`, so
+    // Chains of up to max_fused_substeps substeps per launch.  The number of launches keeps the parity of `steps`, so
     // the result lands in the buffer the substep-by-substep chain would leave it in.
-    const int64_t launches = abm_diffusion_launches(steps);
+    const int64_t launches = abm_diffusion_launches(steps, max_fused_substeps);
     const int64_t per = steps / launches, longer = steps % launches;    // the first `longer` launches take per+1
     int64_t k = 0;
     for (int64_t l = 0; l < launches; ++l) {
@@ -478,9 +481,9 @@ ABM_EXPORT int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t
     return 0;
 }
 
-ABM_EXPORT int64_t abm_diffusion_launches(int64_t steps) {
+ABM_EXPORT int64_t abm_diffusion_launches(int64_t steps, int max_fused_substeps) {
     if (steps < 1) return 0;
-    const int64_t fuse = g_diffusion_fuse;
+    const int64_t fuse = max_fused_substeps < 1 ? kMaxFuse : (max_fused_substeps > kMaxFuse ? kMaxFuse : max_fused_substeps);
     int64_t launches = (steps + fuse - 1) / fuse;
     if ((launches ^ steps) & 1) ++launches;
     return launches;

@@ -107,6 +107,9 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 #if (ABM_JKR_EXP & 12) && !defined(ABM_ALLOW_WRONG_RESULTS)
 #error "ABM_JKR_EXP bits 4 and 8 are timing ablations that produce wrong results: add -DABM_ALLOW_WRONG_RESULTS"
 #endif
+#ifndef ABM_PDL_LATE
+#define ABM_PDL_LATE 0      // 1: trigger the dependent launch after the contact loop instead of at kernel entry
+#endif
 #ifndef ABM_JKR_MAXHITS
 #define ABM_JKR_MAXHITS 16
 #endif
@@ -197,7 +200,9 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     // column tid: first the parked partner slots, then (overwritten from the front) the ids of the new bond row
     __shared__ int column[kMaxHits][kJkrThreads];
     __shared__ float4 tiles[kJkrThreads / 32][kTileRows * kTileCap];
+#if !ABM_PDL_LATE
     pdl_launch_dependents();
+#endif
     const int tid = threadIdx.x;
     const int s = blockIdx.x * kJkrThreads + tid;
     pdl_wait();
@@ -431,6 +436,12 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
         }
     }
 
+#if ABM_PDL_LATE
+    // the successor (the next sort's scan) may start being scheduled once every CTA of this grid has come this far:
+    // its CTAs then take the place of this grid's last CTAs as they retire, instead of holding registers beside
+    // a whole wave that still has its contact loop to run
+    pdl_launch_dependents();
+#endif
     // ---- phase 4: the bond row.  cnt entries sit in the column; a crowded cell has `direct` more already in
     // global memory from row[kMaxHits] on (cnt == kMaxHits then, so the row is dense)
     const int total = cnt + direct;
@@ -536,7 +547,7 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                             const int32_t *global_id, const int32_t *slot_gid, double uniform_radius,
                             const double *next_extent_host, const double *next_origin_host,
                             int32_t *next_bin_counts, void *next_sort_workspace, void *stream,
-                            const int32_t *prev_slot = nullptr, int row_keys = 0) {
+                            const int32_t *prev_slot = nullptr, int row_keys = 0, bool chained = false) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(!(row_keys & 1) || prev_slot, "rows keyed by the previous slot need the prev_slot index");
@@ -576,7 +587,7 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
         fric.uni_inv = 1.0 / f;
     }
     auto kernel = uniform_radius > 0 ? k_jkr_substep<true> : k_jkr_substep<false>;
-    return check_cuda(launch_chained(kernel, ceil_div(n, kJkrThreads), kJkrThreads, as_stream(stream), bin_start,
+    return check_cuda(launch_chained(kernel, ceil_div(n, kJkrThreads), kJkrThreads, as_stream(stream), chained, bin_start,
                                      sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
                                      Radius(distance), reach * reach, BandConst::make(reach * 1.0000001), old,
                                      new_row_len, new_cols, (int)row_stride, max_len, motility_forces, locations, c,
@@ -620,6 +631,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
     ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
     const bool carry_in = (flags & ABM_LOOP_CARRY_IN) && n > 0 && n_substeps > 0;
     const bool carry_out = (flags & ABM_LOOP_CARRY_OUT) && n > 0;
+    const bool chained = flags & ABM_LOOP_CHAINED;
     ABM_REQUIRE(extent_host && size_host && bin_start_a && bin_start_b && bin_start_a != bin_start_b,
                 "need two distinct offset tables");
     BinGeom g;
@@ -634,7 +646,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
         const bool prebin = n > 0 && (!last || carry_out);        // hand the moved cells to the next sort
         // (the largest bin population is reported for the first sort of the loop only)
         int rc = bin_sort_impl(locations, radii, n, extent_host, origin_host, reach,
-                               (k || carry_in) ? ABM_SORT_PREBINNED : 0, table,
+                               ((k || carry_in) ? ABM_SORT_PREBINNED : 0) | (chained ? ABM_SORT_CHAINED : 0), table,
                                sorted_id, sorted_pos, sorted_bin, k ? nullptr : max_count, sort_workspace,
                                sort_workspace_bytes,
                                prebin ? other : nullptr, global_id, stream);   // the idle table is cleared on the way
@@ -654,7 +666,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                               motility_forces, last ? locations : nullptr, poisson, youngs, adhesion_const, stokes,
                               size_host, dts_host[k], global_id, slot_gid, uniform_radius,
                               prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
-                              prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys);
+                              prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained);
         if (rc) return rc;
         cur_start = nullptr;
         cur_stride = row_stride;

@@ -8,7 +8,6 @@
 namespace abm {
 
 static thread_local char g_error[512] = "";
-int g_chained_launch = 0;
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -47,21 +46,6 @@ JkrConst make_jkr_const(double poisson, double youngs, double adhesion, double u
 ABM_EXPORT int abm_abi_version(void) { return ABM_B200_ABI_VERSION; }
 
 ABM_EXPORT int abm_compiled_arch(void) { return 100; }
-
-ABM_EXPORT int abm_set_option(int option, int value) {
-    if (option == ABM_OPTION_CHAINED_LAUNCH) {
-        int old = abm::g_chained_launch;
-        abm::g_chained_launch = value ? 1 : 0;
-        return old;
-    }
-    if (option == ABM_OPTION_DIFFUSION_FUSE) {
-        int old = abm::g_diffusion_fuse;
-        abm::g_diffusion_fuse = value < 1 ? 1 : (value > 5 ? 5 : value);
-        return old;
-    }
-    abm::set_error("abm_set_option: unknown option %d", option);
-    return -1;
-}
 
 ABM_EXPORT const char *abm_last_error(void) { return abm::g_error; }
 

@@ -172,6 +172,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
                        int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
                        void *workspace, size_t workspace_bytes, int32_t *zero_table, const int32_t *global_id,
                        void *stream) {
+    const bool chained = flags & ABM_SORT_CHAINED;
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     ABM_REQUIRE(size_host && bin_start, "null pointer");
     BinGeom g;
@@ -207,7 +208,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
     const int nb = scan_blocks(nbins + 1);
     if (prebinned) {
         // the mechanics kernel that binned the cells also summed the histogram per scan chunk: one scan launch
-        rc = check_cuda(launch_chained(k_scan_apply, nb, kScanThreads, st, bin_start, nbins + 1,
+        rc = check_cuda(launch_chained(k_scan_apply, nb, kScanThreads, st, chained, bin_start, nbins + 1,
                                        (const int *)w.next_sums, (int *)nullptr, w.cursor, zero_table, max_count),
                         "k_scan_apply");
         if (rc) return rc;
@@ -220,7 +221,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
     }
     double4 *sp = reinterpret_cast<double4 *>(sorted_pos);
     if (prebinned) {
-        rc = check_cuda(launch_chained(k_rescatter, blocks, kThreads, st, (const int *)w.cell_bin,
+        rc = check_cuda(launch_chained(k_rescatter, blocks, kThreads, st, chained, (const int *)w.cell_bin,
                                        (const int *)w.tmp_id, (const double4 *)w.next_pos, w.cursor, (int)n, sorted_id,
                                        sp, sorted_bin, w.next_sums, nb, global_id, w.slot_gid,
                                        (ABM_JKR_EXP & 16) ? w.prev_slot : (int *)nullptr),

@@ -7,6 +7,7 @@ cell_methods.py sit on top of it; bench.py drives it directly for the HBM-reside
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from dataclasses import dataclass
 from typing import Optional
@@ -132,12 +133,37 @@ class GraphTensors:
                             self.row_len.clone(), self.cols.clone(), self.sorted_rows)
 
 
+class _LibOnDevice:
+    """The C-ABI library with every call issued while `device` is the current CUDA device: the kernels are launched
+    with <<<>>> on the engine's stream, which is only valid on the device the stream belongs to.  (An engine on
+    cuda:1 in a process whose current device is cuda:0 would otherwise launch into the wrong context.)"""
+
+    def __init__(self, lib, device):
+        self._lib, self._index = lib, device.index if device.index is not None else torch.cuda.current_device()
+        self._cache = {}
+
+    def __getattr__(self, name):
+        fn = self._cache.get(name)
+        if fn is None:
+            raw, index = getattr(self._lib, name), self._index
+
+            def fn(*args):
+                if torch.cuda.current_device() == index:
+                    return raw(*args)
+                with torch.cuda.device(index):
+                    return raw(*args)
+            self._cache[name] = fn
+        return fn
+
+
 class ColonyEngine:
     def __init__(self, size, device=None):
         if not torch.cuda.is_available():
             raise _lib.AbmError("ColonyEngine needs a CUDA device (B200); there is no CPU path")
-        self.lib = _lib.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.lib = _LibOnDevice(_lib.load(), self.device)
         self.size = np.asarray(size, dtype=np.float64).reshape(3)     # the [0,size] box positions are clamped to
         self._size_c = _lib.d3(self.size)
         self.set_bin_lattice(None, None)
@@ -155,6 +181,9 @@ class ColonyEngine:
         self.cols_capacity_hint = {}
         self.launches = 0      # number of kernels of this library enqueued (bench.py's gpu_launches)
         self.stream = 0
+        # per-engine launch options (arguments of the calls they affect; the library has no process-wide switches)
+        self.chained_launch = False     # abm_mechanics_loop(ABM_LOOP_CHAINED): programmatic dependent launches
+        self.diffusion_fuse = int(os.environ.get("ABM_B200_DIFFUSION_FUSE", "0"))   # substeps per launch, 0 = 5
         self.use_current_stream()
         self.h2d_bytes = 0     # bytes moved by upload()/to_device() and host()/locations_host()
         self.d2h_bytes = 0
@@ -492,6 +521,8 @@ class ColonyEngine:
         # everything the hand-over depends on: lattice, cells, radii (they travel with the positions), the buffers
         key = (nbins, n, self.loc.data_ptr(), self.radii.data_ptr(), reach, sb["ws"].data_ptr(),
                sb["bin_start"].data_ptr(), sb["bin_start_b"].data_ptr())
+        if self.chained_launch:
+            flags |= _lib.LOOP_CHAINED
         if carry and n:
             flags |= _lib.LOOP_CARRY_OUT
             if self._carry is not None and self._carry[:-1] == key:
@@ -553,8 +584,8 @@ class ColonyEngine:
         _lib.check(self.lib.abm_diffusion(_ptr(field), _ptr(scratch), gx, gy, int(steps), float(diffuse_dt),
                                           float(last_dt), float(diffuse_const), float(spat_res2),
                                           float(max_concentration), float(degradation), 1 if use_tma else 0,
-                                          C.byref(where), self.stream), "abm_diffusion")
-        self.launches += int(self.lib.abm_diffusion_launches(int(steps)))
+                                          self.diffusion_fuse, C.byref(where), self.stream), "abm_diffusion")
+        self.launches += int(self.lib.abm_diffusion_launches(int(steps), self.diffusion_fuse))
         return scratch if where.value else field
 
     def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None, n=None) -> torch.Tensor:

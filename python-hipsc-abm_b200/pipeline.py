@@ -12,6 +12,7 @@ silently wrong.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -71,6 +72,11 @@ class HotPathStep:
         n = engine.n
         dev = engine.device
         self.dts = cfg.substep_dts()
+        if len(self.dts) % 2 == 0:
+            # the bond rows alternate between two buffers from step to step, which needs an odd substep count
+            # (the reference's 1800/180 -> 11); checked here, before anything is enqueued
+            raise ValueError(f"HotPathStep needs an odd number of mechanics substeps, got {len(self.dts)} "
+                             f"(step_dt={cfg.step_dt}, move_dt={cfg.move_dt}); use engine.mechanics() for this case")
         cap = int(cfg.search_cols_per_cell * max(n, 1)) + 1024
         self.nbr = dict(row_start=torch.empty(max(n, 1), dtype=torch.int32, device=dev),
                         row_len=torch.zeros(max(n, 1), dtype=torch.int32, device=dev),
@@ -128,9 +134,7 @@ class HotPathStep:
         pair = [1 - src, 2]
         self.bonds = eng.enqueue_mechanics(self.bonds, cfg.contact_radius, self.dts, cfg.bond_stride, STOKES,
                                            pair=pair, zero_flag=False, carry=True)
-        self.parity = 1 - src if len(self.dts) % 2 else src
-        if len(self.dts) % 2 == 0:
-            raise ValueError("even substep counts are not wired in HotPathStep")
+        self.parity = 1 - src
         if overlap:
             torch.cuda.current_stream(eng.device).wait_stream(self._side)      # join
         elif self.field is not None:
@@ -165,8 +169,10 @@ class HotPathStep:
         """Capture the two alternating step variants (bond rows in buffer 0 -> 1 and 1 -> 0)."""
         assert self.parity == 0, "capture() must start from an even step"
         torch.cuda.synchronize(self.eng.device)
-        # programmatic dependent launches pay off for eager launches but cost inside a graph (include/abm_b200.h)
-        chained = self.eng.lib.abm_set_option(_lib.OPTION_CHAINED_LAUNCH, 0)
+        # programmatic dependent launches pay off for eager launches; inside a captured graph they were measured
+        # slower with the early trigger (profiles/r01b_kernels_c3.md) -- ABM_B200_GRAPH_PDL=1 keeps them for A/B runs
+        chained = self.eng.chained_launch
+        self.eng.chained_launch = os.environ.get("ABM_B200_GRAPH_PDL", "0") == "1"
         self.graphs = []
         launches = self.eng.launches
         # the mechanics stream outranks the second stream: search + morphogen kernels fill what the mechanics leave idle
@@ -183,7 +189,7 @@ class HotPathStep:
             self._carry_after.append(self.eng._carry)
             self._launches.append(self.launches_per_step)
         self.eng._carry = self._carry_before[0]
-        self.eng.lib.abm_set_option(_lib.OPTION_CHAINED_LAUNCH, chained)
+        self.eng.chained_launch = chained
         # capturing enqueues nothing on the device: undo the launch accounting, and the state did not advance
         self.eng.use_current_stream()         # leave the capture stream
         self.eng.launches = launches
@@ -237,7 +243,7 @@ class SlabPipeline:
         join_side()."""
         self.geom, self.cfg = geom, cfg
         self.eng = ColonyEngine(geom.size, device)
-        self.eng.lib.abm_set_option(_lib.OPTION_CHAINED_LAUNCH, 1)     # eager launches: chain the mechanics kernels
+        self.eng.chained_launch = True     # eager launches: chain the mechanics kernels (this engine only)
         self.eng.set_bin_lattice(*geom.local_box())
         self.dts = cfg.substep_dts()
         self.max_radius = float(max_radius)

@@ -41,6 +41,13 @@ class SlabGeometry:
     bounds: np.ndarray        # (world+1,) x interfaces, bounds[0] = 0, bounds[-1] = size[0]
     halo: float
 
+    def __post_init__(self):
+        # a slab thinner than the halo would need halo cells from its SECOND neighbour, which nobody sends: its
+        # owned cells would silently get wrong forces
+        if self.world > 1 and float(np.min(np.diff(self.bounds))) < self.halo:
+            raise ValueError(f"slab thinner than the halo ({float(np.min(np.diff(self.bounds))):.3f} < "
+                             f"{self.halo:.3f} um): use fewer slabs or a shallower halo")
+
     @staticmethod
     def uniform(size, world, rank, halo):
         size = np.asarray(size, dtype=np.float64)
@@ -95,11 +102,13 @@ class SlabGeometry:
         return np.array([lo, 0.0, 0.0]), np.array([hi - lo, self.size[1], self.size[2]])
 
 
-def required_halo(substeps, reach, slack=2.0):
+def required_halo(substeps, reach, slack=2.0, spat_res=0.0):
     """Halo depth that keeps owned cells exact for `substeps` communication-free substeps: the influence of a
     wrong halo-edge cell advances by at most reach + slack per substep (slack >= twice the largest
-    per-substep displacement)."""
-    return float(substeps) * (float(reach) + float(slack))
+    per-substep displacement; SlabPipeline.check() verifies that assumption against the displacement the mechanics
+    kernel records).  spat_res: grid pitch of a carried morphogen field -- halo cells deposit on owned grid rows
+    up to one pitch away, so their positions must be exact that much deeper."""
+    return float(substeps) * (float(reach) + float(slack)) + float(spat_res)
 
 
 FIELDS = ("loc", "radii", "mot", "gid", "bond_len", "bond_gid")

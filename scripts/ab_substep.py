@@ -16,8 +16,10 @@ VARIANTS = {                      # -D switches of csrc/jkr.cu (see the comment 
     "no_contact_loop": ["ABM_JKR_EXP=4", "ABM_ALLOW_WRONG_RESULTS"],            # timing ablations
     "no_walk_no_contact": ["ABM_JKR_EXP=12", "ABM_ALLOW_WRONG_RESULTS"],
     "no_pdl": ["ABM_PDL=0"],
+    "pdl_late": ["ABM_PDL_LATE=1"],        # dependent launch triggered after the contact loop (run with ABM_B200_GRAPH_PDL=1)
     "trim_math": ["ABM_JKR_EXP=32"],       # Horner polynomial + rsqrt without special cases (written without a GPU)
     "slot_rows_trim_math": ["ABM_JKR_EXP=48"],
+    "slot_rows_pdl_late": ["ABM_JKR_EXP=16", "ABM_PDL_LATE=1"],
     "slot_rows": ["ABM_JKR_EXP=16"],       # bond rows keyed by slot between substeps (written without a GPU: run the tests)
     # tile of the diffusion kernels (csrc/diffusion.cu); timed by the "diffuse_10_us" entry below
     "diff_16x128": ["ABM_DIFF_TILE_I=16"], "diff_32x64": ["ABM_DIFF_TILE_J=64"],
@@ -34,6 +36,9 @@ elif sys.argv[1] == "run":
     names = sys.argv[3:] or sorted(os.path.basename(f)[len("libabm_"):-3] for f in glob.glob(os.path.join(ROOT, "build_ab", "libabm_*.so")))
     for name in ["default"] + names:
         env = dict(os.environ)
+        if name.endswith("+pdl"):                 # "<variant>+pdl": programmatic dependent launches inside the graph too
+            env["ABM_B200_GRAPH_PDL"] = "1"
+            name = name[:-4]
         if name != "default":
             env["ABM_B200_LIB"] = os.path.join(ROOT, "build_ab", f"libabm_{name}.so")
         if not name.startswith("no_"):
@@ -113,4 +118,4 @@ else:
             z.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(z) * 1e3)
         res["diffuse_10_us"] = float(np.median(ts))
-    print(os.path.basename(os.environ.get("ABM_B200_LIB", "default")), name, {k: round(v, 1) for k, v in res.items()})
+    print(os.path.basename(os.environ.get("ABM_B200_LIB", "default")) + ("+pdl" if os.environ.get("ABM_B200_GRAPH_PDL") == "1" else ""), name, {k: round(v, 1) for k, v in res.items()})

@@ -43,7 +43,16 @@ def test_ctypes_binding_covers_every_symbol(built):
     from hipsc_abm_b200 import _lib
     assert sorted(_lib.SIGNATURES) == declared_symbols()
     lib = _lib.load()
-    assert lib.abm_abi_version() == 1 and lib.abm_compiled_arch() == 100
+    assert lib.abm_abi_version() == _lib.ABI_VERSION == 2 and lib.abm_compiled_arch() == 100
+
+
+def test_no_process_wide_options(built):
+    """no global mutable state.  Launch options are arguments (ABM_LOOP_CHAINED, max_fused_substeps)."""
+    assert "abm_set_option" not in declared_symbols()
+    lib = ctypes.CDLL(built.LIB_PATH)
+    assert not hasattr(lib, "abm_set_option")
+    from hipsc_abm_b200 import _lib
+    assert _lib.load().abm_diffusion_launches(10, 0) == 2 and _lib.load().abm_diffusion_launches(10, 1) == 10
 
 
 def test_host_helpers_need_no_gpu(built):

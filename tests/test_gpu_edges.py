@@ -117,9 +117,8 @@ def test_diffusion_small_and_ragged_grids(shape, steps):
 @pytest.mark.parametrize("steps", [2, 3, 6, 10, 11])
 def test_fused_diffusion_substeps_equal_one_launch_per_substep(steps):
     """abm_diffusion advances up to five substeps per launch in shared memory (k_diffuse_fused): the field is
-    bit-identical to the substep-by-substep chain (ABM_OPTION_DIFFUSION_FUSE = 1), lands in the same buffer, and
+    bit-identical to the substep-by-substep chain (max_fused_substeps = 1), lands in the same buffer, and
     takes the announced number of launches."""
-    from hipsc_abm_b200 import _lib
     rng = np.random.default_rng(steps)
     field = rng.random((203, 390)) * 3 - 0.5               # ragged in both directions, negative and >max values
     h, D = 7.0, 50.0
@@ -127,13 +126,13 @@ def test_fused_diffusion_substeps_equal_one_launch_per_substep(steps):
     eng = ColonyEngine([1, 1, 0])
     out = {}
     for fuse in (1, 5, 3):
-        old = eng.lib.abm_set_option(_lib.OPTION_DIFFUSION_FUSE, fuse)
+        old, eng.diffusion_fuse = eng.diffusion_fuse, fuse          # a per-engine argument of abm_diffusion
         try:
-            assert eng.lib.abm_diffusion_launches(steps) % 2 == steps % 2
+            assert eng.lib.abm_diffusion_launches(steps, fuse) % 2 == steps % 2
             if fuse == 1:
-                assert eng.lib.abm_diffusion_launches(steps) == steps
+                assert eng.lib.abm_diffusion_launches(steps, fuse) == steps
             else:
-                assert eng.lib.abm_diffusion_launches(steps) <= (steps + fuse - 1) // fuse + 1
+                assert eng.lib.abm_diffusion_launches(steps, fuse) <= (steps + fuse - 1) // fuse + 1
             for tma in (False, True):
                 src = torch.from_numpy(field.copy()).cuda()
                 scratch = torch.full_like(src, float("nan"))
@@ -141,7 +140,7 @@ def test_fused_diffusion_substeps_equal_one_launch_per_substep(steps):
                 assert (res.data_ptr() == scratch.data_ptr()) == bool(steps % 2)
                 out[fuse, tma] = res.cpu().numpy()
         finally:
-            eng.lib.abm_set_option(_lib.OPTION_DIFFUSION_FUSE, old)
+            eng.diffusion_fuse = old
     ref = orc.diffuse_field(field, steps, dt, dt * 0.4, D, h * h, 2.0, 0.1)
     for key, got in out.items():
         assert np.array_equal(got, ref), key
