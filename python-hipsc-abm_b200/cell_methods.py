@@ -26,7 +26,7 @@ class B200CellMethods:
         g = graph.device_tensors(eng)
         eng.jkr_forces(g)
         graph.set_device(g, eng)
-        self.jkr_forces = eng.host(eng.jkr)
+        self.b200_adopt_host("jkr_forces", eng.host(eng.jkr), eng.jkr)
 
     jkr_neighbor_forces = calculate_jkr
 
@@ -57,17 +57,30 @@ class B200CellMethods:
                 # a graph left un-resized after division / death would be read out of bounds on the device
                 raise ValueError(f"jkr_graph has {graph.n} vertices for {self.number_agents} agents")
             old = graph.device_tensors(eng)
+            # Forces already sitting in jkr_forces at entry: the reference's first calculate_jkr accumulates on top
+            # of them and the first integration consumes them (cell_backend.py:108-109, cell_methods.py:435-436).
+            # The array is known to be zero if nobody wrote to it since this method zeroed it last time.
+            pre = self._b200_pending_jkr()
+            if pre is not None:
+                first_mot = eng.mot + eng.to_device(pre, "jkr_forces")
+                keep = eng.mot
+                eng.mot = first_mot
+                try:
+                    old, graph.row_stride_hint = eng.mechanics(old, distance, dts[:1], graph.row_stride_hint, STOKES)
+                finally:
+                    eng.mot = keep
+                dts = dts[1:]
 
             def reset_forces():
                 # the reference leaves both force arrays zeroed (cell_methods.py:436,439); do it while the device
                 # runs the loop -- jkr_forces is not read by the fused loop, motility_forces once its upload is done
-                self.jkr_forces[:, :] = 0
+                self._b200_zero("jkr_forces")
                 uploaded.synchronize()
-                self.motility_forces[:, :] = 0
+                self._b200_zero("motility_forces")
             bonds, graph.row_stride_hint, moved = eng.mechanics(old, distance, dts, graph.row_stride_hint, STOKES,
                                                                 meanwhile=reset_forces, fetch_locations=True)
             graph.set_device(bonds, eng)
-            self.locations = moved
+            self.b200_adopt_host("locations", moved, eng.loc)
             return
         else:
             for step in range(total_steps):
@@ -75,23 +88,79 @@ class B200CellMethods:
                 self.calculate_jkr()
                 eng = self.b200_upload(with_forces=True)
                 eng.integrate(dts[step], zero_jkr=False, stokes=STOKES)
-                self.locations = eng.locations_host()
+                self.b200_adopt_host("locations", eng.locations_host(), eng.loc)
                 self.jkr_forces[:, :] = 0
         self.motility_forces[:, :] = 0
 
+    def _b200_zero(self, name):
+        """array[:, :] = 0 on the host, remembered: an array nobody has written to since is known to be zero."""
+        a = self.__dict__[name]
+        zeros = self.__dict__.setdefault("_b200_zeroed", {})
+        known = zeros.get(name)
+        from .arrays import TrackedArray, track
+        if known is not None and isinstance(a, TrackedArray) and a._b200 is known[0] and a._b200.gen == known[1]:
+            return                                          # still the zeros written last time
+        t = track(a)
+        if t is not a:
+            self.__dict__[name] = t
+        t.view(np.ndarray)[...] = 0
+        t._touch()
+        zeros[name] = (t._b200, t._b200.gen)
+        entry = self.__dict__.get("_b200_cache", {}).get(name)
+        if entry is not None and entry.state is t._b200 and entry.shape == t.shape:
+            entry.tensor.zero_()             # (stream-ordered behind the loop that read it) device copy == host zeros
+            entry.refresh()
+
+    def _b200_pending_jkr(self):
+        """jkr_forces if it may hold non-zero values at entry of apply_forces, else None."""
+        a = self.__dict__.get("jkr_forces")
+        if a is None:
+            return None
+        known = self.__dict__.get("_b200_zeroed", {}).get("jkr_forces")
+        from .arrays import TrackedArray
+        if known is not None and isinstance(a, TrackedArray) and a._b200 is known[0] and a._b200.gen == known[1]:
+            return None
+        plain = np.asarray(a).view(np.ndarray)
+        return np.ascontiguousarray(plain, dtype=np.float64) if plain.any() else None
+
     # ---- a10/a11 ---------------------------------------------------------------------------------------------
+    def _b200_field(self, gradient_name):
+        """(host field, device tensor of the same shape).  Uploaded only if the host array changed since the device
+        copy was made or downloaded (arrays.py); the three morphogen calls of a step then share one device copy."""
+        f, _ = self.b200_device_array(gradient_name)
+        return self.__dict__[gradient_name], f
+
+    def _b200_field_to_host(self, gradient_name, device_field):
+        """The device field is the newer one: bring the host array up to date (in place, it keeps its identity)."""
+        eng = self.b200_engine()
+        field = self.__dict__[gradient_name]
+        plain = np.asarray(field).view(np.ndarray)
+        eng.host_into(device_field.view(plain.shape), plain)
+        entry = self.__dict__.get("_b200_cache", {}).get(gradient_name)
+        if entry is not None:
+            entry.tensor = device_field
+            entry.refresh()
+
     @record_time
     def update_diffusion(self, gradient_name):
         """reference cell_methods.py:441-468 for the (gx,gy,1) float64 field `gradient_name`."""
-        import torch
         steps, last_dt = divmod(self.step_dt, self.diffuse_dt)
         steps = int(steps) + 1
         eng = self.b200_engine()
-        field = self.__dict__[gradient_name]
-        plane = eng.to_device(np.ascontiguousarray(field[:, :, 0], dtype=np.float64), "field")
+        field, f = self._b200_field(gradient_name)
+        out = self._b200_diffuse_plane(eng, f, steps, last_dt)
+        self._b200_field_to_host(gradient_name, out)
+
+    def _b200_diffuse_plane(self, eng, f, steps, last_dt):
+        """`steps` diffusion substeps on the z = 0 plane of the device field f (gx,gy,1); returns the device field
+        holding the result (f itself, or its ping-pong partner)."""
+        if f.dim() == 3 and f.shape[2] != 1:
+            raise NotImplementedError("update_diffusion follows the reference: the z = 0 plane of a (gx,gy,1) field; "
+                                      "3-D fields go through update_diffusion_3d")
+        plane = f.view(f.shape[0], f.shape[1])
         out = eng.diffuse(plane, steps, self.diffuse_dt, last_dt, self.diffuse_const, self.spat_res2,
                           self.max_concentration, self.degradation)
-        eng.host_into(out, field[:, :, 0])
+        return out.view(f.shape)
 
     # ---- a12/a13 ---------------------------------------------------------------------------------------------
     def get_concentration(self, gradient_name, index):
@@ -103,26 +172,45 @@ class B200CellMethods:
         self.update_concentrations(gradient_name, np.array([amount], dtype=np.float64),
                                    cells=slice(index, index + 1), sample=False)
 
-    def update_concentrations(self, gradient_name, amounts=None, cells=slice(None), sample=True):
-        """Batched get_concentration + adjust_morphogens over `cells` (default: all): every cell first reads
-        its nearest grid point, then -- if `amounts` is given -- deposits amounts[i] on its in-range corner
-        points.  Returns the sampled concentrations (or None if sample=False)."""
+    def update_concentrations(self, gradient_name, amounts=None, cells=slice(None), sample=True, diffuse=False):
+        """Batched get_concentration + adjust_morphogens over `cells` (default: all).  Order of the stages:
+
+          diffuse=False (default)  every cell first reads its nearest grid point (if sample), then -- if `amounts` is
+                                   given -- deposits amounts[i] on its in-range corner points;
+          diffuse=True             deposit -> update_diffusion -> sample as ONE pass over a device-resident field
+                                   (the north star's "diffusion fused with the per-cell gradient sampling"): what three
+                                   separate calls update_concentrations(amounts, sample=False); update_diffusion();
+                                   update_concentrations(None) compute, with one download of the field instead of two
+                                   and none of the intermediate uploads.
+
+        Returns the sampled concentrations (or None if sample=False)."""
         eng = self.b200_engine()
-        field = self.__dict__[gradient_name]
-        locations = np.ascontiguousarray(self.locations[cells], dtype=np.float64)
-        saved = (eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng._max_radius)
-        eng.n = len(locations)
-        eng.loc = eng.to_device(locations, "loc")
-        try:
-            f = eng.to_device(np.ascontiguousarray(field, dtype=np.float64), "field")
-            sampled = eng.host(eng.sample(f, self.spat_res)) if sample else None
-            if amounts is not None:
-                if np.ndim(amounts) == 0:                     # one amount for every cell: no array travels
-                    eng.deposit(f, float(amounts), self.spat_res)
-                else:
-                    a = np.ascontiguousarray(np.broadcast_to(np.asarray(amounts, dtype=np.float64), (eng.n,)))
-                    eng.deposit(f, eng.to_device(a, "amounts"), self.spat_res)
-                eng.host_into(f.view(field.shape), field)
-        finally:
-            eng.n, eng.loc, eng.radii, eng.mot, eng.jkr, eng._max_radius = saved
+        whole = isinstance(cells, slice) and cells == slice(None)
+        n = int(self.number_agents)
+        if whole:
+            loc, _ = self.b200_device_array("locations", (n, 3))
+            count = n
+        else:
+            part = np.ascontiguousarray(np.asarray(self.locations).view(np.ndarray)[cells], dtype=np.float64)
+            loc, count = eng.to_device(part, "loc_part"), len(part)
+        field, f = self._b200_field(gradient_name)
+        sampled = None
+        changed = False
+        if sample and not diffuse:
+            sampled = eng.host(eng.sample(f, self.spat_res, loc=loc, n=count))
+        if amounts is not None:
+            if np.ndim(amounts) == 0:                     # one amount for every cell: no array travels
+                eng.deposit(f, float(amounts), self.spat_res, loc=loc, n=count)
+            else:
+                a = np.ascontiguousarray(np.broadcast_to(np.asarray(amounts, dtype=np.float64), (count,)))
+                eng.deposit(f, eng.to_device(a, "amounts"), self.spat_res, loc=loc, n=count)
+            changed = True
+        if diffuse:
+            steps, last_dt = divmod(self.step_dt, self.diffuse_dt)
+            f = self._b200_diffuse_plane(eng, f, int(steps) + 1, last_dt)
+            changed = True
+            if sample:
+                sampled = eng.host(eng.sample(f, self.spat_res, loc=loc, n=count), sync=False)
+        if changed:
+            self._b200_field_to_host(gradient_name, f)     # synchronises the stream: `sampled` is complete too
         return sampled

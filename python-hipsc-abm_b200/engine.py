@@ -282,6 +282,25 @@ class ColonyEngine:
         self.jkr = (self.to_device(np.asarray(jkr, dtype=np.float64), "jkr")
                     if jkr is not None else self._zeros((n, 3), torch.float64))
 
+    def adopt(self, n, loc=None, radii=None, radii_host=None, mot=None, jkr=None):
+        """Replace individual device arrays (tensors that already live on the device) and keep the others: what
+        the reference-facing methods use when only some of the host arrays changed since the last call
+        (arrays.py).  Radius statistics are re-evaluated only when the radii change."""
+        self.use_current_stream()
+        if n != self.n or loc is not None or radii is not None:
+            self._carry = None
+        self.n = int(n)
+        if loc is not None:
+            self.loc = loc
+        if radii is not None:
+            self.radii = radii
+            self._radii_host = radii_host
+            self._max_radius = self._uniform_radius = None if n else 0.0
+        if mot is not None:
+            self.mot = mot
+        if jkr is not None:
+            self.jkr = jkr
+
     def set_device_state(self, loc, radii, mot=None, jkr=None, max_radius=None, uniform_radius=0.0):
         """Adopt tensors that already live on the device (no copies)."""
         self.use_current_stream()

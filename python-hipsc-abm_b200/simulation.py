@@ -48,21 +48,84 @@ class B200Simulation:
             self.__dict__["_b200_engine"] = eng
         return eng
 
-    def b200_upload(self, with_forces=False):
-        """Phase boundary host -> device: the rule methods replace / edit the numpy agent arrays freely
-        (np.delete, np.concatenate, in-place +=; reference cell_methods.py:39-44, 86-105), so the arrays the
-        path reads are re-sent at the start of every public hot-path call."""
+    # "tracked": a host array is uploaded only when it changed since the device copy was made (arrays.py);
+    # "always": every public call re-uploads what it reads (always correct, also for writes numpy cannot show)
+    b200_coherence = "tracked"
+
+    def b200_mark_dirty(self, *names):
+        """Tell the path that `names` (all agent arrays / fields if none given) were modified behind numpy's back
+        (raw pointers, ctypes, a JIT kernel): their device copies are dropped and re-uploaded at the next use."""
+        cache = self.__dict__.setdefault("_b200_cache", {})
+        for name in (names or list(cache)):
+            cache.pop(name, None)
+
+    def b200_device_array(self, name, shape=None, dtype=np.float64, view=None):
+        """Device tensor holding the current contents of the host array `self.<name>`.  Uploads -- and from then on
+        tracks the array's in-place writes -- only if the device copy is not known to be current.
+        shape: required shape (a scalar / strided array is materialised first); view: callable taking the host array
+        to the part that travels (e.g. the [:, :, 0] plane of a morphogen field)."""
+        from .arrays import DeviceCopy, track
         eng = self.b200_engine()
-        want_jkr = with_forces is True            # with_forces="motility": the fused loop never reads jkr_forces
-        eng.upload(self.locations, self.radii,
-                   self.motility_forces if with_forces and hasattr(self, "motility_forces") else None,
-                   self.jkr_forces if want_jkr and hasattr(self, "jkr_forces") else None)
+        cache = self.__dict__.setdefault("_b200_cache", {})
+        a = self.__dict__[name]
+        entry = cache.get(name)
+        if entry is not None and self.b200_coherence == "tracked" and entry.current_for(a):
+            return entry.tensor, False
+        host = np.asarray(a)
+        if shape is not None and host.shape != tuple(shape):
+            host = np.ascontiguousarray(np.broadcast_to(host, shape))     # scalar radius etc.: untracked, re-sent
+            tracked = None
+        else:
+            tracked = track(a)
+            if tracked is not a:
+                self.__dict__[name] = tracked                    # same memory, now with a write counter
+            host = tracked.view(np.ndarray)
+        part = host if view is None else view(host)
+        tensor = eng.to_device(np.ascontiguousarray(part, dtype=dtype), name)
+        if tracked is not None:
+            cache[name] = DeviceCopy(tracked, tensor)
+        else:
+            cache.pop(name, None)
+        return tensor, True
+
+    def b200_adopt_host(self, name, array, tensor):
+        """`array` (fresh from a device download of `tensor`) becomes self.<name>, known to be coherent."""
+        from .arrays import DeviceCopy, track
+        tracked = track(array)
+        self.__dict__[name] = tracked
+        self.__dict__.setdefault("_b200_cache", {})[name] = DeviceCopy(tracked, tensor)
+        return tracked
+
+    def b200_upload(self, with_forces=False):
+        """Phase boundary host -> device.  The rule methods replace / edit the numpy agent arrays freely
+        (np.delete, np.concatenate, in-place +=; reference cell_methods.py:39-44, 86-105); each array the path
+        reads is sent again only if it changed since its device copy was made (arrays.py), so an unchanged
+        `locations` / `radii` costs nothing at the next call."""
+        eng = self.b200_engine()
+        eng.use_current_stream()
+        n = int(self.number_agents)
+        loc, loc_new = self.b200_device_array("locations", (n, 3))
+        rad, rad_new = self.b200_device_array("radii", (n,))
+        mot = jkr = None
+        if with_forces and hasattr(self, "motility_forces"):
+            mot, _ = self.b200_device_array("motility_forces", (n, 3))
+        if with_forces is True and hasattr(self, "jkr_forces"):    # "motility": the fused loop handles jkr itself
+            jkr, _ = self.b200_device_array("jkr_forces", (n, 3))
+        stale_n = eng.n != n
+        eng.adopt(n, loc if (loc_new or stale_n or eng.loc is not loc) else None,
+                  rad if (rad_new or stale_n or eng.radii is not rad) else None,
+                  np.asarray(self.radii).view(np.ndarray) if np.shape(self.radii) == (n,) else None, mot, jkr)
+        if mot is None and (eng.mot is None or eng.mot.shape[0] != n):
+            eng.mot = eng._zeros((n, 3), __import__("torch").float64)
+        if jkr is None and (eng.jkr is None or eng.jkr.shape[0] != n):
+            eng.jkr = eng._zeros((n, 3), __import__("torch").float64)
         return eng
 
     def __getstate__(self):
         # Simulation.temp() pickles the whole object (reference simulation.py:290-298): drop device handles
         state = dict(self.__dict__)
         state.pop("_b200_engine", None)
+        state.pop("_b200_cache", None)           # device copies; the arrays themselves pickle as plain ndarrays
         return state
 
     # ---- reference surface --------------------------------------------------------------------------------
