@@ -59,8 +59,10 @@ def test_steady_state_traffic_and_identity_with_always_upload():
         outs.append((sim.locations.copy(), sim.fgf4_values.copy(), sampled.copy(), sim.jkr_graph.edge_array(),
                      sim.neighbor_graph.edge_array(), per_step))
     a, b = outs
-    for x, y in zip(a[:5], b[:5]):
-        assert np.array_equal(x, y)                               # skipping uploads changes nothing, bit for bit
+    for k in (0, 3, 4):
+        assert np.array_equal(a[k], b[k])                         # skipping uploads changes nothing, bit for bit
+    # (the field is built by fp64 atomic adds, whose order -- and with it the last bit -- is not fixed: gate 1e-6)
+    assert np.abs(a[1] - b[1]).max() <= 1e-12 and np.abs(a[2] - b[2]).max() <= 1e-12
     field_bytes = g * g * 8
     # tracked, from the second step on: only the step's motility forces go up; positions, the field and the sampled
     # concentrations come down once each

@@ -8,11 +8,19 @@ with the restated host rules (oracle/model.py) on top of
 
 Free-running identity has a horizon: the colony mechanics amplify ulp-level arithmetic differences (libm sqrt/pow
 vs BLAS dnrm2 / LLVM pow, summation order) by roughly x10 every 15 steps until a contact at the edge of a
-threshold flips (hazard iii).  Against the reference's recording the CPU oracle stays identical in every
-discrete array through step 84 of the 100-step run, so the free-running tests assert the first FREE_HORIZON steps,
-and the full 100 steps are asserted with teacher forcing: every step starts from the teacher's state, and the
-student must reproduce its discrete states and graphs exactly and its positions to 1e-12 (the fp64-mode gate).
+threshold flips (hazard iii).  The horizon is a property of the MODEL, not of an implementation:
+oracle/horizon_probe.py runs the reference itself (Numba, one thread) from the recording's seed with one coordinate
+of one cell moved by ONE unit in the last place before the first step, and the reference leaves its own recording
+after step 83 (five perturbations) / 86 (one) -- tests/golden/horizon_c1_100.json.  No implementation whose
+arithmetic is not bit-identical to Numba's LLVM code can stay on the recording longer than that.  So:
+  * the free-running tests MEASURE how long each backend stays identical in every discrete array, agent count and
+    edge count (the number is printed and, on the GPU box, written to gpurun_out/horizon_b200.json) and require it to
+    reach REQUIRED_FRACTION of the reference's own 1-ulp horizon;
+  * all 100 steps are asserted with teacher forcing: every step starts from the teacher's state, and the student
+    must reproduce its discrete states and graphs exactly and its positions to 1e-12 (the fp64-mode gate).
 """
+import json
+import os
 import random
 
 import numpy as np
@@ -22,8 +30,16 @@ from conftest import load_golden
 from oracle import oracle as orc
 from oracle.model import ColonyRules
 
+from conftest import GOLDEN, ROOT
+
 DISCRETE = ("states", "GATA6", "NANOG", "FGF4", "FGFR", "ERK")
-FREE_HORIZON = 60
+with open(os.path.join(GOLDEN, "horizon_c1_100.json")) as _f:
+    REFERENCE_HORIZON = json.load(_f)["horizon_min"]          # 83: the reference vs itself after a 1-ulp nudge
+REQUIRED_FRACTION = 0.9
+
+
+class Diverged(Exception):
+    pass
 
 
 class OracleBacked(ColonyRules, orc.OracleSim):
@@ -37,6 +53,8 @@ class OracleBacked(ColonyRules, orc.OracleSim):
 
 
 def run_and_compare(sim, g):
+    """Free run from the recording's seed.  Returns (steps identical to the recording, what differed first, worst
+    position difference while identical)."""
     seed, n0, end_step = int(g["meta"][0]), int(g["meta"][1]), int(g["meta"][2])
     random.seed(seed)
     np.random.seed(seed)
@@ -46,24 +64,49 @@ def run_and_compare(sim, g):
 
     def check(s):
         k = s.current_step
-        assert s.number_agents == int(g[f"n_{k}"]), f"agent count differs at step {k}"
+        if s.number_agents != int(g[f"n_{k}"]):
+            raise Diverged(k, "agent count")
         for name in DISCRETE:
-            assert np.array_equal(getattr(s, name), g[f"{name}_{k}"]), f"{name} differs at step {k}"
-        assert s.neighbor_graph.ecount() == int(g[f"nbr_edges_{k}"]), f"neighbour edges differ at step {k}"
-        assert s.jkr_graph.ecount() == int(g[f"jkr_edges_{k}"]), f"JKR bonds differ at step {k}"
+            if not np.array_equal(getattr(s, name), g[f"{name}_{k}"]):
+                raise Diverged(k, name)
+        if s.neighbor_graph.ecount() != int(g[f"nbr_edges_{k}"]):
+            raise Diverged(k, "neighbour edge count")
+        if s.jkr_graph.ecount() != int(g[f"jkr_edges_{k}"]):
+            raise Diverged(k, "JKR bond count")
         if f"locations_{k}" in g:
             worst[0] = max(worst[0], np.abs(s.locations - g[f"locations_{k}"]).max())
             assert np.array_equal(s.div_counters, g[f"div_counters_{k}"])
 
-    sim.run(min(end_step, FREE_HORIZON), check)
-    return worst[0]
+    try:
+        sim.run(end_step, check)
+    except Diverged as d:
+        return d.args[0] - 1, d.args[1], worst[0]
+    return end_step, None, worst[0]
+
+
+def required_steps(end_step):
+    return min(end_step, int(REQUIRED_FRACTION * REFERENCE_HORIZON))
+
+
+def record_horizon(backend, case, horizon, what, drift):
+    print(f"\n[horizon] {backend} {case}: identical to the reference recording through step {horizon}"
+          f"{'' if what is None else ' (first difference: ' + what + ')'}; reference vs itself after a 1-ulp nudge: "
+          f"{REFERENCE_HORIZON}; worst position difference while identical {drift:.2e} um")
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        path = os.path.join(out, "horizon_b200.json")
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[f"{backend}:{case}"] = {"identical_through_step": horizon, "first_difference": what,
+                                     "reference_1ulp_horizon": REFERENCE_HORIZON, "worst_dx_um": drift}
+        json.dump(data, open(path, "w"), indent=1)
 
 
 @pytest.mark.parametrize("case", ["c1_20", "c1_3d_10", "c1_100"])
 def test_oracle_backend_reproduces_reference_states(case):
     g = load_golden("model_" + case)
-    drift = run_and_compare(OracleBacked(g["meta"][4:7]), g)
-    assert drift <= 1e-9            # positions: libm vs Numba arithmetic, accumulated over the run
+    horizon, what, drift = run_and_compare(OracleBacked(g["meta"][4:7]), g)
+    record_horizon("oracle", case, horizon, what, drift)
+    assert horizon >= required_steps(int(g["meta"][2])), f"left the recording after step {horizon}: {what}"
 
 
 @pytest.mark.gpu
@@ -78,8 +121,32 @@ def test_b200_backend_reproduces_reference_states(case):
             self.init_constants(size)
 
     g = load_golden("model_" + case)
-    drift = run_and_compare(B200Backed(g["meta"][4:7]), g)
-    assert drift <= 1e-9            # fp64 mode gate is 1e-12 relative per step; this is the whole-run drift
+    horizon, what, drift = run_and_compare(B200Backed(g["meta"][4:7]), g)
+    record_horizon("b200_fused", case, horizon, what, drift)
+    assert horizon >= required_steps(int(g["meta"][2])), f"left the recording after step {horizon}: {what}"
+
+
+@pytest.mark.gpu
+def test_b200_strict_order_backend_horizon():
+    """The stage-by-stage path (get_neighbors -> calculate_jkr -> integrate per substep): k_jkr_rows evaluates the
+    contact model in the reference's operation order (division, cbrt, sqrt; cell_backend.py:79-109) and sums each
+    cell's bonds in ascending partner id, which is the serial reference's += order.  Its horizon against the recording
+    is measured next to the fused kernel's; both are bounded by the reference's own 1-ulp horizon."""
+    from hipsc_abm_b200.cell_methods import B200CellMethods
+    from hipsc_abm_b200.simulation import ColonySimulation
+
+    class Strict(ColonyRules, B200CellMethods, ColonySimulation):
+        def __init__(self, size):
+            ColonySimulation.__init__(self, size)
+            self.init_constants(size)
+
+        def calculate_jkr(self):                  # any override of calculate_jkr selects the unfused loop
+            return B200CellMethods.calculate_jkr(self)
+
+    g = load_golden("model_c1_100")
+    horizon, what, drift = run_and_compare(Strict(g["meta"][4:7]), g)
+    record_horizon("b200_strict_order", "c1_100", horizon, what, drift)
+    assert horizon >= required_steps(100), f"left the recording after step {horizon}: {what}"
 
 
 def copy_state(src, dst):
