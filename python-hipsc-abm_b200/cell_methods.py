@@ -79,6 +79,9 @@ class B200CellMethods:
                 self._b200_zero("motility_forces")
             bonds, graph.row_stride_hint, moved = eng.mechanics(old, distance, dts, graph.row_stride_hint, STOKES,
                                                                 meanwhile=reset_forces, fetch_locations=True)
+            # only now (a row overflow makes eng.mechanics run the loop again, and the loop reads the device forces):
+            # the device copy follows the host array to zero, so an untouched array is not uploaded next time
+            self._b200_zero_device("motility_forces")
             graph.set_device(bonds, eng)
             self.b200_adopt_host("locations", moved, eng.loc)
             return
@@ -106,9 +109,16 @@ class B200CellMethods:
         t.view(np.ndarray)[...] = 0
         t._touch()
         zeros[name] = (t._b200, t._b200.gen)
+
+    def _b200_zero_device(self, name):
+        """The host array `name` is known to be all zeros: make its device copy (if any) the same and current."""
+        a = self.__dict__[name]
+        known = self.__dict__.get("_b200_zeroed", {}).get(name)
         entry = self.__dict__.get("_b200_cache", {}).get(name)
-        if entry is not None and entry.state is t._b200 and entry.shape == t.shape:
-            entry.tensor.zero_()             # (stream-ordered behind the loop that read it) device copy == host zeros
+        from .arrays import TrackedArray
+        if (known is not None and entry is not None and isinstance(a, TrackedArray) and a._b200 is known[0] and
+                a._b200.gen == known[1] and entry.state is a._b200 and entry.shape == a.shape):
+            entry.tensor.zero_()
             entry.refresh()
 
     def _b200_pending_jkr(self):

@@ -607,7 +607,8 @@ class ColonyEngine:
         self.launches += int(self.lib.abm_diffusion_launches(int(steps), self.diffusion_fuse))
         return scratch if where.value else field
 
-    def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None, n=None) -> torch.Tensor:
+    def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None, n=None,
+               out=None) -> torch.Tensor:
         """get_concentration for every cell.  `field` is the whole (gx,gy[,gz]) grid, or -- with rows=(lo,hi) and
         grid_rows=gx -- the slab of global rows [lo,hi) of it."""
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
@@ -615,7 +616,8 @@ class ColonyEngine:
         if grid_rows is not None:
             gs[0] = int(grid_rows)
         n = self.n if n is None else int(n)
-        out = self._empty(max(n, 1), torch.float64)
+        if out is None:                  # (a caller that replays captured graphs passes its own persistent buffer)
+            out = self._empty(max(n, 1), torch.float64)
         _lib.check(self.lib.abm_sample_concentrations(_ptr(self.loc if loc is None else loc), n, _ptr(field),
                                                       _lib.l3(gs),
                                                       float(spat_res), int(lo), int(hi), _ptr(out), self.stream),

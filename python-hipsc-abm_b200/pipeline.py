@@ -92,6 +92,9 @@ class HotPathStep:
             self.field = torch.zeros((gx, gy), dtype=torch.float64, device=dev)
             self.scratch = torch.empty_like(self.field)
             self.amounts = torch.full((max(n, 1),), cfg.deposit_amount, dtype=torch.float64, device=dev)
+            # one persistent result buffer: every captured graph writes the same tensor (a buffer allocated during a
+            # capture would belong to that graph alone)
+            self.sampled = torch.zeros(max(n, 1), dtype=torch.float64, device=dev)
             if cfg.diffuse_steps % 2:
                 raise ValueError("HotPathStep keeps the field in place: use an even number of diffusion substeps")
         self.graphs = None
@@ -158,7 +161,7 @@ class HotPathStep:
                           cfg.spat_res ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma,
                           scratch=self.scratch)
         assert out.data_ptr() == self.field.data_ptr()
-        self.sampled = eng.sample(self.field, cfg.spat_res, loc=loc)
+        eng.sample(self.field, cfg.spat_res, loc=loc, out=self.sampled)
 
     def step(self):
         """Eager step (no graph)."""
