@@ -448,7 +448,7 @@ def run_b200(args, rank, world, local_rank):
             n, _l.i3(srt.dims), cfg.contact_radius, reach, 0, old.row_stride, old.row_len.data_ptr(),
             old.cols.data_ptr(), b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride,
             b["max_len"].data_ptr(), 0, eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0,
-            _l.d3(wl["size"]), 180.0, 0, eng.uniform_radius, None, None, 0, 0, eng.stream), "abm_jkr_substep")
+            _l.d3(wl["size"]), 180.0, 0, eng.uniform_radius, None, None, 0, 0, 0, eng.stream), "abm_jkr_substep")
 
     def time_launches(cold, reps=20):
         out = []

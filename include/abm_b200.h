@@ -19,6 +19,10 @@
  *     abm_slab_pack).  The caller reads the counter when it next synchronises (abm_read_i32_sync), and if it
  *     exceeds the capacity it grows the buffer and calls again -- the reference's grow-and-retry loops
  *     (simulation.py:217-221, 277-281) with the check moved off the critical path.
+ *   - Device-side cell counts: every per-cell entry point takes `n` (int64, on the host: sizes the launch and the
+ *     buffers) and `n_device` (may be NULL).  If n_device is given, the number of cells is min(n, *n_device), read
+ *     by the kernels themselves: a pipeline whose cell count is decided on the device (cells migrating between
+ *     slabs) enqueues -- or replays as a CUDA graph -- whole steps without bringing the count to the host.
  *   - No process-wide mutable state: every option is an argument of the call it affects (flags below); the only
  *     things the library caches are per-device kernel attributes and the per-thread text of the last error.
  *   - Cell ids, bin ids, row offsets are int32; positions/forces/fields are float64 exactly as the
@@ -87,7 +91,7 @@ size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins);
 int abm_bin_sort(const double *locations, const double *radii, int64_t n, const double size_host[3],
                  const double *origin_host, double distance, int flags, int32_t *bin_start, int32_t *sorted_id, double *sorted_pos,
                  int32_t *sorted_bin, int32_t *max_count, void *workspace, size_t workspace_bytes,
-                 void *stream);
+                 const int32_t *n_device, void *stream);
 
 /* Reference-shaped dense outputs of assign_bins (simulation.py:206-213) from a finished sort:
  *   bins (dims0,dims1,dims2,max_agents) int64 [reference index order x,y,z], bins_help (dims0,dims1,dims2)
@@ -112,7 +116,8 @@ int abm_neighbor_search(const int32_t *bin_start, const int32_t *sorted_id, cons
                         const int32_t *sorted_bin, int64_t n, const int32_t dims_host[3], double distance,
                         const double *locations, const int32_t *old_row_start, int64_t old_row_stride,
                         const int32_t *old_row_len, const int32_t *old_cols, int32_t *row_start,
-                        int32_t *row_len, int32_t *cols, int64_t cols_capacity, int32_t *cursor, void *stream);
+                        int32_t *row_len, int32_t *cols, int64_t cols_capacity, int32_t *cursor,
+                        const int32_t *n_device, void *stream);
 
 /* synchronises `stream` and returns *device_value through value_host */
 int abm_read_i32_sync(const int32_t *device_value, int32_t *value_host, void *stream);
@@ -177,7 +182,7 @@ int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const do
                     double poisson, double youngs, double adhesion_const, double stokes,
                     const double size_host[3], double move_dt, const int32_t *global_id, double uniform_radius,
                     const double *next_extent_host, const double *next_origin_host, int32_t *next_bin_counts,
-                    void *next_sort_workspace, void *stream);
+                    void *next_sort_workspace, const int32_t *n_device, void *stream);
 
 /* The whole substep loop of CellMethods.apply_forces (cell_methods.py:399-436) enqueued by ONE call:
  * n_substeps x [abm_bin_sort at bin edge `reach` over (origin, extent) + abm_jkr_substep with dts_host[k]].
@@ -193,7 +198,8 @@ int abm_mechanics_loop(const double *radii, double *locations, const double *mot
                        const int32_t *old_row_start, int64_t old_row_stride, const int32_t *old_row_len,
                        const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
                        int64_t row_stride, int32_t *max_len, const int32_t *global_id, double uniform_radius,
-                       double poisson, double youngs, double adhesion_const, double stokes, int flags, void *stream);
+                       double poisson, double youngs, double adhesion_const, double stokes, int flags,
+                       const int32_t *n_device, void *stream);
 
 /* ---- morphogen diffusion ---------------------------------------------------------------------------
  * Replaces CellMethods.update_diffusion + update_diffusion_jit (cell_methods.py:441-468,
@@ -219,7 +225,7 @@ int64_t abm_diffusion_launches(int64_t steps, int max_fused_substeps);
  * row-major (the whole grid: row_lo=0,row_hi=gx; a slab of it for a slab-decomposed colony).  sampled (N,) f64. */
 int abm_sample_concentrations(const double *locations, int64_t n, const double *field,
                               const int64_t gsize_host[3], double spat_res, int64_t row_lo, int64_t row_hi,
-                              double *sampled, void *stream);
+                              double *sampled, const int32_t *n_device, void *stream);
 
 /* Replaces per-cell adjust_morphogens (cell_methods.py:485-521) for all cells: amounts[i] is shared
  * equally by the in-bounds corner points closer than spat_res (fp64 atomic adds); amounts == NULL: every cell
@@ -227,7 +233,7 @@ int abm_sample_concentrations(const double *locations, int64_t n, const double *
  * outside [row_lo,row_hi) belong to another slab and are skipped (the share size still counts them).  */
 int abm_deposit_morphogens(const double *locations, const double *amounts, double uniform_amount, int64_t n,
                            double *field, const int64_t gsize_host[3], double spat_res, int64_t row_lo,
-                           int64_t row_hi, void *stream);
+                           int64_t row_hi, const int32_t *n_device, void *stream);
 
 /* ---- slab decomposition plumbing (no reference counterpart; see hipsc_abm_b200/slab.py) -------------------
  * A cell travels between ranks as one byte record:
@@ -244,7 +250,11 @@ int abm_deposit_morphogens(const double *locations, const double *amounts, doubl
  * [cells owned after the exchange | halo cells] -- owned iff x in [x_lo,x_hi) (open towards a missing
  * neighbour) -- keeping input order inside each part, and writes them to the out_* arrays (capacity
  * n_own + n_received + n_received_b); n_owned_out (1) int32 receives the size of the first part.
- * workspace (merge only): abm_slab_workspace_bytes(n_own + n_received + n_received_b).  No host synchronisation. */
+ * workspace (merge only): abm_slab_workspace_bytes(n_own + n_received + n_received_b).  No host synchronisation.
+ * Device-side counts (merge): n_own_device (may be NULL) caps the owned input rows at min(n_own, *n_own_device);
+ * received_counts_device (may be NULL) = int32[2], the valid records of the two segments (clipped to n_received /
+ * n_received_b, which are then the segments' capacities); n_local_out (may be NULL) receives the total number of
+ * cells written (owned + halo).  With them a whole slab step is enqueued without a host round trip.              */
 size_t abm_slab_workspace_bytes(int64_t n);
 int abm_slab_pack(const double *locations, const double *radii, const double *motility_forces,
                   const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t n_own,
@@ -257,7 +267,8 @@ int abm_slab_merge(const double *locations, const double *radii, const double *m
                    int64_t row_stride, double x_lo, double x_hi,
                    int has_left, int has_right, double *out_locations, double *out_radii, double *out_motility,
                    int32_t *out_global_id, int32_t *out_bond_len, int32_t *out_bond_rows, int32_t *n_owned_out,
-                   void *workspace, size_t workspace_bytes, void *stream);
+                   void *workspace, size_t workspace_bytes, const int32_t *n_own_device,
+                   const int32_t *received_counts_device, int32_t *n_local_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -27,9 +27,9 @@ SIGNATURES = {
     "abm_device_info": (I32, [C.POINTER(I32), C.POINTER(I32), C.POINTER(I32)]),
     "abm_bin_dims_host": (I32, [D3, F64, I32, I3]),
     "abm_bin_sort_workspace_bytes": (SZ, [I64, I64]),
-    "abm_bin_sort": (I32, [P, P, I64, D3, D3, F64, I32, P, P, P, P, P, P, SZ, P]),
+    "abm_bin_sort": (I32, [P, P, I64, D3, D3, F64, I32, P, P, P, P, P, P, SZ, P, P]),
     "abm_bins_dense": (I32, [P, I64, D3, F64, P, P, I64, P, P, P, P]),
-    "abm_neighbor_search": (I32, [P, P, P, P, I64, I3, F64, P, P, I64, P, P, P, P, P, I64, P, P]),
+    "abm_neighbor_search": (I32, [P, P, P, P, I64, I3, F64, P, P, I64, P, P, P, P, P, I64, P, P, P]),
     "abm_read_i32_sync": (I32, [P, C.POINTER(C.c_int32), P]),
     "abm_graph_edge_list_workspace_bytes": (SZ, [I64]),
     "abm_graph_edge_list": (I32, [P, I64, P, P, I64, P, SZ, P, I64, P, P]),
@@ -37,18 +37,18 @@ SIGNATURES = {
     "abm_apply_forces": (I32, [P, P, P, P, I64, F64, D3, F64, P, P]),
     "abm_jkr_reach": (F64, [F64, F64, F64, F64, F64]),
     "abm_jkr_substep": (I32, [P, P, P, P, I64, I3, F64, F64, P, I64, P, P, P, P, I64, P, I32, P, P,
-                              F64, F64, F64, F64, D3, F64, P, F64, D3, D3, P, P, P]),
+                              F64, F64, F64, F64, D3, F64, P, F64, D3, D3, P, P, P, P]),
     "abm_mechanics_loop": (I32, [P, P, P, I64, D3, D3, D3, F64, F64, I32, C.POINTER(C.c_double),
                                  P, P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, P,
-                                 F64, F64, F64, F64, F64, I32, P]),
+                                 F64, F64, F64, F64, F64, I32, P, P]),
     "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, I32, C.POINTER(I32), P]),
     "abm_diffusion_launches": (I64, [I64, I32]),
-    "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P]),
+    "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P, P]),
     "abm_slab_workspace_bytes": (SZ, [I64]),
     "abm_slab_pack": (I32, [P, P, P, P, P, P, I64, P, I64, F64, F64, I32, I32, P, I64, P, I64, P, P, SZ, P]),
     "abm_slab_merge": (I32, [P, P, P, P, P, P, I64, P, I64, P, I64, I64, F64, F64, I32, I32, P, P, P, P, P, P, P, P, SZ,
-                             P]),
-    "abm_deposit_morphogens": (I32, [P, P, F64, I64, P, L3, F64, I64, I64, P]),
+                             P, P, P, P]),
+    "abm_deposit_morphogens": (I32, [P, P, F64, I64, P, L3, F64, I64, I64, P, P]),
 }
 
 

@@ -156,6 +156,19 @@ inline int current_device_slot() {
     return dev;
 }
 
+// ---- device-side cell count ----------------------------------------------------------------------------
+// Every per-cell kernel takes its cell count as a launch parameter n (grid size) and, optionally, as a pointer to a
+// device int: the count is then min(n, *n_dev), n being only the capacity the launch was sized for.  A pipeline
+// whose cell count is decided on the device (cells migrating between slabs) can so enqueue -- or replay as a CUDA
+// graph -- a whole step without ever bringing the count to the host.
+__device__ __forceinline__ int device_count(int n, const int *__restrict__ n_dev) {
+    if (n_dev) {
+        int m = *n_dev;
+        n = m < n ? (m < 0 ? 0 : m) : n;
+    }
+    return n;
+}
+
 // ---- warp helpers ----------------------------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 

@@ -262,8 +262,9 @@ k_diffuse_fused(const __grid_constant__ CUtensorMap src_map, const double *__res
 // on the global grid exactly as the reference does and then shifted.
 __global__ void k_sample(const double *__restrict__ loc, int n, const double *__restrict__ field, long long g0,
                          long long g1, long long g2, double h, long long row_lo, long long row_hi,
-                         double *__restrict__ out) {
+                         double *__restrict__ out, const int *__restrict__ n_dev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    n = device_count(n, n_dev);
     if (i >= n) return;
     long long g[3] = {g0, g1, g2};
     long long idx[3];
@@ -282,8 +283,9 @@ __global__ void k_sample(const double *__restrict__ loc, int n, const double *__
 // amounts == nullptr: every cell deposits uniform_amount
 __global__ void k_deposit(const double *__restrict__ loc, const double *__restrict__ amounts, double uniform_amount,
                           int n, double *__restrict__ field, long long g0, long long g1, long long g2, double h,
-                          long long row_lo, long long row_hi) {
+                          long long row_lo, long long row_hi, const int *__restrict__ n_dev) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    n = device_count(n, n_dev);
     if (i >= n) return;
     double lx = loc[3 * (long long)i + 0], ly = loc[3 * (long long)i + 1], lz = loc[3 * (long long)i + 2];
     long long x = (long long)floor(lx / h), y = (long long)floor(ly / h);
@@ -491,7 +493,7 @@ ABM_EXPORT int64_t abm_diffusion_launches(int64_t steps, int max_fused_substeps)
 
 ABM_EXPORT int abm_sample_concentrations(const double *locations, int64_t n, const double *field,
                                          const int64_t gsize_host[3], double spat_res, int64_t row_lo,
-                                         int64_t row_hi, double *sampled, void *stream) {
+                                         int64_t row_hi, double *sampled, const int32_t *n_device, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(locations && field && gsize_host && sampled, "null pointer");
@@ -499,14 +501,14 @@ ABM_EXPORT int abm_sample_concentrations(const double *locations, int64_t n, con
     ABM_REQUIRE(row_lo >= 0 && row_hi <= gsize_host[0] && row_lo < row_hi, "bad row window");
     k_sample<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(locations, (int)n, field, gsize_host[0],
                                                               gsize_host[1], gsize_host[2], spat_res, row_lo,
-                                                              row_hi, sampled);
+                                                              row_hi, sampled, n_device);
     ABM_CHECK_LAUNCH("k_sample");
     return 0;
 }
 
 ABM_EXPORT int abm_deposit_morphogens(const double *locations, const double *amounts, double uniform_amount,
                                       int64_t n, double *field, const int64_t gsize_host[3], double spat_res,
-                                      int64_t row_lo, int64_t row_hi, void *stream) {
+                                      int64_t row_lo, int64_t row_hi, const int32_t *n_device, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(locations && field && gsize_host, "null pointer");
@@ -515,7 +517,7 @@ ABM_EXPORT int abm_deposit_morphogens(const double *locations, const double *amo
     k_deposit<<<ceil_div(n, 256), 256, 0, as_stream(stream)>>>(locations, amounts, uniform_amount, (int)n, field,
                                                                gsize_host[0],
                                                                gsize_host[1], gsize_host[2], spat_res, row_lo,
-                                                               row_hi);
+                                                               row_hi, n_device);
     ABM_CHECK_LAUNCH("k_deposit");
     return 0;
 }

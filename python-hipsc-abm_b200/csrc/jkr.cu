@@ -196,7 +196,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
               double stokes, Friction fric, Box box, double dt, const int *__restrict__ gid_of,
               const int *__restrict__ slot_pid, NextSort next, int sort_rows, const int *__restrict__ prev_slot,
-              int row_keys) {
+              int row_keys, const int *__restrict__ n_dev) {
     // column tid: first the parked partner slots, then (overwritten from the front) the ids of the new bond row
     __shared__ int column[kMaxHits][kJkrThreads];
     __shared__ float4 tiles[kJkrThreads / 32][kTileRows * kTileCap];
@@ -206,6 +206,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     const int tid = threadIdx.x;
     const int s = blockIdx.x * kJkrThreads + tid;
     pdl_wait();
+    n = device_count(n, n_dev);
     if (s - (tid & 31) >= n) return;                           // the whole warp is past the last cell
     const bool live = s < n;
     float4 *tile = tiles[tid >> 5];
@@ -547,7 +548,8 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                             const int32_t *global_id, const int32_t *slot_gid, double uniform_radius,
                             const double *next_extent_host, const double *next_origin_host,
                             int32_t *next_bin_counts, void *next_sort_workspace, void *stream,
-                            const int32_t *prev_slot = nullptr, int row_keys = 0, bool chained = false) {
+                            const int32_t *prev_slot = nullptr, int row_keys = 0, bool chained = false,
+                            const int32_t *n_device = nullptr) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(!(row_keys & 1) || prev_slot, "rows keyed by the previous slot need the prev_slot index");
@@ -592,7 +594,7 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                                      Radius(distance), reach * reach, BandConst::make(reach * 1.0000001), old,
                                      new_row_len, new_cols, (int)row_stride, max_len, motility_forces, locations, c,
                                      stokes, fric, box, move_dt, global_id, global_id ? slot_gid : sorted_id, next,
-                                     sort_rows, prev_slot, row_keys),
+                                     sort_rows, prev_slot, row_keys, n_device),
                       "k_jkr_substep");
 }
 
@@ -605,12 +607,12 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
                                double adhesion_const, double stokes, const double size_host[3], double move_dt,
                                const int32_t *global_id, double uniform_radius, const double *next_extent_host,
                                const double *next_origin_host, int32_t *next_bin_counts, void *next_sort_workspace,
-                               void *stream) {
+                               const int32_t *n_device, void *stream) {
     return jkr_substep_impl(bin_start, sorted_id, sorted_pos, sorted_bin, n, dims_host, distance, reach,
                             old_row_start, old_row_stride, old_row_len, old_cols, new_row_len, new_cols, row_stride,
                             max_len, sort_rows, motility_forces, locations, poisson, youngs, adhesion_const, stokes,
                             size_host, move_dt, global_id, nullptr, uniform_radius, next_extent_host,
-                            next_origin_host, next_bin_counts, next_sort_workspace, stream);
+                            next_origin_host, next_bin_counts, next_sort_workspace, stream, nullptr, 0, false, n_device);
 }
 
 // The whole substep loop of CellMethods.apply_forces (reference cell_methods.py:399-436) enqueued by one call:
@@ -627,7 +629,8 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                                   const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a,
                                   int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
                                   int32_t *max_len, const int32_t *global_id, double uniform_radius, double poisson,
-                                  double youngs, double adhesion_const, double stokes, int flags, void *stream) {
+                                  double youngs, double adhesion_const, double stokes, int flags,
+                                  const int32_t *n_device, void *stream) {
     ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
     const bool carry_in = (flags & ABM_LOOP_CARRY_IN) && n > 0 && n_substeps > 0;
     const bool carry_out = (flags & ABM_LOOP_CARRY_OUT) && n > 0;
@@ -649,7 +652,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                                ((k || carry_in) ? ABM_SORT_PREBINNED : 0) | (chained ? ABM_SORT_CHAINED : 0), table,
                                sorted_id, sorted_pos, sorted_bin, k ? nullptr : max_count, sort_workspace,
                                sort_workspace_bytes,
-                               prebin ? other : nullptr, global_id, stream);   // the idle table is cleared on the way
+                               prebin ? other : nullptr, global_id, stream, n_device);   // (idle table cleared on the way)
         if (rc) return rc;
         int32_t *nl = (k & 1) ? len_b : len_a, *nc = (k & 1) ? cols_b : cols_a;
         const int32_t *slot_gid = (global_id && n > 0) ? sort_ws_carve(sort_workspace, n, nbins).slot_gid : nullptr;
@@ -666,7 +669,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                               motility_forces, last ? locations : nullptr, poisson, youngs, adhesion_const, stokes,
                               size_host, dts_host[k], global_id, slot_gid, uniform_radius,
                               prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
-                              prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained);
+                              prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained, n_device);
         if (rc) return rc;
         cur_start = nullptr;
         cur_stride = row_stride;

@@ -71,12 +71,13 @@ __global__ void __launch_bounds__(kSearchThreads)
 k_search(const int *__restrict__ bin_start, const int *__restrict__ sorted_id, const double4 *__restrict__ spos,
          const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad, const double *__restrict__ loc,
          GraphView old, int *__restrict__ row_start, int *__restrict__ row_len, int *__restrict__ cols,
-         long long capacity, int *__restrict__ cursor) {
+         long long capacity, int *__restrict__ cursor, const int *__restrict__ n_dev) {
     __shared__ int column[kRowCap][kSearchThreads];
     __shared__ float4 tiles[kSearchThreads / 32][kTileRows * kTileCap];
     __shared__ int tile_ids[kSearchThreads / 32][kTileRows * kTileCap];
     const int tid = threadIdx.x;
     const int s = blockIdx.x * kSearchThreads + tid;
+    n = device_count(n, n_dev);
     if (s - (tid & 31) >= n) return;                           // the whole warp is past the last cell
     const bool active = s < n;
     float4 *tile = tiles[tid >> 5];
@@ -219,7 +220,7 @@ ABM_EXPORT int abm_neighbor_search(const int32_t *bin_start, const int32_t *sort
                                    const double *locations, const int32_t *old_row_start, int64_t old_row_stride,
                                    const int32_t *old_row_len, const int32_t *old_cols, int32_t *row_start,
                                    int32_t *row_len, int32_t *cols, int64_t cols_capacity, int32_t *cursor,
-                                   void *stream) {
+                                   const int32_t *n_device, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     ABM_REQUIRE(cursor && dims_host, "null pointer");
     ABM_REQUIRE(distance > 0, "distance must be positive");
@@ -234,7 +235,7 @@ ABM_EXPORT int abm_neighbor_search(const int32_t *bin_start, const int32_t *sort
     stc.set(dims_host);
     k_search<<<ceil_div(n, kSearchThreads), kSearchThreads, 0, st>>>(
         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
-        Radius(distance), locations, old, row_start, row_len, cols, (long long)cols_capacity, cursor);
+        Radius(distance), locations, old, row_start, row_len, cols, (long long)cols_capacity, cursor, n_device);
     ABM_CHECK_LAUNCH("k_search");
     return 0;
 }

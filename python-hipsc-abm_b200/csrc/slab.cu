@@ -88,6 +88,16 @@ __global__ void __launch_bounds__(256) k_slab_pack(CellArrays a, int n, const in
 struct Received {
     const unsigned char *a, *b;
     int k_a, k_b;
+    // the valid record counts may live on the device (counts[0], counts[1], clipped to the capacities k_a / k_b) and
+    // so may the number of owned input rows: resolve() is the first thing a kernel does
+    const int *counts, *n_own_dev;
+    __device__ __forceinline__ void resolve(int &n_own) {
+        n_own = device_count(n_own, n_own_dev);
+        if (counts) {
+            k_a = min(k_a, max(counts[0], 0));
+            k_b = min(k_b, max(counts[1], 0));
+        }
+    }
     __device__ __forceinline__ const unsigned char *record(int j, int rec_bytes) const {
         return j < k_a ? a + (long long)j * rec_bytes : b + (long long)(j - k_a) * rec_bytes;
     }
@@ -96,10 +106,13 @@ struct Received {
 // keep[i] for the n_own owned cells followed by the k received records: 1 = owned after the exchange
 __global__ void __launch_bounds__(256) k_slab_keep(const double *__restrict__ loc, int n_own, Received recv,
                                                    int rec_bytes, double x_lo, double x_hi, int has_left,
-                                                   int has_right, int *__restrict__ keep) {
+                                                   int has_right, int *__restrict__ keep, int capacity,
+                                                   int *__restrict__ n_local_out) {
     int i = blockIdx.x * 256 + threadIdx.x;
+    recv.resolve(n_own);
     int total = n_own + recv.k_a + recv.k_b;
-    if (i > total) return;
+    if (i == 0 && n_local_out) *n_local_out = total;
+    if (i > capacity) return;                      // flags up to the capacity: the scan runs over all of them
     int f = 0;
     if (i < n_own) f = owns(loc[3 * (long long)i], x_lo, x_hi, has_left, has_right);
     else if (i < total)
@@ -112,6 +125,7 @@ __global__ void __launch_bounds__(256) k_slab_keep(const double *__restrict__ lo
 __global__ void __launch_bounds__(256) k_slab_merge(CellArrays in, int n_own, Received recv, int rec_bytes,
                                                     int stride, const int *__restrict__ pos, CellArrays out) {
     int i = blockIdx.x * 256 + threadIdx.x;
+    recv.resolve(n_own);
     int total = n_own + recv.k_a + recv.k_b;
     if (i >= total) return;
     int n_keep = pos[total];
@@ -189,14 +203,16 @@ ABM_EXPORT int abm_slab_merge(const double *locations, const double *radii, cons
                               double x_lo, double x_hi, int has_left, int has_right, double *out_locations,
                               double *out_radii, double *out_motility, int32_t *out_global_id, int32_t *out_bond_len,
                               int32_t *out_bond_rows, int32_t *n_owned_out, void *workspace, size_t workspace_bytes,
-                              void *stream) {
-    int64_t total = n_own + n_received + n_received_b;
+                              const int32_t *n_own_device, const int32_t *received_counts_device,
+                              int32_t *n_local_out, void *stream) {
+    int64_t total = n_own + n_received + n_received_b;          // the capacity when the counts live on the device
     ABM_REQUIRE(n_own >= 0 && n_received >= 0 && n_received_b >= 0 && total < 0x7fffffff && row_stride > 0, "bad sizes");
     ABM_REQUIRE((received || n_received == 0) && (received_b || n_received_b == 0), "null record segment");
-    Received recv{received, received_b, (int)n_received, (int)n_received_b};
+    Received recv{received, received_b, (int)n_received, (int)n_received_b, received_counts_device, n_own_device};
     ABM_REQUIRE(n_owned_out && workspace && workspace_bytes >= abm_slab_workspace_bytes(total), "workspace too small");
     cudaStream_t st = as_stream(stream);
     int rc = check_cuda(cudaMemsetAsync(n_owned_out, 0, 4, st), "memset n_owned_out");
+    if (!rc && n_local_out) rc = check_cuda(cudaMemsetAsync(n_local_out, 0, 4, st), "memset n_local_out");
     if (rc || total == 0) return rc;
     ABM_REQUIRE(out_locations && out_radii && out_motility && out_global_id && out_bond_len && out_bond_rows,
                 "null output");
@@ -205,7 +221,7 @@ ABM_EXPORT int abm_slab_merge(const double *locations, const double *radii, cons
     int *sums = keep + ((size_t)(total + 1) + 63) / 64 * 64;
     int rec_bytes = 64 + 4 * (int)row_stride;
     k_slab_keep<<<ceil_div(total + 1, 256), 256, 0, st>>>(locations, (int)n_own, recv, rec_bytes, x_lo, x_hi, has_left,
-                                                          has_right, keep);
+                                                          has_right, keep, (int)total, n_local_out);
     ABM_CHECK_LAUNCH("k_slab_keep");
     rc = exclusive_scan_inplace(keep, total + 1, sums, nullptr, nullptr, st);
     if (rc) return rc;

@@ -23,8 +23,10 @@ namespace abm {
 constexpr int kThreads = 256;
 
 __global__ void __launch_bounds__(kThreads) k_bin_count(const double *__restrict__ loc, int n, BinGeom g,
-                                                        int *__restrict__ counts, int *__restrict__ cell_bin) {
+                                                        int *__restrict__ counts, int *__restrict__ cell_bin,
+                                                        const int *__restrict__ n_dev) {
     int i = blockIdx.x * kThreads + threadIdx.x;
+    n = device_count(n, n_dev);
     if (i >= n) return;
     int b = cell_bin_of(loc[3 * (int64_t)i + 0], loc[3 * (int64_t)i + 1], loc[3 * (int64_t)i + 2], g);
     cell_bin[i] = b;
@@ -37,9 +39,11 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const int *__restrict__ ce
                                                       int n, int *__restrict__ sorted_id,
                                                       double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
                                                       int *__restrict__ next_sums, int n_sums,
-                                                      const int *__restrict__ gid_of, int *__restrict__ slot_gid) {
+                                                      const int *__restrict__ gid_of, int *__restrict__ slot_gid,
+                                                      const int *__restrict__ n_dev) {
     int i = blockIdx.x * kThreads + threadIdx.x;
     for (int k = i; k < n_sums; k += gridDim.x * kThreads) next_sums[k] = 0;
+    n = device_count(n, n_dev);
     if (i >= n) return;
     int b = cell_bin[i];
     int dest = atomicAdd(&cursor[b], 1);
@@ -63,10 +67,11 @@ __global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ 
                                                         double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
                                                         int *__restrict__ next_sums, int n_sums,
                                                         const int *__restrict__ gid_of, int *__restrict__ slot_gid,
-                                                        int *__restrict__ prev_slot) {
+                                                        int *__restrict__ prev_slot, const int *__restrict__ n_dev) {
     pdl_launch_dependents();
     int s = blockIdx.x * kThreads + threadIdx.x;
     pdl_wait();
+    n = device_count(n, n_dev);
     // consumed by this sort's scan; the next hand-over adds to it
     for (int k = s; k < n_sums; k += gridDim.x * kThreads) next_sums[k] = 0;
     if (s >= n) return;
@@ -158,10 +163,11 @@ ABM_EXPORT size_t abm_bin_sort_workspace_bytes(int64_t n, int64_t nbins) {
 ABM_EXPORT int abm_bin_sort(const double *locations, const double *radii, int64_t n, const double size_host[3],
                             const double *origin_host, double distance, int flags, int32_t *bin_start,
                             int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
-                            void *workspace, size_t workspace_bytes, void *stream) {
+                            void *workspace, size_t workspace_bytes, const int32_t *n_device, void *stream) {
     ABM_REQUIRE(max_count, "null pointer");
     return abm::bin_sort_impl(locations, radii, n, size_host, origin_host, distance, flags, bin_start, sorted_id,
-                              sorted_pos, sorted_bin, max_count, workspace, workspace_bytes, nullptr, nullptr, stream);
+                              sorted_pos, sorted_bin, max_count, workspace, workspace_bytes, nullptr, nullptr, stream,
+                              n_device);
 }
 
 // zero_table: optional second (nbins+1) offset table cleared on the way (the mechanics loop alternates two tables
@@ -171,7 +177,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
                        const double *origin_host, double distance, int flags, int32_t *bin_start,
                        int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin, int32_t *max_count,
                        void *workspace, size_t workspace_bytes, int32_t *zero_table, const int32_t *global_id,
-                       void *stream) {
+                       void *stream, const int32_t *n_device) {
     const bool chained = flags & ABM_SORT_CHAINED;
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     ABM_REQUIRE(size_host && bin_start, "null pointer");
@@ -198,11 +204,12 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
     ABM_REQUIRE(sorted_id && sorted_pos && sorted_bin && workspace, "null pointer");
     ABM_REQUIRE(prebinned || (locations && radii), "null pointer");
     ABM_REQUIRE(!(prebinned && (flags & ABM_SORT_STABLE)), "ABM_SORT_PREBINNED cannot be combined with ABM_SORT_STABLE");
+    ABM_REQUIRE(!(n_device && (flags & ABM_SORT_STABLE)), "a device-side cell count cannot be combined with ABM_SORT_STABLE");
     ABM_REQUIRE(((uintptr_t)sorted_pos & 31) == 0, "sorted_pos must be 32-byte aligned");
     SortWs w = sort_ws_carve(workspace, n, nbins);
     int blocks = ceil_div(n, kThreads);
     if (!prebinned) {
-        k_bin_count<<<blocks, kThreads, 0, st>>>(locations, (int)n, g, bin_start, w.cell_bin);
+        k_bin_count<<<blocks, kThreads, 0, st>>>(locations, (int)n, g, bin_start, w.cell_bin, n_device);
         ABM_CHECK_LAUNCH("k_bin_count");
     }
     const int nb = scan_blocks(nbins + 1);
@@ -224,7 +231,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
         rc = check_cuda(launch_chained(k_rescatter, blocks, kThreads, st, chained, (const int *)w.cell_bin,
                                        (const int *)w.tmp_id, (const double4 *)w.next_pos, w.cursor, (int)n, sorted_id,
                                        sp, sorted_bin, w.next_sums, nb, global_id, w.slot_gid,
-                                       (ABM_JKR_EXP & 16) ? w.prev_slot : (int *)nullptr),
+                                       (ABM_JKR_EXP & 16) ? w.prev_slot : (int *)nullptr, n_device),
                         "k_rescatter");
         if (rc) return rc;
     } else if (flags & ABM_SORT_STABLE) {
@@ -237,7 +244,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
         ABM_CHECK_LAUNCH("k_gather");
     } else {
         k_scatter<<<blocks, kThreads, 0, st>>>(w.cell_bin, w.cursor, locations, radii, (int)n, sorted_id, sp,
-                                               sorted_bin, w.next_sums, nb, global_id, w.slot_gid);
+                                               sorted_bin, w.next_sums, nb, global_id, w.slot_gid, n_device);
         ABM_CHECK_LAUNCH("k_scatter");
     }
     return 0;

@@ -63,7 +63,8 @@ inline int make_bin_geom(const double extent[3], const double *origin, double di
 int bin_sort_impl(const double *locations, const double *radii, int64_t n, const double size_host[3],
                   const double *origin_host, double distance, int flags, int32_t *bin_start, int32_t *sorted_id,
                   double *sorted_pos, int32_t *sorted_bin, int32_t *max_count, void *workspace,
-                  size_t workspace_bytes, int32_t *zero_table, const int32_t *global_id, void *stream);
+                  size_t workspace_bytes, int32_t *zero_table, const int32_t *global_id, void *stream,
+                  const int32_t *n_device = nullptr);
 
 __device__ __forceinline__ int cell_bin_of(double x, double y, double z, const BinGeom &g) {
     return lin_bin(bin_coord_fast(x - g.origin[0], g.distance, g.inv_distance, g.dims[0]),

@@ -173,6 +173,8 @@ class ColonyEngine:
         self._uniform_radius = 0.0  # common radius when all radii are equal (contact constants evaluated once)
         self._radii_host = None     # the numpy array the radii were last uploaded from (None: device-resident state)
         self.global_id = None   # int32 (n,) when bond rows are kept by global id (slab decomposition)
+        self.n_device = None    # int32 (1,) tensor: the cell count lives on the device, self.n is only the capacity
+                                # the launches and buffers are sized for (include/abm_b200.h, `n_device`)
         self._sort_wss = {}     # sort scratch per bin count (sorts of different lattices may run on different streams)
         self._carry = None      # (nbins, n, pointers..., table index) when the last mechanics loop handed its cells over
         self._sort_bufs = {}
@@ -395,7 +397,8 @@ class ColonyEngine:
                                          self._extent_c, self._origin_c,
                                          float(distance), int(flags), _ptr(b["bin_start"]), _ptr(b["sorted_id"]),
                                          _ptr(b["sorted_pos"]), _ptr(b["sorted_bin"]), _ptr(b["max_count"]),
-                                         _ptr(b["ws"]), b["ws"].numel(), self.stream), "abm_bin_sort")
+                                         _ptr(b["ws"]), b["ws"].numel(), _ptr(self.n_device), self.stream),
+                   "abm_bin_sort")
         self.launches += (5 if flags & _lib.SORT_STABLE else 4) if n else 0
         return SortState(float(distance), dims, nbins, n, b["bin_start"], b["sorted_id"], b["sorted_pos"],
                          b["sorted_bin"], b["max_count"])
@@ -451,7 +454,7 @@ class ColonyEngine:
             _lib.i3(sort.dims), float(distance), _ptr(self.loc if loc is None else loc),
             _ptr(old.row_start) if old is not None else 0, old.row_stride if old is not None else 0,
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
-            _ptr(row_start), _ptr(row_len), _ptr(cols), cols.numel(), _ptr(cursor), self.stream),
+            _ptr(row_start), _ptr(row_len), _ptr(cols), cols.numel(), _ptr(cursor), _ptr(self.n_device), self.stream),
             "abm_neighbor_search")
         self.launches += 1 if n else 0
         return GraphTensors(n, row_start, 0, row_len, cols, True)
@@ -556,7 +559,7 @@ class ColonyEngine:
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
             _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),
             stride, _ptr(b["max_len"]), _ptr(self.global_id), float(self.uniform_radius), JKR_POISSON, JKR_YOUNGS,
-            JKR_ADHESION, float(stokes), flags, self.stream), "abm_mechanics_loop")
+            JKR_ADHESION, float(stokes), flags, _ptr(self.n_device), self.stream), "abm_mechanics_loop")
         # the last substep k = K-1 sorted with table (first + K-1) % 2 and left the next histogram in the other one
         self._carry = key + ((first + len(dts)) % 2,) if flags & _lib.LOOP_CARRY_OUT else None
         # first substep: histogram, scan x2, scatter, substep (scan, rescatter, substep when the cells were handed
@@ -608,7 +611,7 @@ class ColonyEngine:
         return scratch if where.value else field
 
     def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None, n=None,
-               out=None) -> torch.Tensor:
+               out=None, use_count=True) -> torch.Tensor:
         """get_concentration for every cell.  `field` is the whole (gx,gy[,gz]) grid, or -- with rows=(lo,hi) and
         grid_rows=gx -- the slab of global rows [lo,hi) of it."""
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
@@ -620,12 +623,14 @@ class ColonyEngine:
             out = self._empty(max(n, 1), torch.float64)
         _lib.check(self.lib.abm_sample_concentrations(_ptr(self.loc if loc is None else loc), n, _ptr(field),
                                                       _lib.l3(gs),
-                                                      float(spat_res), int(lo), int(hi), _ptr(out), self.stream),
+                                                      float(spat_res), int(lo), int(hi), _ptr(out),
+                                                      _ptr(self.n_device) if use_count else 0, self.stream),
                    "abm_sample_concentrations")
         self.launches += 1 if n else 0
         return out[:n]
 
-    def deposit(self, field: torch.Tensor, amounts, spat_res, rows=None, grid_rows=None, loc=None, n=None):
+    def deposit(self, field: torch.Tensor, amounts, spat_res, rows=None, grid_rows=None, loc=None, n=None,
+                use_count=True):
         """adjust_morphogens for every cell; amounts: a device tensor (one per cell) or a python float (all cells)."""
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
         lo, hi = (0, gs[0]) if rows is None else rows
@@ -636,6 +641,7 @@ class ColonyEngine:
         _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc if loc is None else loc),
                                                    0 if scalar else _ptr(amounts), float(amounts) if scalar else 0.0,
                                                    n, _ptr(field), _lib.l3(gs),
-                                                   float(spat_res), int(lo), int(hi), self.stream),
+                                                   float(spat_res), int(lo), int(hi),
+                                                   _ptr(self.n_device) if use_count else 0, self.stream),
                    "abm_deposit_morphogens")
         self.launches += 1 if n else 0
