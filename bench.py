@@ -210,10 +210,16 @@ def workload_label(name, cells=None, world=1, cpu_arm=False):
     return label
 
 
-def common_config(name, wl, sm, world=1, cpu_arm=False):
+def common_config(name, wl, sm, world=1, cpu_arm=False, scaling="weak"):
     """The part of `config` that defines the workload: identical, key for key, in the B200 line and in the
     `--impl reference` line whenever both run the same colony."""
     spec = WORKLOADS[name]
+    if world > 1 and scaling == "strong":
+        return {"workload": f"{name}: {spec['desc']}, one colony slab-decomposed over {world} GPUs",
+                "cells_per_gpu": wl["n"] // world, "dim": spec["dim"], "mechanics_substeps": sm,
+                "diffusion_substeps": spec["sd"], "grid": list(wl["grid"]) if wl["grid"] else None,
+                "motility": MOTILITY_NOTE,
+                "l2": "B200 arm: flushed between timed steps (256 MiB memset); CPU arm: not applicable"}
     return {"workload": workload_label(name, wl["n"], world, cpu_arm), "cells_per_gpu": wl["n"], "dim": spec["dim"],
             "mechanics_substeps": sm, "diffusion_substeps": spec["sd"],
             "grid": list(wl["grid"]) if wl["grid"] else None, "motility": MOTILITY_NOTE,
@@ -355,7 +361,8 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    wl = make_workload(args.workload, seed=rank)          # weak scaling: one workload-sized colony per GPU
+    # weak scaling: one workload-sized colony per GPU; strong scaling: every rank builds the same colony and keeps its slab
+    wl = make_workload(args.workload, seed=rank if (world == 1 or args.scaling == "weak") else 0)
     spec = wl["spec"]
     n = wl["n"]
     cfg = StepConfig(grid=wl["grid"], spat_res=spec["h"] or 1.0, diffuse_dt=spec["diffuse_dt"] or 1.0,
@@ -642,39 +649,53 @@ def field_wanted(wl):
 
 
 def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
-    """N > 1: ONE colony of world x workload cells, slab-decomposed along x (hipsc_abm_b200/slab.py): per step
-    one cell-halo exchange (which also carries the migrating cells), the whole step on owned+halo cells
-    without further communication, and one morphogen-row exchange, over NCCL send/recv."""
+    """N > 1: ONE colony of world x workload cells, slab-decomposed along x (hipsc_abm_b200/slab_device.py): per step
+    one cell-halo exchange (which also carries the migrating cells) and one morphogen-row exchange over NCCL
+    send/recv; the whole step on owned+halo cells without further communication.  Every count lives on the device:
+    no host synchronisation inside a step, the phases between the exchanges are replayed as CUDA graphs."""
     import torch
     from hipsc_abm_b200 import slab
-    from hipsc_abm_b200.pipeline import NativeSlabOps, SlabPipeline
+    from hipsc_abm_b200.engine import ColonyEngine
+    from hipsc_abm_b200.slab_device import DeviceSlab, DistSlab
 
     spec, n = wl["spec"], wl["n"]
     side = wl["size"][0]
     gsize = wl["size"].copy()
-    gsize[0] = side * world
-    probe = SlabPipeline(slab.SlabGeometry.uniform(gsize, world, rank, 1.0), cfg, dev, side_stream=False)
-    reach = probe.eng.jkr_reach(cfg.contact_radius)
-    halo = slab.required_halo(len(cfg.substep_dts()), reach, slack=4.0) + (spec["h"] or 0.0)
+    weak = args.scaling == "weak"
+    if weak:
+        gsize[0] = side * world                 # weak scaling: one workload-sized slab per GPU
+        n_rank = n
+    else:
+        n_rank = n // world                     # strong scaling: the workload's colony cut into `world` slabs
+    probe = ColonyEngine(gsize, dev)
+    probe.max_radius = 5.0
+    reach = probe.jkr_reach(cfg.contact_radius)
+    halo = slab.required_halo(len(cfg.substep_dts()), reach, slack=4.0, spat_res=spec["h"] or 0.0)
     geom = slab.SlabGeometry.uniform(gsize, world, rank, halo)
-    pipe = SlabPipeline(geom, cfg, dev, max_radius=5.0, uniform_radius=5.0)
-    first = cfg.overlap_morphogen and field_wanted(wl)
-    loc = wl["loc"].copy()
-    loc[:, 0] += geom.x_lo
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
-    state = slab.SlabState(t(loc), t(wl["radii"]), t(wl["mot"]), t(np.arange(n, dtype=np.int64) + rank * n),
-                           cfg.bond_stride)
+    width = gsize[0] / world
+    if weak:
+        loc = wl["loc"].copy()
+        loc[:, 0] += geom.x_lo
+        radii, mot = wl["radii"], wl["mot"]
+        gid = np.arange(n, dtype=np.int64) + rank * n
+    else:
+        m = (wl["loc"][:, 0] >= geom.x_lo) & ((wl["loc"][:, 0] < geom.x_hi) | (rank == world - 1))
+        loc, radii, mot, gid = wl["loc"][m], wl["radii"][m], wl["mot"][m], np.nonzero(m)[0]
+        n_rank = int(m.sum())
     field = None
     if wl["grid"]:
         gx = int(np.ceil(gsize[0] / spec["h"])) + 1
         field = slab.FieldSlab(geom, (gx, wl["grid"][1]), spec["h"], spec["sd"] + 1, dev)
+    # capacities, the same on every rank: the expected cells within `halo` of an interface, with headroom
+    expect = n_rank if weak else n / world
+    send_cap = int(1.6 * expect * halo / width) + 4096
+    rows = int(1.15 * expect * (1 + 2 * halo / width)) + 8192
+    ds = DeviceSlab(geom, cfg, dev, rows=rows, send_cap=send_cap, max_radius=5.0, uniform_radius=5.0, field=field)
+    ds.load(loc, radii, mot, gid)
     # the field rows travel on their own communicator: they are exchanged on the second stream and must not queue in
     # front of the next step's cell exchange
-    fabric = slab.DistFabric(rank, world, dev, rows_group=dist.new_group(list(range(world))) if first else None)
+    rank_step = DistSlab(ds, rank, world, rows_group=dist.new_group(list(range(world))) if field is not None else None)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    # message capacity, the same on every rank: 1.6x the cells expected within `halo` of an interface
-    ops = NativeSlabOps(pipe.eng, send_cap=int(1.6 * n * halo / side) + 4096)
 
     # the step's main stream outranks the second stream (search + morphogen stage), whose kernels then fill what the
     # mechanics leave idle instead of competing with them
@@ -683,19 +704,19 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     torch.cuda.set_stream(main_stream)
 
     def step():
-        slab.slab_step(state, geom, fabric, pipe.compute, field, pipe if field is not None else None, ops,
-                       morphogen_first=first)
-        state.negate_motility()           # alternating motility sign (make_workload); no wait for the owned count
+        rank_step.step()
+        ds.negate_motility()              # alternating motility sign (make_workload)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(2 * ((max(args.warmup, 3) + 1) // 2)):       # an even number of eager steps, then capture
         step()
-    pipe.check()
-    ops.check()
+    ds.check()
+    if not args.no_graphs:
+        rank_step.capture()
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     for _ in range(40):                   # a few clock samples under load (a fixed count: ranks stay in lock-step)
         step()
-    launches0, bytes0, ex0 = pipe.eng.launches, fabric.bytes_sent, fabric.exchanges
+    launches0, bytes0, ex0 = ds.launches, rank_step.bytes_sent, rank_step.exchanges
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k, (a, b) in enumerate(evs):
@@ -703,42 +724,43 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         a.record()
         step()
         if k == len(evs) - 1:
-            pipe.join_side()              # the last step's second-stream work belongs to the timed region
+            rank_step.join()              # the last step's second-stream work belongs to the timed region
         b.record()
     barrier()
     clocks = sampler.stop()
-    pipe.check()
-    ops.check()
+    ds.check()
     total_s = sum(a.elapsed_time(b) for a, b in evs) / 1e3
     tt = torch.tensor([total_s], device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_s = float(tt.item())
-    cells = torch.tensor([state.n], device=dev)
+    n_own = int(ds.sets[ds.cur]["n_own"].item())
+    cells = torch.tensor([n_own], device=dev)
     dist.all_reduce(cells)
-    launches = pipe.eng.launches - launches0
+    n_total = int(cells.item())
+    per_step_launches = (ds.launches - launches0) // max(args.steps, 1) if not rank_step.captured else None
 
     # e2e: the same step with the host in the loop -- the rule methods' inputs (motility forces of the owned
     # cells) are uploaded from pinned memory and the positions + sampled concentrations downloaded, every step
     e_steps = max(3, min(args.steps, 10))
-    pin_mot = torch.zeros((state.n + 4096, 3), dtype=torch.float64).pin_memory()
-    pin_mot[:state.n].copy_(state.mot)                    # realistic values (rows beyond the current count: no force)
+    pin_mot = torch.zeros((ds.R, 3), dtype=torch.float64).pin_memory()
+    pin_mot[:n_own].copy_(ds.sets[ds.cur]["mot"][:n_own])     # realistic values (rows beyond the count: no force)
     h2d = d2h = 0
     barrier()
     t0 = time.perf_counter()
     for it in range(e_steps):
-        k = state.n
-        if k > pin_mot.shape[0]:
-            grown = torch.zeros((k + 4096, 3), dtype=torch.float64).pin_memory()
-            grown[:pin_mot.shape[0]].copy_(pin_mot)
-            pin_mot = grown
-        state.mot = pin_mot[:k].to(dev, non_blocking=True)
+        cur = ds.sets[ds.cur]
+        k = int(cur["n_own"].item())
+        cur["mot"][:k].copy_(pin_mot[:k], non_blocking=True)
         if it % 2:
-            state.mot.neg_()                              # the alternating sign of make_workload
-        step()
-        out_loc = state.loc.cpu()
-        out_c = pipe.sampled.cpu() if pipe.sampled is not None else None
+            cur["mot"][:k].neg_()                             # the alternating sign of make_workload
+        rank_step.step()
+        rank_step.join()
+        now = ds.sets[ds.cur]
+        k2 = int(now["n_own"].item())
+        out_loc = now["loc"][:k2].cpu()
+        out_c = ds.sampled[:k2].cpu() if field is not None else None
         h2d += k * 24
-        d2h += out_loc.numel() * 8 + (out_c.numel() * 8 if out_c is not None else 0)
+        d2h += out_loc.numel() * 8 + (out_c.numel() * 8 if out_c is not None else 0) + 8
     torch.cuda.synchronize(dev)
     e_s = time.perf_counter() - t0
     tt = torch.tensor([e_s], device=dev)
@@ -746,27 +768,41 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     e_s = float(tt.item())
     if rank != 0:
         return None
-    value = n * world * args.steps / total_s
+    value = n_total * args.steps / total_s
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": common_config(args.workload, wl, len(cfg.substep_dts()), world),
-        "method": {"cells_total": int(cells.item()), "halo_um": halo,
-                   "morphogen_stage": ("reference order (before the mechanics), with its row exchange on a second "
-                                       "stream beside search + mechanics") if first else "after the mechanics",
-                   "exchanges_per_step": (fabric.exchanges - ex0) / max(args.steps + e_steps, 1),
-                   "bytes_sent_per_step_rank0": (fabric.bytes_sent - bytes0) // max(args.steps + e_steps, 1),
+        "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": common_config(args.workload, wl, len(cfg.substep_dts()), world, scaling=args.scaling),
+        "method": {"cells_total": n_total, "halo_um": halo, "rows_capacity": rows, "message_capacity": send_cap,
+                   "morphogen_stage": "reference order (before the mechanics), with its row exchange on a second "
+                                      "stream beside search + mechanics" if field is not None else "none",
+                   "exchanges_per_step": (rank_step.exchanges - ex0) / max(args.steps + e_steps, 1),
+                   "bytes_sent_per_step_rank0": (rank_step.bytes_sent - bytes0) // max(args.steps + e_steps, 1),
                    "timing": "CUDA events per step, summed; max over ranks",
+                   "host_synchronisations_per_step": 0,
+                   "cuda_graphs": bool(rank_step.captured),
                    "parallelism": f"slab{world}: 1-D slab decomposition along x; per step one cell-halo exchange "
-                                  "(migration rides on it; fixed-capacity messages, no size handshake) and one "
+                                  "(migration rides on it; fixed-capacity messages, counts on the device) and one "
                                   "morphogen-row exchange over NCCL send/recv"},
         "clocks": clocks,
-        "e2e": {"value": n * world * e_steps / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e_steps,
+        "e2e": {"value": n_total * e_steps / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // e_steps,
                 "d2h_bytes_per_step": d2h // e_steps, "steps": e_steps, "ms_per_step": e_s / e_steps * 1e3,
-                "api": "slab.slab_step with host-resident motility forces in, positions + concentrations out"},
-        "gpu_launches": launches, "roofline": None, "cpu_baseline": None,
+                "api": "slab_device.DistSlab.step with host-resident motility forces in, positions + "
+                       "concentrations out"},
+        "gpu_launches": (per_step_launches if per_step_launches is not None else ds_launches_per_step(ds)) * args.steps,
+        "roofline": None, "cpu_baseline": None,
     }
+
+
+def ds_launches_per_step(ds):
+    """Kernels of this library inside one captured slab step (the graphs replay what an eager step enqueues):
+    pack 1 + merge 4 + deposit 1 + mechanics 3 x substeps + 2 + sort/search 5 + diffusion + sample."""
+    sm = len(ds.dts)
+    n = 1 + 4 + 3 * sm + 2 + 5
+    if ds.field is not None:
+        n += 1 + int(ds.eng.lib.abm_diffusion_launches(ds.cfg.diffuse_steps, ds.eng.diffusion_fuse)) + 1
+    return n
 
 
 def run_reference(args, rank, world):
@@ -794,6 +830,10 @@ def main():
                     help="c3 = BASELINE configs[2], the 500k-cell headline colony quoted at 1 and 8 B200 (default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = one workload-sized slab per GPU (default); strong = the workload's colony cut "
+                         "into N slabs (BASELINE configs[3]: --workload c4 --scaling strong)")
+    ap.add_argument("--no-graphs", action="store_true", help="N > 1: eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-clocks", action="store_true",
                     help="no nvidia-smi sampling (profiler runs: keeps the launch sequence deterministic)")
     ap.add_argument("--no-overlap", action="store_true",

@@ -254,7 +254,9 @@ int abm_deposit_morphogens(const double *locations, const double *amounts, doubl
  * Device-side counts (merge): n_own_device (may be NULL) caps the owned input rows at min(n_own, *n_own_device);
  * received_counts_device (may be NULL) = int32[2], the valid records of the two segments (clipped to n_received /
  * n_received_b, which are then the segments' capacities); n_local_out (may be NULL) receives the total number of
- * cells written (owned + halo).  With them a whole slab step is enqueued without a host round trip.              */
+ * cells written (owned + halo).  With them a whole slab step is enqueued without a host round trip.
+ * out_capacity (0 = n_own + n_received + n_received_b): rows of the out_* arrays; cells that do not fit are
+ * dropped and *n_local_out (> out_capacity then) tells the caller how many rows it needed.                       */
 size_t abm_slab_workspace_bytes(int64_t n);
 int abm_slab_pack(const double *locations, const double *radii, const double *motility_forces,
                   const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t n_own,
@@ -268,7 +270,8 @@ int abm_slab_merge(const double *locations, const double *radii, const double *m
                    int has_left, int has_right, double *out_locations, double *out_radii, double *out_motility,
                    int32_t *out_global_id, int32_t *out_bond_len, int32_t *out_bond_rows, int32_t *n_owned_out,
                    void *workspace, size_t workspace_bytes, const int32_t *n_own_device,
-                   const int32_t *received_counts_device, int32_t *n_local_out, void *stream);
+                   const int32_t *received_counts_device, int32_t *n_local_out, int64_t out_capacity,
+                   void *stream);
 
 #ifdef __cplusplus
 }

@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(256) k_slab_keep(const double *__restrict__ lo
 
 // stable two-way partition: owned-next cells first (in input order), then everything else (halo cells)
 __global__ void __launch_bounds__(256) k_slab_merge(CellArrays in, int n_own, Received recv, int rec_bytes,
-                                                    int stride, const int *__restrict__ pos, CellArrays out) {
+                                                    int stride, const int *__restrict__ pos, CellArrays out,
+                                                    int out_capacity) {
     int i = blockIdx.x * 256 + threadIdx.x;
     recv.resolve(n_own);
     int total = n_own + recv.k_a + recv.k_b;
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(256) k_slab_merge(CellArrays in, int n_own, Re
     int n_keep = pos[total];
     bool kept = pos[i + 1] != pos[i];
     int dst = kept ? pos[i] : n_keep + (i - pos[i]);
+    if (dst >= out_capacity) return;               // does not fit: dropped; n_local_out tells the caller how many rows it needed
     if (i < n_own) {
         out.loc[3 * (long long)dst + 0] = in.loc[3 * (long long)i + 0];
         out.loc[3 * (long long)dst + 1] = in.loc[3 * (long long)i + 1];
@@ -204,7 +206,7 @@ ABM_EXPORT int abm_slab_merge(const double *locations, const double *radii, cons
                               double *out_radii, double *out_motility, int32_t *out_global_id, int32_t *out_bond_len,
                               int32_t *out_bond_rows, int32_t *n_owned_out, void *workspace, size_t workspace_bytes,
                               const int32_t *n_own_device, const int32_t *received_counts_device,
-                              int32_t *n_local_out, void *stream) {
+                              int32_t *n_local_out, int64_t out_capacity, void *stream) {
     int64_t total = n_own + n_received + n_received_b;          // the capacity when the counts live on the device
     ABM_REQUIRE(n_own >= 0 && n_received >= 0 && n_received_b >= 0 && total < 0x7fffffff && row_stride > 0, "bad sizes");
     ABM_REQUIRE((received || n_received == 0) && (received_b || n_received_b == 0), "null record segment");
@@ -230,7 +232,9 @@ ABM_EXPORT int abm_slab_merge(const double *locations, const double *radii, cons
     CellArrays in{const_cast<double *>(locations), const_cast<double *>(radii), const_cast<double *>(motility_forces),
                   const_cast<int *>(global_id), const_cast<int *>(bond_len), const_cast<int *>(bond_rows)};
     CellArrays out{out_locations, out_radii, out_motility, out_global_id, out_bond_len, out_bond_rows};
-    k_slab_merge<<<ceil_div(total, 256), 256, 0, st>>>(in, (int)n_own, recv, rec_bytes, (int)row_stride, keep, out);
+    if (out_capacity <= 0 || out_capacity > total) out_capacity = total;
+    k_slab_merge<<<ceil_div(total, 256), 256, 0, st>>>(in, (int)n_own, recv, rec_bytes, (int)row_stride, keep, out,
+                                                       (int)out_capacity);
     ABM_CHECK_LAUNCH("k_slab_merge");
     return 0;
 }

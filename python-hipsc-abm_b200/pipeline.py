@@ -523,7 +523,7 @@ class NativeSlabOps:
             from_l.data_ptr() if n_l else 0, n_l, from_r.data_ptr() if n_r else 0, n_r, stride, geom.x_lo, geom.x_hi,
             int(geom.has_left), int(geom.has_right), o["loc"].data_ptr(), o["radii"].data_ptr(), o["mot"].data_ptr(),
             o["gid"].data_ptr(), o["blen"].data_ptr(), o["rows"].data_ptr(), o["n_owned"].data_ptr(), ws.data_ptr(),
-            ws.numel(), 0, 0, 0, eng.stream), "abm_slab_merge")
+            ws.numel(), 0, 0, 0, 0, eng.stream), "abm_slab_merge")
         eng.launches += 4
         # owned count read when first needed
         return LocalProblem(o["n_owned"], o["loc"][:total], o["radii"][:total], o["mot"][:total], o["gid"][:total],

@@ -1,0 +1,377 @@
+"""Slab decomposition with every count on the device (VERDICT r01 "slab step without a host round trip").
+
+`slab.py` describes the decomposition (geometry, halo depth, the generic rank_step used by the CPU/gloo tests).  This
+module is the production path on GPUs.  One rank keeps its cells in FIXED-CAPACITY device arrays and all counts
+(owned cells, local cells = owned + halo, message rows) in device memory; every kernel of the path reads its cell
+count from there (`n_device` of the C-ABI).  A step therefore needs no host synchronisation at all, its launch
+parameters never change, and it is replayed as CUDA graphs:
+
+    main stream                                              side stream
+    ---------------------------------------------------     -------------------------------------------------
+    [G pack]      cells within `halo` of an interface -> fixed-capacity messages + their row counts
+    NCCL          one send/recv group with both x-neighbours (messages and counts together)
+    [G merge]     owned | halo partition into the other buffer set (migration = ownership by position),
+                  snapshot of the positions, morphogen deposit on the snapshot
+                                                              NCCL   morphogen rows (own communicator)
+    [G mechanics] 11 x (sort + fused substep) on owned+halo   [G side] absorb rows, r=15 search on the snapshot,
+                  cells, no communication                               diffusion substeps, per-cell sampling
+
+The morphogen stage and the neighbour search work on the positions the step STARTS with (the reference's order:
+update_diffusion before apply_forces, cell_simulation.py:101-112), which is what makes them independent of the
+mechanics.  Capacities are checked after the fact: the kernels record what they needed, `check()` raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .engine import ColonyEngine, GraphTensors, STOKES
+from .slab import FieldSlab, SlabGeometry
+
+
+class DeviceSlab:
+    def __init__(self, geom: SlabGeometry, cfg, device, rows: int, send_cap: int, max_radius=5.0, uniform_radius=0.0,
+                 field: Optional[FieldSlab] = None):
+        """rows: capacity of every per-cell array (owned + halo cells of this rank, with headroom);
+        send_cap: rows of a cell message -- the SAME value on every rank (the receiver posts a buffer of that size)."""
+        self.geom, self.cfg, self.dev = geom, cfg, torch.device(device)
+        self.eng = ColonyEngine(geom.size, device)
+        self.eng.set_bin_lattice(*geom.local_box())
+        self.R, self.send_cap, self.stride = int(rows), int(send_cap), int(cfg.bond_stride)
+        self.rec = 64 + 4 * self.stride
+        self.dts = cfg.substep_dts()
+        self.max_radius, self.uniform_radius = float(max_radius), float(uniform_radius)
+        f64, i32, dev, R = torch.float64, torch.int32, self.dev, self.R
+
+        def cells():
+            return dict(loc=torch.zeros((R, 3), dtype=f64, device=dev), radii=torch.zeros(R, dtype=f64, device=dev),
+                        mot=torch.zeros((R, 3), dtype=f64, device=dev), gid=torch.zeros(R, dtype=i32, device=dev),
+                        blen=torch.zeros(R, dtype=i32, device=dev),
+                        rows=torch.zeros((R, self.stride), dtype=i32, device=dev),
+                        n_own=torch.zeros(1, dtype=i32, device=dev), n_local=torch.zeros(1, dtype=i32, device=dev))
+        self.sets = [cells(), cells()]
+        self.cur = 0
+        self.bonds = (self.sets[0]["blen"], self.sets[0]["rows"])        # where the current bonds live
+        u8 = torch.uint8
+        self.send = [torch.zeros((self.send_cap, self.rec), dtype=u8, device=dev) for _ in range(2)]
+        self.recv = [torch.zeros((self.send_cap, self.rec), dtype=u8, device=dev) for _ in range(2)]
+        self.counts_out = torch.zeros(2, dtype=i32, device=dev)
+        self.counts_in = torch.zeros(2, dtype=i32, device=dev)
+        self.worst = torch.zeros(3, dtype=i32, device=dev)               # largest message counts, largest n_local
+        need = int(self.eng.lib.abm_slab_workspace_bytes(R + 2 * self.send_cap))
+        self.ws = torch.empty(need + 4096, dtype=u8, device=dev)
+        self.snap = torch.zeros((R, 3), dtype=f64, device=dev)
+        cap = int(cfg.search_cols_per_cell * R) + 1024
+        self.nbr = dict(row_start=torch.zeros(R, dtype=i32, device=dev), row_len=torch.zeros(R, dtype=i32, device=dev),
+                        cols=torch.empty(cap, dtype=i32, device=dev), cursor=torch.zeros(1, dtype=i32, device=dev),
+                        worst=torch.zeros(1, dtype=i32, device=dev))
+        self.neighbor_graph = None
+        self.field = field
+        self.sampled = torch.zeros(R, dtype=f64, device=dev)
+        if field is not None:
+            self.amounts = torch.full((R,), cfg.deposit_amount, dtype=f64, device=dev)
+            k, gy = field.halo_rows, field.gy
+            self.rows_out = [torch.zeros((k, gy), dtype=f64, device=dev) for _ in range(2)]
+            self.rows_in = [torch.zeros((k, gy), dtype=f64, device=dev) for _ in range(2)]
+        self.launches = 0
+
+    # ---- set-up / read-out (these may synchronise) --------------------------------------------------------------
+    def load(self, loc, radii, mot, gid):
+        """The cells this rank owns at the start (device or host tensors / arrays)."""
+        s = self.sets[self.cur]
+        n = int(loc.shape[0])
+        if n > self.R:
+            raise _lib.AbmError(f"{n} cells for a capacity of {self.R} rows")
+        t = lambda a, dt: torch.as_tensor(a).to(self.dev, dt)
+        s["loc"][:n] = t(loc, torch.float64)
+        s["radii"][:n] = t(radii, torch.float64)
+        s["mot"][:n] = t(mot, torch.float64)
+        s["gid"][:n] = t(gid, torch.int32)
+        s["blen"].zero_()
+        s["n_own"].fill_(n)
+        s["n_local"].fill_(n)
+        self.bonds = (s["blen"], s["rows"])
+
+    def owned(self):
+        """Host synchronisation: the owned cells as tensors (loc, radii, mot, gid, bond_len, bond_rows)."""
+        s = self.sets[self.cur]
+        n = int(s["n_own"].item())
+        blen, rows = self.bonds
+        return dict(loc=s["loc"][:n], radii=s["radii"][:n], mot=s["mot"][:n], gid=s["gid"][:n], bond_len=blen[:n],
+                    bond_gid=rows[:n], n=n)
+
+    def negate_motility(self):
+        self.sets[self.cur]["mot"].neg_()          # all rows: the halo rows behind the owned ones are never sent
+
+    def check(self):
+        """Host synchronisation: raise if any fixed-capacity buffer was too small in a step since the last check."""
+        w = [int(v) for v in self.worst.tolist()]
+        if max(w[0], w[1]) > self.send_cap:
+            raise _lib.AbmError(f"cell message capacity too small: needed {max(w[0], w[1])} rows, have {self.send_cap}")
+        if w[2] > self.R:
+            raise _lib.AbmError(f"cell arrays too small: needed {w[2]} rows, have {self.R}")
+        used = int(self.nbr["worst"].item())
+        if used > self.nbr["cols"].numel():
+            raise _lib.AbmError(f"neighbour column buffer too small: needed {used}")
+        b = self.eng._bond_bufs
+        if b is not None and int(b["max_len"].item()) > b["stride"]:
+            raise _lib.AbmError(f"bond rows too narrow: needed {int(b['max_len'].item())}, have {b['stride']}")
+
+    # ---- the phases of a step: each only ENQUEUES on the current stream ---------------------------------------------
+    def enqueue_pack(self):
+        eng, g, s = self.eng, self.geom, self.sets[self.cur]
+        eng.use_current_stream()
+        blen, rows = self.bonds
+        _lib.check(eng.lib.abm_slab_pack(
+            s["loc"].data_ptr(), s["radii"].data_ptr(), s["mot"].data_ptr(), s["gid"].data_ptr(), blen.data_ptr(),
+            rows.data_ptr(), self.R, s["n_own"].data_ptr(), self.stride, g.x_lo + g.halo, g.x_hi - g.halo,
+            int(g.has_left), int(g.has_right), self.send[0].data_ptr(), self.send_cap, self.send[1].data_ptr(),
+            self.send_cap, self.counts_out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), eng.stream),
+            "abm_slab_pack")
+        torch.maximum(self.worst[:2], self.counts_out, out=self.worst[:2])
+        self.launches += 1
+
+    def enqueue_merge(self):
+        """Owned | halo partition of (current owned cells + received records) into the other buffer set; then the
+        snapshot of the positions and the morphogen deposit on it."""
+        eng, g = self.eng, self.geom
+        eng.use_current_stream()
+        s, o = self.sets[self.cur], self.sets[1 - self.cur]
+        blen, rows = self.bonds
+        _lib.check(eng.lib.abm_slab_merge(
+            s["loc"].data_ptr(), s["radii"].data_ptr(), s["mot"].data_ptr(), s["gid"].data_ptr(), blen.data_ptr(),
+            rows.data_ptr(), self.R, self.recv[0].data_ptr(), self.send_cap if g.has_left else 0,
+            self.recv[1].data_ptr(), self.send_cap if g.has_right else 0, self.stride, g.x_lo, g.x_hi,
+            int(g.has_left), int(g.has_right), o["loc"].data_ptr(), o["radii"].data_ptr(), o["mot"].data_ptr(),
+            o["gid"].data_ptr(), o["blen"].data_ptr(), o["rows"].data_ptr(), o["n_own"].data_ptr(),
+            self.ws.data_ptr(), self.ws.numel(), s["n_own"].data_ptr(), self.counts_in.data_ptr(),
+            o["n_local"].data_ptr(), self.R, eng.stream), "abm_slab_merge")
+        torch.maximum(self.worst[2:3], o["n_local"], out=self.worst[2:3])
+        self.launches += 4
+        self.cur = 1 - self.cur
+        self.bonds = (o["blen"], o["rows"])
+        eng.set_device_state(o["loc"], o["radii"], o["mot"], max_radius=self.max_radius,
+                             uniform_radius=self.uniform_radius)
+        eng.n_device = o["n_local"]
+        eng.global_id = o["gid"]
+        self.snap.copy_(o["loc"])
+        if self.field is not None:
+            f = self.field
+            eng.deposit(f.data, self.amounts, f.h, rows=(f.ext_lo, f.ext_hi), grid_rows=f.gx, loc=self.snap, n=self.R)
+            if f.has_left:
+                self.rows_out[0].copy_(f.owned()[:f.halo_rows])
+            if f.has_right:
+                own = f.owned()
+                self.rows_out[1].copy_(own[own.shape[0] - f.halo_rows:])
+
+    def enqueue_mechanics(self):
+        eng, cfg, s = self.eng, self.cfg, self.sets[self.cur]
+        eng.use_current_stream()
+        before = eng.launches
+        old = GraphTensors(self.R, None, self.stride, s["blen"], s["rows"], True)
+        bonds = eng.enqueue_mechanics(old, cfg.contact_radius, self.dts, self.stride, STOKES, pair=[0, 1],
+                                      zero_flag=False)
+        self.bonds = (bonds.row_len, bonds.cols)
+        self.launches += eng.launches - before
+
+    def enqueue_side(self):
+        """Everything that depends only on the step's starting positions (the snapshot): the r = search_radius
+        neighbour graph the rule methods consume, and the diffusion + per-cell sampling of the morphogen field
+        (whose halo rows have arrived in rows_in)."""
+        eng, cfg = self.eng, self.cfg
+        eng.use_current_stream()
+        before = eng.launches
+        srt = eng.sort(cfg.search_radius, loc=self.snap)
+        self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self.nbr["row_start"],
+                                                 self.nbr["row_len"], self.nbr["cols"], self.nbr["cursor"],
+                                                 loc=self.snap)
+        torch.maximum(self.nbr["worst"], self.nbr["cursor"], out=self.nbr["worst"])
+        if self.field is not None:
+            f = self.field
+            f.absorb(self.rows_in[0], self.rows_in[1])
+            last = cfg.diffuse_dt if cfg.diffuse_last_dt is None else cfg.diffuse_last_dt
+            out = eng.diffuse(f.data, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const, f.h ** 2,
+                              cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma)
+            if out.data_ptr() != f.data.data_ptr():
+                f.data.copy_(out)
+            eng.sample(f.data, f.h, rows=(f.ext_lo, f.ext_hi), grid_rows=f.gx, loc=self.snap, n=self.R,
+                       out=self.sampled)
+        self.launches += eng.launches - before
+
+
+class _Phase:
+    """One phase of the step as either a direct call or a pair of captured CUDA graphs (one per buffer parity)."""
+
+    def __init__(self, fn):
+        self.fn, self.graphs = fn, None
+
+    def run(self, parity):
+        if self.graphs is None:
+            self.fn()
+        else:
+            self.graphs[parity].replay()
+
+
+class SlabStepper:
+    """Drives one DeviceSlab (one rank).  exchange_cells / exchange_rows are supplied by the driver below (NCCL) or
+    by the loopback emulation (several ranks on one GPU)."""
+
+    def __init__(self, slab: DeviceSlab, side_stream=True):
+        self.slab = slab
+        self.phases = dict(pack=_Phase(slab.enqueue_pack), merge=_Phase(slab.enqueue_merge),
+                           mechanics=_Phase(slab.enqueue_mechanics), side=_Phase(slab.enqueue_side))
+        self.side = torch.cuda.Stream(device=slab.dev) if side_stream else None
+        self.side_done = None
+        self.captured = False
+        self.steps = 0
+
+    def capture(self):
+        """Capture the four phases for both buffer parities.  Call after at least two eager steps (every scratch
+        buffer then exists) and with an even number of steps done."""
+        s = self.slab
+        assert s.cur == 0 and s.bonds[0].data_ptr() != s.sets[0]["blen"].data_ptr(), \
+            "capture() needs an even number (>= 2) of eager steps first"
+        torch.cuda.synchronize(s.dev)
+        launches, cur, bonds = s.launches, s.cur, s.bonds
+        eng_launches = s.eng.launches
+        stream = torch.cuda.Stream(device=s.dev)
+        graphs = {k: [None, None] for k in self.phases}
+        for parity in range(2):
+            for name in ("pack", "merge", "mechanics", "side"):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=stream):
+                    self.phases[name].fn()
+                graphs[name][parity] = g
+        assert s.cur == cur
+        s.bonds, s.launches, s.eng.launches = bonds, launches, eng_launches
+        s.eng.use_current_stream()
+        self._per_step = None
+        for name, g in graphs.items():
+            self.phases[name].graphs = g
+        self.captured = True
+
+    # The bookkeeping a captured phase would have done in Python (which set is current, where the bonds live).
+    def _after_merge(self):
+        s = self.slab
+        if self.captured:
+            s.cur = 1 - s.cur
+            o = s.sets[s.cur]
+            s.bonds = (o["blen"], o["rows"])
+
+    def _after_mechanics(self):
+        s = self.slab
+        if self.captured:
+            b = s.eng._bond_bufs
+            k = (len(s.dts) - 1) & 1
+            s.bonds = (b["len"][k], b["cols"][k])
+
+    def run(self, exchange_cells, exchange_rows):
+        """One step.  exchange_cells() / exchange_rows() enqueue the transfers of this rank on the CURRENT stream
+        (cells on the main stream, rows on the side stream)."""
+        s = self.slab
+        main = torch.cuda.current_stream(s.dev)
+        parity = s.cur
+        self.phases["pack"].run(parity)
+        exchange_cells()
+        if self.side_done is not None:
+            main.wait_event(self.side_done)       # last step's side work read the snapshot the merge overwrites
+        self.phases["merge"].run(parity)
+        self._after_merge()
+        side = self.side or main
+        if self.side is not None:
+            side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if s.field is not None:
+                exchange_rows()
+        self.phases["mechanics"].run(parity)
+        self._after_mechanics()
+        with torch.cuda.stream(side):
+            self.phases["side"].run(parity)
+            if self.side is not None:
+                self.side_done = torch.cuda.Event()
+                self.side_done.record(side)
+        s.eng.use_current_stream()
+        self.steps += 1
+
+    def join(self):
+        """Make the current stream wait for the side stream's work of the last step."""
+        if self.side_done is not None:
+            torch.cuda.current_stream(self.slab.dev).wait_event(self.side_done)
+
+
+class DistSlab(SlabStepper):
+    """One rank over torch.distributed (NCCL): cells and counts in one send/recv group with both x-neighbours, the
+    morphogen rows on their own communicator (`rows_group`) so that they never queue behind the cell exchange."""
+
+    def __init__(self, slab: DeviceSlab, rank, world, rows_group=None, side_stream=True):
+        super().__init__(slab, side_stream)
+        import torch.distributed as dist
+        self.dist, self.rank, self.world, self.rows_group = dist, rank, world, rows_group
+        self.bytes_sent = 0
+        self.exchanges = 0
+
+    def _post(self, ops):
+        for w in self.dist.batch_isend_irecv(ops) if ops else []:
+            w.wait()
+
+    def _cells(self):
+        s, d = self.slab, self.dist
+        ops = []
+        for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= peer < self.world:
+                ops += [d.P2POp(d.isend, s.send[side], peer), d.P2POp(d.irecv, s.recv[side], peer),
+                        d.P2POp(d.isend, s.counts_out[side:side + 1], peer),
+                        d.P2POp(d.irecv, s.counts_in[side:side + 1], peer)]
+                self.bytes_sent += s.send[side].numel()
+        self._post(ops)
+        self.exchanges += 1
+
+    def _rows(self):
+        s, d = self.slab, self.dist
+        ops = []
+        for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= peer < self.world:
+                kw = {} if self.rows_group is None else dict(group=self.rows_group)
+                ops += [d.P2POp(d.isend, s.rows_out[side], peer, **kw), d.P2POp(d.irecv, s.rows_in[side], peer, **kw)]
+                self.bytes_sent += s.rows_out[side].numel() * 8
+        self._post(ops)
+        self.exchanges += 1
+
+    def step(self):
+        self.run(self._cells, self._rows)
+
+
+def loopback_step(steppers):
+    """The same step for several ranks emulated on ONE device (tests): the exchanges are device copies between the
+    ranks' message buffers.  The ranks advance phase by phase in lock-step, which is what a collective implies."""
+    world = len(steppers)
+    slabs = [st.slab for st in steppers]
+    parities = [s.cur for s in slabs]
+    for st, p in zip(steppers, parities):
+        st.phases["pack"].run(p)
+    for k, s in enumerate(slabs):
+        s.counts_in.zero_()
+        if k > 0:
+            s.recv[0].copy_(slabs[k - 1].send[1])
+            s.counts_in[0:1].copy_(slabs[k - 1].counts_out[1:2])
+        if k < world - 1:
+            s.recv[1].copy_(slabs[k + 1].send[0])
+            s.counts_in[1:2].copy_(slabs[k + 1].counts_out[0:1])
+    for st, p in zip(steppers, parities):
+        st.phases["merge"].run(p)
+        st._after_merge()
+    for k, s in enumerate(slabs):
+        if s.field is not None:
+            if k > 0:
+                s.rows_in[0].copy_(slabs[k - 1].rows_out[1])
+            if k < world - 1:
+                s.rows_in[1].copy_(slabs[k + 1].rows_out[0])
+    for st, p in zip(steppers, parities):
+        st.phases["mechanics"].run(p)
+        st._after_mechanics()
+        st.phases["side"].run(p)
+        st.slab.eng.use_current_stream()
+        st.steps += 1
