@@ -220,6 +220,17 @@ int abm_diffusion(double *field, double *scratch, int64_t gx, int64_t gy, int64_
  * parity of `steps`, so the result lands where the substep-by-substep ping-pong would leave it) */
 int64_t abm_diffusion_launches(int64_t steps, int max_fused_substeps);
 
+/* 3-D extension (no reference counterpart: the reference's diffusion is 2-D only, cell_backend.py:184 "currently 2D";
+ * oracle: oracle/abm_oracle.c orc_update_diffusion3d, bit-identical).  Same contract as abm_diffusion for a
+ * (gx,gy,gz) float64 field with z contiguous (the reference's gradient[x][y][z]): clamp -> `steps` 7-point FTCS Jacobi
+ * substeps (a = dt*D/h^2, b = 1-6a, reflecting walls, the last one with last_dt) -> multiply by (1-degradation).
+ * One launch per substep; use_tma: 1 = planes staged by TMA (cp.async.bulk.tensor.3d; needs gz even and 16-byte
+ * aligned fields), 0 = plain staged loads.                                                                    */
+int abm_diffusion3d(double *field, double *scratch, int64_t gx, int64_t gy, int64_t gz, int64_t steps,
+                    double diffuse_dt, double last_dt, double diffuse_const, double spat_res2,
+                    double max_concentration, double degradation, int use_tma, int *result_in_scratch_host,
+                    void *stream);
+
 /* Replaces per-cell get_concentration (cell_methods.py:470-483) for all cells: nearest grid point
  * idx = ceil(floor(2x/h)/2) on the (gx,gy,gz) grid.  `field` holds the global rows [row_lo,row_hi) of that grid,
  * row-major (the whole grid: row_lo=0,row_hi=gx; a slab of it for a slab-decomposed colony).  sampled (N,) f64. */
@@ -234,6 +245,13 @@ int abm_sample_concentrations(const double *locations, int64_t n, const double *
 int abm_deposit_morphogens(const double *locations, const double *amounts, double uniform_amount, int64_t n,
                            double *field, const int64_t gsize_host[3], double spat_res, int64_t row_lo,
                            int64_t row_hi, const int32_t *n_device, void *stream);
+
+/* 3-D extension of the deposit: amounts[i] is shared by the in-bounds corner points of the cell's grid CUBE (eight)
+ * closer than spat_res (the reference deposits on the z = 0 plane only, cell_methods.py:499; oracle:
+ * orc_adjust_morphogens3d).  Same arguments as abm_deposit_morphogens.                                          */
+int abm_deposit_morphogens3d(const double *locations, const double *amounts, double uniform_amount, int64_t n,
+                             double *field, const int64_t gsize_host[3], double spat_res, int64_t row_lo,
+                             int64_t row_hi, const int32_t *n_device, void *stream);
 
 /* ---- slab decomposition plumbing (no reference counterpart; see hipsc_abm_b200/slab.py) -------------------
  * A cell travels between ranks as one byte record:

@@ -69,6 +69,10 @@ def lib():
         L.orc_update_diffusion_field.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_int64, C.c_double, C.c_double,
                                                  C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_update_diffusion_field.restype = C.c_int
+        L.orc_update_diffusion3d_field.argtypes = [_f64p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                                                   C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.orc_update_diffusion3d_field.restype = C.c_int
+        L.orc_adjust_morphogens3d.argtypes = [C.c_int64, _f64p, _f64p, _f64p, _i64p, C.c_double]
         L.orc_get_concentrations.argtypes = [C.c_int64, _f64p, _f64p, _i64p, C.c_double, _f64p]
         L.orc_adjust_morphogens.argtypes = [C.c_int64, _f64p, _f64p, _f64p, _i64p, C.c_double]
         _lib = L
@@ -286,6 +290,28 @@ def diffuse_field(plane, steps, diffuse_dt, last_dt, diffuse_const, spat_res2, m
     if rc != 0:
         raise MemoryError("oracle diffusion scratch allocation failed")
     return plane
+
+
+def diffuse_field3d(field, steps, diffuse_dt, last_dt, diffuse_const, spat_res2, max_concentration, degradation):
+    """3-D extension of update_diffusion on a (gx,gy,gz) field (PARITY UNPINNED: no reference counterpart; the 2-D
+    algorithm of cell_backend.py:175-204 with a third axis, b = 1-6a); returns the new field."""
+    field = np.ascontiguousarray(field, dtype=np.float64).copy()
+    assert field.ndim == 3
+    rc = lib().orc_update_diffusion3d_field(field, field.shape[0], field.shape[1], field.shape[2], int(steps),
+                                            float(diffuse_dt), float(last_dt), float(diffuse_const), float(spat_res2),
+                                            float(max_concentration), float(degradation))
+    if rc != 0:
+        raise MemoryError("oracle diffusion scratch allocation failed")
+    return field
+
+
+def adjust_morphogens3d(locations, amounts, gradient, spat_res):
+    """adjust_morphogens over the eight corners of the cell's grid cube (3-D extension, PARITY UNPINNED)."""
+    assert gradient.flags.c_contiguous and gradient.dtype == np.float64 and gradient.ndim == 3
+    amounts = np.ascontiguousarray(np.broadcast_to(np.asarray(amounts, dtype=np.float64), (len(locations),)))
+    lib().orc_adjust_morphogens3d(len(locations), np.ascontiguousarray(locations, dtype=np.float64), amounts, gradient,
+                                  np.array(gradient.shape, dtype=np.int64), float(spat_res))
+    return gradient
 
 
 def get_concentrations(locations, gradient, spat_res):

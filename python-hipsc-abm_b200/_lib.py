@@ -43,6 +43,8 @@ SIGNATURES = {
                                  F64, F64, F64, F64, F64, I32, P, P]),
     "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, I32, C.POINTER(I32), P]),
     "abm_diffusion_launches": (I64, [I64, I32]),
+    "abm_diffusion3d": (I32, [P, P, I64, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),
+    "abm_deposit_morphogens3d": (I32, [P, P, F64, I64, P, L3, F64, I64, I64, P, P]),
     "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P, P]),
     "abm_slab_workspace_bytes": (SZ, [I64]),
     "abm_slab_pack": (I32, [P, P, P, P, P, P, I64, P, I64, F64, F64, I32, I32, P, I64, P, I64, P, P, SZ, P]),

@@ -161,16 +161,27 @@ class B200CellMethods:
         out = self._b200_diffuse_plane(eng, f, steps, last_dt)
         self._b200_field_to_host(gradient_name, out)
 
+    # The reference's update_diffusion only ever touches the z = 0 plane ("currently 2D", cell_backend.py:184), also
+    # of a (gx,gy,gz) field.  b200_diffusion_3d = True selects the 3-D extension for fields with gz > 1: 7-point
+    # stencil over the whole field (abm_diffusion3d) and deposits over the eight corners of the cell's grid cube.
+    b200_diffusion_3d = False
+
+    def _b200_volume(self, f):
+        return bool(self.b200_diffusion_3d) and f.dim() == 3 and f.shape[2] > 1
+
     def _b200_diffuse_plane(self, eng, f, steps, last_dt):
-        """`steps` diffusion substeps on the z = 0 plane of the device field f (gx,gy,1); returns the device field
-        holding the result (f itself, or its ping-pong partner)."""
-        if f.dim() == 3 and f.shape[2] != 1:
-            raise NotImplementedError("update_diffusion follows the reference: the z = 0 plane of a (gx,gy,1) field; "
-                                      "3-D fields go through update_diffusion_3d")
+        """`steps` diffusion substeps on the device field f (gx,gy,gz); returns the device field holding the result
+        (f itself, or its ping-pong partner)."""
+        args = (steps, self.diffuse_dt, last_dt, self.diffuse_const, self.spat_res2, self.max_concentration,
+                self.degradation)
+        if self._b200_volume(f):
+            return eng.diffuse3d(f, *args)
+        if f.dim() == 3 and f.shape[2] != 1:                      # reference semantics: the z = 0 plane of a volume
+            plane = f[:, :, 0].contiguous()
+            f[:, :, 0] = eng.diffuse(plane, *args)
+            return f
         plane = f.view(f.shape[0], f.shape[1])
-        out = eng.diffuse(plane, steps, self.diffuse_dt, last_dt, self.diffuse_const, self.spat_res2,
-                          self.max_concentration, self.degradation)
-        return out.view(f.shape)
+        return eng.diffuse(plane, *args).view(f.shape)
 
     # ---- a12/a13 ---------------------------------------------------------------------------------------------
     def get_concentration(self, gradient_name, index):
@@ -209,11 +220,12 @@ class B200CellMethods:
         if sample and not diffuse:
             sampled = eng.host(eng.sample(f, self.spat_res, loc=loc, n=count))
         if amounts is not None:
+            cube = self._b200_volume(f)
             if np.ndim(amounts) == 0:                     # one amount for every cell: no array travels
-                eng.deposit(f, float(amounts), self.spat_res, loc=loc, n=count)
+                eng.deposit(f, float(amounts), self.spat_res, loc=loc, n=count, cube=cube)
             else:
                 a = np.ascontiguousarray(np.broadcast_to(np.asarray(amounts, dtype=np.float64), (count,)))
-                eng.deposit(f, eng.to_device(a, "amounts"), self.spat_res, loc=loc, n=count)
+                eng.deposit(f, eng.to_device(a, "amounts"), self.spat_res, loc=loc, n=count, cube=cube)
             changed = True
         if diffuse:
             steps, last_dt = divmod(self.step_dt, self.diffuse_dt)

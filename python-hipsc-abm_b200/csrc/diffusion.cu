@@ -18,6 +18,7 @@
 #include <string.h>
 
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace abm {
 
@@ -50,35 +51,6 @@ struct DiffParams {
     double keep;            // 1-degradation applied to the RESULT when degrade_out
     int clamp_in, degrade_out;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
 
 template <bool kTma>
 __global__ void __launch_bounds__(kDiffThreads)
@@ -316,25 +288,10 @@ __global__ void k_deposit(const double *__restrict__ loc, const double *__restri
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static int make_field_map(CUtensorMap *map, const double *ptr, long long gx, long long gy, int box_j = kBoxJ,
                           int box_i = kBoxI) {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void *fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        int rc = check_cuda(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q),
-                            "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
-        if (rc) return rc;
-        if (!fn || q != cudaDriverEntryPointSuccess) {
-            set_error("cuTensorMapEncodeTiled is not available from this driver");
-            return -1;
-        }
-        encode = (EncodeTiledFn)fn;
-    }
+    EncodeTiledFn encode = tensor_map_encoder();
+    if (!encode) return -1;
     cuuint64_t gdim[2] = {(cuuint64_t)gy, (cuuint64_t)gx};
     cuuint64_t gstride[1] = {(cuuint64_t)gy * 8};
     cuuint32_t box[2] = {(cuuint32_t)box_j, (cuuint32_t)box_i};

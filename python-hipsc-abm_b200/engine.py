@@ -610,6 +610,23 @@ class ColonyEngine:
         self.launches += int(self.lib.abm_diffusion_launches(int(steps), self.diffusion_fuse))
         return scratch if where.value else field
 
+    def diffuse3d(self, field: torch.Tensor, steps, diffuse_dt, last_dt, diffuse_const, spat_res2, max_concentration,
+                  degradation, use_tma=None, scratch=None) -> torch.Tensor:
+        """7-point diffusion of a (gx,gy,gz) float64 device field (3-D extension, abm_diffusion3d); returns the
+        tensor holding the result (either `field` or the scratch field -- no copy back)."""
+        gx, gy, gz = (int(v) for v in field.shape)
+        if use_tma is None:
+            use_tma = (gz % 2 == 0)
+        if scratch is None:
+            scratch = torch.empty_like(field)
+        where = C.c_int(0)
+        _lib.check(self.lib.abm_diffusion3d(_ptr(field), _ptr(scratch), gx, gy, gz, int(steps), float(diffuse_dt),
+                                            float(last_dt), float(diffuse_const), float(spat_res2),
+                                            float(max_concentration), float(degradation), 1 if use_tma else 0,
+                                            C.byref(where), self.stream), "abm_diffusion3d")
+        self.launches += int(steps)
+        return scratch if where.value else field
+
     def sample(self, field: torch.Tensor, spat_res, rows=None, grid_rows=None, loc=None, n=None,
                out=None, use_count=True) -> torch.Tensor:
         """get_concentration for every cell.  `field` is the whole (gx,gy[,gz]) grid, or -- with rows=(lo,hi) and
@@ -630,18 +647,19 @@ class ColonyEngine:
         return out[:n]
 
     def deposit(self, field: torch.Tensor, amounts, spat_res, rows=None, grid_rows=None, loc=None, n=None,
-                use_count=True):
-        """adjust_morphogens for every cell; amounts: a device tensor (one per cell) or a python float (all cells)."""
+                use_count=True, cube=False):
+        """adjust_morphogens for every cell; amounts: a device tensor (one per cell) or a python float (all cells).
+        cube: the 3-D extension -- the eight corners of the cell's grid cube instead of the reference's four corner
+        points on the z = 0 plane."""
         gs = list(tuple(field.shape) + (1,) * (3 - field.dim()))
         lo, hi = (0, gs[0]) if rows is None else rows
         if grid_rows is not None:
             gs[0] = int(grid_rows)
         n = self.n if n is None else int(n)
         scalar = not isinstance(amounts, torch.Tensor)
-        _lib.check(self.lib.abm_deposit_morphogens(_ptr(self.loc if loc is None else loc),
-                                                   0 if scalar else _ptr(amounts), float(amounts) if scalar else 0.0,
-                                                   n, _ptr(field), _lib.l3(gs),
-                                                   float(spat_res), int(lo), int(hi),
-                                                   _ptr(self.n_device) if use_count else 0, self.stream),
+        fn = self.lib.abm_deposit_morphogens3d if cube else self.lib.abm_deposit_morphogens
+        _lib.check(fn(_ptr(self.loc if loc is None else loc),
+                      0 if scalar else _ptr(amounts), float(amounts) if scalar else 0.0, n, _ptr(field), _lib.l3(gs),
+                      float(spat_res), int(lo), int(hi), _ptr(self.n_device) if use_count else 0, self.stream),
                    "abm_deposit_morphogens")
         self.launches += 1 if n else 0

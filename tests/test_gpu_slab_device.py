@@ -52,11 +52,11 @@ def test_emulated_device_slabs_match_single_domain(world, dim, graphs):
     halo = slab.required_halo(len(cfg.substep_dts()), eng.jkr_reach(10.0), slack=5.0, spat_res=h if grid else 0.0)
     geoms = [slab.SlabGeometry.uniform(size, world, r, halo) for r in range(world)]
     steppers = []
+    send_cap = int(1.2 * n / world) + 512              # the same on every rank (the receiver posts that size)
     for g in geoms:
         m = (loc[:, 0] >= g.x_lo) & ((loc[:, 0] < g.x_hi) | (g.rank == world - 1))
         field = slab.FieldSlab(g, grid, h, sd + 1, dev) if grid else None
-        s = DeviceSlab(g, cfg, dev, rows=int(2.2 * m.sum()) + 512, send_cap=int(1.2 * m.sum()) + 256,
-                       uniform_radius=5.0, field=field)
+        s = DeviceSlab(g, cfg, dev, rows=int(2.2 * m.sum()) + 512, send_cap=send_cap, uniform_radius=5.0, field=field)
         s.load(loc[m], radii[m], mot[m], np.arange(n)[m])
         steppers.append(SlabStepper(s, side_stream=False))
     done = 0
