@@ -126,6 +126,7 @@ class B200Simulation:
         state = dict(self.__dict__)
         state.pop("_b200_engine", None)
         state.pop("_b200_cache", None)           # device copies; the arrays themselves pickle as plain ndarrays
+        state.pop("_b200_zeroed", None)
         return state
 
     # ---- reference surface --------------------------------------------------------------------------------
