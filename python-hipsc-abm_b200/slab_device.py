@@ -8,10 +8,10 @@ parameters never change, and it is replayed as CUDA graphs:
 
     main stream                                              side stream
     ---------------------------------------------------     -------------------------------------------------
-    [G pack]      cells within `halo` of an interface -> fixed-capacity messages + their row counts
-    NCCL          one send/recv group with both x-neighbours (messages and counts together)
+    [G pack]      cells within `halo` of an interface -> fixed-capacity messages (row count in a trailing header)
+    NCCL          one send + one receive per x-neighbour
     [G merge]     owned | halo partition into the other buffer set (migration = ownership by position),
-                  snapshot of the positions, morphogen deposit on the snapshot
+                  snapshot of the positions                   [G deposit] morphogen deposit on the snapshot
                                                               NCCL   morphogen rows (own communicator)
     [G mechanics] 11 x (sort + fused substep) on owned+halo   [G side] absorb rows, r=15 search on the snapshot,
                   cells, no communication                               diffusion substeps, per-cell sampling
@@ -56,10 +56,14 @@ class DeviceSlab:
         self.cur = 0
         self.bonds = (self.sets[0]["blen"], self.sets[0]["rows"])        # where the current bonds live
         u8 = torch.uint8
-        self.send = [torch.zeros((self.send_cap, self.rec), dtype=u8, device=dev) for _ in range(2)]
-        self.recv = [torch.zeros((self.send_cap, self.rec), dtype=u8, device=dev) for _ in range(2)]
+        # a message = send_cap records + one trailing header row whose first int32 is the number of valid records: the
+        # count travels inside the message, so an exchange is ONE send and ONE receive per neighbour
+        self.send = [torch.zeros((self.send_cap + 1, self.rec), dtype=u8, device=dev) for _ in range(2)]
+        self.recv = [torch.zeros((self.send_cap + 1, self.rec), dtype=u8, device=dev) for _ in range(2)]
         self.counts_out = torch.zeros(2, dtype=i32, device=dev)
         self.counts_in = torch.zeros(2, dtype=i32, device=dev)
+        self._hdr_out = [self.send[k][self.send_cap, :4].view(i32) for k in range(2)]
+        self._hdr_in = [self.recv[k][self.send_cap, :4].view(i32) for k in range(2)]
         self.worst = torch.zeros(3, dtype=i32, device=dev)               # largest message counts, largest n_local
         need = int(self.eng.lib.abm_slab_workspace_bytes(R + 2 * self.send_cap))
         self.ws = torch.empty(need + 4096, dtype=u8, device=dev)
@@ -132,6 +136,8 @@ class DeviceSlab:
             self.send_cap, self.counts_out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), eng.stream),
             "abm_slab_pack")
         torch.maximum(self.worst[:2], self.counts_out, out=self.worst[:2])
+        self._hdr_out[0].copy_(self.counts_out[0:1])
+        self._hdr_out[1].copy_(self.counts_out[1:2])
         self.launches += 1
 
     def enqueue_merge(self):
@@ -141,6 +147,11 @@ class DeviceSlab:
         eng.use_current_stream()
         s, o = self.sets[self.cur], self.sets[1 - self.cur]
         blen, rows = self.bonds
+        self.counts_in.zero_()
+        if g.has_left:
+            self.counts_in[0:1].copy_(self._hdr_in[0])
+        if g.has_right:
+            self.counts_in[1:2].copy_(self._hdr_in[1])
         _lib.check(eng.lib.abm_slab_merge(
             s["loc"].data_ptr(), s["radii"].data_ptr(), s["mot"].data_ptr(), s["gid"].data_ptr(), blen.data_ptr(),
             rows.data_ptr(), self.R, self.recv[0].data_ptr(), self.send_cap if g.has_left else 0,
@@ -158,14 +169,21 @@ class DeviceSlab:
         eng.n_device = o["n_local"]
         eng.global_id = o["gid"]
         self.snap.copy_(o["loc"])
-        if self.field is not None:
-            f = self.field
-            eng.deposit(f.data, self.amounts, f.h, rows=(f.ext_lo, f.ext_hi), grid_rows=f.gx, loc=self.snap, n=self.R)
-            if f.has_left:
-                self.rows_out[0].copy_(f.owned()[:f.halo_rows])
-            if f.has_right:
-                own = f.owned()
-                self.rows_out[1].copy_(own[own.shape[0] - f.halo_rows:])
+
+    def enqueue_deposit(self):
+        """Morphogen deposit of the local cells at the snapshot positions, and the rows the x-neighbours need."""
+        if self.field is None:
+            return
+        eng, f = self.eng, self.field
+        eng.use_current_stream()
+        eng.n_device = self.sets[self.cur]["n_local"]
+        eng.deposit(f.data, self.amounts, f.h, rows=(f.ext_lo, f.ext_hi), grid_rows=f.gx, loc=self.snap, n=self.R)
+        self.launches += 1
+        if f.has_left:
+            self.rows_out[0].copy_(f.owned()[:f.halo_rows])
+        if f.has_right:
+            own = f.owned()
+            self.rows_out[1].copy_(own[own.shape[0] - f.halo_rows:])
 
     def enqueue_mechanics(self):
         eng, cfg, s = self.eng, self.cfg, self.sets[self.cur]
@@ -183,6 +201,7 @@ class DeviceSlab:
         (whose halo rows have arrived in rows_in)."""
         eng, cfg = self.eng, self.cfg
         eng.use_current_stream()
+        eng.n_device = self.sets[self.cur]["n_local"]
         before = eng.launches
         srt = eng.sort(cfg.search_radius, loc=self.snap)
         self.neighbor_graph = eng.enqueue_search(srt, cfg.search_radius, None, self.nbr["row_start"],
@@ -221,8 +240,11 @@ class SlabStepper:
 
     def __init__(self, slab: DeviceSlab, side_stream=True):
         self.slab = slab
+        # (the pack stays at the START of a step: the host may have given the cells new motility forces since the
+        # previous one, and the records carry them)
         self.phases = dict(pack=_Phase(slab.enqueue_pack), merge=_Phase(slab.enqueue_merge),
-                           mechanics=_Phase(slab.enqueue_mechanics), side=_Phase(slab.enqueue_side))
+                           deposit=_Phase(slab.enqueue_deposit), mechanics=_Phase(slab.enqueue_mechanics),
+                           side=_Phase(slab.enqueue_side))
         self.side = torch.cuda.Stream(device=slab.dev) if side_stream else None
         self.side_done = None
         self.captured = False
@@ -240,7 +262,7 @@ class SlabStepper:
         stream = torch.cuda.Stream(device=s.dev)
         graphs = {k: [None, None] for k in self.phases}
         for parity in range(2):
-            for name in ("pack", "merge", "mechanics", "side"):
+            for name in ("pack", "merge", "deposit", "mechanics", "side"):
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g, stream=stream):
                     self.phases[name].fn()
@@ -284,6 +306,7 @@ class SlabStepper:
         if self.side is not None:
             side.wait_stream(main)
         with torch.cuda.stream(side):
+            self.phases["deposit"].run(parity)
             if s.field is not None:
                 exchange_rows()
         self.phases["mechanics"].run(parity)
@@ -322,9 +345,7 @@ class DistSlab(SlabStepper):
         ops = []
         for side, peer in ((0, self.rank - 1), (1, self.rank + 1)):
             if 0 <= peer < self.world:
-                ops += [d.P2POp(d.isend, s.send[side], peer), d.P2POp(d.irecv, s.recv[side], peer),
-                        d.P2POp(d.isend, s.counts_out[side:side + 1], peer),
-                        d.P2POp(d.irecv, s.counts_in[side:side + 1], peer)]
+                ops += [d.P2POp(d.isend, s.send[side], peer), d.P2POp(d.irecv, s.recv[side], peer)]
                 self.bytes_sent += s.send[side].numel()
         self._post(ops)
         self.exchanges += 1
@@ -353,16 +374,14 @@ def loopback_step(steppers):
     for st, p in zip(steppers, parities):
         st.phases["pack"].run(p)
     for k, s in enumerate(slabs):
-        s.counts_in.zero_()
         if k > 0:
             s.recv[0].copy_(slabs[k - 1].send[1])
-            s.counts_in[0:1].copy_(slabs[k - 1].counts_out[1:2])
         if k < world - 1:
             s.recv[1].copy_(slabs[k + 1].send[0])
-            s.counts_in[1:2].copy_(slabs[k + 1].counts_out[0:1])
     for st, p in zip(steppers, parities):
         st.phases["merge"].run(p)
         st._after_merge()
+        st.phases["deposit"].run(p)
     for k, s in enumerate(slabs):
         if s.field is not None:
             if k > 0:
