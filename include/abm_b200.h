@@ -253,6 +253,56 @@ int abm_deposit_morphogens3d(const double *locations, const double *amounts, dou
                              double *field, const int64_t gsize_host[3], double spat_res, int64_t row_lo,
                              int64_t row_hi, const int32_t *n_device, void *stream);
 
+/* ---- device-resident rule methods ----------------------------------------------------------------
+ * cell_division, cell_death, cell_pathway, cell_differentiate, cell_motility (cell_methods.py:11-340) on a colony
+ * that lives in fixed-capacity device arrays with its cell count in device memory.  Random draws follow
+ * include/abm_rng.h (counter-based: seed, step, rule, persistent cell id, draw index); cell_pathway reads its
+ * neighbours' FGF4 as of before the pass.  Both differ from the reference's serial Mersenne-Twister loop by design;
+ * the CPU restatement these calls reproduce bit for bit is oracle/abm_oracle.c orc_rule_*.
+ * Every array of abm_colony_arrays has `capacity` rows (bond_rows: capacity x bond_stride ids).  nbr_start / nbr_len
+ * are the rows of the step's neighbour graph (abm_neighbor_search, searched BEFORE division and death as in
+ * cell_simulation.py:90-97) and travel with their cells; its column entries keep the indices of search time and are
+ * translated through index_map (written by abm_rule_death: new index, or -1 for a cell that died).            */
+typedef struct abm_colony_arrays {
+    double *locations, *radii, *motility_forces;
+    int32_t *gid;                                  /* persistent cell id; array order is id order */
+    int32_t *states, *GATA6, *NANOG, *FGF4, *FGFR, *ERK;
+    int32_t *death_counters, *diff_counters, *div_counters, *fds_counters;
+    int32_t *bond_len, *bond_rows;                 /* JKR bonds by id, fixed stride (abm_mechanics_loop, global_id) */
+    int32_t *nbr_start, *nbr_len;
+} abm_colony_arrays;
+
+typedef struct abm_rule_params {                  /* cell_simulation.py:33-57, templates/experimental.yaml */
+    int64_t seed, step;
+    int32_t field, dox_step, lonely_thresh, guye_move;
+    int32_t pluri_div_thresh, diff_div_thresh, pluri_to_diff, death_thresh, fds_thresh, three_d;
+    double max_radius, min_radius, motility_force;
+} abm_rule_params;
+
+size_t abm_rules_workspace_bytes(int64_t capacity);
+
+/* cell_division: stochastic division counters, thresholds, contact inhibition; every dividing cell's daughter is
+ * appended behind the last cell (a copy of the mother, both displaced by +-random_vector*(max_radius-min_radius), new
+ * id *next_gid_device + rank, no bonds, no neighbours).  *n_device and *next_gid_device are advanced on the device;
+ * needed_device (int32[2], zeroed by the caller once) keeps the largest row count needed in [0] (daughters beyond
+ * `capacity` are dropped: the caller checks it when it next synchronises).                                       */
+int abm_rule_division(const abm_colony_arrays *cells, int64_t capacity, int64_t bond_stride, int32_t *n_device,
+                      int32_t *next_gid_device, const abm_rule_params *params, int32_t *needed_device,
+                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* cell_death: death counters of lonely pluripotent cells; the survivors are compacted (stable) into cells_out,
+ * *n_device_out = their number, index_map (capacity) int32 = old index -> new index or -1.                        */
+int abm_rule_death(const abm_colony_arrays *cells, const abm_colony_arrays *cells_out, int64_t capacity,
+                   int64_t bond_stride, const int32_t *n_device, int32_t *n_device_out,
+                   const abm_rule_params *params, int32_t *index_map, void *workspace, size_t workspace_bytes,
+                   void *stream);
+
+/* cell_pathway + cell_differentiate + cell_motility on the compacted colony.  nbr_cols: column buffer of the
+ * neighbour search; fgf4_scratch: `capacity` int32.  motility_forces are ADDED to, as in the reference.            */
+int abm_rule_update(const abm_colony_arrays *cells, int64_t capacity, const int32_t *n_device,
+                    const int32_t *nbr_cols, const int32_t *index_map, const abm_rule_params *params,
+                    int32_t *fgf4_scratch, void *stream);
+
 /* ---- slab decomposition plumbing (no reference counterpart; see hipsc_abm_b200/slab.py) -------------------
  * A cell travels between ranks as one byte record:
  *   [0,24) position  [24,32) radius  [32,56) motility force  [56,60) global id  [60,64) bond_len

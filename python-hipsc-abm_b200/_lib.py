@@ -20,6 +20,25 @@ I3 = C.POINTER(C.c_int32)     # host int32[3]
 L3 = C.POINTER(C.c_int64)     # host int64[3]
 
 # name -> (restype, argtypes); must list every symbol of include/abm_b200.h (tests/test_abi.py checks)
+class ColonyArrays(C.Structure):
+    """abm_colony_arrays: device pointers of every per-cell array of a device-resident colony."""
+    _fields_ = [(name, C.c_void_p) for name in (
+        "locations", "radii", "motility_forces", "gid", "states", "GATA6", "NANOG", "FGF4", "FGFR", "ERK",
+        "death_counters", "diff_counters", "div_counters", "fds_counters", "bond_len", "bond_rows", "nbr_start",
+        "nbr_len")]
+
+
+class RuleParams(C.Structure):
+    """abm_rule_params (cell_simulation.py:33-57, templates/experimental.yaml)."""
+    _fields_ = [("seed", C.c_int64), ("step", C.c_int64), ("field", C.c_int32), ("dox_step", C.c_int32),
+                ("lonely_thresh", C.c_int32), ("guye_move", C.c_int32), ("pluri_div_thresh", C.c_int32),
+                ("diff_div_thresh", C.c_int32), ("pluri_to_diff", C.c_int32), ("death_thresh", C.c_int32),
+                ("fds_thresh", C.c_int32), ("three_d", C.c_int32), ("max_radius", C.c_double),
+                ("min_radius", C.c_double), ("motility_force", C.c_double)]
+
+
+CA, RP = C.POINTER(ColonyArrays), C.POINTER(RuleParams)
+
 SIGNATURES = {
     "abm_abi_version": (I32, []),
     "abm_compiled_arch": (I32, []),
@@ -46,6 +65,10 @@ SIGNATURES = {
     "abm_diffusion3d": (I32, [P, P, I64, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),
     "abm_deposit_morphogens3d": (I32, [P, P, F64, I64, P, L3, F64, I64, I64, P, P]),
     "abm_sample_concentrations": (I32, [P, I64, P, L3, F64, I64, I64, P, P, P]),
+    "abm_rules_workspace_bytes": (SZ, [I64]),
+    "abm_rule_division": (I32, [CA, I64, I64, P, P, RP, P, P, SZ, P]),
+    "abm_rule_death": (I32, [CA, CA, I64, I64, P, P, RP, P, P, SZ, P]),
+    "abm_rule_update": (I32, [CA, I64, P, P, P, RP, P, P]),
     "abm_slab_workspace_bytes": (SZ, [I64]),
     "abm_slab_pack": (I32, [P, P, P, P, P, P, I64, P, I64, F64, F64, I32, I32, P, I64, P, I64, P, P, SZ, P]),
     "abm_slab_merge": (I32, [P, P, P, P, P, P, I64, P, I64, P, I64, I64, F64, F64, I32, I32, P, P, P, P, P, P, P, P, SZ,

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabm_b200.so")
-SOURCES = ["lib.cu", "sort.cu", "search.cu", "jkr.cu", "diffusion.cu", "diffusion3d.cu", "slab.cu"]
+SOURCES = ["lib.cu", "sort.cu", "search.cu", "jkr.cu", "diffusion.cu", "diffusion3d.cu", "slab.cu", "rules.cu"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 
@@ -28,7 +28,8 @@ def source_hash(defines=()):
     """sha256 over every file of csrc/, the public header, this recipe's flags and the -D switches."""
     import hashlib
     h = hashlib.sha256()
-    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(ROOT, "include", "abm_b200.h")]
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + \
+        [os.path.join(ROOT, "include", "abm_b200.h"), os.path.join(ROOT, "include", "abm_rng.h")]
     for d in deps:
         h.update(os.path.basename(d).encode() + b"\0")
         with open(d, "rb") as f:

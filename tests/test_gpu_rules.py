@@ -1,0 +1,116 @@
+"""Device-resident model step (rules.DeviceColony, csrc/rules.cu) against its restated CPU oracle
+(oracle/rules_oracle.py): after every step the integer agent arrays, the cell count, the persistent ids and the JKR
+bond set must be IDENTICAL, positions within the fp64 gate -- through divisions, deaths, differentiation and the
+Boolean network -- with no agent array visiting the host inside a step; and the same step replayed as a CUDA graph."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import torch
+import hipsc_abm_b200  # noqa: F401
+from hipsc_abm_b200 import _lib
+from hipsc_abm_b200.rules import DeviceColony, INT_FIELDS, default_rule_params
+from oracle import rules_oracle as ro
+
+NAMES = {"death_counters": "death_counters", "diff_counters": "diff_counters", "div_counters": "div_counters",
+         "fds_counters": "fds_counters"}
+
+
+def build(n, size, seed, dox_step, death_thresh=None, dim3=False):
+    rng = np.random.default_rng(seed)
+    size = np.array(size, dtype=float)
+    P_ref = ro.default_params(size, seed=seed, dox_step=dox_step)
+    P_dev = default_rule_params(size, seed=seed, dox_step=dox_step)
+    if death_thresh is not None:
+        P_ref.death_thresh = P_dev.death_thresh = death_thresh
+    loc = rng.random((n, 3)) * size
+    state = ro.initial_state(n, seed, P_ref)
+    ref = ro.RulesOracle(loc, 5.0, size, state, P_ref)
+    dev = DeviceColony(size, capacity=int(2.5 * n) + 256, params=P_dev, bond_stride=32 if dim3 else 16,
+                       search_cols_per_cell=40.0 if dim3 else 14.0)
+    dev.load(loc, 5.0, state)
+    return ref, dev
+
+
+def compare(ref, dev, step, teacher=True):
+    got = dev.host_state()
+    assert got["n"] == ref.number_agents, f"step {step}: cell count {got['n']} vs {ref.number_agents}"
+    for name in INT_FIELDS:
+        assert np.array_equal(got[name], getattr(ref, name)), f"step {step}: {name}"
+    e = ref.jkr_graph.edge_array()
+    want = np.unique(np.sort(ref.gid[e].astype(np.int64), axis=1), axis=0) if len(e) else np.zeros((0, 2), np.int64)
+    assert np.array_equal(got["bond_ids"], want), f"step {step}: JKR bonds"
+    err = np.abs(got["locations"] - ref.locations).max()
+    scale = np.abs(ref.locations).max()
+    return err / scale
+
+
+@pytest.mark.parametrize("dim3", [False, True], ids=["2d", "3d"])
+def test_device_model_step_equals_the_restated_oracle(dim3):
+    size = [180.0, 180.0, 180.0] if dim3 else [450.0, 450.0, 0.0]
+    # a low death threshold so that cells die within the run (the default 144 steps of loneliness never trigger here)
+    ref, dev = build(1500 if dim3 else 1400, size, seed=11, dox_step=3, death_thresh=4, dim3=dim3)
+    n0 = ref.number_agents
+    added = removed = 0
+    worst = 0.0
+    for step in range(1, 26):
+        ref.step(step)
+        dev.step(step)
+        worst = max(worst, compare(ref, dev, step))
+        added += ref.added
+        removed += ref.removed
+    dev.check()
+    assert added > 100 and removed > 0 and ref.states.sum() > 0      # the run exercised every rule
+    assert ref.number_agents == n0 + added - removed
+    # free-running over 25 steps from a random start (see tests/test_gpu_scale.py on its conditioning)
+    assert worst <= 1e-8
+
+
+def test_step_replayed_as_a_cuda_graph_and_no_host_traffic():
+    ref, dev = build(3000, [600.0, 600.0, 0.0], seed=5, dox_step=2)
+    for step in (1, 2):
+        ref.step(step)
+        dev.step(step)
+    torch.cuda.synchronize()
+    compare(ref, dev, 2)
+    # capture one step per buffer parity; the step number (a kernel parameter of the rule kernels) is fixed at capture
+    # time, so the graphs below replay steps 3 and 4 exactly once each -- enough to show the step is capturable, i.e.
+    # that nothing in it waits for the device or touches host memory
+    eng = dev.eng
+    h2d, d2h = eng.h2d_bytes, eng.d2h_bytes
+    stream = torch.cuda.Stream()
+    graphs = []
+    cur, bonds, done = dev.cur, dev.bonds, dev.steps_done
+    for step in (3, 4):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            dev.enqueue_step(step)
+        graphs.append(g)
+    dev.cur, dev.bonds, dev.steps_done = cur, bonds, done
+    for step, g in zip((3, 4), graphs):
+        g.replay()
+        dev.cur = 1 - dev.cur
+        b = eng._bond_bufs
+        k = (len(dev.dts) - 1) & 1
+        dev.bonds = (b["len"][k], b["cols"][k])
+        ref.step(step)
+        torch.cuda.synchronize()
+        compare(ref, dev, step)
+    assert (eng.h2d_bytes, eng.d2h_bytes) == (h2d, d2h)
+    dev.check()
+
+
+def test_capacity_overflow_is_reported():
+    rng = np.random.default_rng(0)
+    size = np.array([200.0, 200.0, 0.0])
+    P = default_rule_params(size, seed=1)
+    P.pluri_div_thresh = 1                                   # every cell divides at once
+    n = 500
+    state = ro.initial_state(n, 1, ro.default_params(size, seed=1))
+    dev = DeviceColony(size, capacity=n + 100, params=P)
+    dev.load(rng.random((n, 3)) * size, 5.0, state)
+    dev.step(1)
+    torch.cuda.synchronize()
+    with pytest.raises(_lib.AbmError, match="colony arrays too small"):
+        dev.check()
