@@ -43,6 +43,11 @@ def compare(ref, dev, step, teacher=True):
     assert np.array_equal(got["bond_ids"], want), f"step {step}: JKR bonds"
     err = np.abs(got["locations"] - ref.locations).max()
     scale = np.abs(ref.locations).max()
+    if teacher:
+        # per-step gate: the next step starts from the oracle's positions (a daughter is born 2.9 um from its mother,
+        # i.e. deep inside her: their separation is as ill-conditioned as a random start, tests/test_gpu_scale.py)
+        s = dev.sets[dev.cur]
+        s["locations"][:got["n"]] = torch.from_numpy(ref.locations).to(s["locations"].device)
     return err / scale
 
 
@@ -63,8 +68,7 @@ def test_device_model_step_equals_the_restated_oracle(dim3):
     dev.check()
     assert added > 100 and removed > 0 and ref.states.sum() > 0      # the run exercised every rule
     assert ref.number_agents == n0 + added - removed
-    # free-running over 25 steps from a random start (see tests/test_gpu_scale.py on its conditioning)
-    assert worst <= 1e-8
+    assert worst <= 1e-9
 
 
 def test_step_replayed_as_a_cuda_graph_and_no_host_traffic():
