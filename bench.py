@@ -717,6 +717,13 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     for _ in range(40):                   # a few clock samples under load (a fixed count: ranks stay in lock-step)
         step()
     launches0, bytes0, ex0 = ds.launches, rank_step.bytes_sent, rank_step.exchanges
+    timeline = None
+    if args.timeline:                     # a few extra (untimed) steps with events around the main-stream phases
+        rank_step.timeline = []
+        for _ in range(10):
+            step()
+        timeline = {k: round(v, 1) for k, v in rank_step.timeline_us().items()}
+        rank_step.timeline = None
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k, (a, b) in enumerate(evs):
@@ -780,7 +787,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
                    "exchanges_per_step": (rank_step.exchanges - ex0) / max(args.steps + e_steps, 1),
                    "bytes_sent_per_step_rank0": (rank_step.bytes_sent - bytes0) // max(args.steps + e_steps, 1),
                    "timing": "CUDA events per step, summed; max over ranks",
-                   "host_synchronisations_per_step": 0,
+                   "host_synchronisations_per_step": 0, "main_stream_phases_us_rank0": timeline,
                    "cuda_graphs": bool(rank_step.captured),
                    "parallelism": f"slab{world}: 1-D slab decomposition along x; per step one cell-halo exchange "
                                   "(migration rides on it; fixed-capacity messages, counts on the device) and one "
@@ -834,6 +841,7 @@ def main():
                     help="N > 1: weak = one workload-sized slab per GPU (default); strong = the workload's colony cut "
                          "into N slabs (BASELINE configs[3]: --workload c4 --scaling strong)")
     ap.add_argument("--no-graphs", action="store_true", help="N > 1: eager launches instead of CUDA-graph replays")
+    ap.add_argument("--timeline", action="store_true", help="N > 1: device time of every main-stream phase of a step")
     ap.add_argument("--no-clocks", action="store_true",
                     help="no nvidia-smi sampling (profiler runs: keeps the launch sequence deterministic)")
     ap.add_argument("--no-overlap", action="store_true",

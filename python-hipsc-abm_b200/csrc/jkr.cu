@@ -100,7 +100,12 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 //      row is found through the prev_slot index the placement kernel records); the first substep still reads and
 //      the last one still writes rows keyed by cell id                               (written blind: not yet measured)
 //  32: contact model with a Horner-form force polynomial and an rsqrt without special-case handling (s2 is a normal
-//      number; forces move by ~1e-16 relative, inside the 1e-12 gate)                (written blind: not yet measured)
+//      number; forces move by ~1e-16 relative, inside the 1e-12 gate)
+// Measured and REMOVED in round 2 (profiles/r02_kernels_c3.md; the code is in git history, commit "k_jkr_substep_flat"):
+// a lane-balanced contact phase -- the warp's pairs flattened into one shared-memory list and evaluated 32 at a time,
+// in-warp pairs evaluated once, forces and bond rows accumulated with 32-bit shared-memory atomics.  Bit-identical
+// results (all GPU tests green), 3.0 rounds instead of 8.1 iterations, but 78.8 us instead of 56.3 us per launch:
+// the ~14 conflicting shared atomics per pair cost more than the idle lanes they remove.
 #ifndef ABM_JKR_EXP
 #define ABM_JKR_EXP 0
 #endif
@@ -109,9 +114,6 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 #endif
 #ifndef ABM_PDL_LATE
 #define ABM_PDL_LATE 0      // 1: trigger the dependent launch after the contact loop instead of at kernel entry
-#endif
-#ifndef ABM_JKR_FLAT
-#define ABM_JKR_FLAT 0      // 1: k_jkr_substep_flat (lane-balanced contact phase, in-warp pairs evaluated once)
 #endif
 #ifndef ABM_JKR_MAXHITS
 #define ABM_JKR_MAXHITS 16
@@ -510,362 +512,6 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
 }
 
 
-// ---- the same substep with a LANE-BALANCED contact phase ----------------------------------------------------------
-// k_jkr_substep above walks every cell's partners in the cell's own lane: the trip count of the contact loop is the
-// largest partner count among the 32 lanes (8.1 iterations for 4.2 partners on average at 500k cells, 20 of 32 lanes
-// active), and every pair is evaluated from both ends.  Here the warp's candidate pairs are flattened into ONE list
-// in shared memory and evaluated 32 at a time whatever cell they belong to, and a pair whose two cells sit in the
-// same warp is evaluated ONCE (by the lower slot) and applied to both cells:
-//   * per-cell state the evaluating lane needs (position, radius, ids) is parked in shared memory;
-//   * forces are accumulated with 32-bit shared-memory integer atomics on the two halves of the 64-bit 2^-76 N
-//     fixed-point value, the carry of the low word handed to the high word (exact 64-bit integer sums whatever the
-//     order: trajectories stay bit-identical to k_jkr_substep's; a 64-bit shared atomicAdd would be a CAS loop);
-//   * a bond is appended to the row of its cell(s) through a shared counter (row order is unspecified until the last
-//     substep sorts it, as before);
-//   * shell partners (distance < d <= reach) are collected in a second list and looked up in the previous rows in a
-//     final balanced round.
-// Anything out of the ordinary (a cell with more than kMaxHits candidates, a candidate run longer than the tile, an
-// overflowing shell list) makes the WHOLE warp take the exact slow path of k_jkr_substep, which recomputes every
-// cell from global memory on its own.
-struct WarpCells {
-    double x[32], y[32], z[32], r[32];
-    int pid[32];           // id written into a partner's row (cell index, or global id)
-    int key[32];           // cell index: key of the cell's previous and new bond row
-    unsigned lo[3][32];    // force accumulators: the two words of a 64-bit two's complement sum
-    unsigned hi[3][32];
-    int cnt[32];           // bonds appended to the cell's row
-    int nshell;
-};
-constexpr int kFlatCap = 32 * kMaxHits;                      // flattened pairs of a warp
-constexpr int kShellCap = 256;
-static_assert(kFlatCap * 5 + kShellCap * 2 <= kTileRows * kTileCap * 16, "the flat list lives in the warp's tile");
-
-template <bool kUniform>
-__global__ void __launch_bounds__(kJkrThreads, kJkrMinBlocks)
-k_jkr_substep_flat(const int *__restrict__ bin_start, const int *__restrict__ sorted_id,
-                   const double4 *__restrict__ spos, const int *__restrict__ sorted_bin, int n, Stencil st, Radius rad,
-                   double reach2, BandConst bandc, GraphView old, int *__restrict__ new_len,
-                   int *__restrict__ new_cols, int stride, int *__restrict__ max_len, const double *__restrict__ mot,
-                   double *__restrict__ loc, JkrConst c, double stokes, Friction fric, Box box, double dt,
-                   const int *__restrict__ gid_of, const int *__restrict__ slot_pid, NextSort next, int sort_rows,
-                   const int *__restrict__ n_dev) {
-    __shared__ int column[kMaxHits][kJkrThreads];
-    __shared__ float4 tiles[kJkrThreads / 32][kTileRows * kTileCap];
-    __shared__ WarpCells cells[kJkrThreads / 32];
-    pdl_launch_dependents();
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int s = blockIdx.x * kJkrThreads + tid;
-    pdl_wait();
-    n = device_count(n, n_dev);
-    if (s - lane >= n) return;                                 // the whole warp is past the last cell
-    const bool live = s < n;
-    const int s0 = s - lane;                                   // first slot of the warp
-    float4 *tile = tiles[tid >> 5];
-    WarpCells &W = cells[tid >> 5];
-    int i = 0, bx = 0, by = 0, bz = 0;
-    double4 p = make_double4(0.0, 0.0, 0.0, 1.0);
-    if (live) {
-        i = sorted_id[s];
-        p = spos[s];
-        st.decode(sorted_bin[s], bx, by, bz);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(mot + 3 * (long long)i));
-    }
-    auto partner_id = [&](int t) {
-        if (slot_pid) return slot_pid[t];
-        int j = sorted_id[t];
-        return gid_of ? gid_of[j] : j;
-    };
-
-    // ---- phase 1: fp32 filter; a partner in a LOWER slot of this warp is not parked (that lane has the pair) ---------
-    TileOrigin org;
-    org.x = __shfl_sync(kFullWarp, p.x, 0);
-    org.y = __shfl_sync(kFullWarp, p.y, 0);
-    org.z = __shfl_sync(kFullWarp, p.z, 0);
-    const float pfx = (float)(p.x - org.x), pfy = (float)(p.y - org.y), pfz = (float)(p.z - org.z);
-    const float t_out = (float)reach2 + bandc.band(pfx, pfy, pfz);
-    int nh = 0;
-    bool slow = false;
-    for (int dz = -1; dz <= 1; ++dz) {
-        const int z = bz + dz;
-        if (__all_sync(kFullWarp, !live || z < 0 || z >= st.dims[2])) continue;
-        const LayerRuns R = stage_layer(live, bx, by, z, st, bin_start, spos, org, tile);
-#pragma unroll
-        for (int r = 0; r < kTileRows; ++r) {
-            if (!((R.staged >> r) & 1u)) {                     // warp-uniform
-                slow |= R.n[r] > 0;
-                continue;
-            }
-            const float4 *run = tile + R.first[r];
-            const int nr = R.n[r];
-            for (int u = 0; u < nr; ++u) {
-                const float4 q = run[u];
-                const float dx = pfx - q.x, dy = pfy - q.y, dzf = pfz - q.z;
-                const float s2f = fmaf(dzf, dzf, fmaf(dy, dy, dx * dx));
-                const int t = __float_as_int(q.w);
-                if (s2f <= t_out && (t > s || t < s0)) {       // (t == s: itself; s0 <= t < s: the other lane's pair)
-                    if (nh < kMaxHits) column[nh][tid] = t;
-                    ++nh;
-                }
-            }
-        }
-        __syncwarp();                                         // the tile is overwritten by the next layer
-    }
-    slow |= nh > kMaxHits;
-    bool redo = __any_sync(kFullWarp, live && slow);          // warp-uniform: everybody takes the exact slow path
-
-    long long fxi = 0, fyi = 0, fzi = 0;
-    int cnt = 0, direct = 0;
-    int *row = new_cols + (long long)i * stride;
-    const long long os = old.valid() ? old.start(i) : 0;
-
-    if (!redo) {
-        // ---- phase 2: park the cells, flatten the pairs ------------------------------------------------------------
-        const int my_pid = live ? partner_id(s) : -1;
-        W.x[lane] = p.x;
-        W.y[lane] = p.y;
-        W.z[lane] = p.z;
-        W.r[lane] = p.w;
-        W.pid[lane] = my_pid;
-        W.key[lane] = i;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            W.lo[k][lane] = 0u;
-            W.hi[k][lane] = 0u;
-        }
-        W.cnt[lane] = 0;
-        if (lane == 0) W.nshell = 0;
-        const int mine = live ? nh : 0;
-        const int incl = warp_inclusive_scan(mine);
-        const int total = __shfl_sync(kFullWarp, incl, 31);
-        int *flat_t = reinterpret_cast<int *>(tile);
-        unsigned char *flat_o = reinterpret_cast<unsigned char *>(tile) + kFlatCap * 4;
-        unsigned short *shell = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(tile) + kFlatCap * 5);
-        {
-            const int off = incl - mine;
-            for (int k = 0; k < mine; ++k) {
-                flat_t[off + k] = column[k][tid];
-                flat_o[off + k] = (unsigned char)lane;
-            }
-        }
-        __syncwarp();
-
-        BondEval ev;
-        ev.memo_r = -2.0;
-        ev.rsum = 0.0;
-        // 64-bit add into (hi:lo)[k][cell] with two 32-bit shared atomics: the low word wraps, its carry goes up
-        auto add64 = [&](int k, int cell, long long v) {
-            const unsigned l = (unsigned)v;
-            const unsigned old_lo = atomicAdd(&W.lo[k][cell], l);
-            atomicAdd(&W.hi[k][cell], (unsigned)(v >> 32) + (unsigned)((old_lo + l) < old_lo));
-        };
-        // the contact model for the pair (cell parked in lane o, partner in slot t at q); applies the result to the
-        // cell and -- if the partner is a higher slot of this warp -- to the partner as well
-        auto apply = [&](int o, int t, const double4 &q, double vx, double vy, double vz, double s2) {
-            double rsum, inv_scale, force_scale;
-            if (kUniform) {
-                rsum = c.uni_r + c.uni_r;
-                inv_scale = c.uni_inv_scale;
-                force_scale = c.uni_force_scale;
-            } else {
-                const double rp = W.r[o];
-                if (ev.memo_r != q.w || ev.rsum != rp + q.w) {          // memo on the pair of radii
-                    ev.memo_r = -1.0;
-                    ev.refresh(rp, q.w, c);
-                }
-                rsum = ev.rsum;
-                inv_scale = ev.inv_scale;
-                force_scale = ev.force_scale;
-            }
-            const double inv_mag = s2 > 1e-30 ? rsqrt_normal(s2) : (s2 > 0.0 ? rsqrt(s2) : 0.0);
-            const double mag = s2 * inv_mag;
-            const double d = (rsum - mag) * inv_scale;
-            if (!(d > -0.360562)) return;
-            const int tl = t - s0;                             // partner's lane if it is a cell of this warp
-            const bool both = tl >= 0 && tl < 32;              // (then t > slot of o: lower pairs were not parked)
-            if (s2 > 0.0) {
-                const double f = fma(fma(fma(-0.0204, d, 0.4942), d, 1.0801), d, -1.324);
-                const double w = f * force_scale * inv_mag * kForceUnitInv;
-                const double comp[3] = {w * vx, w * vy, w * vz};
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const long long F = __double2ll_rn(comp[k]);
-                    add64(k, o, F);
-                    if (both) add64(k, tl, -F);
-                }
-            }
-            // the bond goes into the row of the cell (and of the partner)
-            const int j = both ? W.pid[tl] : partner_id(t);
-            int pos = atomicAdd(&W.cnt[o], 1);
-            if (pos < kMaxHits) column[pos][(tid & ~31) + o] = j;
-            else if (pos < stride) new_cols[(long long)W.key[o] * stride + pos] = j;
-            if (both) {
-                pos = atomicAdd(&W.cnt[tl], 1);
-                if (pos < kMaxHits) column[pos][(tid & ~31) + tl] = W.pid[o];
-                else if (pos < stride) new_cols[(long long)W.key[tl] * stride + pos] = W.pid[o];
-            }
-        };
-
-        // ---- phase 3: all pairs of the warp, 32 at a time ----------------------------------------------------------
-        for (int base = 0; base < total; base += 32) {
-            const int f = base + lane;
-            if (f < total) {
-                const int t = flat_t[f], o = flat_o[f];
-                const double4 q = spos[t];
-                const double vx = W.x[o] - q.x, vy = W.y[o] - q.y, vz = W.z[o] - q.z;
-                const double s2 = sumsq_nofma(vx, vy, vz);
-                if (s2 <= reach2) {                            // else: let through by the fp32 filter's error band only
-                    if (rad.within(s2)) {
-                        apply(o, t, q, vx, vy, vz, s2);
-                    } else if (old.valid()) {                  // thin shell: only pre-existing bonds persist
-                        const int k = atomicAdd(&W.nshell, 1);
-                        if (k < kShellCap) shell[k] = (unsigned short)f;
-                    }
-                }
-            }
-        }
-        __syncwarp();
-        // ---- phase 4: hysteresis -- shell pairs that were bonded before ------------------------------------------------
-        const int nshell = W.nshell;
-        if (nshell > kShellCap) {
-            redo = true;                                       // (warp-uniform: everybody reads the same counter)
-        } else {
-            for (int base = 0; base < nshell; base += 32) {
-                const int k = base + lane;
-                if (k < nshell) {
-                    const int f = shell[k];
-                    const int t = flat_t[f], o = flat_o[f];
-                    const int tl = t - s0;
-                    const int j = (tl >= 0 && tl < 32) ? W.pid[tl] : partner_id(t);
-                    if (old.contains(W.key[o], j)) {
-                        const double4 q = spos[t];
-                        const double vx = W.x[o] - q.x, vy = W.y[o] - q.y, vz = W.z[o] - q.z;
-                        apply(o, t, q, vx, vy, vz, sumsq_nofma(vx, vy, vz));
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        if (!redo && live) {
-            fxi = (long long)(((unsigned long long)W.hi[0][lane] << 32) | W.lo[0][lane]);
-            fyi = (long long)(((unsigned long long)W.hi[1][lane] << 32) | W.lo[1][lane]);
-            fzi = (long long)(((unsigned long long)W.hi[2][lane] << 32) | W.lo[2][lane]);
-            const int all = W.cnt[lane];
-            cnt = min(all, kMaxHits);
-            direct = all - cnt;
-        }
-    }
-    if (!live) return;                                         // no warp-wide operation below this line
-
-    if (redo) {
-        // ---- exact slow path (k_jkr_substep's): every candidate of the stencil from global memory, own side only ----
-        fxi = fyi = fzi = 0;
-        cnt = direct = 0;
-        BondEval ev;
-        if (!kUniform) ev.preset(c, p.w);
-        auto bond = [&](double vx, double vy, double vz, double s2, double rq, int j) {
-            if (!kUniform) ev.refresh(p.w, rq, c);
-            const double rsum = kUniform ? c.uni_r + c.uni_r : ev.rsum;
-            const double inv_scale = kUniform ? c.uni_inv_scale : ev.inv_scale;
-            const double force_scale = kUniform ? c.uni_force_scale : ev.force_scale;
-            const double inv_mag = s2 > 1e-30 ? rsqrt_normal(s2) : (s2 > 0.0 ? rsqrt(s2) : 0.0);
-            const double mag = s2 * inv_mag;
-            const double d = (rsum - mag) * inv_scale;
-            if (d > -0.360562) {
-                if (s2 > 0.0) {
-                    const double f = fma(fma(fma(-0.0204, d, 0.4942), d, 1.0801), d, -1.324);
-                    const double w = f * force_scale * inv_mag * kForceUnitInv;
-                    fxi += __double2ll_rn(w * vx);
-                    fyi += __double2ll_rn(w * vy);
-                    fzi += __double2ll_rn(w * vz);
-                }
-                if (cnt < kMaxHits) {
-                    column[cnt++][tid] = j;
-                } else {
-                    if (kMaxHits + direct < stride) row[kMaxHits + direct] = j;
-                    ++direct;
-                }
-            }
-        };
-        const int x0 = max(bx - 1, 0), x1 = min(bx + 1, st.dims[0] - 1);
-        for (int dz = -1; dz <= 1; ++dz) {
-            const int z = bz + dz;
-            if (z < 0 || z >= st.dims[2]) continue;
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int y = by + dy;
-                if (y < 0 || y >= st.dims[1]) continue;
-                const int rowb = (z * st.dims[1] + y) * st.dims[0];
-                const int lo = bin_start[rowb + x0], hi = bin_start[rowb + x1 + 1];
-                for (int t = lo; t < hi; ++t) {
-                    if (t == s) continue;
-                    const double4 q = spos[t];
-                    const double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
-                    const double s2 = sumsq_nofma(vx, vy, vz);
-                    if (s2 > reach2) continue;
-                    const int j = partner_id(t);
-                    if (rad.within(s2) || (old.valid() && old.contains(i, j))) bond(vx, vy, vz, s2, q.w, j);
-                }
-            }
-        }
-    }
-    (void)os;
-
-    // ---- phase 5: the bond row, the integration, the hand-over to the next sort (as in k_jkr_substep) ----------------
-    const int total_bonds = cnt + direct;
-    const int kept = min(total_bonds, stride);
-    if (sort_rows && direct == 0) {
-        for (int a = 1; a < cnt; ++a) {
-            int v = column[a][tid], b = a - 1;
-            while (b >= 0 && column[b][tid] > v) {
-                column[b + 1][tid] = column[b][tid];
-                --b;
-            }
-            column[b + 1][tid] = v;
-        }
-    }
-    {
-        const int m = min(cnt, stride);
-        if ((stride & 3) == 0) {
-            for (int k = 0; k < m; k += 4) {
-                int4 v;
-                v.x = column[k][tid];
-                v.y = k + 1 < m ? column[k + 1][tid] : -1;
-                v.z = k + 2 < m ? column[k + 2][tid] : -1;
-                v.w = k + 3 < m ? column[k + 3][tid] : -1;
-                *reinterpret_cast<int4 *>(row + k) = v;
-            }
-        } else {
-            for (int k = 0; k < m; ++k) row[k] = column[k][tid];
-        }
-        if (sort_rows && direct > 0) insertion_sort(row, kept);
-    }
-    new_len[i] = kept;
-    if (total_bonds > stride) atomicMax(max_len, total_bonds);
-    double friction = fric.uni, inv_f = fric.uni_inv;
-    if (!kUniform) {
-        friction = stokes_friction(p.w, stokes);
-        inv_f = __drcp_rn(friction);
-    }
-    const double mx = mot[3 * (long long)i + 0], my = mot[3 * (long long)i + 1], mz = mot[3 * (long long)i + 2];
-    const double nx = stokes_move_y(p.x, mx, (double)fxi * kForceUnit, friction, inv_f, dt, box.size[0]);
-    const double ny = stokes_move_y(p.y, my, (double)fyi * kForceUnit, friction, inv_f, dt, box.size[1]);
-    const double nz = stokes_move_y(p.z, mz, (double)fzi * kForceUnit, friction, inv_f, dt, box.size[2]);
-    if (loc) {
-        loc[3 * (long long)i + 0] = nx;
-        loc[3 * (long long)i + 1] = ny;
-        loc[3 * (long long)i + 2] = nz;
-    }
-    if (next.counts) {
-        int b = cell_bin_of_loose(nx, ny, nz, next.geom);
-        next.next_pos[s] = make_double4(nx, ny, nz, p.w);
-        next.cell_bin[s] = b;
-        next.prev_id[s] = i;
-        atomicAdd(&next.counts[b], 1);
-        const int chunk = b / kScanChunk;
-        const unsigned peers = __match_any_sync(__activemask(), chunk);
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&next.chunk_sums[chunk], __popc(peers));
-    }
-}
-
 }  // namespace abm
 
 using namespace abm;
@@ -948,30 +594,6 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
         fric.uni = f;
         fric.uni_inv = 1.0 / f;
     }
-#if ABM_JKR_FLAT
-    if (!(row_keys)) {
-        auto flat = uniform_radius > 0 ? k_jkr_substep_flat<true> : k_jkr_substep_flat<false>;
-        {   // 7 CTAs x 30 KB of static shared memory per SM: ask for the largest shared-memory carve-out (per device)
-            static bool carved[kMaxDevices][2] = {};
-            const int slot = current_device_slot(), which = uniform_radius > 0 ? 1 : 0;
-            if (slot < 0 || !carved[slot][which]) {
-                int rc = check_cuda(cudaFuncSetAttribute(flat, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                         cudaSharedmemCarveoutMaxShared),
-                                    "cudaFuncSetAttribute(k_jkr_substep_flat carve-out)");
-                if (rc) return rc;
-                if (slot >= 0) carved[slot][which] = true;
-            }
-        }
-        return check_cuda(launch_chained(flat, ceil_div(n, kJkrThreads), kJkrThreads, as_stream(stream), chained,
-                                         bin_start, sorted_id, reinterpret_cast<const double4 *>(sorted_pos),
-                                         sorted_bin, (int)n, stc, Radius(distance), reach * reach,
-                                         BandConst::make(reach * 1.0000001), old, new_row_len, new_cols,
-                                         (int)row_stride, max_len, motility_forces, locations, c, stokes, fric, box,
-                                         move_dt, global_id, global_id ? slot_gid : sorted_id, next, sort_rows,
-                                         n_device),
-                          "k_jkr_substep_flat");
-    }
-#endif
     auto kernel = uniform_radius > 0 ? k_jkr_substep<true> : k_jkr_substep<false>;
     return check_cuda(launch_chained(kernel, ceil_div(n, kJkrThreads), kJkrThreads, as_stream(stream), chained, bin_start,
                                      sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,

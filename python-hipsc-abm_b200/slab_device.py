@@ -249,6 +249,25 @@ class SlabStepper:
         self.side_done = None
         self.captured = False
         self.steps = 0
+        self.timeline = None          # set to [] to record (name, start event, end event) of every main-stream phase
+
+    def _timed(self, name, fn):
+        if self.timeline is None:
+            return fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = fn()
+        b.record()
+        self.timeline.append((name, a, b))
+        return out
+
+    def timeline_us(self):
+        """Host synchronisation: mean device time per recorded main-stream phase, in microseconds."""
+        torch.cuda.synchronize(self.slab.dev)
+        acc = {}
+        for name, a, b in self.timeline or []:
+            acc.setdefault(name, []).append(a.elapsed_time(b) * 1e3)
+        return {k: float(np.mean(v)) for k, v in acc.items()}
 
     def capture(self):
         """Capture the four phases for both buffer parities.  Call after at least two eager steps (every scratch
@@ -296,11 +315,11 @@ class SlabStepper:
         s = self.slab
         main = torch.cuda.current_stream(s.dev)
         parity = s.cur
-        self.phases["pack"].run(parity)
-        exchange_cells()
+        self._timed("pack", lambda: self.phases["pack"].run(parity))
+        self._timed("exchange_cells", exchange_cells)
         if self.side_done is not None:
             main.wait_event(self.side_done)       # last step's side work read the snapshot the merge overwrites
-        self.phases["merge"].run(parity)
+        self._timed("merge", lambda: self.phases["merge"].run(parity))
         self._after_merge()
         side = self.side or main
         if self.side is not None:
@@ -309,7 +328,7 @@ class SlabStepper:
             self.phases["deposit"].run(parity)
             if s.field is not None:
                 exchange_rows()
-        self.phases["mechanics"].run(parity)
+        self._timed("mechanics", lambda: self.phases["mechanics"].run(parity))
         self._after_mechanics()
         with torch.cuda.stream(side):
             self.phases["side"].run(parity)
