@@ -341,6 +341,31 @@ int abm_slab_merge(const double *locations, const double *radii, const double *m
                    const int32_t *received_counts_device, int32_t *n_local_out, int64_t out_capacity,
                    void *stream);
 
+/* The same two steps for the pipeline that keeps every count on the device (hipsc_abm_b200/slab_device.py):
+ *   - a message is `capacity` records followed by one header row whose first int32 is the number of valid records
+ *     (buffers of (capacity+1) x (64+4*row_stride) bytes), so an exchange is one send and one receive per neighbour;
+ *   - abm_slab_exchange_pack: one launch; counters (int32[3], zeroed by the caller ONCE, left zeroed by every call);
+ *     worst (int32[2]) keeps the largest record counts ever claimed (> capacity: records were dropped);
+ *   - abm_slab_exchange_merge: two launches; the owned rows (min(rows, *n_own_device)) and the valid records of the two
+ *     messages are partitioned into [owned after the exchange | halo] of the out_* arrays (out_rows rows) in NO
+ *     particular order inside each part, and their positions are also written to `snapshot` (out_rows x 3) -- the
+ *     positions the step starts with.  tally (int32[5], zeroed by the caller once, left zeroed by every call);
+ *     *n_owned_out / *n_local_out receive the two counts (clipped to out_rows), worst_rows (int32[1]) the largest
+ *     total ever needed.                                                                                          */
+int abm_slab_exchange_pack(const double *locations, const double *radii, const double *motility_forces,
+                           const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t rows,
+                           const int32_t *n_own_device, int64_t row_stride, double x_send_left, double x_send_right,
+                           int has_left, int has_right, uint8_t *message_left, uint8_t *message_right,
+                           int64_t capacity, int32_t *counters, int32_t *worst, void *stream);
+int abm_slab_exchange_merge(const double *locations, const double *radii, const double *motility_forces,
+                            const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows, int64_t rows,
+                            const int32_t *n_own_device, const uint8_t *message_left, const uint8_t *message_right,
+                            int64_t capacity, int64_t row_stride, double x_lo, double x_hi, int has_left,
+                            int has_right, double *out_locations, double *out_radii, double *out_motility,
+                            int32_t *out_global_id, int32_t *out_bond_len, int32_t *out_bond_rows, double *snapshot,
+                            int64_t out_rows, int32_t *n_owned_out, int32_t *n_local_out, int32_t *tally,
+                            int32_t *worst_rows, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,9 @@ SIGNATURES = {
     "abm_slab_pack": (I32, [P, P, P, P, P, P, I64, P, I64, F64, F64, I32, I32, P, I64, P, I64, P, P, SZ, P]),
     "abm_slab_merge": (I32, [P, P, P, P, P, P, I64, P, I64, P, I64, I64, F64, F64, I32, I32, P, P, P, P, P, P, P, P, SZ,
                              P, P, P, I64, P]),
+    "abm_slab_exchange_pack": (I32, [P, P, P, P, P, P, I64, P, I64, F64, F64, I32, I32, P, P, I64, P, P, P]),
+    "abm_slab_exchange_merge": (I32, [P, P, P, P, P, P, I64, P, P, P, I64, I64, F64, F64, I32, I32, P, P, P, P, P, P, P,
+                                      I64, P, P, P, P, P]),
     "abm_deposit_morphogens": (I32, [P, P, F64, I64, P, L3, F64, I64, I64, P, P]),
 }
 

@@ -238,3 +238,199 @@ ABM_EXPORT int abm_slab_merge(const double *locations, const double *radii, cons
     ABM_CHECK_LAUNCH("k_slab_merge");
     return 0;
 }
+
+// ---- the device-count pipeline (hipsc_abm_b200/slab_device.py): leaner variants ---------------------------------
+// A message is `capacity` records followed by ONE header row whose first int32 is the number of valid records, so an
+// exchange is one send and one receive per neighbour.  Nothing here depends on the order of the cells inside the
+// owned / halo parts (rows are kept by global id, force sums are integer sums), which allows placement by atomic
+// cursors instead of a stable scan: two launches per merge instead of five.
+namespace abm {
+
+// pack + header + overflow record in one launch (the header is written by the last block to finish)
+__global__ void __launch_bounds__(256)
+k_slab_pack_hdr(CellArrays a, int rows, const int *__restrict__ n_own_dev, int stride, int rec_bytes,
+                double x_send_left, double x_send_right, int has_left, int has_right,
+                unsigned char *__restrict__ out_l, unsigned char *__restrict__ out_r, long long cap,
+                int *__restrict__ counts /*[0,1]: rows claimed, [2]: block counter*/, int *__restrict__ worst) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int n = device_count(rows, n_own_dev);
+    bool l = false, r = false;
+    if (i < n) {
+        const double x = a.loc[3 * (long long)i];
+        l = has_left && x < x_send_left;
+        r = has_right && x >= x_send_right;
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const bool f = side ? r : l;
+        const unsigned m = __ballot_sync(0xffffffffu, f);
+        if (m == 0) continue;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&counts[side], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (f) {
+            const long long pos = base + __popc(m & ((1u << lane) - 1));
+            if (pos < cap) write_record((side ? out_r : out_l) + pos * rec_bytes, a, i, stride);
+        }
+    }
+    __shared__ bool last;
+    __threadfence();
+    if (threadIdx.x == 0) last = atomicAdd(&counts[2], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        const int cl = counts[0], cr = counts[1];
+        *reinterpret_cast<int *>(out_l + cap * rec_bytes) = cl;
+        *reinterpret_cast<int *>(out_r + cap * rec_bytes) = cr;
+        atomicMax(&worst[0], cl);
+        atomicMax(&worst[1], cr);
+        counts[0] = counts[1] = counts[2] = 0;                 // ready for the next step
+    }
+}
+
+struct Incoming {
+    const unsigned char *l, *r;      // messages (capacity records + header row), or nullptr
+    int cap;
+    __device__ __forceinline__ void counts(int rec_bytes, int &kl, int &kr) const {
+        kl = l ? min(max(*reinterpret_cast<const int *>(l + (long long)cap * rec_bytes), 0), cap) : 0;
+        kr = r ? min(max(*reinterpret_cast<const int *>(r + (long long)cap * rec_bytes), 0), cap) : 0;
+    }
+    __device__ __forceinline__ const unsigned char *record(int j, int kl, int rec_bytes) const {
+        return j < kl ? l + (long long)j * rec_bytes : r + (long long)(j - kl) * rec_bytes;
+    }
+};
+
+// pass 1: how many of (owned rows + received records) are owned after the exchange
+__global__ void __launch_bounds__(256)
+k_slab_count(const double *__restrict__ loc, int rows, const int *__restrict__ n_own_dev, Incoming in, int rec_bytes,
+             double x_lo, double x_hi, int has_left, int has_right, int *__restrict__ tally /*[0] owned, [1] total*/) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int n = device_count(rows, n_own_dev);
+    int kl, kr;
+    in.counts(rec_bytes, kl, kr);
+    const int total = n + kl + kr;
+    bool f = false;
+    if (i < n) f = owns(loc[3 * (long long)i], x_lo, x_hi, has_left, has_right);
+    else if (i < total)
+        f = owns(*reinterpret_cast<const double *>(in.record(i - n, kl, rec_bytes)), x_lo, x_hi, has_left, has_right);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&tally[0], __popc(m));
+    if (i == 0) tally[1] = total;
+}
+
+// pass 2: owned cells claim slots from the front, halo cells behind them; also the position snapshot of the step
+__global__ void __launch_bounds__(256)
+k_slab_place(CellArrays a, int rows, const int *__restrict__ n_own_dev, Incoming in, int rec_bytes, int stride,
+             double x_lo, double x_hi, int has_left, int has_right, CellArrays out, double *__restrict__ snap,
+             int out_rows, int *__restrict__ tally /*[0] owned, [1] total, [2],[3] cursors, [4] block counter*/,
+             int *__restrict__ n_owned_out, int *__restrict__ n_local_out, int *__restrict__ worst_rows) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int n = device_count(rows, n_own_dev);
+    int kl, kr;
+    in.counts(rec_bytes, kl, kr);
+    const int total = n + kl + kr, n_keep = tally[0];
+    const bool valid = i < total;
+    bool f = false;
+    if (i < n) f = owns(a.loc[3 * (long long)i], x_lo, x_hi, has_left, has_right);
+    else if (valid)
+        f = owns(*reinterpret_cast<const double *>(in.record(i - n, kl, rec_bytes)), x_lo, x_hi, has_left, has_right);
+    const int lane = threadIdx.x & 31;
+    int dst = -1;
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+        const bool mine = valid && (part == 0 ? f : !f);
+        const unsigned m = __ballot_sync(0xffffffffu, mine);
+        if (m == 0) continue;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&tally[2 + part], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (mine) dst = (part ? n_keep : 0) + base + __popc(m & ((1u << lane) - 1));
+    }
+    if (valid && dst < out_rows) {
+        if (i < n) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double x = a.loc[3 * (long long)i + k];
+                out.loc[3 * (long long)dst + k] = x;
+                snap[3 * (long long)dst + k] = x;
+                out.mot[3 * (long long)dst + k] = a.mot[3 * (long long)i + k];
+            }
+            out.radii[dst] = a.radii[i];
+            out.gid[dst] = a.gid[i];
+            const int len = min(a.bond_len[i], stride);
+            out.bond_len[dst] = len;
+            const int *src = a.bond_rows + (long long)i * stride;
+            int *row = out.bond_rows + (long long)dst * stride;
+            for (int c = 0; c < len; ++c) row[c] = src[c];
+        } else {
+            read_record(in.record(i - n, kl, rec_bytes), out, dst, stride);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) snap[3 * (long long)dst + k] = out.loc[3 * (long long)dst + k];
+        }
+    }
+    __shared__ bool last;
+    __threadfence();
+    if (threadIdx.x == 0) last = atomicAdd(&tally[4], 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *n_owned_out = min(n_keep, out_rows);
+        *n_local_out = min(total, out_rows);
+        atomicMax(worst_rows, total);
+        tally[0] = tally[1] = tally[2] = tally[3] = tally[4] = 0;   // ready for the next step
+    }
+}
+
+}  // namespace abm
+
+ABM_EXPORT int abm_slab_exchange_pack(const double *locations, const double *radii, const double *motility_forces,
+                                      const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows,
+                                      int64_t rows, const int32_t *n_own_device, int64_t row_stride,
+                                      double x_send_left, double x_send_right, int has_left, int has_right,
+                                      uint8_t *message_left, uint8_t *message_right, int64_t capacity,
+                                      int32_t *counters, int32_t *worst, void *stream) {
+    ABM_REQUIRE(rows > 0 && rows < 0x7fffffff && row_stride > 0 && capacity >= 0, "bad sizes");
+    ABM_REQUIRE(locations && radii && motility_forces && global_id && bond_len && bond_rows && n_own_device &&
+                    message_left && message_right && counters && worst,
+                "null pointer");
+    CellArrays a{const_cast<double *>(locations), const_cast<double *>(radii), const_cast<double *>(motility_forces),
+                 const_cast<int *>(global_id), const_cast<int *>(bond_len), const_cast<int *>(bond_rows)};
+    k_slab_pack_hdr<<<ceil_div(rows, 256), 256, 0, as_stream(stream)>>>(
+        a, (int)rows, n_own_device, (int)row_stride, 64 + 4 * (int)row_stride, x_send_left, x_send_right, has_left,
+        has_right, message_left, message_right, (long long)capacity, counters, worst);
+    ABM_CHECK_LAUNCH("k_slab_pack_hdr");
+    return 0;
+}
+
+ABM_EXPORT int abm_slab_exchange_merge(const double *locations, const double *radii, const double *motility_forces,
+                                       const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows,
+                                       int64_t rows, const int32_t *n_own_device, const uint8_t *message_left,
+                                       const uint8_t *message_right, int64_t capacity, int64_t row_stride, double x_lo,
+                                       double x_hi, int has_left, int has_right, double *out_locations,
+                                       double *out_radii, double *out_motility, int32_t *out_global_id,
+                                       int32_t *out_bond_len, int32_t *out_bond_rows, double *snapshot,
+                                       int64_t out_rows, int32_t *n_owned_out, int32_t *n_local_out, int32_t *tally,
+                                       int32_t *worst_rows, void *stream) {
+    ABM_REQUIRE(rows > 0 && rows + 2 * capacity < 0x7fffffff && row_stride > 0 && capacity >= 0 && out_rows > 0,
+                "bad sizes");
+    ABM_REQUIRE(locations && radii && motility_forces && global_id && bond_len && bond_rows && n_own_device &&
+                    out_locations && out_radii && out_motility && out_global_id && out_bond_len && out_bond_rows &&
+                    snapshot && n_owned_out && n_local_out && tally && worst_rows,
+                "null pointer");
+    ABM_REQUIRE(out_locations != locations && out_bond_rows != bond_rows, "merge is out of place");
+    ABM_REQUIRE((!has_left || message_left) && (!has_right || message_right), "missing message");
+    CellArrays in{const_cast<double *>(locations), const_cast<double *>(radii), const_cast<double *>(motility_forces),
+                  const_cast<int *>(global_id), const_cast<int *>(bond_len), const_cast<int *>(bond_rows)};
+    CellArrays out{out_locations, out_radii, out_motility, out_global_id, out_bond_len, out_bond_rows};
+    Incoming msg{has_left ? message_left : nullptr, has_right ? message_right : nullptr, (int)capacity};
+    const int rec_bytes = 64 + 4 * (int)row_stride;
+    const int blocks = ceil_div(rows + 2 * capacity, 256);
+    cudaStream_t st = as_stream(stream);
+    k_slab_count<<<blocks, 256, 0, st>>>(locations, (int)rows, n_own_device, msg, rec_bytes, x_lo, x_hi, has_left,
+                                         has_right, tally);
+    ABM_CHECK_LAUNCH("k_slab_count");
+    k_slab_place<<<blocks, 256, 0, st>>>(in, (int)rows, n_own_device, msg, rec_bytes, (int)row_stride, x_lo, x_hi,
+                                         has_left, has_right, out, snapshot, (int)out_rows, tally, n_owned_out,
+                                         n_local_out, worst_rows);
+    ABM_CHECK_LAUNCH("k_slab_place");
+    return 0;
+}

@@ -60,10 +60,8 @@ class DeviceSlab:
         # count travels inside the message, so an exchange is ONE send and ONE receive per neighbour
         self.send = [torch.zeros((self.send_cap + 1, self.rec), dtype=u8, device=dev) for _ in range(2)]
         self.recv = [torch.zeros((self.send_cap + 1, self.rec), dtype=u8, device=dev) for _ in range(2)]
-        self.counts_out = torch.zeros(2, dtype=i32, device=dev)
-        self.counts_in = torch.zeros(2, dtype=i32, device=dev)
-        self._hdr_out = [self.send[k][self.send_cap, :4].view(i32) for k in range(2)]
-        self._hdr_in = [self.recv[k][self.send_cap, :4].view(i32) for k in range(2)]
+        self.pack_counters = torch.zeros(3, dtype=i32, device=dev)       # kernel scratch, left zeroed by every call
+        self.tally = torch.zeros(5, dtype=i32, device=dev)               # likewise (abm_slab_exchange_merge)
         self.worst = torch.zeros(3, dtype=i32, device=dev)               # largest message counts, largest n_local
         need = int(self.eng.lib.abm_slab_workspace_bytes(R + 2 * self.send_cap))
         self.ws = torch.empty(need + 4096, dtype=u8, device=dev)
@@ -129,46 +127,34 @@ class DeviceSlab:
         eng, g, s = self.eng, self.geom, self.sets[self.cur]
         eng.use_current_stream()
         blen, rows = self.bonds
-        _lib.check(eng.lib.abm_slab_pack(
+        _lib.check(eng.lib.abm_slab_exchange_pack(
             s["loc"].data_ptr(), s["radii"].data_ptr(), s["mot"].data_ptr(), s["gid"].data_ptr(), blen.data_ptr(),
             rows.data_ptr(), self.R, s["n_own"].data_ptr(), self.stride, g.x_lo + g.halo, g.x_hi - g.halo,
-            int(g.has_left), int(g.has_right), self.send[0].data_ptr(), self.send_cap, self.send[1].data_ptr(),
-            self.send_cap, self.counts_out.data_ptr(), self.ws.data_ptr(), self.ws.numel(), eng.stream),
-            "abm_slab_pack")
-        torch.maximum(self.worst[:2], self.counts_out, out=self.worst[:2])
-        self._hdr_out[0].copy_(self.counts_out[0:1])
-        self._hdr_out[1].copy_(self.counts_out[1:2])
+            int(g.has_left), int(g.has_right), self.send[0].data_ptr(), self.send[1].data_ptr(), self.send_cap,
+            self.pack_counters.data_ptr(), self.worst.data_ptr(), eng.stream), "abm_slab_exchange_pack")
         self.launches += 1
 
     def enqueue_merge(self):
-        """Owned | halo partition of (current owned cells + received records) into the other buffer set; then the
-        snapshot of the positions and the morphogen deposit on it."""
+        """Owned | halo partition of (current owned cells + received records) into the other buffer set, and the
+        snapshot of the positions the step starts with (two launches)."""
         eng, g = self.eng, self.geom
         eng.use_current_stream()
         s, o = self.sets[self.cur], self.sets[1 - self.cur]
         blen, rows = self.bonds
-        self.counts_in.zero_()
-        if g.has_left:
-            self.counts_in[0:1].copy_(self._hdr_in[0])
-        if g.has_right:
-            self.counts_in[1:2].copy_(self._hdr_in[1])
-        _lib.check(eng.lib.abm_slab_merge(
+        _lib.check(eng.lib.abm_slab_exchange_merge(
             s["loc"].data_ptr(), s["radii"].data_ptr(), s["mot"].data_ptr(), s["gid"].data_ptr(), blen.data_ptr(),
-            rows.data_ptr(), self.R, self.recv[0].data_ptr(), self.send_cap if g.has_left else 0,
-            self.recv[1].data_ptr(), self.send_cap if g.has_right else 0, self.stride, g.x_lo, g.x_hi,
-            int(g.has_left), int(g.has_right), o["loc"].data_ptr(), o["radii"].data_ptr(), o["mot"].data_ptr(),
-            o["gid"].data_ptr(), o["blen"].data_ptr(), o["rows"].data_ptr(), o["n_own"].data_ptr(),
-            self.ws.data_ptr(), self.ws.numel(), s["n_own"].data_ptr(), self.counts_in.data_ptr(),
-            o["n_local"].data_ptr(), self.R, eng.stream), "abm_slab_merge")
-        torch.maximum(self.worst[2:3], o["n_local"], out=self.worst[2:3])
-        self.launches += 4
+            rows.data_ptr(), self.R, s["n_own"].data_ptr(), self.recv[0].data_ptr(), self.recv[1].data_ptr(),
+            self.send_cap, self.stride, g.x_lo, g.x_hi, int(g.has_left), int(g.has_right), o["loc"].data_ptr(),
+            o["radii"].data_ptr(), o["mot"].data_ptr(), o["gid"].data_ptr(), o["blen"].data_ptr(),
+            o["rows"].data_ptr(), self.snap.data_ptr(), self.R, o["n_own"].data_ptr(), o["n_local"].data_ptr(),
+            self.tally.data_ptr(), self.worst[2:3].data_ptr(), eng.stream), "abm_slab_exchange_merge")
+        self.launches += 2
         self.cur = 1 - self.cur
         self.bonds = (o["blen"], o["rows"])
         eng.set_device_state(o["loc"], o["radii"], o["mot"], max_radius=self.max_radius,
                              uniform_radius=self.uniform_radius)
         eng.n_device = o["n_local"]
         eng.global_id = o["gid"]
-        self.snap.copy_(o["loc"])
 
     def enqueue_deposit(self):
         """Morphogen deposit of the local cells at the snapshot positions, and the rows the x-neighbours need."""
