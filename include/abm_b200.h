@@ -50,6 +50,12 @@ extern "C" {
 #define ABM_SORT_PREBINNED 4  /* histogram + per-cell bin already written by abm_jkr_substep */
 #define ABM_SORT_CHAINED 8    /* abm_bin_sort(ABM_SORT_PREBINNED): launch its kernels with programmatic stream
                                  serialization (see ABM_LOOP_CHAINED) */
+#define ABM_LOOP_FP32 8       /* abm_mechanics_loop: the dtype flag of SURVEY 8(b).  The substeps run in SINGLE precision on
+                                 bin-relative coordinates (position = bin + fp32 offset inside the bin: one ulp is
+                                 1e-6 um whatever the colony size), forces and positions within rel 1e-5 of the fp64
+                                 path per step; clamp and re-binning stay exact (fp64).  Inputs and outputs keep their
+                                 fp64 types.  Bond sets may differ from the fp64 path for pairs within ~1e-6 um of a
+                                 threshold.  Not combinable with ABM_LOOP_CARRY_*.  (csrc/jkr32.cu) */
 #define ABM_LOOP_CHAINED 4    /* abm_mechanics_loop: launch the kernels of the loop with programmatic stream
                                  serialization, so that a kernel's CTAs become resident while the last wave of its
                                  predecessor drains (they wait for its completion before touching memory) */

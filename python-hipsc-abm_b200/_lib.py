@@ -120,7 +120,7 @@ def check(rc: int, what: str) -> int:
 
 
 SORT_STABLE, SORT_REFERENCE, SORT_PREBINNED, SORT_CHAINED = 1, 2, 4, 8
-LOOP_CARRY_OUT, LOOP_CARRY_IN, LOOP_CHAINED = 1, 2, 4
+LOOP_CARRY_OUT, LOOP_CARRY_IN, LOOP_CHAINED, LOOP_FP32 = 1, 2, 4, 8
 
 
 def d3(values):

@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabm_b200.so")
-SOURCES = ["lib.cu", "sort.cu", "search.cu", "jkr.cu", "diffusion.cu", "diffusion3d.cu", "slab.cu", "rules.cu"]
+SOURCES = ["lib.cu", "sort.cu", "search.cu", "jkr.cu", "jkr32.cu", "diffusion.cu", "diffusion3d.cu", "slab.cu", "rules.cu"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
          "-Xcompiler", "-fPIC,-fvisibility=hidden"]
 

@@ -638,6 +638,13 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                                   double youngs, double adhesion_const, double stokes, int flags,
                                   const int32_t *n_device, void *stream) {
     ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
+    if (flags & ABM_LOOP_FP32)
+        return mechanics_loop32(radii, locations, motility_forces, n, extent_host, origin_host, size_host, distance,
+                                reach, n_substeps, dts_host, bin_start_a, bin_start_b, sorted_id, sorted_pos,
+                                sorted_bin, max_count, sort_workspace, sort_workspace_bytes, old_row_start,
+                                old_row_stride, old_row_len, old_cols, len_a, cols_a, len_b, cols_b, row_stride,
+                                max_len, global_id, uniform_radius, poisson, youngs, adhesion_const, stokes, flags,
+                                n_device, stream);
     const bool carry_in = (flags & ABM_LOOP_CARRY_IN) && n > 0 && n_substeps > 0;
     const bool carry_out = (flags & ABM_LOOP_CARRY_OUT) && n > 0;
     const bool chained = flags & ABM_LOOP_CHAINED;

@@ -31,7 +31,15 @@ __device__ __forceinline__ void write_record(unsigned char *rec, const CellArray
     w[0] = a.gid[i];
     w[1] = a.bond_len[i];
     const int *row = a.bond_rows + (long long)i * stride;
-    for (int k = 0; k < stride; ++k) w[2 + k] = row[k];
+    // only the live part of the row travels (entries beyond bond_len are never read); 16 bytes at a time when the
+    // record and the row are aligned (record = 64 + 4*stride bytes: a multiple of 16 when stride % 4 == 0)
+    const int len = min(w[1], stride);
+    if ((stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(rec) | reinterpret_cast<uintptr_t>(row)) & 15) == 0) {
+        for (int k = 0; k < len; k += 4)
+            *reinterpret_cast<int4 *>(w + 2 + k) = *reinterpret_cast<const int4 *>(row + k);
+    } else {
+        for (int k = 0; k < len; ++k) w[2 + k] = row[k];
+    }
 }
 
 __device__ __forceinline__ void read_record(const unsigned char *rec, const CellArrays &a, int dst, int stride) {
@@ -47,7 +55,13 @@ __device__ __forceinline__ void read_record(const unsigned char *rec, const Cell
     a.gid[dst] = w[0];
     a.bond_len[dst] = w[1];
     int *row = a.bond_rows + (long long)dst * stride;
-    for (int k = 0; k < stride; ++k) row[k] = w[2 + k];
+    const int len = min(w[1], stride);
+    if ((stride & 3) == 0 && ((reinterpret_cast<uintptr_t>(rec) | reinterpret_cast<uintptr_t>(row)) & 15) == 0) {
+        for (int k = 0; k < len; k += 4)
+            *reinterpret_cast<int4 *>(row + k) = *reinterpret_cast<const int4 *>(w + 2 + k);
+    } else {
+        for (int k = 0; k < len; ++k) row[k] = w[2 + k];
+    }
 }
 
 // One pass: a cell to be sent claims its record slot from the message's counter (one atomic per warp and side).
@@ -361,7 +375,13 @@ k_slab_place(CellArrays a, int rows, const int *__restrict__ n_own_dev, Incoming
             out.bond_len[dst] = len;
             const int *src = a.bond_rows + (long long)i * stride;
             int *row = out.bond_rows + (long long)dst * stride;
-            for (int c = 0; c < len; ++c) row[c] = src[c];
+            if ((stride & 3) == 0 &&
+                ((reinterpret_cast<uintptr_t>(a.bond_rows) | reinterpret_cast<uintptr_t>(out.bond_rows)) & 15) == 0) {
+                for (int c = 0; c < len; c += 4)
+                    *reinterpret_cast<int4 *>(row + c) = *reinterpret_cast<const int4 *>(src + c);
+            } else {
+                for (int c = 0; c < len; ++c) row[c] = src[c];
+            }
         } else {
             read_record(in.record(i - n, kl, rec_bytes), out, dst, stride);
 #pragma unroll

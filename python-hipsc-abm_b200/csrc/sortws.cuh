@@ -66,6 +66,18 @@ int bin_sort_impl(const double *locations, const double *radii, int64_t n, const
                   size_t workspace_bytes, int32_t *zero_table, const int32_t *global_id, void *stream,
                   const int32_t *n_device = nullptr);
 
+// the substep loop in fp32 on bin-relative coordinates (jkr32.cu); same arguments as abm_mechanics_loop
+int mechanics_loop32(const double *radii, double *locations, const double *motility_forces, int64_t n,
+                     const double extent_host[3], const double *origin_host, const double size_host[3],
+                     double distance, double reach, int n_substeps, const double *dts_host, int32_t *bin_start_a,
+                     int32_t *bin_start_b, int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin,
+                     int32_t *max_count, void *sort_workspace, size_t sort_workspace_bytes,
+                     const int32_t *old_row_start, int64_t old_row_stride, const int32_t *old_row_len,
+                     const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
+                     int64_t row_stride, int32_t *max_len, const int32_t *global_id, double uniform_radius,
+                     double poisson, double youngs, double adhesion_const, double stokes, int flags,
+                     const int32_t *n_device, void *stream);
+
 __device__ __forceinline__ int cell_bin_of(double x, double y, double z, const BinGeom &g) {
     return lin_bin(bin_coord_fast(x - g.origin[0], g.distance, g.inv_distance, g.dims[0]),
                    bin_coord_fast(y - g.origin[1], g.distance, g.inv_distance, g.dims[1]),

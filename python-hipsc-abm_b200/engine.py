@@ -185,6 +185,7 @@ class ColonyEngine:
         self.stream = 0
         # per-engine launch options (arguments of the calls they affect; the library has no process-wide switches)
         self.chained_launch = False     # abm_mechanics_loop(ABM_LOOP_CHAINED): programmatic dependent launches
+        self.mechanics_dtype = "f64"    # "f32": abm_mechanics_loop(ABM_LOOP_FP32), bin-relative single precision
         self.diffusion_fuse = int(os.environ.get("ABM_B200_DIFFUSION_FUSE", "0"))   # substeps per launch, 0 = 5
         self.use_current_stream()
         self.h2d_bytes = 0     # bytes moved by upload()/to_device() and host()/locations_host()
@@ -545,6 +546,11 @@ class ColonyEngine:
                sb["bin_start"].data_ptr(), sb["bin_start_b"].data_ptr())
         if self.chained_launch:
             flags |= _lib.LOOP_CHAINED
+        if self.mechanics_dtype == "f32":
+            flags |= _lib.LOOP_FP32
+            carry = False                                    # the fp32 loop does not chain calls
+        elif self.mechanics_dtype != "f64":
+            raise _lib.AbmError(f"mechanics_dtype must be 'f64' or 'f32', not {self.mechanics_dtype!r}")
         if carry and n:
             flags |= _lib.LOOP_CARRY_OUT
             if self._carry is not None and self._carry[:-1] == key:

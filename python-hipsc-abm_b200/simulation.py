@@ -48,6 +48,11 @@ class B200Simulation:
             self.__dict__["_b200_engine"] = eng
         return eng
 
+    # Arithmetic of the mechanics loop (the dtype flag of SURVEY 8(b)): "f64" = the reference's dtype, forces and
+    # positions within 1e-12 of the oracle; "f32" = single precision on bin-relative coordinates, within 1e-5
+    # (csrc/jkr32.cu).  The agent arrays keep their float64 type either way.
+    b200_dtype = "f64"
+
     # "tracked": a host array is uploaded only when it changed since the device copy was made (arrays.py);
     # "always": every public call re-uploads what it reads (always correct, also for writes numpy cannot show)
     b200_coherence = "tracked"
@@ -103,6 +108,7 @@ class B200Simulation:
         `locations` / `radii` costs nothing at the next call."""
         eng = self.b200_engine()
         eng.use_current_stream()
+        eng.mechanics_dtype = self.b200_dtype
         n = int(self.number_agents)
         loc, loc_new = self.b200_device_array("locations", (n, 3))
         rad, rad_new = self.b200_device_array("radii", (n,))
