@@ -129,10 +129,13 @@ class ClockSampler:
 
 
 # ---- byte accounting -----------------------------------------------------------------------------
-def step_bytes(n, b15, b10, e15, e10, ej, g, sm, sd):
+def step_bytes(n, b15, b10, e15, e10, ej, g, sm, sd, w_mech=W):
+    """SURVEY 8(d) bytes of one step.  w_mech: bytes per real inside the mechanics substeps (4 in fp32 mode; the
+    r=15 search, the diffusion and the per-cell coupling always compute in float64)."""
     search15 = 7 * W * n + 4 * n + 8 * b15 + 4 * W * n + 4 * b15 + 8 * e15
-    substep = (7 * W * n + 4 * n + 8 * b10) + (4 * W * n + 4 * b10 + 8 * e10) + 8 * (2 * ej + e10) + \
-              (9 * ej + 4 * W * n) + 6 * W * n
+    w = w_mech
+    substep = (7 * w * n + 4 * n + 8 * b10) + (4 * w * n + 4 * b10 + 8 * e10) + 8 * (2 * ej + e10) + \
+              (9 * ej + 4 * w * n) + 6 * w * n
     return search15 + sm * substep + sd * 2 * W * g + 5 * W * n
 
 
@@ -142,11 +145,16 @@ def substep_kernel_bytes(n, b10, ej):
     return 10 * W * n + 12 * n + 4 * b10 + 8 * ej
 
 
-def substep_algorithmic_bytes(n, b10, e10, ej):
+def substep_algorithmic_bytes(n, b10, e10, ej, w=W):
     """SURVEY 8(d)'s algorithmic bytes of the stages ONE k_jkr_substep launch replaces: search(r=10)
     4wN+4B+8E, merge/dedupe 8(2E_j+E), force 9E_j+4wN, integrate 6wN (the sort's 7wN+4N+8B belongs to the sort
     kernels)."""
-    return (4 * W * n + 4 * b10 + 8 * e10) + 8 * (2 * ej + e10) + (9 * ej + 4 * W * n) + 6 * W * n
+    return (4 * w * n + 4 * b10 + 8 * e10) + 8 * (2 * ej + e10) + (9 * ej + 4 * w * n) + 6 * w * n
+
+
+def sort_algorithmic_bytes(n, b10, w=W):
+    """SURVEY 8(d) bin/sort: 7wN + 4N + 8B."""
+    return 7 * w * n + 4 * n + 8 * b10
 
 
 # ---- the CPU arm (oracle port) ----------------------------------------------------------------------------------
@@ -245,7 +253,7 @@ def run_cpu(name, steps, warmup, threads=None, cells=None):
     return wl["n"] * steps / dt, dt / steps, threads, sample, wl
 
 
-def parity_check(name, dev, steps=5, cells=100_000):
+def parity_check(name, dev, steps=5, cells=100_000, dtype="f64"):
     """The colony bench.py times is not compared with anything while it is timed; this runs the same step recipe on
     a `cells`-cell sample of the workload through BOTH arms (the B200 path through the reference-facing API, the CPU
     oracle with its serial force pass) for a few steps and reports how far they are apart.  The gates are PER STEP
@@ -261,6 +269,7 @@ def parity_check(name, dev, steps=5, cells=100_000):
     class Cells(B200CellMethods, ColonySimulation):
         pass
     sim = Cells(wl["size"], dev)
+    sim.b200_dtype = dtype
     sim.add_agents(n)
     sim.agent_array("locations", override=wl["loc"].copy())
     sim.agent_array("radii", override=wl["radii"].copy())
@@ -279,6 +288,7 @@ def parity_check(name, dev, steps=5, cells=100_000):
             o.max_concentration, o.degradation = 2.0, 0.1
             o.fgf4_values = np.zeros(wl["grid"] + (1,))
     free = Cells(wl["size"], dev)                 # the same colony, never reset to the oracle (free-running drift)
+    free.b200_dtype = dtype
     free.add_agents(n)
     free.agent_array("locations", override=wl["loc"].copy())
     free.agent_array("radii", override=wl["radii"].copy())
@@ -308,7 +318,14 @@ def parity_check(name, dev, steps=5, cells=100_000):
         ref.apply_forces()
         free.motility_forces[:] = mot
         free.apply_forces()
-        out["jkr_bonds_equal"] &= bool(np.array_equal(sim.jkr_graph.edge_array(), ref.jkr_graph.edge_array()))
+        same = bool(np.array_equal(sim.jkr_graph.edge_array(), ref.jkr_graph.edge_array()))
+        out["jkr_bonds_equal"] &= same
+        if not same and dtype == "f32":           # fp32: pairs at a threshold may differ; teacher-force the bonds too
+            a = set(map(tuple, sim.jkr_graph.edge_array().tolist()))
+            b = set(map(tuple, ref.jkr_graph.edge_array().tolist()))
+            out["jkr_bonds_differing"] = out.get("jkr_bonds_differing", 0) + len(a ^ b)
+            sim.jkr_graph.delete_edges(None)
+            sim.jkr_graph.add_edges(ref.jkr_graph.edge_array())
         dx = float(np.abs(sim.locations - ref.locations).max())
         out["rel_dx_per_step"].append(dx / float(np.abs(ref.locations).max()))
         if k >= relax:
@@ -332,9 +349,16 @@ def parity_check(name, dev, steps=5, cells=100_000):
     scale = float(np.abs(ref.locations).max())
     out["max_rel_dx"] = out["max_abs_dx_um"] / scale
     out["free_running_abs_dx_um_after_all_steps"] = float(np.abs(free.locations - ref.locations).max())
-    out["gates"] = "per step: edges identical; positions 1e-12 relative (fp64 mode); field 1e-6"
-    out["ok"] = bool(out["neighbor_edges_equal"] and out["jkr_bonds_equal"] and out["max_rel_dx"] <= 1e-12 and
-                     (out["max_abs_dfield"] is None or out["max_abs_dfield"] <= 1e-6))
+    if dtype == "f32":
+        out["gates"] = ("per step: neighbour edges identical; positions 1e-5 relative (fp32 mode); JKR bonds identical "
+                        "up to pairs at a threshold (counted); field 1e-6")
+        out["ok"] = bool(out["neighbor_edges_equal"] and out["max_rel_dx"] <= 1e-5 and
+                         out.get("jkr_bonds_differing", 0) <= 1e-4 * max(len(ref.jkr_graph.edge_array()), 1) * steps and
+                         (out["max_abs_dfield"] is None or out["max_abs_dfield"] <= 1e-6))
+    else:
+        out["gates"] = "per step: edges identical; positions 1e-12 relative (fp64 mode); field 1e-6"
+        out["ok"] = bool(out["neighbor_edges_equal"] and out["jkr_bonds_equal"] and out["max_rel_dx"] <= 1e-12 and
+                         (out["max_abs_dfield"] is None or out["max_abs_dfield"] <= 1e-6))
     return out
 
 
@@ -375,6 +399,8 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
         return line
     eng = ColonyEngine(wl["size"], dev)
+    eng.mechanics_dtype = args.dtype
+    w_mech = 4 if args.dtype == "f32" else W
     eng.upload(wl["loc"], wl["radii"], wl["mot"])
     # the motility forces alternate in sign from step to step (see make_workload): the colony then stays statistically
     # stationary, so the timed steps do the same work whatever --steps / --warmup say
@@ -433,7 +459,7 @@ def run_b200(args, rank, world, local_rank):
     b10 = int(np.prod(eng.bin_dims(reach)))
     g = wl["grid"][0] * wl["grid"][1] if wl["grid"] else 0
     sm = len(pipe.dts)
-    bytes_step = step_bytes(n, b15, b10, e15, ej, ej, g, sm, spec["sd"])
+    bytes_step = step_bytes(n, b15, b10, e15, ej, ej, g, sm, spec["sd"], w_mech)
 
     # ---- roofline of the dominant kernel: event-timed single launches, L2 flushed before each -----------------------
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -472,6 +498,11 @@ def run_b200(args, rank, world, local_rank):
             out.append(a.elapsed_time(z) * 1e3)
         return float(np.median(out))
 
+    if args.dtype == "f32":
+        # the fp32 substep kernel has no stand-alone entry point: the dominant "kernel" of the fp32 line is the
+        # mechanics loop, 11 x [scan + placement + k_jkr_substep32], timed as a whole and divided by the substeps
+        def launch_substep():
+            eng.enqueue_mechanics(old, cfg.contact_radius, pipe.dts, cfg.bond_stride, zero_flag=False)
     for _ in range(3):
         launch_substep()
     cold_us = time_launches(True)
@@ -479,8 +510,16 @@ def run_b200(args, rank, world, local_rank):
     eng.loc.copy_(loc_save)
     kbytes = substep_kernel_bytes(n, b10, ej)
     abytes = substep_algorithmic_bytes(n, b10, ej, ej)
+    kernel_name, bytes_model = "k_jkr_substep<uniform radius>", (
+        "SURVEY 8(d) algorithmic bytes of the stages the launch fuses: search(r=10) + merge/dedupe + force + integrate")
+    if args.dtype == "f32":
+        cold_us, hot_us = cold_us / sm, hot_us / sm
+        kbytes = None
+        abytes = substep_algorithmic_bytes(n, b10, ej, ej, 4) + sort_algorithmic_bytes(n, b10, 4)
+        kernel_name = "mechanics loop per substep: k_scan_apply + k_rescatter32 + k_jkr_substep32 (fp32, bin-relative)"
+        bytes_model = "SURVEY 8(d) algorithmic bytes with w = 4: bin/sort + search(r=10) + merge/dedupe + force + integrate"
     achieved = abytes / (cold_us * 1e-6) / 1e9
-    achieved_c = kbytes / (cold_us * 1e-6) / 1e9
+    achieved_c = (kbytes or 0) / (cold_us * 1e-6) / 1e9
     traffic = l2_hit = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -488,12 +527,11 @@ def run_b200(args, rank, world, local_rank):
         traffic = prof.get(args.workload, {}).get("k_jkr_substep")
         l2_hit = prof.get("l2_hit_pct", {}).get(args.workload, {}).get("k_jkr_substep")
     nominal = 8000.0                                                     # B200 HBM3e nominal, SURVEY 8(d)
-    roofline = {"bound": "hbm", "kernel": "k_jkr_substep<uniform radius>", "achieved": round(achieved, 1),
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": round(achieved, 1),
                 "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
                 "peak_source": peak_src, "frac_of_nominal_8000": round(achieved / nominal, 4),
                 "l2_hit_pct_ncu": l2_hit, "bytes_per_launch": abytes,
-                "bytes_model": "SURVEY 8(d) algorithmic bytes of the stages the launch fuses: search(r=10) + "
-                               "merge/dedupe + force + integrate",
+                "bytes_model": bytes_model,
                 "compulsory_bytes_per_launch": kbytes, "achieved_on_compulsory_bytes": round(achieved_c, 1),
                 "frac_on_compulsory_bytes": round(achieved_c / peak, 4), "launch_us_cold_l2": round(cold_us, 2),
                 "launch_us_warm_l2": round(hot_us, 2), "launches_per_step": sm,
@@ -534,6 +572,7 @@ def run_b200(args, rank, world, local_rank):
         class Cells(B200CellMethods, ColonySimulation):
             pass
         sim = Cells(wl["size"], dev)
+        sim.b200_dtype = args.dtype
         sim.add_agents(n)
         sim.agent_array("locations", override=wl["loc"].copy())
         sim.agent_array("radii", override=wl["radii"].copy())
@@ -615,7 +654,7 @@ def run_b200(args, rank, world, local_rank):
 
     cpu = parity = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        parity = parity_check(args.workload, dev)
+        parity = parity_check(args.workload, dev, dtype=args.dtype)
         v, spp, threads, sample, _ = run_cpu(args.workload, 2, 1)
         v1, spp1, _, sample1, _ = run_cpu(args.workload, 1, 1, threads=1)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
@@ -630,7 +669,7 @@ def run_b200(args, rank, world, local_rank):
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": args.dtype, "data": "synthetic",
         "config": common_config(args.workload, wl, sm),
         "method": {"edges_r15": e15, "jkr_bonds": ej,
                    "morphogen_stage": ("reference order (before the mechanics, on the step's starting positions), "
@@ -837,6 +876,9 @@ def main():
                     help="c3 = BASELINE configs[2], the 500k-cell headline colony quoted at 1 and 8 B200 (default)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"],
+                    help="arithmetic of the mechanics loop: f64 = the reference's dtype (default, the headline); f32 = "
+                         "single precision on bin-relative coordinates (north-star gate 1e-5)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak = one workload-sized slab per GPU (default); strong = the workload's colony cut "
                          "into N slabs (BASELINE configs[3]: --workload c4 --scaling strong)")
