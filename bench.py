@@ -730,6 +730,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     send_cap = int(1.6 * expect * halo / width) + 4096
     rows = int(1.15 * expect * (1 + 2 * halo / width)) + 8192
     ds = DeviceSlab(geom, cfg, dev, rows=rows, send_cap=send_cap, max_radius=5.0, uniform_radius=5.0, field=field)
+    ds.eng.mechanics_dtype = args.dtype
     ds.load(loc, radii, mot, gid)
     # the field rows travel on their own communicator: they are exchanged on the second stream and must not queue in
     # front of the next step's cell exchange
@@ -818,7 +819,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": common_config(args.workload, wl, len(cfg.substep_dts()), world, scaling=args.scaling),
         "method": {"cells_total": n_total, "halo_um": halo, "rows_capacity": rows, "message_capacity": send_cap,
                    "morphogen_stage": "reference order (before the mechanics), with its row exchange on a second "
