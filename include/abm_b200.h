@@ -55,7 +55,7 @@ extern "C" {
                                  1e-6 um whatever the colony size), forces and positions within rel 1e-5 of the fp64
                                  path per step; clamp and re-binning stay exact (fp64).  Inputs and outputs keep their
                                  fp64 types.  Bond sets may differ from the fp64 path for pairs within ~1e-6 um of a
-                                 threshold.  Not combinable with ABM_LOOP_CARRY_*.  (csrc/jkr32.cu) */
+                                 threshold.  (csrc/jkr32.cu) */
 #define ABM_LOOP_CHAINED 4    /* abm_mechanics_loop: launch the kernels of the loop with programmatic stream
                                  serialization, so that a kernel's CTAs become resident while the last wave of its
                                  predecessor drains (they wait for its completion before touching memory) */
@@ -174,9 +174,11 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  *                      sort that produced the current order) expects them.  `locations` may then be NULL (the
  *                      moved cells are only handed to the next sort).
  *   reach            : bin edge of the sort, >= abm_jkr_reach(distance, max(radii), ...).
- *   max_len (1) int32: raised (atomicMax) by rows that needed more than row_stride entries; a value
+ *   max_len (2) int32: [0] is raised (atomicMax) by rows that needed more than row_stride entries; a value
  *   > row_stride afterwards means those rows were truncated: grow row_stride and redo the substep
- *   from the saved locations.  The caller zeroes it.                                                */
+ *   from the saved locations.  [1] is raised to the bit pattern of the largest squared displacement (float, um^2)
+ *   of a cell in one substep -- what the slab decomposition's halo depth has to be checked against.  The caller
+ *   zeroes both.                                                                                    */
 double abm_jkr_reach(double distance, double max_radius, double poisson, double youngs, double adhesion_const);
 
 int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,

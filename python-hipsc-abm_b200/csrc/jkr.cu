@@ -492,6 +492,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     const double nx = stokes_move_y(p.x, mx, (double)fxi * kForceUnit, friction, inv_f, dt, box.size[0]);
     const double ny = stokes_move_y(p.y, my, (double)fyi * kForceUnit, friction, inv_f, dt, box.size[1]);
     const double nz = stokes_move_y(p.z, mz, (double)fzi * kForceUnit, friction, inv_f, dt, box.size[2]);
+    record_move(max_len, (float)((nx - p.x) * (nx - p.x) + (ny - p.y) * (ny - p.y) + (nz - p.z) * (nz - p.z)));
     if (loc) {
         loc[3 * (long long)i + 0] = nx;
         loc[3 * (long long)i + 1] = ny;

@@ -14,6 +14,9 @@
 // bound the number of such pairs and check that each one sits at a threshold.  The r = 15 neighbour search is
 // unaffected (it always runs on fp64 positions with the exact predicate).
 //
+// With equal radii (the shipped model) the record's fourth slot carries the cell's linear bin instead of the radius, so
+// that a partner's position is ONE 16-byte gather (no second gather of sorted_bin).
+//
 // Same launch structure as the fp64 loop (jkr.cu): per substep one scan, one placement, one fused kernel; the moved
 // cells are handed to the next sort in slot order.  Records are 16-byte float4 {ox, oy, oz, radius} instead of
 // 32-byte double4: the working set of a substep shrinks from ~124 MB to ~90 MB at 500k cells.
@@ -54,7 +57,7 @@ __device__ __forceinline__ void offset_of(double x, double origin, double edge, 
 __global__ void __launch_bounds__(256)
 k_bin_count32(const double *__restrict__ loc, const double *__restrict__ radii, int n, Lattice32 L,
               int *__restrict__ counts, int *__restrict__ cell_bin, float4 *__restrict__ tmp_off,
-              const int *__restrict__ n_dev) {
+              const int *__restrict__ n_dev, int bin_in_w) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     n = device_count(n, n_dev);
     if (i >= n) return;
@@ -64,7 +67,7 @@ k_bin_count32(const double *__restrict__ loc, const double *__restrict__ radii, 
     for (int k = 0; k < 3; ++k) offset_of(loc[3 * (long long)i + k], L.origin[k], L.edge, L.inv_edge, L.dims[k], b[k], o[k]);
     const int lin = lin_bin(b[0], b[1], b[2], L.dims);
     cell_bin[i] = lin;
-    tmp_off[i] = make_float4(o[0], o[1], o[2], (float)radii[i]);
+    tmp_off[i] = make_float4(o[0], o[1], o[2], bin_in_w ? __int_as_float(lin) : (float)radii[i]);
     atomicAdd(&counts[lin], 1);
 }
 
@@ -114,7 +117,8 @@ struct Next32 {
 __device__ __forceinline__ LayerRuns stage_layer32(bool live, int bx, int by, int z, const Stencil &st,
                                                    const int *__restrict__ bin_start, const float4 *__restrict__ spos,
                                                    const int *__restrict__ sorted_bin, int obx, int oby, int obz,
-                                                   float oox, float ooy, float ooz, float edgef, float4 *tile) {
+                                                   float oox, float ooy, float ooz, float edgef, float4 *tile,
+                                                   bool bin_in_w) {
     LayerRuns R;
     const int lane = threadIdx.x & 31;
     const bool zok = live && z >= 0 && z < st.dims[2];
@@ -149,7 +153,7 @@ __device__ __forceinline__ LayerRuns stage_layer32(bool live, int bx, int by, in
                     const int t = L[r] + c;
                     const float4 q = spos[t];
                     int qx, qy, qz;
-                    st.decode(sorted_bin[t], qx, qy, qz);
+                    st.decode(bin_in_w ? __float_as_int(q.w) : sorted_bin[t], qx, qy, qz);
                     tile[r * kTileCap + c] = make_float4(fmaf((float)(qx - obx), edgef, q.x - oox),
                                                          fmaf((float)(qy - oby), edgef, q.y - ooy),
                                                          fmaf((float)(qz - obz), edgef, q.z - ooz), __int_as_float(t));
@@ -184,9 +188,10 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
     if (live) {
         i = sorted_id[s];
         p = spos[s];
-        st.decode(sorted_bin[s], bx, by, bz);
+        st.decode(kUniform ? __float_as_int(p.w) : sorted_bin[s], bx, by, bz);
         asm volatile("prefetch.global.L2 [%0];" ::"l"(mot + 3 * (long long)i));
     }
+    const float my_radius = kUniform ? 0.5f * c.uni_rsum : p.w;
     // ---- phase 1: filter over the staged stencil, coordinates relative to the warp's first cell ---------------------
     const int obx = __shfl_sync(kFullWarp, bx, 0), oby = __shfl_sync(kFullWarp, by, 0), obz = __shfl_sync(kFullWarp, bz, 0);
     const float oox = __shfl_sync(kFullWarp, p.x, 0), ooy = __shfl_sync(kFullWarp, p.y, 0),
@@ -200,7 +205,7 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
         const int z = bz + dz;
         if (__all_sync(kFullWarp, !live || z < 0 || z >= st.dims[2])) continue;
         const LayerRuns R = stage_layer32(live, bx, by, z, st, bin_start, spos, sorted_bin, obx, oby, obz, oox, ooy,
-                                          ooz, L.edgef, tile);
+                                          ooz, L.edgef, tile, kUniform);
 #pragma unroll
         for (int r = 0; r < kTileRows; ++r) {
             if (!((R.staged >> r) & 1u)) {
@@ -241,10 +246,10 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
             inv_scale = c.uni_inv_scale;
             force_fixed = c.uni_force_fixed;
         } else {
-            const float r_hat = 1.0f / (1e6f * ((1.0f / p.w) + (1.0f / rq)));
+            const float r_hat = 1.0f / (1e6f * ((1.0f / my_radius) + (1.0f / rq)));
             inv_scale = 1.0f / (1e6f * (c.k23 * cbrtf(r_hat)));
             force_fixed = c.pi_adh * r_hat * 0x1p76f;
-            rsum = p.w + rq;
+            rsum = my_radius + rq;
         }
         const float inv_mag = s2 > 0.0f ? rsqrtf(s2) : 0.0f;
         const float mag = s2 * inv_mag;
@@ -267,7 +272,7 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
     };
     auto separation = [&](int t, const float4 &q, float &vx, float &vy, float &vz) {
         int qx, qy, qz;
-        st.decode(sorted_bin[t], qx, qy, qz);
+        st.decode(kUniform ? __float_as_int(q.w) : sorted_bin[t], qx, qy, qz);
         vx = fmaf((float)(bx - qx), L.edgef, p.x - q.x);
         vy = fmaf((float)(by - qy), L.edgef, p.y - q.y);
         vz = fmaf((float)(bz - qz), L.edgef, p.z - q.z);
@@ -276,15 +281,15 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
         // ---- phase 2: the parked partners (next partner fetched while the current one is evaluated) -----------------
         int t_next = nh > 0 ? column[0][tid] : s;
         float4 q_next = spos[t_next];
-        int b_next = sorted_bin[t_next];
+        int b_next = kUniform ? 0 : sorted_bin[t_next];
         for (int k = 0; k < nh; ++k) {
             const int t = t_next;
             const float4 q = q_next;
-            const int bq = b_next;
+            const int bq = kUniform ? __float_as_int(q.w) : b_next;
             if (k + 1 < nh) {
                 t_next = column[k + 1][tid];
                 q_next = spos[t_next];
-                b_next = sorted_bin[t_next];
+                if (!kUniform) b_next = sorted_bin[t_next];
             }
             int qx, qy, qz;
             st.decode(bq, qx, qy, qz);
@@ -355,24 +360,27 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
     new_len[i] = kept;
     if (total > stride) atomicMax(max_len, total);
     // ---- phase 4: integration (cell_backend.py:155-170): the displacement in fp32, clamp and re-binning in fp64 ------
-    const float friction = kUniform ? c.friction_uni : 6.0f * 3.14159265f * c.stokes * (p.w / 1e6f);
+    const float friction = kUniform ? c.friction_uni : 6.0f * 3.14159265f * c.stokes * (my_radius / 1e6f);
     const float m3[3] = {(float)mot[3 * (long long)i + 0], (float)mot[3 * (long long)i + 1],
                          (float)mot[3 * (long long)i + 2]};
     const float f3[3] = {(float)fxi * 0x1p-76f, (float)fyi * 0x1p-76f, (float)fzi * 0x1p-76f};
     const int b3[3] = {bx, by, bz};
     const float o3[3] = {p.x, p.y, p.z};
     int nb[3];
-    float no[3];
+    float no[3], moved2 = 0.0f;
     double nx[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         const float velocity = (m3[k] + f3[k]) / friction;
         const float disp = dt * (velocity * 1e6f);
-        double x = fma((double)(b3[k] - 1), L.edge, L.origin[k]) + ((double)o3[k] + (double)disp);
+        const double x0 = fma((double)(b3[k] - 1), L.edge, L.origin[k]) + (double)o3[k];
+        double x = x0 + (double)disp;
         x = x > L.size[k] ? L.size[k] : (x < 0.0 ? 0.0 : x);
         nx[k] = x;
+        moved2 += (float)((x - x0) * (x - x0));
         offset_of(x, L.origin[k], L.edge, L.inv_edge, L.dims[k], nb[k], no[k]);
     }
+    record_move(max_len, moved2);
     if (loc) {
         loc[3 * (long long)i + 0] = nx[0];
         loc[3 * (long long)i + 1] = nx[1];
@@ -380,7 +388,7 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
     }
     if (next.counts) {
         const int b = lin_bin(nb[0], nb[1], nb[2], L.dims);
-        next.next_pos[s] = make_float4(no[0], no[1], no[2], p.w);
+        next.next_pos[s] = make_float4(no[0], no[1], no[2], kUniform ? __int_as_float(b) : p.w);
         next.cell_bin[s] = b;
         next.prev_id[s] = i;
         atomicAdd(&next.counts[b], 1);
@@ -408,8 +416,8 @@ int abm::mechanics_loop32(const double *radii, double *locations, const double *
                           double poisson, double youngs, double adhesion_const, double stokes, int flags,
                           const int32_t *n_device, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff && n_substeps >= 0 && dts_host, "bad sizes");
-    ABM_REQUIRE(!(flags & (ABM_LOOP_CARRY_IN | ABM_LOOP_CARRY_OUT)), "the fp32 loop does not chain calls");
     if (n == 0 || n_substeps == 0) return 0;
+    const bool carry_in = flags & ABM_LOOP_CARRY_IN, carry_out = flags & ABM_LOOP_CARRY_OUT;
     ABM_REQUIRE(radii && locations && motility_forces && extent_host && size_host && bin_start_a && bin_start_b &&
                     bin_start_a != bin_start_b && sorted_id && sorted_pos && sorted_bin && sort_workspace && len_a &&
                     cols_a && len_b && cols_b && max_len,
@@ -453,20 +461,22 @@ int abm::mechanics_loop32(const double *radii, double *locations, const double *
     for (int k = 0; k < n_substeps; ++k) {
         int32_t *table = (k & 1) ? bin_start_b : bin_start_a, *other = (k & 1) ? bin_start_a : bin_start_b;
         const bool last = k + 1 == n_substeps;
+        const bool prebin = !last || carry_out;              // hand the moved cells to the next sort
         int rc;
-        if (k == 0) {
+        if (k == 0 && !carry_in) {
             rc = check_cuda(cudaMemsetAsync(table, 0, (size_t)(nbins + 1) * 4, st), "memset bin_start");
             if (rc) return rc;
             if (max_count) {
                 rc = check_cuda(cudaMemsetAsync(max_count, 0, 4, st), "memset max_count");
                 if (rc) return rc;
             }
-            k_bin_count32<<<blocks, 256, 0, st>>>(locations, radii, (int)n, L, table, w.cell_bin, tmp_off, n_device);
+            k_bin_count32<<<blocks, 256, 0, st>>>(locations, radii, (int)n, L, table, w.cell_bin, tmp_off, n_device,
+                                                  uniform_radius > 0 ? 1 : 0);
             ABM_CHECK_LAUNCH("k_bin_count32");
             k_scan_reduce<<<nb, kScanThreads, 0, st>>>(table, nbins + 1, w.block_sums, max_count);
             ABM_CHECK_LAUNCH("k_scan_reduce");
             k_scan_apply<<<nb, kScanThreads, 0, st>>>(table, nbins + 1, w.block_sums, nullptr, w.cursor,
-                                                      last ? nullptr : other, nullptr);
+                                                      prebin ? other : nullptr, nullptr);
             ABM_CHECK_LAUNCH("k_scan_apply");
             k_scatter32<<<blocks, 256, 0, st>>>(w.cell_bin, tmp_off, w.cursor, (int)n, sorted_id, spos, sorted_bin,
                                                 w.next_sums, nb, global_id, w.slot_gid, n_device);
@@ -474,7 +484,7 @@ int abm::mechanics_loop32(const double *radii, double *locations, const double *
         } else {
             rc = check_cuda(launch_chained(k_scan_apply, nb, kScanThreads, st, chained, table, nbins + 1,
                                            (const int *)w.next_sums, (int *)nullptr, w.cursor,
-                                           last ? (int *)nullptr : other, (int *)nullptr),
+                                           prebin ? other : (int *)nullptr, (int *)nullptr),
                             "k_scan_apply");
             if (rc) return rc;
             rc = check_cuda(launch_chained(k_rescatter32, blocks, 256, st, chained, (const int *)w.cell_bin,
@@ -486,7 +496,7 @@ int abm::mechanics_loop32(const double *radii, double *locations, const double *
         }
         Next32 next;
         memset(&next, 0, sizeof(next));
-        if (!last) {
+        if (prebin) {
             next.counts = other;
             next.cell_bin = w.cell_bin;
             next.prev_id = w.tmp_id;

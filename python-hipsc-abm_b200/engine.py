@@ -510,7 +510,7 @@ class ColonyEngine:
             b = dict(cap=cap, stride=stride,
                      len_full=[self._zeros(cap, torch.int32) for _ in range(3)],
                      cols_full=[self._empty((cap, stride), torch.int32) for _ in range(3)],
-                     max_len=self._zeros(1, torch.int32))
+                     max_len=self._zeros(2, torch.int32))      # [0] longest row, [1] largest substep move (float bits)
             self._bond_bufs = b
         if b.get("n") != n:
             b["n"] = n
@@ -543,12 +543,11 @@ class ColonyEngine:
         flags, first = 0, 0
         # everything the hand-over depends on: lattice, cells, radii (they travel with the positions), the buffers
         key = (nbins, n, self.loc.data_ptr(), self.radii.data_ptr(), reach, sb["ws"].data_ptr(),
-               sb["bin_start"].data_ptr(), sb["bin_start_b"].data_ptr())
+               sb["bin_start"].data_ptr(), sb["bin_start_b"].data_ptr(), self.mechanics_dtype)
         if self.chained_launch:
             flags |= _lib.LOOP_CHAINED
         if self.mechanics_dtype == "f32":
             flags |= _lib.LOOP_FP32
-            carry = False                                    # the fp32 loop does not chain calls
         elif self.mechanics_dtype != "f64":
             raise _lib.AbmError(f"mechanics_dtype must be 'f64' or 'f32', not {self.mechanics_dtype!r}")
         if carry and n:
@@ -573,6 +572,13 @@ class ColonyEngine:
         self.launches += (3 * len(dts) + (0 if flags & _lib.LOOP_CARRY_IN else 2)) if n else 0
         last = pair[(len(dts) - 1) & 1]
         return GraphTensors(n, None, stride, b["len"][last], b["cols"][last], True)
+
+    def max_substep_move(self) -> float:
+        """Host synchronisation: the largest distance (um) a cell moved in ONE substep since the flag was last zeroed."""
+        if self._bond_bufs is None:
+            return 0.0
+        bits = int(self._bond_bufs["max_len"][1].item())
+        return float(np.sqrt(np.array([bits], dtype=np.int32).view(np.float32)[0]))
 
     def mechanics(self, old: Optional[GraphTensors], distance, dts, stride=16, stokes=STOKES, meanwhile=None,
                   fetch_locations=False):

@@ -125,8 +125,8 @@ class DeviceColony:
         if used > self.nbr_cols.numel():
             raise _lib.AbmError(f"neighbour column buffer too small: needed {used}, have {self.nbr_cols.numel()}")
         b = self.eng._bond_bufs
-        if b is not None and int(b["max_len"].item()) > b["stride"]:
-            raise _lib.AbmError(f"bond rows too narrow: needed {int(b['max_len'].item())}, have {b['stride']}")
+        if b is not None and int(b["max_len"][0].item()) > b["stride"]:
+            raise _lib.AbmError(f"bond rows too narrow: needed {int(b['max_len'][0].item())}, have {b['stride']}")
 
     # ---- one step, enqueue only -----------------------------------------------------------------------------------
     def enqueue_step(self, step_number: int):

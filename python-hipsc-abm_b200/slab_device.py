@@ -119,8 +119,15 @@ class DeviceSlab:
         if used > self.nbr["cols"].numel():
             raise _lib.AbmError(f"neighbour column buffer too small: needed {used}")
         b = self.eng._bond_bufs
-        if b is not None and int(b["max_len"].item()) > b["stride"]:
-            raise _lib.AbmError(f"bond rows too narrow: needed {int(b['max_len'].item())}, have {b['stride']}")
+        if b is not None and int(b["max_len"][0].item()) > b["stride"]:
+            raise _lib.AbmError(f"bond rows too narrow: needed {int(b['max_len'][0].item())}, have {b['stride']}")
+        # the halo depth assumes that no cell moves more than slack/2 in one substep (slab.required_halo): verify it
+        reach = self.eng.jkr_reach(self.cfg.contact_radius)
+        slack = (self.geom.halo - (self.field.h if self.field is not None else 0.0)) / len(self.dts) - reach
+        move = self.eng.max_substep_move()
+        if self.geom.world > 1 and 2.0 * move > slack * (1 + 1e-9):
+            raise _lib.AbmError(f"halo too shallow for the observed motion: a cell moved {move:.3f} um in one substep, "
+                                f"the halo of {self.geom.halo:.1f} um allows {slack / 2:.3f} um (slab.required_halo)")
 
     # ---- the phases of a step: each only ENQUEUES on the current stream ---------------------------------------------
     def enqueue_pack(self):

@@ -219,7 +219,7 @@ def test_mechanics_loop_equals_substep_by_substep():
         reach = b.jkr_reach(10.0)
         rows = [torch.zeros((n, stride), dtype=torch.int32, device="cuda") for _ in range(2)]
         lens = [torch.zeros(n, dtype=torch.int32, device="cuda") for _ in range(2)]
-        worst = torch.zeros(1, dtype=torch.int32, device="cuda")
+        worst = torch.zeros(2, dtype=torch.int32, device="cuda")
         old = None
         for k, dt in enumerate(dts):
             srt = b.sort(reach)
@@ -231,7 +231,7 @@ def test_mechanics_loop_equals_substep_by_substep():
                 b.mot.data_ptr(), b.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0, _lib.d3(size), dt, 0,
                 b.uniform_radius, None, None, 0, 0, 0, b.stream), "abm_jkr_substep")
             old = (lens[k & 1], rows[k & 1])
-        assert int(worst.item()) <= stride
+        assert int(worst[0].item()) <= stride
         assert torch.equal(a.loc, b.loc), f"{dim}-D positions differ"
         assert torch.equal(bonds_a.row_len[:n], old[0])
         m = torch.arange(stride, device="cuda")[None, :] < old[0][:, None]

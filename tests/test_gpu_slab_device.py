@@ -110,3 +110,32 @@ def test_capacity_overflows_are_reported_not_silent():
     torch.cuda.synchronize()
     with pytest.raises(Exception, match="message capacity too small"):
         steppers[0].slab.check()
+
+
+def test_halo_depth_assumption_is_verified():
+    """slab.required_halo assumes no cell moves more than slack/2 per substep; the mechanics kernel records the
+    largest substep displacement and check() compares."""
+    rng = np.random.default_rng(2)
+    size, n = np.array([900.0, 300.0, 0.0]), 3500
+    loc = rng.random((n, 3)) * size
+    mot = rng.normal(0, 2e-9, (n, 3)) * [1, 1, 0]
+    cfg = StepConfig(bond_stride=32, search_cols_per_cell=40.0)
+    dev = torch.device("cuda")
+    for slack, ok in ((6.0, True), (0.05, False)):          # 2 nN moves a cell ~0.4 um per substep, contacts more
+        halo = slab.required_halo(11, 10.3100107, slack=slack)
+        steppers = []
+        for r in range(2):
+            g = slab.SlabGeometry.uniform(size, 2, r, halo)
+            m = (loc[:, 0] >= g.x_lo) & ((loc[:, 0] < g.x_hi) | (r == 1))
+            s = DeviceSlab(g, cfg, dev, rows=2 * n, send_cap=n, uniform_radius=5.0)
+            s.load(loc[m], np.full(m.sum(), 5.0), mot[m], np.arange(n)[m])
+            steppers.append(SlabStepper(s, side_stream=False))
+        for _ in range(3):
+            loopback_step(steppers)
+        torch.cuda.synchronize()
+        assert steppers[0].slab.eng.max_substep_move() > 0.1
+        if ok:
+            steppers[0].slab.check()
+        else:
+            with pytest.raises(Exception, match="halo too shallow"):
+                steppers[0].slab.check()

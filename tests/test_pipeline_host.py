@@ -28,7 +28,7 @@ class RecordingEngine:
         if self._bufs is None:
             self._bufs = dict(len=[torch.zeros(n, dtype=torch.int32) for _ in range(3)],
                               cols=[torch.zeros(n * stride, dtype=torch.int32) for _ in range(3)],
-                              max_len=torch.zeros(1, dtype=torch.int32))
+                              max_len=torch.zeros(2, dtype=torch.int32))
         return self._bufs
 
     def sort(self, distance, loc=None):
