@@ -83,26 +83,33 @@ def test_fp32_is_deterministic_and_far_colony_is_as_accurate_as_a_near_one():
     mot = rng.normal(0, 2e-9, (n, 3)) * [1, 1, 0]
     pad = np.array([60.0, 60.0, 0.0])
 
+    # relax the random start first (fp64, three steps): what is compared is ONE step of a settled colony
+    pre = Cells(loc + pad, radii, size + 2 * pad)
+    for step in range(3):
+        pre.motility_forces[:] = mot if step % 2 == 0 else -mot
+        pre.apply_forces()
+    start = np.array(pre.locations) - pad
+    bonds = pre.jkr_graph.edge_array()
+
     def run(shift, dtype):
         off = pad + [shift, shift, 0.0]
-        sim = Cells(loc + off, radii, size + 2 * pad + [shift, shift, 0.0])
+        sim = Cells(start + off, radii, size + 2 * pad + [shift, shift, 0.0])
         sim.b200_dtype = dtype
-        out = None
-        for step in range(3):                      # two steps to relax the random start, the third one is measured
-            before = sim.locations.copy()
-            sim.motility_forces[:] = mot if step % 2 == 0 else -mot
-            sim.apply_forces()
-            out = (sim.locations - before, sim.jkr_graph.edge_array())
-        return out
+        sim.jkr_graph.add_edges(bonds)
+        before = sim.locations.copy()
+        sim.motility_forces[:] = -mot
+        sim.apply_forces()
+        return sim.locations - before, sim.jkr_graph.edge_array()
     a, b = run(0.0, "f32"), run(0.0, "f32")
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
     ref = run(0.0, "f64")[0]
-    near = np.abs(a[0] - ref).max()
-    far = np.abs(run(51200.0, "f32")[0] - run(51200.0, "f64")[0]).max()
     scale = np.abs(ref).max()
-    # free-running over three steps from a random start: the third step's displacement within 1e-3 of the largest one,
-    # and no worse 51 mm away than at the origin (the shifted lattice cuts the bins elsewhere: not bit-equal)
-    assert near <= 1e-3 * scale and far <= 1e-3 * scale and far <= 10 * near + 1e-6
+    near = np.abs(a[0] - ref).max() / scale
+    far = np.abs(run(51200.0, "f32")[0] - run(51200.0, "f64")[0]).max() / scale
+    print(f"\n[fp32] step displacement error relative to the largest displacement: at the origin {near:.2e}, "
+          f"51 mm away {far:.2e}")
+    # (the shifted lattice cuts the bins elsewhere, so the two fp32 runs are not bit-equal -- but equally accurate)
+    assert near <= 1e-5 and far <= 1e-5
 
 
 def test_fp32_walls_overfull_bins_and_empty():

@@ -41,9 +41,12 @@ def make_class(mg):
     from hipsc_abm_b200.cell_methods import B200CellMethods
     from hipsc_abm_b200.simulation import B200Simulation
 
-    class FastCells(B200CellMethods, B200Simulation, mg.cell_simulation.CellSimulation):
-        pass
-    return FastCells, B200CellMethods, B200Simulation
+    if "FastCells" not in globals():
+        class FastCells(B200CellMethods, B200Simulation, mg.cell_simulation.CellSimulation):
+            pass
+        FastCells.__qualname__ = "FastCells"          # module-level name: Simulation.temp() pickles the object
+        globals()["FastCells"] = FastCells
+    return globals()["FastCells"], B200CellMethods, B200Simulation
 
 
 def test_method_resolution_order(ref):
@@ -106,5 +109,58 @@ def test_reference_rules_run_on_the_device_graph_facade_and_hot_path_needs_a_gpu
                 with pytest.raises(AbmError, match="no CPU path"), contextlib.redirect_stdout(io.StringIO()):
                     call()
             assert "get_neighbors" not in sim.method_times      # nothing ran, nothing was timed
+    finally:
+        os.chdir(cwd)
+
+
+def test_reference_outputs_and_checkpoint_work_on_tracked_arrays(ref):
+    """the reference's own step_values (CSV), step_image (OpenCV), data (CSV), temp (pickle) and
+    the mode-1 reload read the agent arrays the hot path hands back -- write-counting ndarray views on pinned memory
+    (arrays.TrackedArray).  They must behave exactly like plain arrays there, and a checkpoint must hold plain arrays."""
+    import csv
+    import pickle
+    mg, work = ref
+    FastCells, _, _ = make_class(mg)
+    from hipsc_abm_b200.arrays import TrackedArray, track
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:
+        random.seed(6)
+        np.random.seed(6)
+        sim = FastCells("fast", str(work / "out") + os.sep)
+        sim.agent_initials()
+        plain = {name: np.array(sim.__dict__[name], copy=True) for name in sim.agent_array_names}
+        for name in sim.agent_array_names:                    # what the path does to the arrays it touches
+            if sim.__dict__[name].dtype != object:
+                sim.__dict__[name] = track(sim.__dict__[name])
+        assert isinstance(sim.locations, TrackedArray)
+        sim.current_step, sim.step_start = 1, 0.0
+        sim.output_values = sim.output_images = True
+        sim.image_quality = 200
+        sim.method_times = {"get_neighbors": 0.1, "apply_forces": 0.2}
+        with contextlib.redirect_stdout(io.StringIO()):
+            sim.step_values(arrays=["locations", "FGF4", "states", "div_counters"])
+            sim.step_image()
+            sim.data()
+            sim.temp()
+        rows = list(csv.reader(open(os.path.join(sim.values_path, "fast_values_1.csv"))))
+        assert rows[0] == ["locations[0]", "locations[1]", "locations[2]", "FGF4", "states", "div_counters"]
+        assert len(rows) == 1 + sim.number_agents
+        assert np.allclose(np.array(rows[1:], dtype=float)[:, :3], plain["locations"])
+        assert os.path.getsize(os.path.join(sim.images_path, "fast_image_1.png")) > 0
+        data = list(csv.reader(open(os.path.join(sim.main_path, "fast_data.csv"))))
+        assert data[0][4:6] == ["get_neighbors", "apply_forces"] and int(data[1][1]) == sim.number_agents
+        with open(os.path.join(sim.main_path, "fast_temp.pkl"), "rb") as f:
+            back = pickle.load(f)                              # mode 1 (simulation.py:524-536)
+        assert type(back.locations) is np.ndarray and "_b200_engine" not in back.__dict__
+        for name, a in plain.items():
+            assert np.array_equal(back.__dict__[name], a), name
+        assert back.neighbor_graph.vcount() == sim.number_agents and back.current_step == 1
+        # the rules keep working on the reloaded object (plain arrays) and on the live one (tracked arrays) alike
+        for s in (sim, back):
+            with contextlib.redirect_stdout(io.StringIO()):
+                s.cell_division()
+                s.cell_motility()
+            assert len(s.locations) == s.number_agents
     finally:
         os.chdir(cwd)
