@@ -41,8 +41,9 @@ WORKLOADS = {
                desc="configs[1]: 50,000-cell 2D colony, JKR adhesion + FGF4 diffusion (318^2 grid, 10 substeps)"),
     "c3": dict(n=500_000, dim=2, density=0.01, h=7.07106, diffuse_dt=0.24, sd=10,
                desc="configs[2]: 500,000-cell 2D colony + FGF4 diffusion (1002^2 grid, 10 substeps)"),
-    "c4": dict(n=4_000_000, dim=3, density=0.001, h=None, diffuse_dt=None, sd=0,
-               desc="configs[3]: 4,000,000-cell 3D colony (no 3D diffusion in the reference)"),
+    "c4": dict(n=4_000_000, dim=3, density=0.001, h=7.07106, diffuse_dt=0.15 * 7.07106 ** 2 / 50.0, sd=10,
+               desc="configs[3]: 4,000,000-cell 3D colony + FGF4 diffusion on a 3D grid (226^3, 10 substeps; the 3-D "
+                    "stencil is this build's extension, the reference's diffusion is 2-D only)"),
     "c5": dict(n=100_000, dim=2, density=0.01, h=1.5441, diffuse_dt=0.011445, sd=10,
                desc="configs[4]: 100,000 cells on a fine 2048^2 morphogen grid, 10 diffusion substeps"),
 }
@@ -77,7 +78,7 @@ def make_workload(name, seed=0, n_override=None):
     if spec["h"]:
         g = int(np.ceil(side / spec["h"])) + 1      # gradient_size, reference cell_simulation.py:67
         g += g % 2                                  # even row length (TMA row pitch multiple of 16 B)
-        grid = (g, g)
+        grid = (g, g) if spec["dim"] == 2 else (g, g, g)
     return dict(name=name, n=n, size=size, loc=loc, radii=np.full(n, 5.0), mot=mot, grid=grid, spec=spec)
 
 
@@ -157,6 +158,26 @@ def sort_algorithmic_bytes(n, b10, w=W):
     return 7 * w * n + 4 * n + 8 * b10
 
 
+def host_field(wl):
+    """The morphogen field as the reference holds it: (gx, gy, 1) for the 2-D colony (cell_simulation.py:67-69), a
+    full (gx, gy, gz) volume for the 3-D extension."""
+    return np.zeros(wl["grid"] + (1,)) if len(wl["grid"]) == 2 else np.zeros(wl["grid"])
+
+
+def oracle_morphogen_stage(orc, sim, wl):
+    """deposit -> diffusion -> per-cell sampling on the CPU oracle; returns the sampled concentrations."""
+    spec = wl["spec"]
+    args = (spec["sd"], sim.diffuse_dt, sim.diffuse_dt, sim.diffuse_const, sim.spat_res2, sim.max_concentration,
+            sim.degradation)
+    if len(wl["grid"]) == 3:
+        orc.adjust_morphogens3d(sim.locations, 1.0, sim.fgf4_values, sim.spat_res)
+        sim.fgf4_values = orc.diffuse_field3d(sim.fgf4_values, *args)
+    else:
+        orc.adjust_morphogens(sim.locations, 1.0, sim.fgf4_values, sim.spat_res)
+        sim.fgf4_values[:, :, 0] = orc.diffuse_field(sim.fgf4_values[:, :, 0], *args)
+    return orc.get_concentrations(sim.locations, sim.fgf4_values, sim.spat_res)
+
+
 # ---- the CPU arm (oracle port) ----------------------------------------------------------------------------------
 def oracle_step_fn(wl, threads):
     from oracle import oracle as orc
@@ -169,7 +190,7 @@ def oracle_step_fn(wl, threads):
         sim.spat_res, sim.spat_res2, sim.diffuse_const = h, h * h, 50.0
         sim.diffuse_dt = spec["diffuse_dt"]
         sim.max_concentration, sim.degradation = 2.0, 0.1
-        sim.fgf4_values = np.zeros(wl["grid"] + (1,))
+        sim.fgf4_values = host_field(wl)
 
     count = [0]
 
@@ -179,11 +200,7 @@ def oracle_step_fn(wl, threads):
         count[0] += 1
         sim.apply_forces()
         if wl["grid"]:
-            orc.adjust_morphogens(sim.locations, 1.0, sim.fgf4_values, sim.spat_res)
-            sim.fgf4_values[:, :, 0] = orc.diffuse_field(sim.fgf4_values[:, :, 0], spec["sd"], sim.diffuse_dt,
-                                                         sim.diffuse_dt, sim.diffuse_const, sim.spat_res2,
-                                                         sim.max_concentration, sim.degradation)
-            orc.get_concentrations(sim.locations, sim.fgf4_values, sim.spat_res)
+            oracle_morphogen_stage(orc, sim, wl)
     return step
 
 
@@ -286,7 +303,8 @@ def parity_check(name, dev, steps=5, cells=100_000, dtype="f64"):
         for o in (sim, ref):
             o.spat_res, o.spat_res2, o.diffuse_const, o.diffuse_dt = h, h * h, 50.0, spec["diffuse_dt"]
             o.max_concentration, o.degradation = 2.0, 0.1
-            o.fgf4_values = np.zeros(wl["grid"] + (1,))
+            o.fgf4_values = host_field(wl)
+        sim.b200_diffusion_3d = len(wl["grid"]) == 3
     free = Cells(wl["size"], dev)                 # the same colony, never reset to the oracle (free-running drift)
     free.b200_dtype = dtype
     free.add_agents(n)
@@ -338,12 +356,7 @@ def parity_check(name, dev, steps=5, cells=100_000, dtype="f64"):
             sim.update_diffusion("fgf4_values")
             got = sim.update_concentrations("fgf4_values", None)
             sim.step_dt = keep
-            orc.adjust_morphogens(ref.locations, 1.0, ref.fgf4_values, ref.spat_res)
-            keep = ref.step_dt
-            ref.step_dt = spec["diffuse_dt"] * (spec["sd"] - 1) + 0.5 * spec["diffuse_dt"]
-            ref.update_diffusion("fgf4_values")
-            ref.step_dt = keep
-            want = orc.get_concentrations(ref.locations, ref.fgf4_values, ref.spat_res)
+            want = oracle_morphogen_stage(orc, ref, wl)
             out["max_abs_dfield"] = max(out["max_abs_dfield"], float(np.abs(sim.fgf4_values - ref.fgf4_values).max()))
             out["max_abs_dsample"] = max(out["max_abs_dsample"], float(np.abs(np.asarray(got) - want).max()))
     scale = float(np.abs(ref.locations).max())
@@ -457,7 +470,7 @@ def run_b200(args, rank, world, local_rank):
     b15 = int(np.prod(eng.bin_dims(cfg.search_radius)))
     reach = eng.jkr_reach(cfg.contact_radius)
     b10 = int(np.prod(eng.bin_dims(reach)))
-    g = wl["grid"][0] * wl["grid"][1] if wl["grid"] else 0
+    g = int(np.prod(wl["grid"])) if wl["grid"] else 0
     sm = len(pipe.dts)
     bytes_step = step_bytes(n, b15, b10, e15, ej, ej, g, sm, spec["sd"], w_mech)
 
@@ -481,7 +494,7 @@ def run_b200(args, rank, world, local_rank):
             n, _l.i3(srt.dims), cfg.contact_radius, reach, 0, old.row_stride, old.row_len.data_ptr(),
             old.cols.data_ptr(), b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride,
             b["max_len"].data_ptr(), 0, eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0,
-            _l.d3(wl["size"]), 180.0, 0, eng.uniform_radius, None, None, 0, 0, 0, eng.stream), "abm_jkr_substep")
+            _l.d3(wl["size"]), 180.0, 0, eng.uniform_radius, None, None, 0, 0, 0, None, eng.stream), "abm_jkr_substep")
 
     def time_launches(cold, reps=20):
         out = []
@@ -587,7 +600,8 @@ def run_b200(args, rank, world, local_rank):
             sim.diffuse_dt = spec["diffuse_dt"]
             sim.step_dt_diffusion = spec["diffuse_dt"] * spec["sd"]
             sim.max_concentration, sim.degradation = 2.0, 0.1
-            sim.fgf4_values = np.zeros(wl["grid"] + (1,))
+            sim.fgf4_values = host_field(wl)
+            sim.b200_diffusion_3d = len(wl["grid"]) == 3
 
         mot_by_parity = (wl["mot"], -wl["mot"])
         api_count = [0]
@@ -722,7 +736,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         loc, radii, mot, gid = wl["loc"][m], wl["radii"][m], wl["mot"][m], np.nonzero(m)[0]
         n_rank = int(m.sum())
     field = None
-    if wl["grid"]:
+    if wl["grid"] and len(wl["grid"]) == 2:     # the slab path carries the reference's 2-D field only
         gx = int(np.ceil(gsize[0] / spec["h"])) + 1
         field = slab.FieldSlab(geom, (gx, wl["grid"][1]), spec["h"], spec["sd"] + 1, dev)
     # capacities, the same on every rank: the expected cells within `halo` of an interface, with headroom
@@ -749,7 +763,10 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
 
     for _ in range(2 * ((max(args.warmup, 3) + 1) // 2)):       # an even number of eager steps, then capture
         step()
-    ds.check()
+    ds.check(halo=False)
+    # the uniformly random start is violent (a few overlapping pairs fly apart by tens of um in the first substeps);
+    # the halo assumption (DeviceSlab.allowed_substep_move) is verified over the timed steps and reported for these
+    warmup_move = ds.eng.max_substep_move()
     if not args.no_graphs:
         rank_step.capture()
     sampler = ClockSampler(dev.index or 0)
@@ -764,6 +781,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
             step()
         timeline = {k: round(v, 1) for k, v in rank_step.timeline_us().items()}
         rank_step.timeline = None
+    ds.reset_monitor()
     barrier()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for k, (a, b) in enumerate(evs):
@@ -775,7 +793,8 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         b.record()
     barrier()
     clocks = sampler.stop()
-    ds.check()
+    ds.check()                            # capacities, and the halo assumption over the timed steps
+    timed_move = ds.eng.max_substep_move()
     total_s = sum(a.elapsed_time(b) for a, b in evs) / 1e3
     tt = torch.tensor([total_s], device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -816,12 +835,20 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     if rank != 0:
         return None
     value = n_total * args.steps / total_s
+    config = common_config(args.workload, wl, len(cfg.substep_dts()), world, scaling=args.scaling)
+    if wl["grid"] and field is None:
+        config.update(diffusion_substeps=0, grid=None,
+                      field_note="the slab path carries the reference's 2-D field only: this colony's 3-D field stage "
+                                 "is not part of the multi-GPU step")
     return {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": total_s / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": common_config(args.workload, wl, len(cfg.substep_dts()), world, scaling=args.scaling),
+        "config": config,
         "method": {"cells_total": n_total, "halo_um": halo, "rows_capacity": rows, "message_capacity": send_cap,
+                   "halo_check_rank0": {"allowed_ghost_zone_move_per_substep_um": round(ds.allowed_substep_move(), 3),
+                                        "largest_in_timed_steps_um": round(timed_move, 3),
+                                        "largest_in_first_warmup_steps_um": round(warmup_move, 3)},
                    "morphogen_stage": "reference order (before the mechanics), with its row exchange on a second "
                                       "stream beside search + mechanics" if field is not None else "none",
                    "exchanges_per_step": (rank_step.exchanges - ex0) / max(args.steps + e_steps, 1),

@@ -178,7 +178,9 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  *   > row_stride afterwards means those rows were truncated: grow row_stride and redo the substep
  *   from the saved locations.  [1] is raised to the bit pattern of the largest squared displacement (float, um^2)
  *   of a cell in one substep -- what the slab decomposition's halo depth has to be checked against.  The caller
- *   zeroes both.                                                                                    */
+ *   zeroes both.
+ *   move_window_device (2) double, may be NULL: only cells with x < [0] or x > [1] count for max_len[1] (a slab's
+ *   ghost zones: the only place a wrong cell can be while the halo holds); NULL = every cell.        */
 double abm_jkr_reach(double distance, double max_radius, double poisson, double youngs, double adhesion_const);
 
 int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const double *sorted_pos,
@@ -190,7 +192,8 @@ int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_id, const do
                     double poisson, double youngs, double adhesion_const, double stokes,
                     const double size_host[3], double move_dt, const int32_t *global_id, double uniform_radius,
                     const double *next_extent_host, const double *next_origin_host, int32_t *next_bin_counts,
-                    void *next_sort_workspace, const int32_t *n_device, void *stream);
+                    void *next_sort_workspace, const int32_t *n_device, const double *move_window_device,
+                    void *stream);
 
 /* The whole substep loop of CellMethods.apply_forces (cell_methods.py:399-436) enqueued by ONE call:
  * n_substeps x [abm_bin_sort at bin edge `reach` over (origin, extent) + abm_jkr_substep with dts_host[k]].
@@ -207,7 +210,7 @@ int abm_mechanics_loop(const double *radii, double *locations, const double *mot
                        const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
                        int64_t row_stride, int32_t *max_len, const int32_t *global_id, double uniform_radius,
                        double poisson, double youngs, double adhesion_const, double stokes, int flags,
-                       const int32_t *n_device, void *stream);
+                       const int32_t *n_device, const double *move_window_device, void *stream);
 
 /* ---- morphogen diffusion ---------------------------------------------------------------------------
  * Replaces CellMethods.update_diffusion + update_diffusion_jit (cell_methods.py:441-468,

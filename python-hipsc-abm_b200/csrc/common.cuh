@@ -171,11 +171,15 @@ __device__ __forceinline__ int device_count(int n, const int *__restrict__ n_dev
 
 // Largest squared displacement of a cell in one substep, kept as the bit pattern of a non-negative float (ordered like
 // an int) in max_len[1]: the slab decomposition's halo depth assumes a bound on it (slab.required_halo) and checks
-// the assumption after the fact.  One REDUX and one atomic per warp.
-__device__ __forceinline__ void record_move(int *__restrict__ max_len, float d2) {
+// the assumption after the fact.  window (device, may be null = every cell): only cells with x < window[0] or
+// x > window[1] are looked at -- a slab's ghost zones, the only place where a wrong cell can exist while the halo
+// holds.  One REDUX and one atomic per warp.
+__device__ __forceinline__ void record_move(int *__restrict__ max_len, const double *__restrict__ window, double x,
+                                            float d2) {
+    if (window && x >= __ldg(window) && x <= __ldg(window + 1)) d2 = 0.0f;
     const unsigned active = __activemask();
     const int bits = __reduce_max_sync(active, __float_as_int(d2 >= 0.0f ? d2 : 0.0f));
-    if ((int)(threadIdx.x & 31) == __ffs(active) - 1) atomicMax(max_len + 1, bits);
+    if (bits && (int)(threadIdx.x & 31) == __ffs(active) - 1) atomicMax(max_len + 1, bits);
 }
 
 // ---- warp helpers ----------------------------------------------------------------------------------

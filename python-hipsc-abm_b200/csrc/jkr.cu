@@ -201,7 +201,7 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
               int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
               double stokes, Friction fric, Box box, double dt, const int *__restrict__ gid_of,
               const int *__restrict__ slot_pid, NextSort next, int sort_rows, const int *__restrict__ prev_slot,
-              int row_keys, const int *__restrict__ n_dev) {
+              int row_keys, const int *__restrict__ n_dev, const double *__restrict__ move_window) {
     // column tid: first the parked partner slots, then (overwritten from the front) the ids of the new bond row
     __shared__ int column[kMaxHits][kJkrThreads];
     __shared__ float4 tiles[kJkrThreads / 32][kTileRows * kTileCap];
@@ -492,7 +492,8 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     const double nx = stokes_move_y(p.x, mx, (double)fxi * kForceUnit, friction, inv_f, dt, box.size[0]);
     const double ny = stokes_move_y(p.y, my, (double)fyi * kForceUnit, friction, inv_f, dt, box.size[1]);
     const double nz = stokes_move_y(p.z, mz, (double)fzi * kForceUnit, friction, inv_f, dt, box.size[2]);
-    record_move(max_len, (float)((nx - p.x) * (nx - p.x) + (ny - p.y) * (ny - p.y) + (nz - p.z) * (nz - p.z)));
+    record_move(max_len, move_window,  p.x,
+                (float)((nx - p.x) * (nx - p.x) + (ny - p.y) * (ny - p.y) + (nz - p.z) * (nz - p.z)));
     if (loc) {
         loc[3 * (long long)i + 0] = nx;
         loc[3 * (long long)i + 1] = ny;
@@ -556,7 +557,7 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                             const double *next_extent_host, const double *next_origin_host,
                             int32_t *next_bin_counts, void *next_sort_workspace, void *stream,
                             const int32_t *prev_slot = nullptr, int row_keys = 0, bool chained = false,
-                            const int32_t *n_device = nullptr) {
+                            const int32_t *n_device = nullptr, const double *move_window = nullptr) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(!(row_keys & 1) || prev_slot, "rows keyed by the previous slot need the prev_slot index");
@@ -601,7 +602,7 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                                      Radius(distance), reach * reach, BandConst::make(reach * 1.0000001), old,
                                      new_row_len, new_cols, (int)row_stride, max_len, motility_forces, locations, c,
                                      stokes, fric, box, move_dt, global_id, global_id ? slot_gid : sorted_id, next,
-                                     sort_rows, prev_slot, row_keys, n_device),
+                                     sort_rows, prev_slot, row_keys, n_device, move_window),
                       "k_jkr_substep");
 }
 
@@ -614,12 +615,13 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
                                double adhesion_const, double stokes, const double size_host[3], double move_dt,
                                const int32_t *global_id, double uniform_radius, const double *next_extent_host,
                                const double *next_origin_host, int32_t *next_bin_counts, void *next_sort_workspace,
-                               const int32_t *n_device, void *stream) {
+                               const int32_t *n_device, const double *move_window_device, void *stream) {
     return jkr_substep_impl(bin_start, sorted_id, sorted_pos, sorted_bin, n, dims_host, distance, reach,
                             old_row_start, old_row_stride, old_row_len, old_cols, new_row_len, new_cols, row_stride,
                             max_len, sort_rows, motility_forces, locations, poisson, youngs, adhesion_const, stokes,
                             size_host, move_dt, global_id, nullptr, uniform_radius, next_extent_host,
-                            next_origin_host, next_bin_counts, next_sort_workspace, stream, nullptr, 0, false, n_device);
+                            next_origin_host, next_bin_counts, next_sort_workspace, stream, nullptr, 0, false, n_device,
+                            move_window_device);
 }
 
 // The whole substep loop of CellMethods.apply_forces (reference cell_methods.py:399-436) enqueued by one call:
@@ -637,7 +639,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                                   int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
                                   int32_t *max_len, const int32_t *global_id, double uniform_radius, double poisson,
                                   double youngs, double adhesion_const, double stokes, int flags,
-                                  const int32_t *n_device, void *stream) {
+                                  const int32_t *n_device, const double *move_window_device, void *stream) {
     ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
     if (flags & ABM_LOOP_FP32)
         return mechanics_loop32(radii, locations, motility_forces, n, extent_host, origin_host, size_host, distance,
@@ -645,7 +647,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                                 sorted_bin, max_count, sort_workspace, sort_workspace_bytes, old_row_start,
                                 old_row_stride, old_row_len, old_cols, len_a, cols_a, len_b, cols_b, row_stride,
                                 max_len, global_id, uniform_radius, poisson, youngs, adhesion_const, stokes, flags,
-                                n_device, stream);
+                                n_device, move_window_device, stream);
     const bool carry_in = (flags & ABM_LOOP_CARRY_IN) && n > 0 && n_substeps > 0;
     const bool carry_out = (flags & ABM_LOOP_CARRY_OUT) && n > 0;
     const bool chained = flags & ABM_LOOP_CHAINED;
@@ -683,7 +685,8 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                               motility_forces, last ? locations : nullptr, poisson, youngs, adhesion_const, stokes,
                               size_host, dts_host[k], global_id, slot_gid, uniform_radius,
                               prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
-                              prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained, n_device);
+                              prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained, n_device,
+                              move_window_device);
         if (rc) return rc;
         cur_start = nullptr;
         cur_stride = row_stride;

@@ -172,7 +172,8 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
                 float dist2, float reach2, BandConst bandc, GraphView old, int *__restrict__ new_len,
                 int *__restrict__ new_cols, int stride, int *__restrict__ max_len, const double *__restrict__ mot,
                 double *__restrict__ loc, Contact32 c, float dt, const int *__restrict__ gid_of,
-                const int *__restrict__ slot_pid, Next32 next, int sort_rows, const int *__restrict__ n_dev) {
+                const int *__restrict__ slot_pid, Next32 next, int sort_rows, const int *__restrict__ n_dev,
+                const double *__restrict__ move_window) {
     __shared__ int column[k32MaxHits][k32Threads];
     __shared__ float4 tiles[k32Threads / 32][kTileRows * kTileCap];
     pdl_launch_dependents();
@@ -380,7 +381,7 @@ k_jkr_substep32(const int *__restrict__ bin_start, const int *__restrict__ sorte
         moved2 += (float)((x - x0) * (x - x0));
         offset_of(x, L.origin[k], L.edge, L.inv_edge, L.dims[k], nb[k], no[k]);
     }
-    record_move(max_len, moved2);
+    record_move(max_len, move_window, nx[0], moved2);
     if (loc) {
         loc[3 * (long long)i + 0] = nx[0];
         loc[3 * (long long)i + 1] = nx[1];
@@ -414,7 +415,7 @@ int abm::mechanics_loop32(const double *radii, double *locations, const double *
                           const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
                           int64_t row_stride, int32_t *max_len, const int32_t *global_id, double uniform_radius,
                           double poisson, double youngs, double adhesion_const, double stokes, int flags,
-                          const int32_t *n_device, void *stream) {
+                          const int32_t *n_device, const double *move_window, void *stream) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff && n_substeps >= 0 && dts_host, "bad sizes");
     if (n == 0 || n_substeps == 0) return 0;
     const bool carry_in = flags & ABM_LOOP_CARRY_IN, carry_out = flags & ABM_LOOP_CARRY_OUT;
@@ -510,7 +511,7 @@ int abm::mechanics_loop32(const double *radii, double *locations, const double *
                                        BandConst::make(reach * 1.0000001), cur, nl, nc, (int)row_stride, max_len,
                                        motility_forces, last ? locations : (double *)nullptr, c, (float)dts_host[k],
                                        global_id, global_id ? (const int *)w.slot_gid : (const int *)sorted_id, next,
-                                       last ? 1 : 0, n_device),
+                                       last ? 1 : 0, n_device, move_window),
                         "k_jkr_substep32");
         if (rc) return rc;
         cur = GraphView{nullptr, (long long)row_stride, nl, nc};

@@ -76,7 +76,7 @@ int mechanics_loop32(const double *radii, double *locations, const double *motil
                      const int32_t *old_cols, int32_t *len_a, int32_t *cols_a, int32_t *len_b, int32_t *cols_b,
                      int64_t row_stride, int32_t *max_len, const int32_t *global_id, double uniform_radius,
                      double poisson, double youngs, double adhesion_const, double stokes, int flags,
-                     const int32_t *n_device, void *stream);
+                     const int32_t *n_device, const double *move_window, void *stream);
 
 __device__ __forceinline__ int cell_bin_of(double x, double y, double z, const BinGeom &g) {
     return lin_bin(bin_coord_fast(x - g.origin[0], g.distance, g.inv_distance, g.dims[0]),

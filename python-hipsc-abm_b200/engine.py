@@ -185,6 +185,7 @@ class ColonyEngine:
         self.stream = 0
         # per-engine launch options (arguments of the calls they affect; the library has no process-wide switches)
         self.chained_launch = False     # abm_mechanics_loop(ABM_LOOP_CHAINED): programmatic dependent launches
+        self.move_window = None         # device (2,) float64: only cells with x outside it count for max_substep_move()
         self.mechanics_dtype = "f64"    # "f32": abm_mechanics_loop(ABM_LOOP_FP32), bin-relative single precision
         self.diffusion_fuse = int(os.environ.get("ABM_B200_DIFFUSION_FUSE", "0"))   # substeps per launch, 0 = 5
         self.use_current_stream()
@@ -564,7 +565,8 @@ class ColonyEngine:
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
             _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),
             stride, _ptr(b["max_len"]), _ptr(self.global_id), float(self.uniform_radius), JKR_POISSON, JKR_YOUNGS,
-            JKR_ADHESION, float(stokes), flags, _ptr(self.n_device), self.stream), "abm_mechanics_loop")
+            JKR_ADHESION, float(stokes), flags, _ptr(self.n_device), _ptr(self.move_window), self.stream),
+            "abm_mechanics_loop")
         # the last substep k = K-1 sorted with table (first + K-1) % 2 and left the next histogram in the other one
         self._carry = key + ((first + len(dts)) % 2,) if flags & _lib.LOOP_CARRY_OUT else None
         # first substep: histogram, scan x2, scatter, substep (scan, rescatter, substep when the cells were handed

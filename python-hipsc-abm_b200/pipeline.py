@@ -30,7 +30,7 @@ class StepConfig:
     step_dt: float = 1800.0              # cell_simulation.py:34
     move_dt: float = 180.0               # cell_simulation.py:35
     # morphogen field (None -> no diffusion stage)
-    grid: Optional[tuple] = None         # (gx, gy)
+    grid: Optional[tuple] = None         # (gx, gy): the reference's 2-D field; (gx, gy, gz): the 3-D extension
     spat_res: float = 7.07106
     diffuse_const: float = 50.0
     diffuse_dt: float = 0.24
@@ -87,9 +87,9 @@ class HotPathStep:
         self.bonds: Optional[GraphTensors] = None
         self.parity = 0
         self.field = self.scratch = self.amounts = self.sampled = None
+        self.volume = cfg.grid is not None and len(cfg.grid) == 3     # 3-D field: 7-point stencil, 8-corner deposit
         if cfg.grid is not None:
-            gx, gy = cfg.grid
-            self.field = torch.zeros((gx, gy), dtype=torch.float64, device=dev)
+            self.field = torch.zeros(tuple(int(g) for g in cfg.grid), dtype=torch.float64, device=dev)
             self.scratch = torch.empty_like(self.field)
             self.amounts = torch.full((max(n, 1),), cfg.deposit_amount, dtype=torch.float64, device=dev)
             # one persistent result buffer: every captured graph writes the same tensor (a buffer allocated during a
@@ -155,12 +155,14 @@ class HotPathStep:
     def _morphogen(self, loc):
         """deposit -> diffuse -> sample on the engine's current stream (loc=None: the engine's positions)."""
         eng, cfg = self.eng, self.cfg
-        eng.deposit(self.field, self.amounts, cfg.spat_res, loc=loc)
+        eng.deposit(self.field, self.amounts, cfg.spat_res, loc=loc, cube=self.volume)
         last = cfg.diffuse_dt if cfg.diffuse_last_dt is None else cfg.diffuse_last_dt
-        out = eng.diffuse(self.field, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const,
-                          cfg.spat_res ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma,
-                          scratch=self.scratch)
-        assert out.data_ptr() == self.field.data_ptr()
+        diffuse = eng.diffuse3d if self.volume else eng.diffuse
+        out = diffuse(self.field, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const,
+                      cfg.spat_res ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma,
+                      scratch=self.scratch)
+        if out.data_ptr() != self.field.data_ptr():      # (3-D, odd substep count: the result is in the scratch volume)
+            self.field.copy_(out)
         eng.sample(self.field, cfg.spat_res, loc=loc, out=self.sampled)
 
     def step(self):

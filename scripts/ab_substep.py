@@ -74,7 +74,7 @@ else:
             n, _l.i3(srt.dims), 10.0, reach, 0, old.row_stride, old.row_len.data_ptr(), old.cols.data_ptr(),
             b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride, b["max_len"].data_ptr(), 0,
             eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0, _l.d3(wl["size"]), 180.0, 0,
-            eng.uniform_radius, None, None, 0, 0, 0, eng.stream), "abm_jkr_substep")
+            eng.uniform_radius, None, None, 0, 0, 0, None, eng.stream), "abm_jkr_substep")
     res = {}
     for cold in (True, False):
         ts = []

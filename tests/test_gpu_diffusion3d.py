@@ -77,3 +77,46 @@ def test_method_surface_3d_extension_and_reference_plane_semantics():
             ref[:, :, 0] = orc.diffuse_field(ref[:, :, 0], 4, dt, 0.5 * dt, D, H * H, 2.0, 0.1)
         assert np.abs(sim.fgf4_values - ref).max() <= 1e-12   # deposits are fp64 atomics: order-dependent last bits
         assert np.abs(sampled - orc.get_concentrations(loc, ref, H)).max() <= 1e-12
+
+
+@pytest.mark.parametrize("substeps", [4, 5])
+def test_hot_path_step_carries_a_3d_field(substeps):
+    """pipeline.HotPathStep with a (gx,gy,gz) grid: deposit over the cube corners, 7-point diffusion, sampling, on the
+    step's starting positions, beside the mechanics -- also when replayed as a CUDA graph."""
+    from hipsc_abm_b200.pipeline import HotPathStep, StepConfig
+    rng = np.random.default_rng(8)
+    n, grid = 4000, (24, 20, 16)
+    size = np.array([(grid[0] - 1) * H, (grid[1] - 1) * H, (grid[2] - 1) * H])
+    loc = rng.random((n, 3)) * size
+    dt = 0.15 * H * H / D
+    cfg = StepConfig(grid=grid, spat_res=H, diffuse_dt=dt, diffuse_steps=substeps, bond_stride=32,
+                     search_cols_per_cell=60.0)
+    ref = np.zeros(grid)
+    pos = loc.copy()
+    want = []
+    for graph in (False, True):
+        eng = ColonyEngine(size)
+        eng.upload(loc, np.full(n, 5.0), np.zeros((n, 3)))
+        one = HotPathStep(eng, cfg)
+        if graph:
+            one.step(); one.step()
+            one.capture()
+            for _ in range(2):
+                one.replay()
+        else:
+            for _ in range(4):
+                one.step()
+        torch.cuda.synchronize()
+        one.check()
+        want.append((one.field.cpu().numpy(), one.sampled[:n].cpu().numpy(), eng.locations_host().copy()))
+    # the oracle: four steps of deposit / diffuse / sample on the positions each step starts from
+    sim = orc.OracleSim(loc, np.full(n, 5.0), size)
+    for _ in range(4):
+        orc.adjust_morphogens3d(sim.locations, 1.0, ref, H)
+        ref = orc.diffuse_field3d(ref, substeps, dt, dt, D, H * H, 2.0, 0.1)
+        sampled = orc.get_concentrations(sim.locations, ref, H)
+        sim.apply_forces()
+    for field, got, _ in want:
+        assert np.abs(field - ref).max() <= 1e-11
+        assert np.abs(got - sampled).max() <= 1e-11
+    assert np.array_equal(want[0][2], want[1][2])

@@ -229,7 +229,7 @@ def test_mechanics_loop_equals_substep_by_substep():
                 old[0].data_ptr() if old is not None else 0, old[1].data_ptr() if old is not None else 0,
                 lens[k & 1].data_ptr(), rows[k & 1].data_ptr(), stride, worst.data_ptr(), int(k == len(dts) - 1),
                 b.mot.data_ptr(), b.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0, _lib.d3(size), dt, 0,
-                b.uniform_radius, None, None, 0, 0, 0, b.stream), "abm_jkr_substep")
+                b.uniform_radius, None, None, 0, 0, 0, None, b.stream), "abm_jkr_substep")
             old = (lens[k & 1], rows[k & 1])
         assert int(worst[0].item()) <= stride
         assert torch.equal(a.loc, b.loc), f"{dim}-D positions differ"

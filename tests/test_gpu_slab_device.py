@@ -16,6 +16,20 @@ from test_gpu_slab import bonds_as_gid_edges
 pytestmark = pytest.mark.gpu
 
 
+def relaxed(loc, size, steps=3):
+    """A uniformly random start has a few cell pairs almost on top of each other; they fly apart by tens of um in the
+    first substeps, more than any reasonable halo depth allows for (DeviceSlab.allowed_substep_move).  Let the colony
+    settle for a few single-domain steps first."""
+    eng = ColonyEngine(size)
+    eng.upload(loc, np.full(len(loc), 5.0), np.zeros_like(loc))
+    one = HotPathStep(eng, StepConfig(bond_stride=32, search_cols_per_cell=40.0))
+    for _ in range(steps):
+        one.step()
+    torch.cuda.synchronize()
+    one.check()
+    return eng.locations_host().copy()
+
+
 @pytest.mark.parametrize("graphs", [False, True], ids=["eager", "graphs"])
 @pytest.mark.parametrize("world,dim", [(3, 2), (2, 3)])
 def test_emulated_device_slabs_match_single_domain(world, dim, graphs):
@@ -27,7 +41,7 @@ def test_emulated_device_slabs_match_single_domain(world, dim, graphs):
     else:
         size, n = np.array([700.0, 120.0, 120.0]), 9000
         h, sd, grid = 1.0, 0, None
-    loc = rng.random((n, 3)) * size
+    loc = relaxed(rng.random((n, 3)) * size, size)
     mot = rng.normal(0, 1.5e-9, (n, 3)) * (np.array([1, 1, 0]) if dim == 2 else 1)
     radii = np.full(n, 5.0)
     steps = 6
@@ -113,14 +127,25 @@ def test_capacity_overflows_are_reported_not_silent():
 
 
 def test_halo_depth_assumption_is_verified():
-    """slab.required_halo assumes no cell moves more than slack/2 per substep; the mechanics kernel records the
-    largest substep displacement and check() compares."""
+    """slab.required_halo assumes no ghost-zone cell moves more than `slack` per substep; the mechanics kernel records
+    the largest such displacement and check() compares."""
     rng = np.random.default_rng(2)
     size, n = np.array([900.0, 300.0, 0.0]), 3500
-    loc = rng.random((n, 3)) * size
+    loc = relaxed(rng.random((n, 3)) * size, size)
     mot = rng.normal(0, 2e-9, (n, 3)) * [1, 1, 0]
     cfg = StepConfig(bond_stride=32, search_cols_per_cell=40.0)
     dev = torch.device("cuda")
+    # two cells almost on top of each other deep inside rank 0's OWNED zone: they fly apart by far more than the
+    # halo allows for, but only ghost-zone cells matter (the move window), so the check must not trip over them
+    loc = np.concatenate([loc, [[200.0, 150.0, 0.0], [200.02, 150.0, 0.0]]])
+    mot = np.concatenate([mot, np.zeros((2, 3))])
+    n += 2
+    eng = ColonyEngine(size)
+    eng.upload(loc, np.full(n, 5.0), mot)
+    one = HotPathStep(eng, cfg)
+    one.step()
+    torch.cuda.synchronize()
+    assert eng.max_substep_move() > 8.0                     # no window: every cell counts
     for slack, ok in ((6.0, True), (0.05, False)):          # 2 nN moves a cell ~0.4 um per substep, contacts more
         halo = slab.required_halo(11, 10.3100107, slack=slack)
         steppers = []
