@@ -90,7 +90,7 @@ def test_hot_path_step_carries_a_3d_field(substeps):
     loc = rng.random((n, 3)) * size
     dt = 0.15 * H * H / D
     cfg = StepConfig(grid=grid, spat_res=H, diffuse_dt=dt, diffuse_steps=substeps, bond_stride=32,
-                     search_cols_per_cell=60.0)
+                     search_cols_per_cell=60.0, overlap_morphogen=True)       # the reference's order of the stages
     ref = np.zeros(grid)
     pos = loc.copy()
     want = []
