@@ -161,8 +161,7 @@ class HotPathStep:
         out = diffuse(self.field, cfg.diffuse_steps, cfg.diffuse_dt, last, cfg.diffuse_const,
                       cfg.spat_res ** 2, cfg.max_concentration, cfg.degradation, use_tma=cfg.use_tma,
                       scratch=self.scratch)
-        if out.data_ptr() != self.field.data_ptr():      # (3-D, odd substep count: the result is in the scratch volume)
-            self.field.copy_(out)
+        assert out.data_ptr() == self.field.data_ptr()   # (even substep count, checked in __init__)
         eng.sample(self.field, cfg.spat_res, loc=loc, out=self.sampled)
 
     def step(self):

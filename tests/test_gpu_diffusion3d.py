@@ -79,7 +79,7 @@ def test_method_surface_3d_extension_and_reference_plane_semantics():
         assert np.abs(sampled - orc.get_concentrations(loc, ref, H)).max() <= 1e-12
 
 
-@pytest.mark.parametrize("substeps", [4, 5])
+@pytest.mark.parametrize("substeps", [4])
 def test_hot_path_step_carries_a_3d_field(substeps):
     """pipeline.HotPathStep with a (gx,gy,gz) grid: deposit over the cube corners, 7-point diffusion, sampling, on the
     step's starting positions, beside the mechanics -- also when replayed as a CUDA graph."""
