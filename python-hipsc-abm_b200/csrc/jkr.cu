@@ -96,6 +96,9 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 //   2: start fetching the previous bond row at the first shell partner             (slower: register pressure)
 //   4: TIMING ABLATION, WRONG RESULTS: skip the contact loop                        (attributes 23 of 56 us)
 //   8: TIMING ABLATION, WRONG RESULTS: skip the candidate walk                      (attributes  9 of 56 us)
+//  64: TIMING ABLATION, WRONG RESULTS (2-D only): the contact loop takes the partner's position (fp32, from the
+//      warp tile) and "id" (its slot) from shared memory instead of gathering spos[] / the id table from global
+//      memory -- an upper bound on what staging fp64 positions and ids with the tile could gain
 //  16: bond rows keyed by sorted slot between the substeps of abm_mechanics_loop (written coalesced; the previous
 //      row is found through the prev_slot index the placement kernel records); the first substep still reads and
 //      the last one still writes rows keyed by cell id                               (written blind: not yet measured)
@@ -109,8 +112,8 @@ k_integrate(const double *__restrict__ jkr, const double *__restrict__ mot, doub
 #ifndef ABM_JKR_EXP
 #define ABM_JKR_EXP 0
 #endif
-#if (ABM_JKR_EXP & 12) && !defined(ABM_ALLOW_WRONG_RESULTS)
-#error "ABM_JKR_EXP bits 4 and 8 are timing ablations that produce wrong results: add -DABM_ALLOW_WRONG_RESULTS"
+#if (ABM_JKR_EXP & (12 | 64)) && !defined(ABM_ALLOW_WRONG_RESULTS)
+#error "ABM_JKR_EXP bits 4, 8 and 64 are timing ablations that produce wrong results: add -DABM_ALLOW_WRONG_RESULTS"
 #endif
 #ifndef ABM_PDL_LATE
 #define ABM_PDL_LATE 0      // 1: trigger the dependent launch after the contact loop instead of at kernel entry
@@ -255,7 +258,11 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
                 const float s2f = fmaf(dzf, dzf, fmaf(dy, dy, dx * dx));
                 const int t = __float_as_int(q.w);
                 if (s2f <= t_out && t != s) {
+#if ABM_JKR_EXP & 64
+                    if (nh < kMaxHits) column[nh][tid] = R.first[r] + u;
+#else
                     if (nh < kMaxHits) column[nh][tid] = t;
+#endif
                     ++nh;
                 }
             }
@@ -345,17 +352,33 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     if (!slow) {
         // ---- phase 2: exact distances and the contact model over the parked partners ---------------------------
         // (the next partner's position and id are fetched while the current one is evaluated)
+#if ABM_JKR_EXP & 64
+        auto fetch = [&](int e, int &t, double4 &q, int &j) {
+            const float4 qf = tile[e];
+            t = __float_as_int(qf.w);
+            q = make_double4(org.x + (double)qf.x, org.y + (double)qf.y, org.z + (double)qf.z, p.w);
+            j = t;
+        };
+        int t_next = s, j_next = 0;
+        double4 q_next = p;
+        if (nh > 0) fetch(column[0][tid], t_next, q_next, j_next);
+#else
         int t_next = nh > 0 ? column[0][tid] : s;
         double4 q_next = spos[t_next];
         int j_next = first_hop[t_next];
+#endif
         for (int k = 0; k < nh; ++k) {
             const int t = t_next;
             const double4 q = q_next;
             int j = j_next;
             if (k + 1 < nh) {
+#if ABM_JKR_EXP & 64
+                fetch(column[k + 1][tid], t_next, q_next, j_next);
+#else
                 t_next = column[k + 1][tid];
                 q_next = spos[t_next];
                 j_next = first_hop[t_next];
+#endif
             }
             const double vx = p.x - q.x, vy = p.y - q.y, vz = p.z - q.z;
             const double s2 = sumsq_nofma(vx, vy, vz);

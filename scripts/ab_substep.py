@@ -15,6 +15,7 @@ VARIANTS = {                      # -D switches of csrc/jkr.cu (see the comment 
     "early_motility": ["ABM_JKR_EXP=1"], "early_old_row": ["ABM_JKR_EXP=2"],
     "no_contact_loop": ["ABM_JKR_EXP=4", "ABM_ALLOW_WRONG_RESULTS"],            # timing ablations
     "no_walk_no_contact": ["ABM_JKR_EXP=12", "ABM_ALLOW_WRONG_RESULTS"],
+    "no_gather": ["ABM_JKR_EXP=64", "ABM_ALLOW_WRONG_RESULTS"],                 # partner data from shared memory (2-D)
     "no_pdl": ["ABM_PDL=0"],
     "pdl_late": ["ABM_PDL_LATE=1"],        # dependent launch triggered after the contact loop (run with ABM_B200_GRAPH_PDL=1)
     "trim_math": ["ABM_JKR_EXP=32"],       # Horner polynomial + rsqrt without special cases (written without a GPU)
