@@ -164,11 +164,13 @@ def host_field(wl):
     return np.zeros(wl["grid"] + (1,)) if len(wl["grid"]) == 2 else np.zeros(wl["grid"])
 
 
-def oracle_morphogen_stage(orc, sim, wl):
-    """deposit -> diffusion -> per-cell sampling on the CPU oracle; returns the sampled concentrations."""
+def oracle_morphogen_stage(orc, sim, wl, last_dt=None):
+    """deposit -> diffusion -> per-cell sampling on the CPU oracle; returns the sampled concentrations.
+    last_dt: dt of the last diffusion substep (default: a full diffuse_dt, what HotPathStep runs; the reference-facing
+    update_diffusion takes it from divmod(step_dt, diffuse_dt), cell_methods.py:447-448)."""
     spec = wl["spec"]
-    args = (spec["sd"], sim.diffuse_dt, sim.diffuse_dt, sim.diffuse_const, sim.spat_res2, sim.max_concentration,
-            sim.degradation)
+    args = (spec["sd"], sim.diffuse_dt, sim.diffuse_dt if last_dt is None else last_dt, sim.diffuse_const,
+            sim.spat_res2, sim.max_concentration, sim.degradation)
     if len(wl["grid"]) == 3:
         orc.adjust_morphogens3d(sim.locations, 1.0, sim.fgf4_values, sim.spat_res)
         sim.fgf4_values = orc.diffuse_field3d(sim.fgf4_values, *args)
@@ -351,12 +353,16 @@ def parity_check(name, dev, steps=5, cells=100_000, dtype="f64"):
         sim.locations = ref.locations.copy()      # teacher forcing: the next step starts from the oracle's positions
         if wl["grid"]:
             keep = sim.step_dt
+            # update_diffusion runs divmod(step_dt, diffuse_dt)[0] + 1 substeps, the last one with the remainder as its
+            # dt (cell_methods.py:447-448): sd substeps, the last of them half a diffuse_dt long -- on both arms
             sim.step_dt = spec["diffuse_dt"] * (spec["sd"] - 1) + 0.5 * spec["diffuse_dt"]
+            q, last_dt = divmod(sim.step_dt, spec["diffuse_dt"])
+            assert int(q) + 1 == spec["sd"]
             sim.update_concentrations("fgf4_values", 1.0, sample=False)
             sim.update_diffusion("fgf4_values")
             got = sim.update_concentrations("fgf4_values", None)
             sim.step_dt = keep
-            want = oracle_morphogen_stage(orc, ref, wl)
+            want = oracle_morphogen_stage(orc, ref, wl, last_dt=last_dt)
             out["max_abs_dfield"] = max(out["max_abs_dfield"], float(np.abs(sim.fgf4_values - ref.fgf4_values).max()))
             out["max_abs_dsample"] = max(out["max_abs_dsample"], float(np.abs(np.asarray(got) - want).max()))
     scale = float(np.abs(ref.locations).max())
@@ -488,12 +494,16 @@ def run_b200(args, rank, world, local_rank):
     loc_save = eng.loc.clone()
     lib, _l = eng.lib, hipsc_abm_b200._lib
 
+    # a flat world's substeps run the two-axis kernel (every z is exactly 0 after the first substep: jkr_plane.cuh)
+    plane = spec["dim"] == 2 and eng.plane_kernel
+    sub_flags = _l.SUBSTEP_FLAT_Z if plane else 0
+
     def launch_substep():
         _l.check(lib.abm_jkr_substep(
             srt.bin_start.data_ptr(), srt.sorted_id.data_ptr(), srt.sorted_pos.data_ptr(), srt.sorted_bin.data_ptr(),
             n, _l.i3(srt.dims), cfg.contact_radius, reach, 0, old.row_stride, old.row_len.data_ptr(),
             old.cols.data_ptr(), b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride,
-            b["max_len"].data_ptr(), 0, eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0,
+            b["max_len"].data_ptr(), sub_flags, eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0,
             _l.d3(wl["size"]), 180.0, 0, eng.uniform_radius, None, None, 0, 0, 0, None, eng.stream), "abm_jkr_substep")
 
     def time_launches(cold, reps=20):
@@ -523,7 +533,7 @@ def run_b200(args, rank, world, local_rank):
     eng.loc.copy_(loc_save)
     kbytes = substep_kernel_bytes(n, b10, ej)
     abytes = substep_algorithmic_bytes(n, b10, ej, ej)
-    kernel_name, bytes_model = "k_jkr_substep<uniform radius>", (
+    kernel_name, bytes_model = ("k_jkr_substep_plane<uniform radius>" if plane else "k_jkr_substep<uniform radius>"), (
         "SURVEY 8(d) algorithmic bytes of the stages the launch fuses: search(r=10) + merge/dedupe + force + integrate")
     if args.dtype == "f32":
         cold_us, hot_us = cold_us / sm, hot_us / sm

@@ -56,6 +56,14 @@ extern "C" {
                                  path per step; clamp and re-binning stay exact (fp64).  Inputs and outputs keep their
                                  fp64 types.  Bond sets may differ from the fp64 path for pairs within ~1e-6 um of a
                                  threshold.  (csrc/jkr32.cu) */
+#define ABM_SUBSTEP_SORT_ROWS 1 /* bits of abm_jkr_substep's sort_rows argument: ascending bond rows */
+#define ABM_SUBSTEP_FLAT_Z 2    /* ... the caller vouches that size[2] == 0 AND every z in sorted_pos is exactly +0.0 (true for
+                                   positions any substep of a flat world has produced): the two-axis kernel
+                                   k_jkr_substep_plane runs, which computes the same bits (csrc/jkr_plane.cuh) */
+#define ABM_LOOP_NO_PLANE 16  /* abm_mechanics_loop: keep the three-axis kernel also in a flat (size[2] == 0) world.  By
+                                 default the substeps whose input z is known to be exactly 0 (all but the first of a
+                                 call without ABM_LOOP_CARRY_IN) run k_jkr_substep_plane, which computes the same bits
+                                 (csrc/jkr_plane.cuh); the flag exists for the test that compares the two */
 #define ABM_LOOP_CHAINED 4    /* abm_mechanics_loop: launch the kernels of the loop with programmatic stream
                                  serialization, so that a kernel's CTAs become resident while the last wave of its
                                  predecessor drains (they wait for its completion before touching memory) */
@@ -158,7 +166,7 @@ int abm_apply_forces(const double *jkr_forces, const double *motility_forces, do
  * Input: a sort of the CURRENT locations made with bin edge >= abm_jkr_reach() (so every bond that
  * can survive lies inside the 27-bin stencil), the bond graph from the previous substep (old_*; rows
  * may be unsorted) and the motility forces.  Output: the new bond graph in fixed-stride rows
- * (row i at new_cols[i*row_stride], length new_row_len[i], ascending if sort_rows) and the moved locations
+ * (row i at new_cols[i*row_stride], length new_row_len[i], ascending if sort_rows & 1) and the moved locations
  * (written in place; the kernel only reads positions from sorted_pos).  The force on a cell is summed in
  * 2^-76 N fixed point (integer adds are associative), so it does not depend on the order inside the bins.
  * A bond (i,j) exists afterwards iff (dist <= distance or it existed before) and d > -0.360562.

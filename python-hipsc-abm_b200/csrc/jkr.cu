@@ -536,8 +536,9 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     }
 }
 
-
 }  // namespace abm
+
+#include "jkr_plane.cuh"
 
 using namespace abm;
 
@@ -580,7 +581,8 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                             const double *next_extent_host, const double *next_origin_host,
                             int32_t *next_bin_counts, void *next_sort_workspace, void *stream,
                             const int32_t *prev_slot = nullptr, int row_keys = 0, bool chained = false,
-                            const int32_t *n_device = nullptr, const double *move_window = nullptr) {
+                            const int32_t *n_device = nullptr, const double *move_window = nullptr,
+                            bool plane = false) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(!(row_keys & 1) || prev_slot, "rows keyed by the previous slot need the prev_slot index");
@@ -619,6 +621,18 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
         fric.uni = f;
         fric.uni_inv = 1.0 / f;
     }
+#if ABM_JKR_EXP == 0
+    // flat world, every z known to be exactly 0 (see jkr_plane.cuh): the two-axis kernel computes the same bits
+    if (plane && stc.dims[2] == 1 && size_host[2] == 0.0) {
+        auto kp = uniform_radius > 0 ? k_jkr_substep_plane<true> : k_jkr_substep_plane<false>;
+        return check_cuda(launch_chained(kp, ceil_div(n, kJkrThreads), kJkrThreads, as_stream(stream), chained, bin_start,
+                                         sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
+                                         Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride,
+                                         max_len, motility_forces, locations, c, stokes, fric, box, move_dt, global_id,
+                                         global_id ? slot_gid : sorted_id, next, sort_rows, n_device, move_window),
+                          "k_jkr_substep_plane");
+    }
+#endif
     auto kernel = uniform_radius > 0 ? k_jkr_substep<true> : k_jkr_substep<false>;
     return check_cuda(launch_chained(kernel, ceil_div(n, kJkrThreads), kJkrThreads, as_stream(stream), chained, bin_start,
                                      sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
@@ -641,10 +655,10 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
                                const int32_t *n_device, const double *move_window_device, void *stream) {
     return jkr_substep_impl(bin_start, sorted_id, sorted_pos, sorted_bin, n, dims_host, distance, reach,
                             old_row_start, old_row_stride, old_row_len, old_cols, new_row_len, new_cols, row_stride,
-                            max_len, sort_rows, motility_forces, locations, poisson, youngs, adhesion_const, stokes,
-                            size_host, move_dt, global_id, nullptr, uniform_radius, next_extent_host,
-                            next_origin_host, next_bin_counts, next_sort_workspace, stream, nullptr, 0, false, n_device,
-                            move_window_device);
+                            max_len, sort_rows & ABM_SUBSTEP_SORT_ROWS, motility_forces, locations, poisson, youngs,
+                            adhesion_const, stokes, size_host, move_dt, global_id, nullptr, uniform_radius,
+                            next_extent_host, next_origin_host, next_bin_counts, next_sort_workspace, stream, nullptr, 0,
+                            false, n_device, move_window_device, (sort_rows & ABM_SUBSTEP_FLAT_Z) != 0);
 }
 
 // The whole substep loop of CellMethods.apply_forces (reference cell_methods.py:399-436) enqueued by one call:
@@ -674,6 +688,9 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
     const bool carry_in = (flags & ABM_LOOP_CARRY_IN) && n > 0 && n_substeps > 0;
     const bool carry_out = (flags & ABM_LOOP_CARRY_OUT) && n > 0;
     const bool chained = flags & ABM_LOOP_CHAINED;
+    // a flat world's z is exactly 0 once a substep has clamped it into [0, size_z]: from the second substep on (or from
+    // the first, when the cells come from the previous call's hand-over) the two-axis kernel takes over
+    const bool plane_ok = !(flags & ABM_LOOP_NO_PLANE);
     ABM_REQUIRE(extent_host && size_host && bin_start_a && bin_start_b && bin_start_a != bin_start_b,
                 "need two distinct offset tables");
     BinGeom g;
@@ -709,7 +726,7 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                               size_host, dts_host[k], global_id, slot_gid, uniform_radius,
                               prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
                               prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained, n_device,
-                              move_window_device);
+                              move_window_device, plane_ok && (k > 0 || carry_in));
         if (rc) return rc;
         cur_start = nullptr;
         cur_stride = row_stride;

@@ -85,6 +85,7 @@ k_division_apply(Colony c, int capacity, int stride, int *__restrict__ n_dev, in
     // the counters move once every thread of the grid has read them: last block to finish
     __shared__ bool last;
     __threadfence();
+    __syncthreads();          // every warp of this block is done before thread 0 reports the block as finished
     if (threadIdx.x == 0) last = atomicAdd(&needed[1], 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (last && threadIdx.x == 0) {

@@ -290,6 +290,7 @@ k_slab_pack_hdr(CellArrays a, int rows, const int *__restrict__ n_own_dev, int s
     }
     __shared__ bool last;
     __threadfence();
+    __syncthreads();          // every warp of this block is done before thread 0 reports the block as finished
     if (threadIdx.x == 0) last = atomicAdd(&counts[2], 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (last && threadIdx.x == 0) {
@@ -390,6 +391,7 @@ k_slab_place(CellArrays a, int rows, const int *__restrict__ n_own_dev, Incoming
     }
     __shared__ bool last;
     __threadfence();
+    __syncthreads();          // every warp of this block is done before thread 0 reports the block as finished
     if (threadIdx.x == 0) last = atomicAdd(&tally[4], 1) == (int)gridDim.x - 1;
     __syncthreads();
     if (last && threadIdx.x == 0) {

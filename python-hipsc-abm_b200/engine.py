@@ -187,6 +187,7 @@ class ColonyEngine:
         self.chained_launch = False     # abm_mechanics_loop(ABM_LOOP_CHAINED): programmatic dependent launches
         self.move_window = None         # device (2,) float64: only cells with x outside it count for max_substep_move()
         self.mechanics_dtype = "f64"    # "f32": abm_mechanics_loop(ABM_LOOP_FP32), bin-relative single precision
+        self.plane_kernel = True        # False: abm_mechanics_loop(ABM_LOOP_NO_PLANE), the three-axis kernel in a flat world too
         self.diffusion_fuse = int(os.environ.get("ABM_B200_DIFFUSION_FUSE", "0"))   # substeps per launch, 0 = 5
         self.use_current_stream()
         self.h2d_bytes = 0     # bytes moved by upload()/to_device() and host()/locations_host()
@@ -547,6 +548,8 @@ class ColonyEngine:
                sb["bin_start"].data_ptr(), sb["bin_start_b"].data_ptr(), self.mechanics_dtype)
         if self.chained_launch:
             flags |= _lib.LOOP_CHAINED
+        if not self.plane_kernel:
+            flags |= _lib.LOOP_NO_PLANE
         if self.mechanics_dtype == "f32":
             flags |= _lib.LOOP_FP32
         elif self.mechanics_dtype != "f64":

@@ -62,6 +62,7 @@ else:
     cfg = StepConfig(grid=wl["grid"] if full else None, spat_res=spec["h"] or 1.0, diffuse_dt=spec["diffuse_dt"] or 1.0,
                      diffuse_steps=spec["sd"], overlap_morphogen=(full == "overlap"), bond_stride=16 if spec["dim"] == 2 else 32, search_cols_per_cell=12.0 if spec["dim"] == 2 else 24.0)
     eng = ColonyEngine(wl["size"]); eng.upload(wl["loc"], wl["radii"], wl["mot"])
+    eng.plane_kernel = os.environ.get("AB_PLANE", "1") != "0"
     pipe = HotPathStep(eng, cfg)
     for _ in range(int(sys.argv[3]) if len(sys.argv) > 3 else 4):
         pipe.step()
@@ -69,11 +70,13 @@ else:
     reach = eng.jkr_reach(10.0); srt = eng.sort(reach); b = eng._bond_bufs; old = pipe.current_bonds()
     spare = [i for i in range(3) if b["cols"][i].data_ptr() != old.cols.data_ptr()][0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    # AB_PLANE=0: the three-axis kernel also in a flat world (single launch: no ABM_SUBSTEP_FLAT_Z; loop: ABM_LOOP_NO_PLANE)
+    sub_flags = _l.SUBSTEP_FLAT_Z if (spec["dim"] == 2 and eng.plane_kernel) else 0
     def launch():
         _l.check(eng.lib.abm_jkr_substep(
             srt.bin_start.data_ptr(), srt.sorted_id.data_ptr(), srt.sorted_pos.data_ptr(), srt.sorted_bin.data_ptr(),
             n, _l.i3(srt.dims), 10.0, reach, 0, old.row_stride, old.row_len.data_ptr(), old.cols.data_ptr(),
-            b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride, b["max_len"].data_ptr(), 0,
+            b["len"][spare].data_ptr(), b["cols"][spare].data_ptr(), cfg.bond_stride, b["max_len"].data_ptr(), sub_flags,
             eng.mot.data_ptr(), eng.loc.data_ptr(), 0.5, 1000.0, 0.000107, 10000.0, _l.d3(wl["size"]), 180.0, 0,
             eng.uniform_radius, None, None, 0, 0, 0, None, eng.stream), "abm_jkr_substep")
     res = {}
@@ -120,4 +123,4 @@ else:
             z.record(); torch.cuda.synchronize()
             ts.append(a.elapsed_time(z) * 1e3)
         res["diffuse_10_us"] = float(np.median(ts))
-    print(os.path.basename(os.environ.get("ABM_B200_LIB", "default")) + ("+pdl" if os.environ.get("ABM_B200_GRAPH_PDL") == "1" else ""), name, {k: round(v, 1) for k, v in res.items()})
+    print(("plane " if sub_flags else "3axis ") + os.path.basename(os.environ.get("ABM_B200_LIB", "default")) + ("+pdl" if os.environ.get("ABM_B200_GRAPH_PDL") == "1" else ""), name, {k: round(v, 1) for k, v in res.items()})

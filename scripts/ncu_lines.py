@@ -1,28 +1,20 @@
-"""Aggregate an `ncu --page source --csv --print-source cuda,sass` dump per CUDA source line:
-   python scripts/ncu_lines.py <dump.csv> [top]   -> file:line, executed warp instructions, stall samples, source"""
+"""Top SASS instructions of a kernel by warp-stall samples, from `ncu -i rep --page source --csv` (run here).
+   python scripts/ncu_lines.py <source-page csv> [top]"""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
+hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+h = rows[hi]
+col = {n: i for i, n in enumerate(h)}
+data = rows[hi + 1:]
+tot = sum(int(r[col["# Samples"]]) for r in data if len(r) > col["# Samples"])
+inst = sum(int(r[col["Instructions Executed"]]) for r in data)
+print("total samples", tot, "warp instructions", inst)
+stalls = [n for n in h if n.startswith("stall_") and "Not Issued" not in n]
+agg = {s: sum(int(r[col[s]]) for r in data) for s in stalls}
+print({k: v for k, v in sorted(agg.items(), key=lambda kv: -kv[1]) if v})
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = []
-fname = ""
-hdr = None
-for r in rows:
-    if not r:
-        continue
-    if r[0] == "File Path":
-        fname = r[1].split("/")[-1]; continue
-    if r[0] == "Line No":
-        hdr = r; continue
-    if r[0] == "Function Name":
-        continue
-    if r[0] and r[0].isdigit() and hdr:
-        try:
-            samples = int(r[6]); inst = int(r[7]); thr = int(r[8])
-        except ValueError:
-            continue
-        out.append((fname, int(r[0]), inst, samples, thr, r[1].strip()))
-ti = sum(o[2] for o in out); ts = sum(o[3] for o in out)
-print(f"total warp inst {ti}  samples {ts}")
-print("--- by samples")
-for o in sorted(out, key=lambda o: -o[3])[:top]:
-    print(f"{o[0]}:{o[1]:<4} inst {o[2]:>9} ({100*o[2]/ti:4.1f}%) samples {o[3]:>6} ({100*o[3]/ts:4.1f}%) lanes {o[4]/max(o[2],1):4.1f} | {o[5][:90]}")
+order = sorted(range(len(data)), key=lambda k: -int(data[k][col["# Samples"]]))[:top]
+for k in sorted(order):
+    r = data[k]
+    why = sorted(((int(r[col[s]]), s[6:]) for s in stalls), reverse=True)[:2]
+    print(f"{k:5d} {int(r[col['# Samples']]):6d} {100*int(r[col['# Samples']])/tot:5.1f}%  exec {int(r[col['Instructions Executed']]):8d} thr {r[col['Avg. Threads Executed']]:>5s}  {why[0][1]}:{why[0][0]} {why[1][1]}:{why[1][0]}   {r[col['Source']].strip()}")
