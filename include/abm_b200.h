@@ -220,6 +220,23 @@ int abm_mechanics_loop(const double *radii, double *locations, const double *mot
                        double poisson, double youngs, double adhesion_const, double stokes, int flags,
                        const int32_t *n_device, const double *move_window_device, void *stream);
 
+/* abm_mechanics_loop with a stopwatch on its dominant kernel: substep_events_host (may be NULL) is a HOST array of
+ * 2*n_substeps cudaEvent_t handles (as void*); events [2k] and [2k+1] are recorded on `stream` right before and right
+ * after substep k's k_jkr_substep launch, so the caller reads every launch's duration inside the running loop
+ * (cudaEventElapsedTime) -- what bench.py's roofline needs.  Not with ABM_LOOP_FP32.  Same results as
+ * abm_mechanics_loop.                                                                               */
+int abm_mechanics_loop_timed(const double *radii, double *locations, const double *motility_forces, int64_t n,
+                             const double extent_host[3], const double *origin_host, const double size_host[3],
+                             double distance, double reach, int n_substeps, const double *dts_host,
+                             int32_t *bin_start_a, int32_t *bin_start_b, int32_t *sorted_id, double *sorted_pos,
+                             int32_t *sorted_bin, int32_t *max_count, void *sort_workspace,
+                             size_t sort_workspace_bytes, const int32_t *old_row_start, int64_t old_row_stride,
+                             const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a, int32_t *cols_a,
+                             int32_t *len_b, int32_t *cols_b, int64_t row_stride, int32_t *max_len,
+                             const int32_t *global_id, double uniform_radius, double poisson, double youngs,
+                             double adhesion_const, double stokes, int flags, const int32_t *n_device,
+                             const double *move_window_device, void *const *substep_events_host, void *stream);
+
 /* ---- morphogen diffusion ---------------------------------------------------------------------------
  * Replaces CellMethods.update_diffusion + update_diffusion_jit (cell_methods.py:441-468,
  * cell_backend.py:175-204) for one (gx,gy) float64 plane, row-major (the reference's field[:,:,0]).

@@ -60,6 +60,9 @@ SIGNATURES = {
     "abm_mechanics_loop": (I32, [P, P, P, I64, D3, D3, D3, F64, F64, I32, C.POINTER(C.c_double),
                                  P, P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, P,
                                  F64, F64, F64, F64, F64, I32, P, P, P]),
+    "abm_mechanics_loop_timed": (I32, [P, P, P, I64, D3, D3, D3, F64, F64, I32, C.POINTER(C.c_double),
+                                       P, P, P, P, P, P, P, SZ, P, I64, P, P, P, P, P, P, I64, P, P,
+                                       F64, F64, F64, F64, F64, I32, P, P, C.POINTER(C.c_void_p), P]),
     "abm_diffusion": (I32, [P, P, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, I32, C.POINTER(I32), P]),
     "abm_diffusion_launches": (I64, [I64, I32]),
     "abm_diffusion3d": (I32, [P, P, I64, I64, I64, I64, F64, F64, F64, F64, F64, F64, I32, C.POINTER(I32), P]),

@@ -666,18 +666,21 @@ ABM_EXPORT int abm_jkr_substep(const int32_t *bin_start, const int32_t *sorted_i
 // substep k-1 (substep 0 reads old_*) and writes row buffer a (k even) or b (k odd); the final bonds are in
 // buffer a when n_substeps is odd, else in b.  Every substep pre-bins the moved cells, so only the first sort
 // of the loop runs the histogram kernel; the two offset tables alternate.
-ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const double *motility_forces, int64_t n,
-                                  const double extent_host[3], const double *origin_host, const double size_host[3],
-                                  double distance, double reach, int n_substeps, const double *dts_host,
-                                  int32_t *bin_start_a, int32_t *bin_start_b, int32_t *sorted_id, double *sorted_pos,
-                                  int32_t *sorted_bin, int32_t *max_count, void *sort_workspace,
-                                  size_t sort_workspace_bytes, const int32_t *old_row_start, int64_t old_row_stride,
-                                  const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a,
-                                  int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
-                                  int32_t *max_len, const int32_t *global_id, double uniform_radius, double poisson,
-                                  double youngs, double adhesion_const, double stokes, int flags,
-                                  const int32_t *n_device, const double *move_window_device, void *stream) {
+// events (may be null): 2 per substep, recorded around the substep kernel (abm_mechanics_loop_timed)
+static int mechanics_loop_impl(const double *radii, double *locations, const double *motility_forces, int64_t n,
+                               const double extent_host[3], const double *origin_host, const double size_host[3],
+                               double distance, double reach, int n_substeps, const double *dts_host,
+                               int32_t *bin_start_a, int32_t *bin_start_b, int32_t *sorted_id, double *sorted_pos,
+                               int32_t *sorted_bin, int32_t *max_count, void *sort_workspace,
+                               size_t sort_workspace_bytes, const int32_t *old_row_start, int64_t old_row_stride,
+                               const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a,
+                               int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
+                               int32_t *max_len, const int32_t *global_id, double uniform_radius, double poisson,
+                               double youngs, double adhesion_const, double stokes, int flags,
+                               const int32_t *n_device, const double *move_window_device, void *const *events,
+                               void *stream) {
     ABM_REQUIRE(n_substeps >= 0 && dts_host, "bad substep list");
+    ABM_REQUIRE(!(events && (flags & ABM_LOOP_FP32)), "the per-launch stopwatch is for the fp64 loop");
     if (flags & ABM_LOOP_FP32)
         return mechanics_loop32(radii, locations, motility_forces, n, extent_host, origin_host, size_host, distance,
                                 reach, n_substeps, dts_host, bin_start_a, bin_start_b, sorted_id, sorted_pos,
@@ -720,6 +723,10 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
             row_keys = (k > 0 ? 1 : 0) | (last ? 0 : 2);          // first reads / last writes rows keyed by cell id
         }
 #endif
+        if (events && n > 0) {
+            rc = check_cuda(cudaEventRecord((cudaEvent_t)events[2 * k], st), "cudaEventRecord");
+            if (rc) return rc;
+        }
         rc = jkr_substep_impl(table, sorted_id, sorted_pos, sorted_bin, n, g.dims, distance, reach, cur_start,
                               cur_stride, cur_len, cur_cols, nl, nc, row_stride, max_len, k == n_substeps - 1,
                               motility_forces, last ? locations : nullptr, poisson, youngs, adhesion_const, stokes,
@@ -728,10 +735,50 @@ ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const 
                               prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained, n_device,
                               move_window_device, plane_ok && (k > 0 || carry_in));
         if (rc) return rc;
+        if (events && n > 0) {
+            rc = check_cuda(cudaEventRecord((cudaEvent_t)events[2 * k + 1], st), "cudaEventRecord");
+            if (rc) return rc;
+        }
         cur_start = nullptr;
         cur_stride = row_stride;
         cur_len = nl;
         cur_cols = nc;
     }
     return 0;
+}
+
+#define ABM_LOOP_ARGS                                                                                                 \
+    radii, locations, motility_forces, n, extent_host, origin_host, size_host, distance, reach, n_substeps, dts_host, \
+        bin_start_a, bin_start_b, sorted_id, sorted_pos, sorted_bin, max_count, sort_workspace, sort_workspace_bytes, \
+        old_row_start, old_row_stride, old_row_len, old_cols, len_a, cols_a, len_b, cols_b, row_stride, max_len,      \
+        global_id, uniform_radius, poisson, youngs, adhesion_const, stokes, flags, n_device, move_window_device
+
+ABM_EXPORT int abm_mechanics_loop(const double *radii, double *locations, const double *motility_forces, int64_t n,
+                                  const double extent_host[3], const double *origin_host, const double size_host[3],
+                                  double distance, double reach, int n_substeps, const double *dts_host,
+                                  int32_t *bin_start_a, int32_t *bin_start_b, int32_t *sorted_id, double *sorted_pos,
+                                  int32_t *sorted_bin, int32_t *max_count, void *sort_workspace,
+                                  size_t sort_workspace_bytes, const int32_t *old_row_start, int64_t old_row_stride,
+                                  const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a,
+                                  int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
+                                  int32_t *max_len, const int32_t *global_id, double uniform_radius, double poisson,
+                                  double youngs, double adhesion_const, double stokes, int flags,
+                                  const int32_t *n_device, const double *move_window_device, void *stream) {
+    return mechanics_loop_impl(ABM_LOOP_ARGS, nullptr, stream);
+}
+
+ABM_EXPORT int abm_mechanics_loop_timed(const double *radii, double *locations, const double *motility_forces,
+                                        int64_t n, const double extent_host[3], const double *origin_host,
+                                        const double size_host[3], double distance, double reach, int n_substeps,
+                                        const double *dts_host, int32_t *bin_start_a, int32_t *bin_start_b,
+                                        int32_t *sorted_id, double *sorted_pos, int32_t *sorted_bin,
+                                        int32_t *max_count, void *sort_workspace, size_t sort_workspace_bytes,
+                                        const int32_t *old_row_start, int64_t old_row_stride,
+                                        const int32_t *old_row_len, const int32_t *old_cols, int32_t *len_a,
+                                        int32_t *cols_a, int32_t *len_b, int32_t *cols_b, int64_t row_stride,
+                                        int32_t *max_len, const int32_t *global_id, double uniform_radius,
+                                        double poisson, double youngs, double adhesion_const, double stokes, int flags,
+                                        const int32_t *n_device, const double *move_window_device,
+                                        void *const *substep_events_host, void *stream) {
+    return mechanics_loop_impl(ABM_LOOP_ARGS, substep_events_host, stream);
 }

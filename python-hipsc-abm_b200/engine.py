@@ -187,6 +187,8 @@ class ColonyEngine:
         self.chained_launch = False     # abm_mechanics_loop(ABM_LOOP_CHAINED): programmatic dependent launches
         self.move_window = None         # device (2,) float64: only cells with x outside it count for max_substep_move()
         self.mechanics_dtype = "f64"    # "f32": abm_mechanics_loop(ABM_LOOP_FP32), bin-relative single precision
+        self.substep_events = None      # list of 2 x (substeps) recorded torch.cuda.Event(enable_timing=True): the next
+                                        # mechanics loop records them around its k_jkr_substep launches (bench.py)
         self.plane_kernel = True        # False: abm_mechanics_loop(ABM_LOOP_NO_PLANE), the three-axis kernel in a flat world too
         self.diffusion_fuse = int(os.environ.get("ABM_B200_DIFFUSION_FUSE", "0"))   # substeps per launch, 0 = 5
         self.use_current_stream()
@@ -559,7 +561,15 @@ class ColonyEngine:
             if self._carry is not None and self._carry[:-1] == key:
                 flags |= _lib.LOOP_CARRY_IN
                 first = self._carry[-1]                      # the table the previous call left the histogram in
-        _lib.check(self.lib.abm_mechanics_loop(
+        events = self.substep_events
+        timed = ()
+        call = self.lib.abm_mechanics_loop
+        if events is not None:
+            if len(events) != 2 * len(dts):
+                raise _lib.AbmError(f"substep_events: {len(events)} events for {len(dts)} substeps")
+            timed = ((C.c_void_p * len(events))(*[int(e.cuda_event) for e in events]),)
+            call = self.lib.abm_mechanics_loop_timed
+        _lib.check(call(
             _ptr(self.radii), _ptr(self.loc), _ptr(self.mot), n, self._extent_c, self._origin_c, self._size_c,
             float(distance), reach, len(dts), dts_c,
             _ptr(tables[first]), _ptr(tables[1 - first]), _ptr(sb["sorted_id"]), _ptr(sb["sorted_pos"]),
@@ -568,7 +578,7 @@ class ColonyEngine:
             _ptr(old.row_len) if old is not None else 0, _ptr(old.cols) if old is not None else 0,
             _ptr(b["len"][pair[0]]), _ptr(b["cols"][pair[0]]), _ptr(b["len"][pair[1]]), _ptr(b["cols"][pair[1]]),
             stride, _ptr(b["max_len"]), _ptr(self.global_id), float(self.uniform_radius), JKR_POISSON, JKR_YOUNGS,
-            JKR_ADHESION, float(stokes), flags, _ptr(self.n_device), _ptr(self.move_window), self.stream),
+            JKR_ADHESION, float(stokes), flags, _ptr(self.n_device), _ptr(self.move_window), *timed, self.stream),
             "abm_mechanics_loop")
         # the last substep k = K-1 sorted with table (first + K-1) % 2 and left the next histogram in the other one
         self._carry = key + ((first + len(dts)) % 2,) if flags & _lib.LOOP_CARRY_OUT else None
