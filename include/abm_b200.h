@@ -45,8 +45,10 @@ extern "C" {
 #define ABM_SORT_STABLE 1     /* ascending cell id inside a bin (the reference's fill order) */
 #define ABM_SORT_REFERENCE 2  /* keep the reference's 3 z-layers in a flat (size_z == 0) world */
 #define ABM_LOOP_CARRY_OUT 1   /* abm_mechanics_loop: the last substep also hands its cells to the NEXT call's first sort */
-#define ABM_LOOP_CARRY_IN 2    /* abm_mechanics_loop: the previous call did so (same n, lattice, workspace; its idle
-                                  offset table is passed as bin_start_a): the first sort needs no histogram pass */
+#define ABM_LOOP_CARRY_IN 2    /* abm_mechanics_loop: the previous call did so (same n, lattice, workspace, uniform_radius,
+                                  ABM_LOOP_FP32 / ABM_LOOP_NO_PLANE flags -- they decide the layout of the handed-over
+                                  records; its idle offset table is passed as bin_start_a): the first sort needs no
+                                  histogram pass */
 #define ABM_SORT_PREBINNED 4  /* histogram + per-cell bin already written by abm_jkr_substep */
 #define ABM_SORT_CHAINED 8    /* abm_bin_sort(ABM_SORT_PREBINNED): launch its kernels with programmatic stream
                                  serialization (see ABM_LOOP_CHAINED) */

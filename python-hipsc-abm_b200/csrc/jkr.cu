@@ -170,6 +170,7 @@ struct NextSort {          // hand-over of the moved cells to the following subs
     BinGeom geom;          // in THIS sort's slot order: the next permutation is then nearly the identity
     int *counts, *cell_bin, *prev_id, *chunk_sums;
     double4 *next_pos;
+    int compact;           // the hand-over's position records are 16-byte {x, y} (kSortCompactXY), not {x, y, z, r}
 };
 
 struct Friction {          // Stokes friction of a colony of equal radii and its correctly rounded reciprocal
@@ -524,7 +525,8 @@ k_jkr_substep(const int *__restrict__ bin_start, const int *__restrict__ sorted_
     }
     if (next.counts) {                                        // hand-over to the next substep's sort, by slot
         int b = cell_bin_of_loose(nx, ny, nz, next.geom);
-        next.next_pos[s] = make_double4(nx, ny, nz, p.w);
+        if (next.compact) reinterpret_cast<double2 *>(next.next_pos)[s] = make_double2(nx, ny);
+        else next.next_pos[s] = make_double4(nx, ny, nz, p.w);
         next.cell_bin[s] = b;
         next.prev_id[s] = i;
         atomicAdd(&next.counts[b], 1);
@@ -582,7 +584,7 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                             int32_t *next_bin_counts, void *next_sort_workspace, void *stream,
                             const int32_t *prev_slot = nullptr, int row_keys = 0, bool chained = false,
                             const int32_t *n_device = nullptr, const double *move_window = nullptr,
-                            bool plane = false) {
+                            bool plane = false, bool compact_in = false, bool compact_out = false) {
     ABM_REQUIRE(n >= 0 && n < 0x7fffffff, "n out of range");
     if (n == 0) return 0;
     ABM_REQUIRE(!(row_keys & 1) || prev_slot, "rows keyed by the previous slot need the prev_slot index");
@@ -613,7 +615,11 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
         next.prev_id = w.tmp_id;
         next.chunk_sums = w.next_sums;
         next.next_pos = w.next_pos;
+        next.compact = compact_out ? 1 : 0;
     }
+    ABM_REQUIRE(!compact_in || (plane && uniform_radius > 0), "compact records are read by the two-axis kernel only");
+    ABM_REQUIRE(!compact_out || (next_bin_counts && uniform_radius > 0 && size_host[2] == 0.0),
+                "compact hand-over needs a flat world of equal radii");
     Friction fric{0.0, 0.0};
     if (uniform_radius > 0) {                                  // stokes_friction() on the host: same IEEE products
         const double kPi = 3.141592653589793;
@@ -629,7 +635,8 @@ static int jkr_substep_impl(const int32_t *bin_start, const int32_t *sorted_id, 
                                          sorted_id, reinterpret_cast<const double4 *>(sorted_pos), sorted_bin, (int)n, stc,
                                          Radius(distance), reach * reach, old, new_row_len, new_cols, (int)row_stride,
                                          max_len, motility_forces, locations, c, stokes, fric, box, move_dt, global_id,
-                                         global_id ? slot_gid : sorted_id, next, sort_rows, n_device, move_window),
+                                         global_id ? slot_gid : sorted_id, next, sort_rows, n_device, move_window,
+                                         compact_in ? 1 : 0),
                           "k_jkr_substep_plane");
     }
 #endif
@@ -694,6 +701,9 @@ static int mechanics_loop_impl(const double *radii, double *locations, const dou
     // a flat world's z is exactly 0 once a substep has clamped it into [0, size_z]: from the second substep on (or from
     // the first, when the cells come from the previous call's hand-over) the two-axis kernel takes over
     const bool plane_ok = !(flags & ABM_LOOP_NO_PLANE);
+    // ... and in a flat world of equal radii the position records between such substeps are 16-byte {x, y} ones
+    // (kSortCompactXY): every hand-over whose consumer is the two-axis kernel, i.e. every hand-over of the loop
+    const bool compact = plane_ok && uniform_radius > 0 && size_host[2] == 0.0 && !(flags & ABM_LOOP_FP32);
     ABM_REQUIRE(extent_host && size_host && bin_start_a && bin_start_b && bin_start_a != bin_start_b,
                 "need two distinct offset tables");
     BinGeom g;
@@ -707,8 +717,10 @@ static int mechanics_loop_impl(const double *radii, double *locations, const dou
         const bool last = k + 1 == n_substeps;
         const bool prebin = n > 0 && (!last || carry_out);        // hand the moved cells to the next sort
         // (the largest bin population is reported for the first sort of the loop only)
+        const bool handed = k || carry_in;                        // this sort's cells come from a hand-over
         int rc = bin_sort_impl(locations, radii, n, extent_host, origin_host, reach,
-                               ((k || carry_in) ? ABM_SORT_PREBINNED : 0) | (chained ? ABM_SORT_CHAINED : 0), table,
+                               (handed ? ABM_SORT_PREBINNED : 0) | (chained ? ABM_SORT_CHAINED : 0) |
+                                   ((handed && compact) ? kSortCompactXY : 0), table,
                                sorted_id, sorted_pos, sorted_bin, k ? nullptr : max_count, sort_workspace,
                                sort_workspace_bytes,
                                prebin ? other : nullptr, global_id, stream, n_device);   // (idle table cleared on the way)
@@ -733,7 +745,7 @@ static int mechanics_loop_impl(const double *radii, double *locations, const dou
                               size_host, dts_host[k], global_id, slot_gid, uniform_radius,
                               prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
                               prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained, n_device,
-                              move_window_device, plane_ok && (k > 0 || carry_in));
+                              move_window_device, plane_ok && handed, handed && compact, prebin && compact);
         if (rc) return rc;
         if (events && n > 0) {
             rc = check_cuda(cudaEventRecord((cudaEvent_t)events[2 * k + 1], st), "cudaEventRecord");

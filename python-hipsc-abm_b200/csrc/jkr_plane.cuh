@@ -39,7 +39,7 @@ k_jkr_substep_plane(const int *__restrict__ bin_start, const int *__restrict__ s
                     int *__restrict__ max_len, const double *__restrict__ mot, double *__restrict__ loc, JkrConst c,
                     double stokes, Friction fric, Box box, double dt, const int *__restrict__ gid_of,
                     const int *__restrict__ slot_pid, NextSort next, int sort_rows, const int *__restrict__ n_dev,
-                    const double *__restrict__ move_window) {
+                    const double *__restrict__ move_window, int compact_in) {
     // column tid: parked tile indices, then (overwritten from the front) the ids of the new bond row
     __shared__ int column[kMaxHits][kJkrThreads];
     __shared__ double2 tiles[kJkrThreads / 32][kTileRows * kTileCap];
@@ -54,6 +54,10 @@ k_jkr_substep_plane(const int *__restrict__ bin_start, const int *__restrict__ s
     const bool live = s < n;
     double2 *tile = tiles[tid >> 5];
     int *tid_ids = tile_ids[tid >> 5];
+    // position records: 32-byte {x, y, z, r} rows of a stand-alone sort, or 16-byte {x, y} rows between the substeps of
+    // a loop (kSortCompactXY: equal radii only); either way {x, y} are the first 16 bytes of record t
+    const double2 *__restrict__ sxy = reinterpret_cast<const double2 *>(spos);
+    const int rec_shift = compact_in ? 0 : 1;
     const int *first_hop = slot_pid ? slot_pid : sorted_id;
     const bool second_hop = !slot_pid && gid_of;
     // fixed-stride previous rows of >= 8 entries (stride % 4 == 0): the first 8 ids come as two 16-byte loads
@@ -62,10 +66,10 @@ k_jkr_substep_plane(const int *__restrict__ bin_start, const int *__restrict__ s
     double px = 0.0, py = 0.0, pr = 1.0;
     if (live) {
         i = sorted_id[s];
-        const double4 p = spos[s];
+        const double2 p = sxy[(long long)s << rec_shift];
         px = p.x;
         py = p.y;
-        pr = p.w;
+        pr = kUniform ? c.uni_r : spos[s].w;
         const int b = sorted_bin[s];
         by = st.magic0 ? (int)__umulhi((unsigned)b, st.magic0) : b / st.dims[0];
         bx = b - by * st.dims[0];
@@ -104,7 +108,7 @@ k_jkr_substep_plane(const int *__restrict__ bin_start, const int *__restrict__ s
                 for (int c0 = 0; c0 < kTileCap; c0 += 32) {
                     const int cidx = c0 + lane;
                     if (cidx < W[r]) {
-                        tile[r * kTileCap + cidx] = *reinterpret_cast<const double2 *>(spos + (L[r] + cidx));
+                        tile[r * kTileCap + cidx] = sxy[(long long)(L[r] + cidx) << rec_shift];
                         tid_ids[r * kTileCap + cidx] = first_hop[L[r] + cidx];
                     }
                 }
@@ -273,12 +277,13 @@ k_jkr_substep_plane(const int *__restrict__ bin_start, const int *__restrict__ s
             const int lo = bin_start[rowb + x0], hi = bin_start[rowb + x1 + 1];
             for (int t = lo; t < hi; ++t) {
                 if (t == s) continue;
-                const double4 q = spos[t];
+                const double2 q = sxy[(long long)t << rec_shift];
                 const double vx = px - q.x, vy = py - q.y;
                 const double s2 = sumsq2_nofma(vx, vy);
                 if (s2 > reach2) continue;
                 const int j = partner_id(t);
-                if (rad.within(s2) || (old.valid() && was_bonded_slow(j))) bond(vx, vy, s2, q.w, j);
+                if (rad.within(s2) || (old.valid() && was_bonded_slow(j)))
+                    bond(vx, vy, s2, kUniform ? pr : spos[t].w, j);
             }
         }
     }
@@ -334,7 +339,8 @@ k_jkr_substep_plane(const int *__restrict__ bin_start, const int *__restrict__ s
         const int nbx = clampi(__double2int_rd((nx - g.origin[0]) * g.inv_distance) + 1, 0, g.dims[0] - 1);
         const int nby = clampi(__double2int_rd((ny - g.origin[1]) * g.inv_distance) + 1, 0, g.dims[1] - 1);
         const int b = nby * g.dims[0] + nbx;
-        next.next_pos[s] = make_double4(nx, ny, 0.0, pr);
+        if (next.compact) reinterpret_cast<double2 *>(next.next_pos)[s] = make_double2(nx, ny);
+        else next.next_pos[s] = make_double4(nx, ny, 0.0, pr);
         next.cell_bin[s] = b;
         next.prev_id[s] = i;
         atomicAdd(&next.counts[b], 1);

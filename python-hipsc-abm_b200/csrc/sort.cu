@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ 
                                                         double4 *__restrict__ sorted_pos, int *__restrict__ sorted_bin,
                                                         int *__restrict__ next_sums, int n_sums,
                                                         const int *__restrict__ gid_of, int *__restrict__ slot_gid,
-                                                        int *__restrict__ prev_slot, const int *__restrict__ n_dev) {
+                                                        int *__restrict__ prev_slot, const int *__restrict__ n_dev,
+                                                        int compact) {
     pdl_launch_dependents();
     int s = blockIdx.x * kThreads + threadIdx.x;
     pdl_wait();
@@ -78,7 +79,10 @@ __global__ void __launch_bounds__(kThreads) k_rescatter(const int *__restrict__ 
     int b = next_bin[s];
     int dest = atomicAdd(&cursor[b], 1);
     int id = prev_id[s];
-    sorted_pos[dest] = next_pos[s];
+    if (compact)                                               // 16-byte {x, y} records on both sides (kSortCompactXY)
+        reinterpret_cast<double2 *>(sorted_pos)[dest] = reinterpret_cast<const double2 *>(next_pos)[s];
+    else
+        sorted_pos[dest] = next_pos[s];
     sorted_id[dest] = id;
     sorted_bin[dest] = b;
     if (gid_of) slot_gid[dest] = gid_of[id];
@@ -188,6 +192,7 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
     ABM_REQUIRE(workspace_bytes >= sort_ws_bytes(n, nbins), "workspace too small");
     cudaStream_t st = as_stream(stream);
     const bool prebinned = flags & ABM_SORT_PREBINNED;
+    ABM_REQUIRE(prebinned || !(flags & kSortCompactXY), "compact records exist only between the substeps of a loop");
     int rc;
     if (!prebinned) {
         rc = check_cuda(cudaMemsetAsync(bin_start, 0, (size_t)(nbins + 1) * 4, st), "memset bin_start");
@@ -231,7 +236,8 @@ int abm::bin_sort_impl(const double *locations, const double *radii, int64_t n, 
         rc = check_cuda(launch_chained(k_rescatter, blocks, kThreads, st, chained, (const int *)w.cell_bin,
                                        (const int *)w.tmp_id, (const double4 *)w.next_pos, w.cursor, (int)n, sorted_id,
                                        sp, sorted_bin, w.next_sums, nb, global_id, w.slot_gid,
-                                       (ABM_JKR_EXP & 16) ? w.prev_slot : (int *)nullptr, n_device),
+                                       (ABM_JKR_EXP & 16) ? w.prev_slot : (int *)nullptr, n_device,
+                                       (flags & kSortCompactXY) ? 1 : 0),
                         "k_rescatter");
         if (rc) return rc;
     } else if (flags & ABM_SORT_STABLE) {

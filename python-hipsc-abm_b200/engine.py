@@ -547,7 +547,8 @@ class ColonyEngine:
         flags, first = 0, 0
         # everything the hand-over depends on: lattice, cells, radii (they travel with the positions), the buffers
         key = (nbins, n, self.loc.data_ptr(), self.radii.data_ptr(), reach, sb["ws"].data_ptr(),
-               sb["bin_start"].data_ptr(), sb["bin_start_b"].data_ptr(), self.mechanics_dtype)
+               sb["bin_start"].data_ptr(), sb["bin_start_b"].data_ptr(), self.mechanics_dtype, self.plane_kernel,
+               float(self.uniform_radius))     # (the last two decide the layout of the handed-over records)
         if self.chained_launch:
             flags |= _lib.LOOP_CHAINED
         if not self.plane_kernel:
