@@ -794,7 +794,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
         field = slab.FieldSlab(geom, (gx, wl["grid"][1]), spec["h"], spec["sd"] + 1, dev)
     # capacities, the same on every rank: the expected cells within `halo` of an interface, with headroom
     expect = n_rank if weak else n / world
-    send_cap = int(1.6 * expect * halo / width) + 4096
+    send_cap = int(1.15 * expect * halo / width) + 1024      # (an overflow is detected: DeviceSlab.check() raises)
     rows = int(1.15 * expect * (1 + 2 * halo / width)) + 8192
     ds = DeviceSlab(geom, cfg, dev, rows=rows, send_cap=send_cap, max_radius=5.0, uniform_radius=5.0, field=field)
     ds.eng.mechanics_dtype = args.dtype

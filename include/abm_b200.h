@@ -66,6 +66,9 @@ extern "C" {
                                  default the substeps whose input z is known to be exactly 0 (all but the first of a
                                  call without ABM_LOOP_CARRY_IN) run k_jkr_substep_plane, which computes the same bits
                                  (csrc/jkr_plane.cuh); the flag exists for the test that compares the two */
+#define ABM_LOOP_FLAT_Z 32    /* abm_mechanics_loop in a flat (size[2] == 0) world: the caller vouches that every z in `locations` is
+                                 exactly +0.0 at entry (true for anything a previous loop has produced), so the first
+                                 substep runs the two-axis kernel as well */
 #define ABM_LOOP_CHAINED 4    /* abm_mechanics_loop: launch the kernels of the loop with programmatic stream
                                  serialization, so that a kernel's CTAs become resident while the last wave of its
                                  predecessor drains (they wait for its completion before touching memory) */

@@ -123,7 +123,7 @@ def check(rc: int, what: str) -> int:
 
 
 SORT_STABLE, SORT_REFERENCE, SORT_PREBINNED, SORT_CHAINED = 1, 2, 4, 8
-LOOP_CARRY_OUT, LOOP_CARRY_IN, LOOP_CHAINED, LOOP_FP32, LOOP_NO_PLANE = 1, 2, 4, 8, 16
+LOOP_CARRY_OUT, LOOP_CARRY_IN, LOOP_CHAINED, LOOP_FP32, LOOP_NO_PLANE, LOOP_FLAT_Z = 1, 2, 4, 8, 16, 32
 SUBSTEP_SORT_ROWS, SUBSTEP_FLAT_Z = 1, 2
 
 

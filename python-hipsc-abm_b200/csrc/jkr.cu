@@ -745,7 +745,8 @@ static int mechanics_loop_impl(const double *radii, double *locations, const dou
                               size_host, dts_host[k], global_id, slot_gid, uniform_radius,
                               prebin ? extent_host : nullptr, origin_host, prebin ? other : nullptr,
                               prebin ? sort_workspace : nullptr, stream, prev_slot, row_keys, chained, n_device,
-                              move_window_device, plane_ok && handed, handed && compact, prebin && compact);
+                              move_window_device, plane_ok && (handed || (flags & ABM_LOOP_FLAT_Z)), handed && compact,
+                              prebin && compact);
         if (rc) return rc;
         if (events && n > 0) {
             rc = check_cuda(cudaEventRecord((cudaEvent_t)events[2 * k + 1], st), "cudaEventRecord");

@@ -189,6 +189,7 @@ class ColonyEngine:
         self.mechanics_dtype = "f64"    # "f32": abm_mechanics_loop(ABM_LOOP_FP32), bin-relative single precision
         self.substep_events = None      # list of 2 x (substeps) recorded torch.cuda.Event(enable_timing=True): the next
                                         # mechanics loop records them around its k_jkr_substep launches (bench.py)
+        self.flat_z_vouched = False     # abm_mechanics_loop(ABM_LOOP_FLAT_Z): every z is known to be 0 at the next loop's entry
         self.plane_kernel = True        # False: abm_mechanics_loop(ABM_LOOP_NO_PLANE), the three-axis kernel in a flat world too
         self.diffusion_fuse = int(os.environ.get("ABM_B200_DIFFUSION_FUSE", "0"))   # substeps per launch, 0 = 5
         self.use_current_stream()
@@ -553,6 +554,8 @@ class ColonyEngine:
             flags |= _lib.LOOP_CHAINED
         if not self.plane_kernel:
             flags |= _lib.LOOP_NO_PLANE
+        if self.flat_z_vouched and float(self._size_c[2]) == 0.0:
+            flags |= _lib.LOOP_FLAT_Z
         if self.mechanics_dtype == "f32":
             flags |= _lib.LOOP_FP32
         elif self.mechanics_dtype != "f64":

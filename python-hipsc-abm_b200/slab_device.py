@@ -81,6 +81,7 @@ class DeviceSlab:
             self.rows_out = [torch.zeros((k, gy), dtype=f64, device=dev) for _ in range(2)]
             self.rows_in = [torch.zeros((k, gy), dtype=f64, device=dev) for _ in range(2)]
         self.launches = 0
+        self.loops_enqueued = 0          # mechanics loops since the cells were loaded (see enqueue_mechanics)
 
     # ---- set-up / read-out (these may synchronise) --------------------------------------------------------------
     def load(self, loc, radii, mot, gid):
@@ -97,6 +98,7 @@ class DeviceSlab:
         s["blen"].zero_()
         s["n_own"].fill_(n)
         s["n_local"].fill_(n)
+        self.loops_enqueued = 0
         self.bonds = (s["blen"], s["rows"])
 
     def owned(self):
@@ -207,8 +209,12 @@ class DeviceSlab:
         eng.use_current_stream()
         before = eng.launches
         old = GraphTensors(self.R, None, self.stride, s["blen"], s["rows"], True)
+        # flat world: once every rank has run a loop, every cell a rank holds -- its own, migrants, ghosts -- has been
+        # through an integration that clamped its z to 0, so the first substep can run the two-axis kernel too
+        eng.flat_z_vouched = self.loops_enqueued >= 1 and len(self.dts) > 0
         bonds = eng.enqueue_mechanics(old, cfg.contact_radius, self.dts, self.stride, STOKES, pair=[0, 1],
                                       zero_flag=False)
+        self.loops_enqueued += 1
         self.bonds = (bonds.row_len, bonds.cols)
         self.launches += eng.launches - before
 

@@ -91,3 +91,32 @@ def test_single_launch_flag_selects_the_plane_kernel():
         outs.append((eng.locations_host(), lens, np.where(np.arange(stride)[None, :] < lens[:, None], rows, -1)))
     for x, y in zip(*outs):
         assert np.array_equal(x, y)
+
+
+def test_flat_z_flag_and_timed_loop_change_nothing_but_the_kernel_and_the_clock():
+    """ABM_LOOP_FLAT_Z (first substep on the two-axis kernel too) and abm_mechanics_loop_timed (events around every
+    substep launch) give the same positions and bonds as the plain loop; the events measure something."""
+    size, loc, rad, mot = colony(15000, 1200.0, 6)
+    assert np.all(loc[:, 2] == 0.0)
+    dts = [180.0] * 10 + [0.0]
+    outs = []
+    for mode in ("plain", "flat_z", "timed"):
+        eng = ColonyEngine(size)
+        eng.upload(loc, rad, mot)
+        eng.flat_z_vouched = mode == "flat_z"
+        events = None
+        if mode == "timed":
+            events = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(dts))]
+            for e in events:
+                e.record()
+            eng.substep_events = events
+        bonds = eng.enqueue_mechanics(None, 10.0, dts, 32)
+        eng.substep_events = None
+        torch.cuda.synchronize()
+        if events:
+            us = [events[2 * k].elapsed_time(events[2 * k + 1]) * 1e3 for k in range(len(dts))]
+            assert all(0.5 < u < 5e4 for u in us), us
+        outs.append((eng.locations_host(), eng.edge_list(bonds)))
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][0], other[0])
+        assert np.array_equal(outs[0][1], other[1])
