@@ -762,7 +762,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     import torch
     from hipsc_abm_b200 import slab
     from hipsc_abm_b200.engine import ColonyEngine
-    from hipsc_abm_b200.slab_device import DeviceSlab, DistSlab
+    from hipsc_abm_b200.slab_device import DeviceSlab, DistSlab, PeerSlab
 
     spec, n = wl["spec"], wl["n"]
     side = wl["size"][0]
@@ -801,7 +801,20 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     ds.load(loc, radii, mot, gid)
     # the field rows travel on their own communicator: they are exchanged on the second stream and must not queue in
     # front of the next step's cell exchange
-    rank_step = DistSlab(ds, rank, world, rows_group=dist.new_group(list(range(world))) if field is not None else None)
+    rows_group = dist.new_group(list(range(world))) if field is not None else None
+    left_group = dist.new_group(list(range(world))) if world > 2 and not os.environ.get("ABM_B200_ONE_CELL_GROUP") else None
+    # cell records over NVLink peer memory (PeerSlab) unless ABM_B200_CELL_EXCHANGE=nccl or the CUDA-IPC mapping of the
+    # neighbours' buffers fails on any rank (then: NCCL send/recv, the two directions on two communicators)
+    rank_step, exchange = None, "nccl send/recv"
+    if os.environ.get("ABM_B200_CELL_EXCHANGE", "peer") == "peer":
+        rank_step = PeerSlab(ds, rank, world, rows_group=rows_group)
+        if rank_step.ok:
+            exchange = "peer-memory copies over NVLink (CUDA IPC) + flag words"
+        else:
+            exchange = "nccl send/recv (peer mapping failed: %s)" % (rank_step.why or "on another rank")
+            rank_step = None
+    if rank_step is None:
+        rank_step = DistSlab(ds, rank, world, rows_group=rows_group, left_group=left_group)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     # the step's main stream outranks the second stream (search + morphogen stage), whose kernels then fill what the
@@ -847,6 +860,8 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
     barrier()
     clocks = sampler.stop()
     ds.check()                            # capacities, and the halo assumption over the timed steps
+    if hasattr(rank_step, "check_peers"):
+        rank_step.check_peers()
     timed_move = ds.eng.max_substep_move()
     total_s = sum(a.elapsed_time(b) for a, b in evs) / 1e3
     tt = torch.tensor([total_s], device=dev)
@@ -909,6 +924,7 @@ def run_b200_slabs(args, rank, world, dev, dist, barrier, wl, cfg):
                    "timing": "CUDA events per step, summed; max over ranks",
                    "host_synchronisations_per_step": 0, "main_stream_phases_us_rank0": timeline,
                    "cuda_graphs": bool(rank_step.captured),
+                   "cell_exchange": exchange,
                    "parallelism": f"slab{world}: 1-D slab decomposition along x; per step one cell-halo exchange "
                                   "(migration rides on it; fixed-capacity messages, counts on the device) and one "
                                   "morphogen-row exchange over NCCL send/recv"},

@@ -5,6 +5,8 @@
 //
 // Record layout (bytes), one per cell, shared with slab.py:
 //   [0,24) position  [24,32) radius  [32,56) motility force  [56,60) global id  [60,64) bond_len  [64,64+4*stride) bond row
+#include <string.h>
+
 #include "scan.cuh"
 
 namespace abm {
@@ -402,7 +404,91 @@ k_slab_place(CellArrays a, int rows, const int *__restrict__ n_own_dev, Incoming
     }
 }
 
+// ---- cell exchange over NVLink peer memory (slab_device.PeerSlab) ----------------------------------------------------
+// The sender copies its message straight into the neighbour's receive buffer (cudaMemcpyAsync over a CUDA-IPC mapping)
+// and then a 4-byte step number into the neighbour's flag word; the receiver's stream waits here until the flag has
+// reached the step it is at.  One thread, polls its OWN device's memory; gives up after max_wait_ns (a neighbour that
+// died must not hang the GPU) and records the step in *timed_out, which the caller reads at its next check.
+__global__ void k_flag_wait(const int *flag, int value, const int *__restrict__ value_dev, long long max_wait_ns,
+                            int *timed_out) {
+    if (value_dev) value += *value_dev;
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        int v;
+        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= value) return;
+        __nanosleep(100);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if ((long long)(t - t0) > max_wait_ns) {
+            atomicMax(timed_out, value > 0 ? value : 1);
+            return;
+        }
+    }
+}
+
+// The valid records of a message (their count sits in its header row, behind `capacity` records) and the header row are
+// stored straight into the neighbour's receive buffer over NVLink; the last block to finish then releases `value` into
+// the neighbour's flag word.  message == nullptr: only the flag (an acknowledgement).
+__global__ void __launch_bounds__(256)
+k_peer_send(int4 *__restrict__ dst, const int4 *__restrict__ src, long long capacity, int rec_bytes,
+            int *__restrict__ dst_flag, int value, const int *__restrict__ value_dev, int *__restrict__ counter) {
+    if (src) {
+        const long long header = capacity * rec_bytes / 16;                      // in 16-byte units
+        int count = *reinterpret_cast<const int *>(src + header);
+        count = count < 0 ? 0 : (count > capacity ? (int)capacity : count);
+        const long long body = (long long)count * rec_bytes / 16;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < body; k += stride) dst[k] = src[k];
+        if (blockIdx.x == 0 && threadIdx.x < rec_bytes / 16) dst[header + threadIdx.x] = src[header + threadIdx.x];
+    }
+    __shared__ bool last;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *counter = 0;
+        if (value_dev) value += *value_dev;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst_flag), "r"(value) : "memory");
+    }
+}
+
 }  // namespace abm
+
+ABM_EXPORT int abm_ipc_open(const uint8_t *handle_host, int64_t handle_bytes, void **base_host) {
+    ABM_REQUIRE(handle_host && base_host && handle_bytes == (int64_t)sizeof(cudaIpcMemHandle_t), "bad IPC handle");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_host, sizeof(h));
+    // opened with the CONSUMER's device current: the mapping then belongs to this device's context and, the exporter
+    // being another GPU, goes over NVLink (peer access is enabled on the way)
+    return check_cuda(cudaIpcOpenMemHandle(base_host, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+}
+
+ABM_EXPORT int abm_peer_send(uint8_t *peer_message, const uint8_t *message, int64_t capacity, int64_t record_bytes,
+                             int32_t *peer_flag, int32_t value, const int32_t *value_device, int32_t *block_counter,
+                             void *stream) {
+    ABM_REQUIRE(peer_flag && block_counter, "null pointer");
+    ABM_REQUIRE(!message || (peer_message && capacity >= 0 && record_bytes > 0 && record_bytes % 16 == 0 &&
+                             ((uintptr_t)peer_message & 15) == 0 && ((uintptr_t)message & 15) == 0),
+                "bad message");
+    const int blocks = message ? 2 * kSMsB200 : 1;
+    k_peer_send<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<int4 *>(peer_message),
+                                                       reinterpret_cast<const int4 *>(message), (long long)capacity,
+                                                       (int)record_bytes, peer_flag, value, value_device,
+                                                       block_counter);
+    ABM_CHECK_LAUNCH("k_peer_send");
+    return 0;
+}
+
+ABM_EXPORT int abm_flag_wait(const int32_t *flag, int32_t value, const int32_t *value_device, int64_t max_wait_ns,
+                             int32_t *timed_out, void *stream) {
+    ABM_REQUIRE(flag && timed_out && max_wait_ns > 0, "bad arguments");
+    k_flag_wait<<<1, 1, 0, as_stream(stream)>>>(flag, value, value_device, (long long)max_wait_ns, timed_out);
+    ABM_CHECK_LAUNCH("k_flag_wait");
+    return 0;
+}
 
 ABM_EXPORT int abm_slab_exchange_pack(const double *locations, const double *radii, const double *motility_forces,
                                       const int32_t *global_id, const int32_t *bond_len, const int32_t *bond_rows,
