@@ -407,23 +407,29 @@ int abm_slab_exchange_merge(const double *locations, const double *radii, const 
                             int64_t out_rows, int32_t *n_owned_out, int32_t *n_local_out, int32_t *tally,
                             int32_t *worst_rows, void *stream);
 
-/* Cell exchange over NVLink peer memory (slab_device.PeerSlab; one process per GPU, the neighbours' receive buffers
- * and flag words mapped through CUDA IPC).
+/* Cell exchange over NVLink peer memory (slab_device.PeerSlab; one node, one process per GPU; the neighbours' receive
+ * buffers and flag words are mapped through CUDA IPC).  Protocol per step k: a rank stores its two messages into the
+ * neighbours' receive buffers and releases k into their "data" flag words (abm_peer_exchange, ONE launch; a side first
+ * polls the "ack" word the neighbour wrote for k-1, so a buffer is never overwritten before it was merged); its stream
+ * then waits for k in its own two data words (abm_peer_flags with wait_*), merges (abm_slab_exchange_merge), and
+ * releases k into the neighbours' ack words (abm_peer_flags with release_*).  No host synchronisation.
  *   abm_ipc_open: cudaIpcOpenMemHandle of a neighbour's allocation (handle_host: the 64 bytes of its
  *     cudaIpcMemHandle_t) with THIS process's device current; *base_host receives the mapped base address.
- *   abm_peer_send: one launch on THIS device that stores the valid records of `message` (their count is in the header
- *     row behind `capacity` records of `record_bytes`) and the header row into `peer_message` -- the neighbour's
- *     buffer -- and, when every block has finished, releases `value` into `peer_flag` (system scope).  message ==
- *     NULL: only the flag (an acknowledgement).  block_counter (int32[1], this device, zeroed once by the caller).
- *   abm_flag_wait: `stream` waits until *flag >= value, *flag being a word of THIS device's memory that a peer
- *     writes; after max_wait_ns it gives up and raises *timed_out (int32, device) to `value` instead of hanging.
- *   In both, the flag value is value + *value_device when value_device is given (this device's memory): a captured
- *   CUDA graph, whose arguments are frozen, reads the step number from a counter it increments itself.          */
+ *   abm_peer_exchange: only the valid records (their count is in the header row behind `capacity` records of
+ *     `record_bytes`) and the header row travel.  A side whose peer_message_* is NULL does not exist.
+ *     block_counters: int32[2] on this device, zeroed once by the caller.
+ *   Every poll reads a word of the polling device's own memory, gives up after max_wait_ns and then raises
+ *   *timed_out (int32, device) to the step it waited for instead of hanging the GPU.  A flag value is
+ *   value + *value_device when value_device is given: a captured CUDA graph, whose arguments are frozen, reads the
+ *   step number from a counter it increments itself.                                                          */
 int abm_ipc_open(const uint8_t *handle_host, int64_t handle_bytes, void **base_host);
-int abm_peer_send(uint8_t *peer_message, const uint8_t *message, int64_t capacity, int64_t record_bytes,
-                  int32_t *peer_flag, int32_t value, const int32_t *value_device, int32_t *block_counter, void *stream);
-int abm_flag_wait(const int32_t *flag, int32_t value, const int32_t *value_device, int64_t max_wait_ns,
-                  int32_t *timed_out, void *stream);
+int abm_peer_exchange(uint8_t *peer_message_left, const uint8_t *message_left, int32_t *peer_data_flag_left,
+                      const int32_t *ack_flag_left, uint8_t *peer_message_right, const uint8_t *message_right,
+                      int32_t *peer_data_flag_right, const int32_t *ack_flag_right, int64_t capacity,
+                      int64_t record_bytes, int32_t value, const int32_t *value_device, int32_t *block_counters,
+                      int64_t max_wait_ns, int32_t *timed_out, void *stream);
+int abm_peer_flags(const int32_t *wait_a, const int32_t *wait_b, int32_t *release_a, int32_t *release_b,
+                   int32_t value, const int32_t *value_device, int64_t max_wait_ns, int32_t *timed_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -80,8 +80,8 @@ SIGNATURES = {
     "abm_slab_exchange_merge": (I32, [P, P, P, P, P, P, I64, P, P, P, I64, I64, F64, F64, I32, I32, P, P, P, P, P, P, P,
                                       I64, P, P, P, P, P]),
     "abm_ipc_open": (I32, [C.c_char_p, I64, C.POINTER(C.c_void_p)]),
-    "abm_peer_send": (I32, [P, P, I64, I64, P, I32, P, P, P]),
-    "abm_flag_wait": (I32, [P, I32, P, I64, P, P]),
+    "abm_peer_exchange": (I32, [P, P, P, P, P, P, P, P, I64, I64, I32, P, P, I64, P, P]),
+    "abm_peer_flags": (I32, [P, P, P, P, I32, P, I64, P, P]),
     "abm_deposit_morphogens": (I32, [P, P, F64, I64, P, L3, F64, I64, I64, P, P]),
 }
 

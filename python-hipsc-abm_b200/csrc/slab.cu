@@ -405,13 +405,14 @@ k_slab_place(CellArrays a, int rows, const int *__restrict__ n_own_dev, Incoming
 }
 
 // ---- cell exchange over NVLink peer memory (slab_device.PeerSlab) ----------------------------------------------------
-// The sender copies its message straight into the neighbour's receive buffer (cudaMemcpyAsync over a CUDA-IPC mapping)
-// and then a 4-byte step number into the neighbour's flag word; the receiver's stream waits here until the flag has
-// reached the step it is at.  One thread, polls its OWN device's memory; gives up after max_wait_ns (a neighbour that
-// died must not hang the GPU) and records the step in *timed_out, which the caller reads at its next check.
-__global__ void k_flag_wait(const int *flag, int value, const int *__restrict__ value_dev, long long max_wait_ns,
-                            int *timed_out) {
-    if (value_dev) value += *value_dev;
+// A rank stores the valid records of its two messages straight into its neighbours' receive buffers (CUDA-IPC
+// mappings, NVLink) and then releases the step number into each neighbour's "data" flag word; its own stream waits
+// until both neighbours' step numbers have arrived in ITS flag words, merges, and acknowledges with the step number in
+// the neighbours' "ack" words -- which a sender polls before it overwrites a buffer.  Every poll reads the polling
+// device's own memory and gives up after max_wait_ns (a neighbour that died must not hang the GPU), recording the
+// step in *timed_out, which the caller reads at its next check.  A flag value is value + *value_dev when value_dev is
+// given: a captured graph, whose arguments are frozen, reads the step number from a counter it increments itself.
+__device__ __forceinline__ void poll_flag(const int *flag, int value, long long max_wait_ns, int *timed_out) {
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
@@ -427,32 +428,53 @@ __global__ void k_flag_wait(const int *flag, int value, const int *__restrict__ 
     }
 }
 
-// The valid records of a message (their count sits in its header row, behind `capacity` records) and the header row are
-// stored straight into the neighbour's receive buffer over NVLink; the last block to finish then releases `value` into
-// the neighbour's flag word.  message == nullptr: only the flag (an acknowledgement).
+struct PeerSide {
+    int4 *dst;               // the neighbour's receive buffer (nullptr: no neighbour on this side)
+    const int4 *src;         // my message for it
+    int *data_flag;          // the neighbour's "data" flag word for messages from my side
+    const int *ack_flag;     // MY flag word the neighbour writes when it has merged a message of mine
+};
+
+constexpr int kPeerBlocks = kSMsB200;        // blocks per side
+
+// both sides in one launch: blocks [0, kPeerBlocks) serve the left neighbour, the rest the right one
 __global__ void __launch_bounds__(256)
-k_peer_send(int4 *__restrict__ dst, const int4 *__restrict__ src, long long capacity, int rec_bytes,
-            int *__restrict__ dst_flag, int value, const int *__restrict__ value_dev, int *__restrict__ counter) {
-    if (src) {
-        const long long header = capacity * rec_bytes / 16;                      // in 16-byte units
-        int count = *reinterpret_cast<const int *>(src + header);
-        count = count < 0 ? 0 : (count > capacity ? (int)capacity : count);
-        const long long body = (long long)count * rec_bytes / 16;
-        const long long stride = (long long)gridDim.x * blockDim.x;
-        for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < body; k += stride) dst[k] = src[k];
-        if (blockIdx.x == 0 && threadIdx.x < rec_bytes / 16) dst[header + threadIdx.x] = src[header + threadIdx.x];
-    }
+k_peer_exchange(PeerSide left, PeerSide right, long long capacity, int rec_bytes, int value,
+                const int *__restrict__ value_dev, int *__restrict__ counters, long long max_wait_ns,
+                int *__restrict__ timed_out) {
+    const int side = blockIdx.x / kPeerBlocks, blk = blockIdx.x % kPeerBlocks;
+    const PeerSide p = side ? right : left;
+    if (!p.dst) return;
+    if (value_dev) value += *value_dev;
+    if (threadIdx.x == 0) poll_flag(p.ack_flag, value - 1, max_wait_ns, timed_out);   // my previous message was merged
+    __syncthreads();
+    const long long header = capacity * rec_bytes / 16;                              // in 16-byte units
+    int count = *reinterpret_cast<const int *>(p.src + header);
+    count = count < 0 ? 0 : (count > capacity ? (int)capacity : count);
+    const long long body = (long long)count * rec_bytes / 16;
+    for (long long k = (long long)blk * 256 + threadIdx.x; k < body; k += (long long)kPeerBlocks * 256) p.dst[k] = p.src[k];
+    if (blk == 0 && threadIdx.x < rec_bytes / 16) p.dst[header + threadIdx.x] = p.src[header + threadIdx.x];
     __shared__ bool last;
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(counter, 1) == (int)gridDim.x - 1;
+    if (threadIdx.x == 0) last = atomicAdd(&counters[side], 1) == kPeerBlocks - 1;
     __syncthreads();
     if (last && threadIdx.x == 0) {
-        *counter = 0;
-        if (value_dev) value += *value_dev;
+        counters[side] = 0;
         __threadfence_system();
-        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(dst_flag), "r"(value) : "memory");
+        asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p.data_flag), "r"(value) : "memory");
     }
+}
+
+// thread k < 2: wait until my flag word k has reached the value (wait_flags), or release the value into the
+// neighbour's word k (release_flags); a null pointer = no neighbour on that side
+__global__ void k_peer_flags(const int *wait_a, const int *wait_b, int *release_a, int *release_b, int value,
+                             const int *__restrict__ value_dev, long long max_wait_ns, int *timed_out) {
+    if (value_dev) value += *value_dev;
+    const int *w = threadIdx.x ? wait_b : wait_a;
+    int *r = threadIdx.x ? release_b : release_a;
+    if (w) poll_flag(w, value, max_wait_ns, timed_out);
+    if (r) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(r), "r"(value) : "memory");
 }
 
 }  // namespace abm
@@ -466,27 +488,40 @@ ABM_EXPORT int abm_ipc_open(const uint8_t *handle_host, int64_t handle_bytes, vo
     return check_cuda(cudaIpcOpenMemHandle(base_host, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
 }
 
-ABM_EXPORT int abm_peer_send(uint8_t *peer_message, const uint8_t *message, int64_t capacity, int64_t record_bytes,
-                             int32_t *peer_flag, int32_t value, const int32_t *value_device, int32_t *block_counter,
-                             void *stream) {
-    ABM_REQUIRE(peer_flag && block_counter, "null pointer");
-    ABM_REQUIRE(!message || (peer_message && capacity >= 0 && record_bytes > 0 && record_bytes % 16 == 0 &&
-                             ((uintptr_t)peer_message & 15) == 0 && ((uintptr_t)message & 15) == 0),
-                "bad message");
-    const int blocks = message ? 2 * kSMsB200 : 1;
-    k_peer_send<<<blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<int4 *>(peer_message),
-                                                       reinterpret_cast<const int4 *>(message), (long long)capacity,
-                                                       (int)record_bytes, peer_flag, value, value_device,
-                                                       block_counter);
-    ABM_CHECK_LAUNCH("k_peer_send");
+ABM_EXPORT int abm_peer_exchange(uint8_t *peer_message_left, const uint8_t *message_left, int32_t *peer_data_flag_left,
+                                 const int32_t *ack_flag_left, uint8_t *peer_message_right,
+                                 const uint8_t *message_right, int32_t *peer_data_flag_right,
+                                 const int32_t *ack_flag_right, int64_t capacity, int64_t record_bytes, int32_t value,
+                                 const int32_t *value_device, int32_t *block_counters, int64_t max_wait_ns,
+                                 int32_t *timed_out, void *stream) {
+    ABM_REQUIRE(block_counters && timed_out && max_wait_ns > 0 && capacity >= 0 && record_bytes > 0 &&
+                    record_bytes % 16 == 0,
+                "bad arguments");
+    ABM_REQUIRE(!peer_message_left || (message_left && peer_data_flag_left && ack_flag_left), "left side incomplete");
+    ABM_REQUIRE(!peer_message_right || (message_right && peer_data_flag_right && ack_flag_right),
+                "right side incomplete");
+    ABM_REQUIRE((((uintptr_t)peer_message_left | (uintptr_t)message_left | (uintptr_t)peer_message_right |
+                  (uintptr_t)message_right) & 15) == 0, "messages must be 16-byte aligned");
+    if (!peer_message_left && !peer_message_right) return 0;
+    PeerSide l{reinterpret_cast<int4 *>(peer_message_left), reinterpret_cast<const int4 *>(message_left),
+               peer_data_flag_left, ack_flag_left};
+    PeerSide r{reinterpret_cast<int4 *>(peer_message_right), reinterpret_cast<const int4 *>(message_right),
+               peer_data_flag_right, ack_flag_right};
+    k_peer_exchange<<<2 * kPeerBlocks, 256, 0, as_stream(stream)>>>(l, r, (long long)capacity, (int)record_bytes, value,
+                                                                    value_device, block_counters,
+                                                                    (long long)max_wait_ns, timed_out);
+    ABM_CHECK_LAUNCH("k_peer_exchange");
     return 0;
 }
 
-ABM_EXPORT int abm_flag_wait(const int32_t *flag, int32_t value, const int32_t *value_device, int64_t max_wait_ns,
-                             int32_t *timed_out, void *stream) {
-    ABM_REQUIRE(flag && timed_out && max_wait_ns > 0, "bad arguments");
-    k_flag_wait<<<1, 1, 0, as_stream(stream)>>>(flag, value, value_device, (long long)max_wait_ns, timed_out);
-    ABM_CHECK_LAUNCH("k_flag_wait");
+ABM_EXPORT int abm_peer_flags(const int32_t *wait_a, const int32_t *wait_b, int32_t *release_a, int32_t *release_b,
+                              int32_t value, const int32_t *value_device, int64_t max_wait_ns, int32_t *timed_out,
+                              void *stream) {
+    ABM_REQUIRE(timed_out && max_wait_ns > 0, "bad arguments");
+    if (!wait_a && !wait_b && !release_a && !release_b) return 0;
+    k_peer_flags<<<1, 2, 0, as_stream(stream)>>>(wait_a, wait_b, release_a, release_b, value, value_device,
+                                                 (long long)max_wait_ns, timed_out);
+    ABM_CHECK_LAUNCH("k_peer_flags");
     return 0;
 }
 

@@ -502,35 +502,33 @@ class PeerSlab(DistSlab):
 
     # A flag value is `value` + (*step_dev if on_device): eager steps pass the step number from the host, the captured
     # front graph reads it from the device counter it increments itself (a graph's kernel arguments are frozen).
-    def _send(self, side, message, flag_index, value, on_device):
-        """One launch: `message` (or nothing) into the neighbour's buffer on `side`, then the value into its flag word."""
-        eng, p = self.slab.eng, self.peer[side]
-        there = 1 - side                     # my left neighbour receives from ITS right, and the other way round
-        dst = p["recv%d" % there] if message is not None else 0
-        _lib.check(eng.lib.abm_peer_send(dst, message.data_ptr() if message is not None else 0, self.slab.send_cap,
-                                         self.slab.rec, p["flags"] + 4 * (flag_index + there), int(value),
-                                         self.step_dev.data_ptr() if on_device else 0,
-                                         self.counters[side:].data_ptr(), eng.stream), "abm_peer_send")
-
-    def _wait(self, flag_index, value, on_device):
-        lib, eng = self.slab.eng.lib, self.slab.eng
-        _lib.check(lib.abm_flag_wait(self.flags[flag_index:].data_ptr(), int(value),
-                                     self.step_dev.data_ptr() if on_device else 0, self.max_wait_ns,
-                                     self.timed_out.data_ptr(), eng.stream), "abm_flag_wait")
+    def _flag(self, index):
+        return self.flags[index:].data_ptr()
 
     def _exchange(self, k, on_device):
-        s = self.slab
-        s.eng.use_current_stream()
-        for side in self.peer:
-            self._wait(self.FLAG_ACK + side, k - 1, on_device)   # the neighbour has merged my previous message
-            self._send(side, s.send[side], self.FLAG_DATA, k, on_device)
-        for side in self.peer:
-            self._wait(self.FLAG_DATA + side, k, on_device)      # this step's message from that side is here
+        """Both messages into the neighbours' buffers + their data flags (one launch), then wait for the neighbours'."""
+        s, eng = self.slab, self.slab.eng
+        eng.use_current_stream()
+        step = self.step_dev.data_ptr() if on_device else 0
+        args = []
+        for side in (0, 1):
+            p, there = self.peer.get(side), 1 - side     # my left neighbour receives from ITS right, and vice versa
+            args += ([p["recv%d" % there], s.send[side].data_ptr(), p["flags"] + 4 * (self.FLAG_DATA + there),
+                      self._flag(self.FLAG_ACK + side)] if p else [0, 0, 0, 0])
+        _lib.check(eng.lib.abm_peer_exchange(*args, s.send_cap, s.rec, int(k), step, self.counters.data_ptr(),
+                                             self.max_wait_ns, self.timed_out.data_ptr(), eng.stream),
+                   "abm_peer_exchange")
+        waits = [self._flag(self.FLAG_DATA + side) if side in self.peer else 0 for side in (0, 1)]
+        _lib.check(eng.lib.abm_peer_flags(waits[0], waits[1], 0, 0, int(k), step, self.max_wait_ns,
+                                          self.timed_out.data_ptr(), eng.stream), "abm_peer_flags")
 
     def _acks(self, k, on_device):
-        self.slab.eng.use_current_stream()
-        for side in self.peer:                                   # my receive buffers may be overwritten now
-            self._send(side, None, self.FLAG_ACK, k, on_device)
+        """My receive buffers may be overwritten now: the step number into the neighbours' ack words."""
+        eng = self.slab.eng
+        eng.use_current_stream()
+        rel = [self.peer[side]["flags"] + 4 * (self.FLAG_ACK + 1 - side) if side in self.peer else 0 for side in (0, 1)]
+        _lib.check(eng.lib.abm_peer_flags(0, 0, rel[0], rel[1], int(k), self.step_dev.data_ptr() if on_device else 0,
+                                          self.max_wait_ns, self.timed_out.data_ptr(), eng.stream), "abm_peer_flags")
 
     def _cells(self):                                            # (eager steps)
         self.peer_step += 1
