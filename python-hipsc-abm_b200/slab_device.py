@@ -441,20 +441,23 @@ class DistSlab(SlabStepper):
 
 class PeerSlab(DistSlab):
     """DistSlab whose CELL exchange goes over NVLink peer memory instead of NCCL send/recv (one node, one process per
-    GPU).  At set-up every rank maps its neighbours' receive buffers and flag words through CUDA IPC.  Per step a rank
-    copies each message straight into the neighbour's receive buffer (abm_peer_copy, a peer cudaMemcpyAsync on the main
-    stream), then the step number into the neighbour's "data" flag; its own stream waits until both neighbours' step
-    numbers have arrived (abm_flag_wait, a one-thread poll of local memory), merges, and acknowledges by writing the
-    step number into the neighbours' "ack" flags -- which a sender waits for before it overwrites the buffer at the
-    next step.  No host synchronisation, no rendezvous kernel: 2 copies + 1 poll per neighbour instead of NCCL's two
-    latency-bound send/recv rounds (37 us at 2 GPUs, 72 us at 8).  The morphogen rows stay on NCCL (side stream,
-    hidden behind the mechanics).  A neighbour that never answers makes the poll give up after `max_wait_s` and
-    check() raise, instead of hanging the GPU."""
+    GPU).  At set-up every rank maps its neighbours' receive buffers and flag words through CUDA IPC (handles exported
+    by torch's allocator, opened by abm_ipc_open with THIS rank's device current).  Per step ONE launch stores the valid
+    records of both messages straight into the neighbours' receive buffers and releases the step number into their
+    "data" flag words (abm_peer_exchange); the rank's own stream then waits until both neighbours' step numbers have
+    arrived in ITS data words (abm_peer_flags: a poll of local memory), merges, and releases the step number into the
+    neighbours' "ack" words -- which a sender polls before it overwrites a buffer at the next step.  No host
+    synchronisation, no rendezvous: NCCL needs two latency-bound send/recv rounds for the same exchange (37 us at 2
+    GPUs, 72 us at 8).  Once captured, pack -> exchange -> merge -> acknowledgements replay as ONE CUDA graph (the
+    step number then comes from a device counter the graph increments itself).  The morphogen rows stay on NCCL (side
+    stream, hidden behind the mechanics).  A neighbour that never answers makes a poll give up after `max_wait_s`
+    (generous: a neighbour's host may sit in a lazy NCCL communicator set-up for seconds during the first steps) and
+    check_peers() raise, instead of hanging the GPU."""
 
     FLAG_DATA, FLAG_ACK = 0, 2          # flags[FLAG_DATA + side]: step of the last message received from that side;
                                         # flags[FLAG_ACK + side]: last step whose message the neighbour on that side merged
 
-    def __init__(self, slab: DeviceSlab, rank, world, rows_group=None, side_stream=True, max_wait_s=5.0):
+    def __init__(self, slab: DeviceSlab, rank, world, rows_group=None, side_stream=True, max_wait_s=30.0):
         super().__init__(slab, rank, world, rows_group, side_stream)
         dev = slab.dev
         self.flags = torch.zeros(8, dtype=torch.int32, device=dev)
