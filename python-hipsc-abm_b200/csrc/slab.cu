@@ -330,8 +330,17 @@ k_slab_count(const double *__restrict__ loc, int rows, const int *__restrict__ n
     if (i < n) f = owns(loc[3 * (long long)i], x_lo, x_hi, has_left, has_right);
     else if (i < total)
         f = owns(*reinterpret_cast<const double *>(in.record(i - n, kl, rec_bytes)), x_lo, x_hi, has_left, has_right);
+    // one atomic per BLOCK (16 k warps adding to one word serialise in L2)
+    __shared__ int warp_owned[8];
     const unsigned m = __ballot_sync(0xffffffffu, f);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&tally[0], __popc(m));
+    if ((threadIdx.x & 31) == 0) warp_owned[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int sum = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += warp_owned[w];
+        if (sum) atomicAdd(&tally[0], sum);
+    }
     if (i == 0) tally[1] = total;
 }
 
@@ -351,17 +360,35 @@ k_slab_place(CellArrays a, int rows, const int *__restrict__ n_own_dev, Incoming
     if (i < n) f = owns(a.loc[3 * (long long)i], x_lo, x_hi, has_left, has_right);
     else if (valid)
         f = owns(*reinterpret_cast<const double *>(in.record(i - n, kl, rec_bytes)), x_lo, x_hi, has_left, has_right);
-    const int lane = threadIdx.x & 31;
-    int dst = -1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // slots are claimed per BLOCK: one atomic per part and block (the order inside a part is free), ranks inside the
+    // block from the warps' ballots
+    __shared__ int part_count[2][8];     // cells of part p in warp w, then the exclusive prefix over the warps
+    __shared__ int part_base[2];
+    unsigned ballots[2];
 #pragma unroll
     for (int part = 0; part < 2; ++part) {
-        const bool mine = valid && (part == 0 ? f : !f);
-        const unsigned m = __ballot_sync(0xffffffffu, mine);
-        if (m == 0) continue;
-        int base = 0;
-        if (lane == __ffs(m) - 1) base = atomicAdd(&tally[2 + part], __popc(m));
-        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-        if (mine) dst = (part ? n_keep : 0) + base + __popc(m & ((1u << lane) - 1));
+        ballots[part] = __ballot_sync(0xffffffffu, valid && (part == 0 ? f : !f));
+        if (lane == 0) part_count[part][warp] = __popc(ballots[part]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int part = threadIdx.x;
+        int sum = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const int c = part_count[part][w];
+            part_count[part][w] = sum;
+            sum += c;
+        }
+        part_base[part] = sum ? atomicAdd(&tally[2 + part], sum) : 0;
+    }
+    __syncthreads();
+    int dst = -1;
+    if (valid) {
+        const int part = f ? 0 : 1;
+        dst = (part ? n_keep : 0) + part_base[part] + part_count[part][warp] +
+              __popc(ballots[part] & ((1u << lane) - 1));
     }
     if (valid && dst < out_rows) {
         if (i < n) {
