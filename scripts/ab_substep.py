@@ -22,7 +22,8 @@ VARIANTS = {                      # -D switches of csrc/jkr.cu (see the comment 
     "slot_rows_trim_math": ["ABM_JKR_EXP=48"],
     "slot_rows_pdl_late": ["ABM_JKR_EXP=16", "ABM_PDL_LATE=1"],
     "slot_rows": ["ABM_JKR_EXP=16"],
-    "flat": ["ABM_JKR_FLAT=1"],            # lane-balanced contact phase, in-warp pairs evaluated once (k_jkr_substep_flat)       # bond rows keyed by slot between substeps (written without a GPU: run the tests)
+    # the two-axis kernel of flat worlds (csrc/jkr_plane.cuh); AB_PLANE=0 in the environment times the three-axis one
+    "plane_9cta": ["ABM_PLANE_MINBLOCKS=9"], "plane_hits12": ["ABM_JKR_MAXHITS=12"],
     # tile of the diffusion kernels (csrc/diffusion.cu); timed by the "diffuse_10_us" entry below
     "diff_16x128": ["ABM_DIFF_TILE_I=16"], "diff_32x64": ["ABM_DIFF_TILE_J=64"],
     "diff_16x64": ["ABM_DIFF_TILE_I=16", "ABM_DIFF_TILE_J=64"], "diff_64x128": ["ABM_DIFF_TILE_I=64"],
