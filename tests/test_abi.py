@@ -102,3 +102,21 @@ def test_product_never_touches_the_oracle():
                     offenders.append(os.path.join(base, f))
     assert not offenders, offenders
     assert "oracle" not in open(os.path.join(ROOT, "hipsc_abm_b200.py")).read()
+
+
+def test_flag_constants_of_the_binding_equal_the_header():
+    """The ctypes side passes flags as plain ints: every ABM_SORT_* / ABM_LOOP_* / ABM_SUBSTEP_* it defines must have
+    the header's value, and the bits of one family must not collide."""
+    import re
+    from hipsc_abm_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "abm_b200.h")).read()
+    defined = {m.group(1): int(m.group(2)) for m in re.finditer(r"#define\s+ABM_((?:SORT|LOOP|SUBSTEP)_[A-Z0-9_]+)\s+(\d+)",
+                                                                 header)}
+    bound = {name: getattr(_lib, name) for name in dir(_lib) if re.match(r"(SORT|LOOP|SUBSTEP)_[A-Z0-9_]+$", name)}
+    assert bound, "no flag constants found in _lib"
+    for name, value in bound.items():
+        assert defined.get(name) == value, f"{name}: binding {value}, header {defined.get(name)}"
+    for family in ("SORT", "LOOP", "SUBSTEP"):
+        bits = [v for k, v in defined.items() if k.startswith(family + "_")]
+        assert all(v and v & (v - 1) == 0 for v in bits), f"ABM_{family}_* must be single bits: {bits}"
+        assert len(set(bits)) == len(bits), f"ABM_{family}_* bits collide: {bits}"
