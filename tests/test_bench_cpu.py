@@ -91,3 +91,23 @@ def test_reference_arm_ignores_torchrun_thread_cap():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["cpu_baseline"]["cores"] == bench.host_cores()
     assert f"on {bench.host_cores()} threads" in line["cpu_baseline"]["sample"]
+
+
+def test_ab_script_variants_name_existing_build_switches():
+    """scripts/ab_substep.py builds variant libraries with -D switches; every switch it names must still exist in csrc/
+    (a renamed or removed experiment would silently build the default kernel and be "measured")."""
+    import ast
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tree = ast.parse(open(os.path.join(root, "scripts", "ab_substep.py")).read())
+    variants = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", "") == "VARIANTS":
+            variants = ast.literal_eval(node.value)
+    assert variants, "VARIANTS not found"
+    sources = "".join(open(f).read() for f in glob.glob(os.path.join(root, "python-hipsc-abm_b200", "csrc", "*")))
+    for name, defines in variants.items():
+        for d in defines:
+            macro = d.split("=")[0]
+            assert re.search(r"\b%s\b" % re.escape(macro), sources), f"variant {name}: {macro} is not used in csrc/"
